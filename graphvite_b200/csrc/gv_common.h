@@ -1,0 +1,22 @@
+// Shared helpers for the libgv_b200 translation units (host side; no CUDA headers needed).
+#pragma once
+
+#include <string>
+
+#include "gv_b200.h"
+
+namespace gv {
+
+// thread-local error slot behind gv_last_error()
+void set_error(const std::string &message);
+int fail(const std::string &message);  // set_error + return -1
+
+}  // namespace gv
+
+#define GV_CUDA_OK(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t gv_err__ = (call);                                                            \
+        if (gv_err__ != cudaSuccess)                                                              \
+            return gv::fail(std::string("CUDA error ") + cudaGetErrorString(gv_err__) + " at " +  \
+                            __FILE__ + ":" + std::to_string(__LINE__));                           \
+    } while (0)

@@ -1,0 +1,31 @@
+// Error slot and version string of libgv_b200 (see include/gv_b200.h, "Error model").
+#include <string>
+
+#include "gv_common.h"
+
+namespace gv {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &message) {
+    g_last_error = message;
+}
+
+int fail(const std::string &message) {
+    set_error(message);
+    return -1;
+}
+
+}  // namespace gv
+
+extern "C" {
+
+const char *gv_last_error(void) {
+    return gv::g_last_error.c_str();
+}
+
+const char *gv_version(void) {
+    return GV_VERSION;
+}
+
+}  // extern "C"

@@ -1,0 +1,362 @@
+// =============================================================================
+// gv_graph.cpp -- host-side Graph and AliasTable builder of libgv_b200.
+//
+// Mirrors graphvite::Graph<uint32> (reference include/instance/graph.cuh:62-277,
+// include/core/graph.h:87-101) and AliasTable::build
+// (include/base/alias_table.cuh:84-128) behind the C ABI of include/gv_b200.h.
+// Storage differs from the reference (append-only edge log + CSR instead of a
+// vector of adjacency vectors) but every observable -- first-seen vertex ids,
+// adjacency order, float accumulation order of the weights, flatten() order --
+// is identical.
+// =============================================================================
+#include "gv_host.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <sstream>
+
+namespace gv {
+
+// ---- AliasTable::build, base/alias_table.cuh:84-128 ---------------------------------
+// Vose's method with two FIFO queues; the order in which entries are paired decides the
+// table, so it is kept exactly (the queues are flat arrays walked by a cursor, which is
+// the same FIFO order as std::queue).
+template<class I>
+void build_alias(const float *weights, size_t count, float *prob, I *alias) {
+    if (count == 0)
+        throw std::runtime_error("Invalid sampling distribution");
+    double norm = 0;  // accumulated in double: alias_table.cuh:92
+    for (size_t i = 0; i < count; i++)
+        norm += weights[i];
+    norm = norm / count;
+    std::vector<I> little, large;
+    little.reserve(count);
+    large.reserve(count);
+    for (size_t i = 0; i < count; i++) {
+        prob[i] = float(double(weights[i]) / norm);
+        if (prob[i] < 1)
+            little.push_back(I(i));
+        else
+            large.push_back(I(i));
+    }
+    // Every pop from `large` is followed by exactly one push to one of the queues, so the
+    // two cursors never run past entries that have not been written yet.
+    size_t little_head = 0, large_head = 0;
+    while (little_head < little.size() && large_head < large.size()) {
+        const I i = little[little_head++], j = large[large_head++];
+        alias[i] = j;
+        const float sum = prob[i] + prob[j];
+        prob[j] = sum - 1;
+        if (prob[j] < 1)
+            little.push_back(j);
+        else
+            large.push_back(j);
+    }
+    // leftovers alias to themselves ("suppress some truncation error", :117-127)
+    for (; little_head < little.size(); little_head++)
+        alias[little[little_head]] = little[little_head];
+    for (; large_head < large.size(); large_head++)
+        alias[large[large_head]] = large[large_head];
+}
+
+template void build_alias<uint32_t>(const float *, size_t, float *, uint32_t *);
+template void build_alias<uint64_t>(const float *, size_t, float *, uint64_t *);
+
+// ---- Graph -----------------------------------------------------------------------------
+void Graph::clear() {
+    *this = Graph();
+}
+
+uint32_t Graph::intern(const std::string &name) {
+    auto found = name2id.find(name);
+    if (found != name2id.end())
+        return found->second;
+    const uint32_t id = uint32_t(id2name.size());
+    name2id.emplace(name, id);
+    id2name.push_back(name);
+    vertex_weights.push_back(0.f);
+    degrees.push_back(0);
+    return id;
+}
+
+// Graph::add_edge, instance/graph.cuh:124-153
+void Graph::add_edge(const std::string &u_name, const std::string &v_name, float w) {
+    const uint32_t u = intern(u_name);
+    const uint32_t v = intern(v_name);
+    log_u.push_back(u);
+    log_v.push_back(v);
+    log_w.push_back(w);
+    degrees[u]++;
+    vertex_weights[u] += w;
+    if (as_undirected && u != v) {
+        log_u.push_back(v);
+        log_v.push_back(u);
+        log_w.push_back(w);
+        degrees[v]++;
+        vertex_weights[v] += w;
+    }
+    num_edge++;  // input lines, not directed edges (:152)
+    flattened = false;
+}
+
+// GraphMixin::flatten, core/graph.h:87-101: edges grouped by source vertex, insertion order
+// kept inside a vertex -- a stable counting sort of the edge log.
+void Graph::flatten() {
+    if (flattened)
+        return;
+    const size_t n = id2name.size(), m = log_u.size();
+    offsets.assign(n + 1, 0);
+    for (size_t v = 0; v < n; v++)
+        offsets[v + 1] = offsets[v] + degrees[v];
+    std::vector<uint64_t> cursor(offsets.begin(), offsets.end() - 1);
+    edge_u.resize(m);
+    edge_v.resize(m);
+    edge_w.resize(m);
+    for (size_t e = 0; e < m; e++) {
+        const uint64_t slot = cursor[log_u[e]]++;
+        edge_u[slot] = log_u[e];
+        edge_v[slot] = log_v[e];
+        edge_w[slot] = log_w[e];
+    }
+    flattened = true;
+}
+
+// Graph::normalize, instance/graph.cuh:103-121
+void Graph::normalize() {
+    flatten();
+    const size_t n = id2name.size();
+    std::vector<float> context_weights(n, 0.f);
+    for (size_t e = 0; e < edge_u.size(); e++)
+        context_weights[edge_v[e]] += edge_w[e];
+    for (size_t u = 0; u < n; u++) {
+        float weight = 0;
+        for (uint64_t e = offsets[u]; e < offsets[u + 1]; e++) {
+            edge_w[e] /= std::sqrt(vertex_weights[u] * context_weights[edge_v[e]]);
+            weight += edge_w[e];
+        }
+        vertex_weights[u] = weight;
+    }
+    // the edge log is no longer consulted once flattened
+}
+
+// Graph::load_file, instance/graph.cuh:163-201
+void Graph::load_file(const char *file_name, bool undirected, bool normalized, const char *delimiters,
+                      const char *comment) {
+    clear();
+    as_undirected = undirected;
+    normalization = normalized;
+    FILE *fin = fopen(file_name, "r");
+    if (!fin)
+        throw std::runtime_error(std::string("File `") + file_name + "` doesn't exist");
+    const size_t kMaxLineLength = size_t(1) << 22;  // util/common.h:30
+    std::vector<char> line(kMaxLineLength);
+    const size_t comment_length = strlen(comment);
+    std::string names[2];
+    for (size_t line_no = 1; fgets(line.data(), int(kMaxLineLength), fin); line_no++) {
+        if (comment_length) {
+            char *cut = strstr(line.data(), comment);
+            if (cut)
+                *cut = 0;
+        }
+        int num_token = 0;
+        float w = 1;
+        bool bad = false;
+        for (char *cursor = line.data(); *cursor;) {
+            cursor += strspn(cursor, delimiters);
+            if (!*cursor)
+                break;
+            const size_t length = strcspn(cursor, delimiters);
+            if (num_token < 2)
+                names[num_token].assign(cursor, length);
+            else if (num_token == 2)
+                w = float(atof(std::string(cursor, length).c_str()));
+            else
+                bad = true;
+            num_token++;
+            cursor += length;
+        }
+        if (num_token == 0)
+            continue;
+        if (num_token < 2 || bad) {
+            fclose(fin);
+            throw std::runtime_error("Invalid format at line " + std::to_string(line_no));
+        }
+        add_edge(names[0], names[1], w);
+    }
+    fclose(fin);
+    flatten();
+    if (normalization)
+        normalize();
+}
+
+// Graph::load_edge_list / load_weighted_edge_list, instance/graph.cuh:209-252
+void Graph::load_edges(const char *const *u_names, const char *const *v_names, const float *weights,
+                       uint64_t count, bool undirected, bool normalized) {
+    clear();
+    as_undirected = undirected;
+    normalization = normalized;
+    for (uint64_t i = 0; i < count; i++)
+        add_edge(u_names[i], v_names[i], weights ? weights[i] : 1.f);
+    flatten();
+    if (normalization)
+        normalize();
+}
+
+// Graph::save, instance/graph.cuh:260-277
+void Graph::save(const char *file_name, bool weighted, bool anonymous) {
+    flatten();
+    FILE *fout = fopen(file_name, "w");
+    if (!fout)
+        throw std::runtime_error(std::string("Can't open `") + file_name + "` for writing");
+    for (size_t e = 0; e < edge_u.size(); e++) {
+        if (anonymous)
+            fprintf(fout, "%llu\t%llu", (unsigned long long)edge_u[e], (unsigned long long)edge_v[e]);
+        else
+            fprintf(fout, "%s\t%s", id2name[edge_u[e]].c_str(), id2name[edge_v[e]].c_str());
+        if (weighted)
+            fprintf(fout, "\t%f", edge_w[e]);
+        fputc('\n', fout);
+    }
+    fclose(fout);
+}
+
+bool Graph::has_dead_end() const {
+    for (size_t v = 0; v < degrees.size(); v++)
+        if (degrees[v] == 0)
+            return true;
+    return false;
+}
+
+// Graph::info, instance/graph.cuh:88-101 + core/graph.h:110-123
+std::string Graph::info() const {
+    std::stringstream ss;
+    ss << "Graph<uint32>" << std::endl;
+    ss << "------------------ Graph -------------------" << std::endl;
+    ss << "#vertex: " << num_vertex() << ", #edge: " << num_edge << std::endl;
+    ss << "as undirected: " << (as_undirected ? "yes" : "no")
+       << ", normalization: " << (normalization ? "yes" : "no");
+    return ss.str();
+}
+
+}  // namespace gv
+
+// =============================================================================
+// C ABI
+// =============================================================================
+using gv::Graph;
+
+struct gv_graph {
+    Graph graph;
+};
+
+#define GV_TRY try {
+#define GV_CATCH(ret)                  \
+    }                                  \
+    catch (const std::exception &e) {  \
+        gv::set_error(e.what());       \
+        return ret;                    \
+    }
+
+extern "C" {
+
+gv_graph_t *gv_graph_create(void) {
+    return new gv_graph();
+}
+
+void gv_graph_destroy(gv_graph_t *graph) {
+    delete graph;
+}
+
+int gv_graph_load_file(gv_graph_t *graph, const char *file_name, int as_undirected, int normalization,
+                       const char *delimiters, const char *comment) {
+    GV_TRY
+    graph->graph.load_file(file_name, as_undirected != 0, normalization != 0, delimiters ? delimiters : " \t\r\n",
+                           comment ? comment : "#");
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_graph_load_edges(gv_graph_t *graph, const char *const *u_names, const char *const *v_names,
+                        const float *weights, uint64_t num_edge, int as_undirected, int normalization) {
+    GV_TRY
+    graph->graph.load_edges(u_names, v_names, weights, num_edge, as_undirected != 0, normalization != 0);
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_graph_save(gv_graph_t *graph, const char *file_name, int weighted, int anonymous) {
+    GV_TRY
+    graph->graph.save(file_name, weighted != 0, anonymous != 0);
+    return 0;
+    GV_CATCH(-1)
+}
+
+uint64_t gv_graph_num_vertex(const gv_graph_t *graph) {
+    return graph->graph.num_vertex();
+}
+
+uint64_t gv_graph_num_edge(const gv_graph_t *graph) {
+    return graph->graph.num_edge;
+}
+
+int gv_graph_as_undirected(const gv_graph_t *graph) {
+    return graph->graph.as_undirected;
+}
+
+int gv_graph_normalization(const gv_graph_t *graph) {
+    return graph->graph.normalization;
+}
+
+const char *gv_graph_id2name(const gv_graph_t *graph, uint64_t id) {
+    if (id >= graph->graph.id2name.size())
+        return nullptr;
+    return graph->graph.id2name[id].c_str();
+}
+
+int64_t gv_graph_name2id(const gv_graph_t *graph, const char *name) {
+    auto found = graph->graph.name2id.find(name);
+    return found == graph->graph.name2id.end() ? -1 : int64_t(found->second);
+}
+
+uint64_t gv_graph_flatten(gv_graph_t *graph, uint32_t *u, uint32_t *v, float *w, uint64_t *flat_offsets,
+                          float *vertex_weights) {
+    Graph &g = graph->graph;
+    g.flatten();
+    const size_t m = g.edge_u.size(), n = g.num_vertex();
+    if (u)
+        memcpy(u, g.edge_u.data(), m * sizeof(uint32_t));
+    if (v)
+        memcpy(v, g.edge_v.data(), m * sizeof(uint32_t));
+    if (w)
+        memcpy(w, g.edge_w.data(), m * sizeof(float));
+    if (flat_offsets)
+        memcpy(flat_offsets, g.offsets.data(), n * sizeof(uint64_t));
+    if (vertex_weights)
+        memcpy(vertex_weights, g.vertex_weights.data(), n * sizeof(float));
+    return m;
+}
+
+int gv_graph_info(const gv_graph_t *graph, char *buffer, size_t capacity) {
+    const std::string info = graph->graph.info();
+    if (buffer && capacity) {
+        strncpy(buffer, info.c_str(), capacity - 1);
+        buffer[capacity - 1] = 0;
+    }
+    return int(info.size());
+}
+
+int gv_alias_build(const float *weights, uint64_t n, float *prob, uint64_t *alias) {
+    GV_TRY
+    gv::build_alias<uint64_t>(weights, n, prob, alias);
+    return 0;
+    GV_CATCH(-1)
+}
+
+}  // extern "C"
+
+gv::Graph &gv_graph_ref(gv_graph_t *graph) {
+    return graph->graph;
+}

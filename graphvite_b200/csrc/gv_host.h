@@ -1,0 +1,53 @@
+// Internal C++ declarations shared by the host runtime of libgv_b200 (gv_graph.cpp, gv_solver.cpp).
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gv_common.h"
+
+namespace gv {
+
+// AliasTable::build (reference include/base/alias_table.cuh:84-128)
+template<class I>
+void build_alias(const float *weights, size_t count, float *prob, I *alias);
+
+// graphvite::Graph<uint32> (reference include/instance/graph.cuh:62-277)
+struct Graph {
+    std::unordered_map<std::string, uint32_t> name2id;
+    std::vector<std::string> id2name;
+    std::vector<float> vertex_weights;
+    std::vector<uint32_t> degrees;  // out-degree = vertex_edges[v].size()
+    uint64_t num_edge = 0;          // input lines
+    bool as_undirected = true, normalization = false;
+
+    // append-only log of directed edges in insertion order
+    std::vector<uint32_t> log_u, log_v;
+    std::vector<float> log_w;
+    // flatten(): CSR in vertex order, insertion order inside a vertex
+    bool flattened = false;
+    std::vector<uint64_t> offsets;  // [num_vertex + 1]
+    std::vector<uint32_t> edge_u, edge_v;
+    std::vector<float> edge_w;
+
+    uint32_t num_vertex() const { return uint32_t(id2name.size()); }
+    void clear();
+    uint32_t intern(const std::string &name);
+    void add_edge(const std::string &u_name, const std::string &v_name, float w);
+    void flatten();
+    void normalize();
+    void load_file(const char *file_name, bool undirected, bool normalized, const char *delimiters,
+                   const char *comment);
+    void load_edges(const char *const *u_names, const char *const *v_names, const float *weights, uint64_t count,
+                    bool undirected, bool normalized);
+    void save(const char *file_name, bool weighted, bool anonymous);
+    bool has_dead_end() const;
+    std::string info() const;
+};
+
+}  // namespace gv
+
+gv::Graph &gv_graph_ref(gv_graph_t *graph);

@@ -1,0 +1,1320 @@
+// =============================================================================
+// gv_solver.cpp -- host runtime of the node-embedding solver (C++ over the CUDA C ABI).
+//
+// Mirrors graphvite::GraphSolver<dim, float, uint32> and the SolverMixin / SamplerMixin /
+// WorkerMixin machinery it inherits (reference include/instance/graph.cuh:587-813,
+// include/core/solver.h:100-1624), re-designed for B200:
+//   * every embedding block, both sample pools, the graph CSR and all alias tables are
+//     RESIDENT in HBM; host memory only holds the matrices behind the numpy views;
+//   * the sampler "threads" are cuRAND streams consumed by device kernels (gv_sampler.cu);
+//     their seeds, stream consumption and pool layout are the reference's, bit for bit;
+//   * one launch of the train kernel consumes a whole chunk of batches (gv_train.cu);
+//   * between sub-episodes vertex blocks move GPU-to-GPU through a caller-provided
+//     exchange (NCCL P2P over NVLink) instead of D2H -> CPU scatter/gather -> H2D.
+// One process drives one GPU; world_size processes form the reference's num_worker.
+// =============================================================================
+#include <cuda_runtime.h>
+#include <curand.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <set>
+#include <sstream>
+#include <thread>
+
+#include "gv_host.h"
+
+
+namespace gv {
+
+// core/solver.h:50-57 and instance/graph.cuh:56
+static std::mt19937 g_engine;
+static const int kMaxPartition = 16;
+static const int kRandBatchSize = 5000000;
+static const int kMinBatchSize = 10000;
+static const int kSamplePerVertex = 175;
+static const int kMinEpisodeSample = 20000000;
+static const int kExpectedDegree = 1600;
+static const uint64_t kMaxWalkChunk = 1 << 18;  // walks per sampler launch (bounds the scratch)
+
+#define GV_CHECK_CUDA(call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t gv_e__ = (call);                                                                     \
+        if (gv_e__ != cudaSuccess)                                                                       \
+            throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(gv_e__) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                         \
+    } while (0)
+#define GV_CHECK_CURAND(call)                                                                      \
+    do {                                                                                           \
+        curandStatus_t gv_e__ = (call);                                                            \
+        if (gv_e__ != CURAND_STATUS_SUCCESS)                                                       \
+            throw std::runtime_error("CURAND error " + std::to_string(int(gv_e__)) + " at " +      \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                   \
+    } while (0)
+#define GV_CHECK_ABI(call)                              \
+    do {                                                \
+        if ((call) != 0)                                \
+            throw std::runtime_error(gv_last_error()); \
+    } while (0)
+
+static void require(bool condition, const std::string &message) {
+    if (!condition)
+        throw std::runtime_error(message);
+}
+
+static bool log_enabled() {
+    static const bool on = getenv("GV_LOG") != nullptr && atoi(getenv("GV_LOG")) > 0;
+    return on;
+}
+
+// RAII device allocation
+struct DeviceArray {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    DeviceArray() {}
+    DeviceArray(const DeviceArray &) = delete;
+    DeviceArray &operator=(const DeviceArray &) = delete;
+    ~DeviceArray() { release(); }
+    void release() {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    void allocate(size_t n) {
+        if (n == bytes && ptr)
+            return;
+        release();
+        if (n) {
+            GV_CHECK_CUDA(cudaMalloc(&ptr, n));
+            bytes = n;
+        }
+    }
+    template<class T>
+    T *as() const { return static_cast<T *>(ptr); }
+    template<class T>
+    void upload(const std::vector<T> &host, cudaStream_t stream = 0) {
+        allocate(host.size() * sizeof(T));
+        if (!host.empty()) {
+            GV_CHECK_CUDA(cudaMemcpyAsync(ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+};
+
+// core/optimizer.h:42-134
+struct HostOptimizer {
+    gv_optimizer_t desc;
+    float init_lr = 0;
+    std::string type_name() const {
+        static const char *names[] = {"SGD", "Momentum", "AdaGrad", "RMSprop", "Adam"};
+        return desc.type < 0 ? "Default" : names[desc.type];
+    }
+    int num_moment() const { return desc.type <= GV_OPT_SGD ? 0 : (desc.type == GV_OPT_ADAM ? 2 : 1); }
+    // LRSchedule::operator() + Optimizer::apply_schedule, core/optimizer.h:65-79,132-134
+    float lr_at(int batch_id, int num_batch) const {
+        float factor = 1;
+        if (desc.schedule == GV_SCHEDULE_LINEAR)
+            factor = std::max(1 - float(batch_id) / num_batch, 1e-4f);
+        else if (desc.schedule == GV_SCHEDULE_CUSTOM && desc.schedule_fn)
+            factor = desc.schedule_fn(batch_id, num_batch, desc.schedule_ctx);
+        return init_lr * factor;
+    }
+    std::string info() const {  // Optimizer::info, core/optimizer.h:137-155
+        static const char *schedules[] = {"constant", "linear", "custom"};
+        std::stringstream ss;
+        ss << "optimizer: " << type_name() << std::endl;
+        ss << "learning rate: " << init_lr << ", lr schedule: " << schedules[desc.schedule] << std::endl;
+        ss << "weight decay: " << desc.weight_decay;
+        if (desc.type == GV_OPT_MOMENTUM)
+            ss << std::endl << "momentum: " << desc.a;
+        if (desc.type == GV_OPT_ADAGRAD)
+            ss << std::endl << "epsilon: " << desc.epsilon;
+        if (desc.type == GV_OPT_RMSPROP)
+            ss << std::endl << "alpha: " << desc.a << ", epsilon: " << desc.epsilon;
+        if (desc.type == GV_OPT_ADAM)
+            ss << std::endl << "beta1: " << desc.a << ", beta2: " << desc.b << ", epsilon: " << desc.epsilon;
+        return ss.str();
+    }
+};
+
+// SolverMixin::partition, core/solver.h:873-887.  std::sort is unstable: the order of equal
+// weights is whatever libstdc++'s introsort leaves, so the very same call is made here.
+static std::vector<std::vector<uint32_t>> partition_vertices(const std::vector<float> &weights, int num_partition) {
+    std::vector<uint32_t> order(weights.size());
+    for (uint32_t i = 0; i < order.size(); i++)
+        order[i] = i;
+    std::sort(order.begin(), order.end(), [&weights](uint32_t x, uint32_t y) { return weights[x] > weights[y]; });
+    std::vector<std::vector<uint32_t>> parts(num_partition);
+    const uint32_t period = num_partition * 2;
+    for (uint32_t i = 0; i < order.size(); i++) {
+        uint32_t slot = i % period;  // zig-zag deal: 0 1 .. P-1 P-1 .. 1 0
+        if (slot >= uint32_t(num_partition))
+            slot = period - 1 - slot;
+        parts[slot].push_back(order[i]);
+    }
+    return parts;
+}
+
+struct Assignment {
+    int head, tail;
+};
+
+// SolverMixin::get_schedule, core/solver.h:519-575 (GraphSolver: partitioned, weights not tied)
+static std::vector<std::vector<Assignment>> make_schedule(int num_partition, int num_worker) {
+    std::vector<std::vector<Assignment>> schedule;
+    if (num_partition == 1) {
+        schedule.push_back({{0, 0}});
+        return schedule;
+    }
+    for (int x = 0; x < num_partition; x += num_worker)
+        for (int y = 0; y < num_partition; y += num_worker)
+            for (int offset = 0; offset < num_worker; offset++) {
+                std::vector<Assignment> step(num_worker);
+                for (int i = 0; i < num_worker; i++)
+                    step[i] = {x + (i + offset) % num_worker, y + i};
+                schedule.push_back(step);
+            }
+    return schedule;
+}
+
+struct Solver {
+    // ---- construction (SolverMixin ctor, core/solver.h:184-213) ----
+    int dim, device, rank, world_size;
+    int num_worker, num_sampler;
+    uint64_t gpu_memory_limit, gpu_memory_cost = 0;
+    std::vector<unsigned long long> sampler_seeds, worker_seeds;
+    cudaStream_t work_stream = nullptr, sample_stream = nullptr, random_stream = nullptr;
+    std::vector<curandGenerator_t> sampler_generators;
+    curandGenerator_t worker_generator = nullptr;
+    gv_exchange_fn exchange_fn = nullptr;
+    void *exchange_ctx = nullptr;
+
+    // ---- build ----
+    Graph *graph = nullptr;
+    HostOptimizer optimizer;
+    int num_partition = 0, num_negative = 1, batch_size = 100000, episode_size = 0;
+    int num_group = 1;  // num_partition / num_worker
+    std::vector<std::vector<uint32_t>> partitions;
+    std::vector<gv_location_t> locations;
+    uint32_t partition_size = 0;
+    bool built = false;
+    std::vector<float> vertex_host, context_host;                       // numpy views
+    std::vector<float> vertex_m1_host, context_m1_host, vertex_m2_host, context_m2_host;
+
+    // ---- train parameters (readonly attributes, bind.h:415-436) ----
+    std::string model;
+    int num_epoch = 0, augmentation_step = 0, random_walk_length = 40, random_walk_batch_size = 100;
+    int shuffle_base = 0, positive_reuse = 1, log_frequency = 1000;
+    float p = 1, q = 1, negative_sample_exponent = 0.75f, negative_weight = 5;
+    bool resume = false;
+    int batch_id = 0, num_batch = 0, pool_id = 0;
+    bool training = false;
+
+    // ---- device state ----
+    size_t block_floats = 0;                       // partition_size * dim
+    int num_state = 1;                             // 1 + num_moment matrices per block
+    std::vector<DeviceArray> vertex_slots;         // each num_state * block_floats floats
+    std::vector<int> slot_of_head;                 // head block -> local slot or -1
+    std::vector<int> owner_of_head;                // head block -> rank
+    std::vector<int> free_slots;
+    std::vector<DeviceArray> context_blocks;       // [num_group]
+    std::vector<DeviceArray> negative_tables;      // [num_group] gv_alias_entry_t
+    std::vector<uint32_t> negative_counts;
+    std::vector<DeviceArray> partition_ids;        // [num_partition] global ids of each partition
+    std::vector<std::vector<DeviceArray>> pools[2];  // [head][group]
+    DeviceArray pool_pointers[2];                  // [P*P] block pointers (NULL if not owned)
+    // device graph
+    DeviceArray d_offsets, d_edge_u, d_edge_v, d_edge_prob, d_edge_alias, d_vertex_tables, d_locations;
+    gv_device_graph_t device_graph;
+    bool sampling_ready = false;
+    int sample_mode = 0;
+    // sampler scratch
+    DeviceArray d_sampler_random, d_chains, d_fill, d_last_walk, d_fill_scratch;
+    // worker scratch
+    DeviceArray d_random[2], d_lr, d_loss, d_negatives_out;
+    cudaEvent_t random_ready[2] = {nullptr, nullptr}, random_free[2] = {nullptr, nullptr};
+    int chunk_batches = 1;
+    bool capture_negatives = false;
+    std::vector<uint32_t> last_negatives;
+    std::vector<float> logged_loss;
+    float previous_batch_loss = 0;  // mean loss of the batch trained before (what the reference logs)
+    // stats
+    double stat_positive = 0, stat_kernel_seconds = 0, stat_train_seconds = 0, stat_sample_seconds = 0;
+    std::atomic<unsigned long long> stat_launches{0};
+
+    Solver(int _dim, const int *device_ids, int num_device, int num_sampler_per_worker, uint64_t memory_limit,
+           int _rank, int _world_size)
+        : dim(_dim), rank(_rank), world_size(_world_size), gpu_memory_limit(memory_limit) {
+        static const std::set<int> dims = {32, 64, 96, 128, 256, 512};  // src/graphvite.cu:52-59
+        require(dims.count(dim) == 1, "unsupported embedding dimension " + std::to_string(dim));
+        require(world_size >= 1 && rank >= 0 && rank < world_size, "invalid rank / world_size");
+        require(num_device <= 1, "one process drives one GPU: launch one process per GPU (torchrun) and pass "
+                                 "rank / world_size instead of several device ids");
+        if (num_device == 1)
+            device = device_ids[0];
+        else {
+            int count = 0;
+            GV_CHECK_CUDA(cudaGetDeviceCount(&count));
+            require(count > 0, "No GPU devices found");
+            device = world_size > 1 ? rank % count : 0;
+        }
+        num_worker = world_size;
+        // The reference defaults to hardware_concurrency / num_worker - 1 CPU sampler threads
+        // (core/solver.h:193-195).  Samplers are cuRAND streams here, not CPU threads: auto = 1.
+        if (num_sampler_per_worker == 0)
+            num_sampler_per_worker = 1;
+        require(num_sampler_per_worker > 0, "num_sampler_per_worker must be positive");
+        num_sampler = num_sampler_per_worker * num_worker;
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        if (gpu_memory_limit == 0) {
+            size_t free_bytes = 0, total_bytes = 0;
+            GV_CHECK_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+            gpu_memory_limit = free_bytes;  // the reference caps at 32 GiB (V100 era), core/solver.h:199-207
+        }
+        // seeds: samplers first, then workers, from the process-wide engine (core/solver.h:208-212,
+        // :950-952, :1247-1249).  Every rank draws the full sequence and keeps its own worker seed.
+        std::uniform_int_distribution<unsigned long long> random_seed(0, ULLONG_MAX);
+        for (int i = 0; i < num_sampler; i++)
+            sampler_seeds.push_back(random_seed(g_engine));
+        for (int i = 0; i < num_worker; i++)
+            worker_seeds.push_back(random_seed(g_engine));
+        GV_CHECK_CUDA(cudaStreamCreateWithFlags(&work_stream, cudaStreamNonBlocking));
+        GV_CHECK_CUDA(cudaStreamCreateWithFlags(&sample_stream, cudaStreamNonBlocking));
+        GV_CHECK_CUDA(cudaStreamCreateWithFlags(&random_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < num_sampler; i++) {
+            curandGenerator_t generator;
+            GV_CHECK_CURAND(curandCreateGenerator(&generator, CURAND_RNG_PSEUDO_DEFAULT));
+            GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(generator, sampler_seeds[i]));
+            GV_CHECK_CURAND(curandSetStream(generator, sample_stream));
+            sampler_generators.push_back(generator);
+        }
+        GV_CHECK_CURAND(curandCreateGenerator(&worker_generator, CURAND_RNG_PSEUDO_DEFAULT));
+        GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(worker_generator, worker_seeds[rank]));
+        GV_CHECK_CURAND(curandSetStream(worker_generator, random_stream));
+        for (int i = 0; i < 2; i++) {
+            GV_CHECK_CUDA(cudaEventCreateWithFlags(&random_ready[i], cudaEventDisableTiming));
+            GV_CHECK_CUDA(cudaEventCreateWithFlags(&random_free[i], cudaEventDisableTiming));
+        }
+        memset(&device_graph, 0, sizeof(device_graph));
+    }
+
+    ~Solver() {
+        cudaSetDevice(device);
+        for (auto g : sampler_generators)
+            curandDestroyGenerator(g);
+        if (worker_generator)
+            curandDestroyGenerator(worker_generator);
+        for (int i = 0; i < 2; i++) {
+            if (random_ready[i])
+                cudaEventDestroy(random_ready[i]);
+            if (random_free[i])
+                cudaEventDestroy(random_free[i]);
+        }
+        if (work_stream)
+            cudaStreamDestroy(work_stream);
+        if (sample_stream)
+            cudaStreamDestroy(sample_stream);
+        if (random_stream)
+            cudaStreamDestroy(random_stream);
+    }
+
+    int num_moment() const { return optimizer.num_moment(); }
+    uint64_t pool_size() const { return uint64_t(episode_size) * batch_size; }
+    bool owns_tail(int tail) const { return tail % num_worker == rank; }
+
+    // bytes this rank keeps resident for a given partition count (our memory model; the
+    // reference's gpu_memory_demand, core/solver.h:829-866, budgets ONE cached block pair)
+    uint64_t memory_demand(int P, int episode) const {
+        const uint64_t rows = (graph->num_vertex() + P - 1) / P;
+        const uint64_t block = rows * dim * sizeof(float) * (1 + optimizer.num_moment());
+        const int groups = P / num_worker;
+        const int slots = num_worker > 1 ? groups + 1 : P;
+        uint64_t demand = block * (slots + groups);
+        demand += uint64_t(2) * P * groups * episode * batch_size * 8;             // both sample pools
+        demand += uint64_t(graph->log_u.size()) * (4 + 4 + 4 + 8 + 8);              // CSR + edge/vertex tables
+        demand += uint64_t(graph->num_vertex()) * (8 + 8 + 8);                     // offsets, locations, negatives
+        demand += uint64_t(kRandBatchSize) * 8 + uint64_t(2) * 256 * 1024 * 1024;  // random buffers
+        demand += uint64_t(graph->num_vertex()) * dim * sizeof(float);             // staging for load / write-back
+        return demand;
+    }
+
+    // ---- SolverMixin::build, core/solver.h:287-466 ----
+    void build(Graph *_graph, const gv_optimizer_t *_optimizer, int _num_partition, int _num_negative,
+               int _batch_size, int _episode_size) {
+        require(!training, "build() during training");
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        graph = _graph;
+        require(graph->num_vertex() > 0, "The graph is empty");
+        optimizer.desc = *_optimizer;
+        if (optimizer.desc.type < 0) {  // "Default": SGD(0.025, 5e-3) unless a learning rate was given
+            const float lr = optimizer.desc.lr;
+            optimizer.desc.type = GV_OPT_SGD;  // GraphSolver::get_default_optimizer, graph.cuh:634-636
+            optimizer.desc.lr = lr > 0 ? lr : 0.025f;
+            optimizer.desc.weight_decay = 5e-3f;
+            optimizer.desc.schedule = GV_SCHEDULE_LINEAR;
+        }
+        optimizer.init_lr = optimizer.desc.lr;
+        num_negative = _num_negative;
+        batch_size = _batch_size;
+        require(num_negative >= 0 && batch_size > 0, "invalid num_negative / batch_size");
+        if (batch_size < kMinBatchSize && log_enabled())
+            fprintf(stderr, "It is recommended to a minimum batch size of %d, but %d is specified\n", kMinBatchSize,
+                    batch_size);
+        batch_id = 0;
+        graph->flatten();
+
+        const int min_partition = num_worker;  // get_min_partition, core/solver.h:266-277 (weights never tied)
+        auto auto_episode = [&](int P) {       // core/solver.h:426-436
+            int expected = float(uint64_t(graph->num_vertex()) * kSamplePerVertex) / P / batch_size;
+            expected = std::max(expected, 1);
+            if (P == 1)
+                expected = std::max(expected, kMinEpisodeSample / batch_size);
+            return expected;
+        };
+        num_partition = _num_partition;
+        if (num_partition == 0) {
+            for (num_partition = min_partition; num_partition < kMaxPartition; num_partition += min_partition)
+                if (memory_demand(num_partition, _episode_size ? _episode_size : auto_episode(num_partition)) <
+                    gpu_memory_limit)
+                    break;
+        } else
+            require(num_partition >= min_partition,
+                    "#partition should be no less than " + std::to_string(min_partition));
+        require(num_partition % num_worker == 0, "#partition must be a multiple of #worker");
+        num_group = num_partition / num_worker;
+        episode_size = _episode_size ? _episode_size : auto_episode(num_partition);
+        // the pools are the most elastic part: halve the episode until everything fits (solver.h:437-462)
+        while (episode_size > 1 && memory_demand(num_partition, episode_size) >= gpu_memory_limit)
+            episode_size /= 2;
+        gpu_memory_cost = memory_demand(num_partition, episode_size);
+        require(gpu_memory_cost < gpu_memory_limit, "Can't satisfy the specified GPU memory limit");
+
+        partitions = partition_vertices(graph->vertex_weights, num_partition);
+        partition_size = 0;
+        for (auto &part : partitions)
+            partition_size = std::max<uint32_t>(partition_size, part.size());
+        locations.resize(graph->num_vertex());
+        for (int i = 0; i < num_partition; i++)
+            for (uint32_t j = 0; j < partitions[i].size(); j++)
+                locations[partitions[i][j]] = {uint32_t(i), j};
+
+        const size_t total = size_t(graph->num_vertex()) * dim;
+        vertex_host.assign(total, 0.f);
+        context_host.assign(total, 0.f);
+        const int nm = num_moment();
+        vertex_m1_host.assign(nm >= 1 ? total : 0, 0.f);
+        context_m1_host.assign(nm >= 1 ? total : 0, 0.f);
+        vertex_m2_host.assign(nm >= 2 ? total : 0, 0.f);
+        context_m2_host.assign(nm >= 2 ? total : 0, 0.f);
+
+        // ---- device residency ----
+        block_floats = size_t(partition_size) * dim;
+        num_state = 1 + nm;
+        const int num_slot = num_worker > 1 ? num_group + 1 : num_partition;
+        vertex_slots = std::vector<DeviceArray>(num_slot);
+        for (auto &slot : vertex_slots)
+            slot.allocate(block_floats * num_state * sizeof(float));
+        context_blocks = std::vector<DeviceArray>(num_group);
+        for (auto &block : context_blocks)
+            block.allocate(block_floats * num_state * sizeof(float));
+        partition_ids = std::vector<DeviceArray>(num_partition);
+        for (int i = 0; i < num_partition; i++)
+            partition_ids[i].upload(partitions[i], work_stream);
+        d_locations.upload(locations, work_stream);
+        for (int side = 0; side < 2; side++) {
+            pools[side].clear();
+            pools[side].resize(num_partition);
+            std::vector<uint32_t *> pointers(size_t(num_partition) * num_partition, nullptr);
+            for (int h = 0; h < num_partition; h++) {
+                pools[side][h] = std::vector<DeviceArray>(num_group);
+                for (int g = 0; g < num_group; g++) {
+                    pools[side][h][g].allocate(pool_size() * 2 * sizeof(uint32_t));
+                    const int tail = g * num_worker + rank;
+                    pointers[size_t(h) * num_partition + tail] = pools[side][h][g].as<uint32_t>();
+                }
+            }
+            pool_pointers[side].upload(pointers, work_stream);
+        }
+        negative_tables = std::vector<DeviceArray>(num_group);
+        negative_counts.assign(num_group, 0);
+        // worker scratch
+        const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2 * sizeof(double);
+        chunk_batches = int(std::max<uint64_t>(1, std::min<uint64_t>(episode_size, (uint64_t(192) << 20) /
+                                                                                    std::max<uint64_t>(1, per_batch_random))));
+        for (int i = 0; i < 2; i++)
+            d_random[i].allocate(std::max<uint64_t>(16, per_batch_random * chunk_batches));
+        d_lr.allocate(size_t(episode_size) * sizeof(float));
+        d_loss.allocate(size_t(episode_size) * sizeof(float));
+        // sampler scratch
+        d_sampler_random.allocate(size_t(kRandBatchSize) * sizeof(double));
+        d_fill.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
+        d_last_walk.allocate(sizeof(unsigned long long));
+        sampling_ready = false;
+        pool_id = 0;
+        built = true;
+        logged_loss.clear();
+    }
+
+    // ---- device graph + sampler tables (GraphSolver::get_sample_function, graph.cuh:680-721) ----
+    void prepare_sampling() {
+        require(!graph->has_dead_end() || augmentation_step == 1,
+                "graphs with dead ends (vertices without out-edges) are not supported by the device walker yet");
+        if (augmentation_step == 1)
+            sample_mode = 0;
+        else if (model == "DeepWalk" || model == "LINE")
+            sample_mode = 1;
+        else
+            throw std::runtime_error("the node2vec second-order walker is not implemented in this build");
+        const size_t m = graph->edge_u.size();
+        require(m > 0, "The graph has no edges");
+        // edge_table.build(graph->edge_weights), core/solver.h:255-256
+        std::vector<float> edge_prob(m);
+        std::vector<uint64_t> edge_alias(m);
+        build_alias<uint64_t>(graph->edge_w.data(), m, edge_prob.data(), edge_alias.data());
+        d_offsets.upload(graph->offsets, sample_stream);
+        d_edge_u.upload(graph->edge_u, sample_stream);
+        d_edge_v.upload(graph->edge_v, sample_stream);
+        d_edge_prob.upload(edge_prob, sample_stream);
+        d_edge_alias.upload(edge_alias, sample_stream);
+        device_graph.num_vertex = graph->num_vertex();
+        device_graph.num_edge = m;
+        device_graph.offsets = d_offsets.as<uint64_t>();
+        device_graph.edge_u = d_edge_u.as<uint32_t>();
+        device_graph.edge_v = d_edge_v.as<uint32_t>();
+        device_graph.edge_prob = d_edge_prob.as<float>();
+        device_graph.edge_alias = d_edge_alias.as<uint64_t>();
+        device_graph.locations = d_locations.as<gv_location_t>();
+        device_graph.vertex_tables = nullptr;
+        if (sample_mode == 1) {
+            // build_vertex_edge, graph.cuh:645-653: one alias table per vertex over its out-edges,
+            // laid out at the vertex's CSR range; built by a few host threads.
+            std::vector<gv_alias_entry_t> tables(m);
+            const uint32_t n = graph->num_vertex();
+            const int num_thread = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            std::vector<std::thread> threads;
+            std::atomic<bool> failed(false);
+            for (int t = 0; t < num_thread; t++)
+                threads.emplace_back([&, t]() {
+                    std::vector<float> prob;
+                    std::vector<uint32_t> alias;
+                    const uint32_t work = (n + num_thread - 1) / num_thread;
+                    for (uint32_t v = work * t; v < std::min(n, work * (t + 1)); v++) {
+                        const uint64_t begin = graph->offsets[v], degree = graph->offsets[v + 1] - begin;
+                        if (!degree)
+                            continue;
+                        prob.resize(degree);
+                        alias.resize(degree);
+                        try {
+                            build_alias<uint32_t>(&graph->edge_w[begin], degree, prob.data(), alias.data());
+                        } catch (...) {
+                            failed = true;
+                            return;
+                        }
+                        for (uint64_t i = 0; i < degree; i++)
+                            tables[begin + i] = {prob[i], alias[i]};
+                    }
+                });
+            for (auto &thread : threads)
+                thread.join();
+            require(!failed, "Invalid sampling distribution");
+            d_vertex_tables.upload(tables, sample_stream);
+            device_graph.vertex_tables = d_vertex_tables.as<gv_alias_entry_t>();
+        }
+        const int L = sample_mode == 0 ? 1 : random_walk_length;
+        const uint64_t walks_per_buffer = uint64_t(kRandBatchSize - 2 * L) / (2 * L) + 1;
+        const uint64_t chunk = std::min<uint64_t>(walks_per_buffer, kMaxWalkChunk);
+        d_chains.allocate(chunk * (L + 1) * sizeof(gv_location_t));
+        d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(chunk), num_partition));
+        sampling_ready = true;
+    }
+
+    // ---- one sampler's share of a pool (SamplerMixin::sample / GraphSampler::sample_random_walk) ----
+    void run_sampler(int sampler_id, int side, uint64_t start, uint64_t end) {
+        const int L = sample_mode == 0 ? 1 : random_walk_length;
+        const int aug = sample_mode == 0 ? 1 : augmentation_step;
+        const int shuffle = sample_mode == 0 ? 1 : shuffle_base;
+        // termination is checked once per batch of walks: random_walk_batch_size walks, or
+        // sample_batch_size = L * walk_batch edges in edge mode (graph.cuh:791, solver.h:1026)
+        const uint64_t walk_batch = sample_mode == 0 ? uint64_t(random_walk_length) * random_walk_batch_size
+                                                     : uint64_t(random_walk_batch_size);
+        const uint64_t walks_per_buffer = uint64_t(kRandBatchSize - 2 * L) / (2 * L) + 1;
+        const int num_block = num_partition * num_partition;
+        uint64_t pairs_per_walk = 0;
+        for (int j = 0; j < L; j++)
+            pairs_per_walk += std::min(aug, L - j);
+
+        gv_fill_params_t params;
+        params.num_partition = num_partition;
+        params.walk_length = L;
+        params.augmentation_step = aug;
+        params.shuffle_base = shuffle;
+        params.pool_size = pool_size();
+        params.start = start;
+        params.end = end;
+        const uint64_t slice = end - start;
+        if (slice == 0)
+            return;
+
+        GV_CHECK_CUDA(cudaMemsetAsync(d_fill.ptr, 0, d_fill.bytes, sample_stream));
+        GV_CHECK_CUDA(cudaMemsetAsync(d_last_walk.ptr, 0, sizeof(unsigned long long), sample_stream));
+        std::vector<unsigned long long> fill(num_block, 0);
+        uint64_t buffers = 0, walks_done = 0;
+        bool complete = false;
+        unsigned long long last_walk = 0;
+        while (!complete) {
+            // refill: the next kRandBatchSize doubles of this sampler's stream (solver.h:1015-1016,1028-1031)
+            GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
+                                                        d_sampler_random.as<double>(), kRandBatchSize));
+            buffers++;
+            uint64_t in_buffer = 0;
+            while (in_buffer < walks_per_buffer && !complete) {
+                // how many walks are still needed, judged from the emptiest block
+                uint64_t missing = 0;
+                for (int b = 0; b < num_block; b++)
+                    missing = std::max<uint64_t>(missing, slice - std::min<uint64_t>(slice, fill[b]));
+                uint64_t want = uint64_t(double(missing) * num_block / pairs_per_walk * 1.02) + 2 * walk_batch;
+                want = (want + walk_batch - 1) / walk_batch * walk_batch;
+                const uint32_t count = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, kMaxWalkChunk),
+                                                                   walks_per_buffer - in_buffer));
+                const double *random = d_sampler_random.as<double>() + in_buffer * 2 * L;
+                GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, random, count, L, d_chains.as<gv_location_t>(),
+                                                 sample_stream));
+                GV_CHECK_ABI(gv_cuda_fill_pool(&params, d_chains.as<gv_location_t>(), count, walks_done,
+                                               pool_pointers[side].as<uint32_t *>(),
+                                               d_fill.as<unsigned long long>(),
+                                               d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
+                                               sample_stream));
+                stat_launches += num_partition == 1 ? 3 : 4;
+                GV_CHECK_CUDA(cudaMemcpyAsync(fill.data(), d_fill.ptr, num_block * sizeof(unsigned long long),
+                                              cudaMemcpyDeviceToHost, sample_stream));
+                GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk),
+                                              cudaMemcpyDeviceToHost, sample_stream));
+                GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+                in_buffer += count;
+                walks_done += count;
+                complete = true;
+                for (int b = 0; b < num_block; b++)
+                    complete = complete && fill[b] >= slice;
+            }
+        }
+        // The reference stops at the end of the batch of walks that completed the last block; a
+        // batch that runs past the current buffer pulls one more refill (only possible when
+        // walks_per_buffer is not a multiple of the batch).  Keep the generator in step.
+        const uint64_t executed = (last_walk / walk_batch + 1) * walk_batch;
+        const uint64_t needed_buffers = (executed - 1) / walks_per_buffer + 1;
+        for (; buffers < needed_buffers; buffers++)
+            GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
+                                                        d_sampler_random.as<double>(), kRandBatchSize));
+        require(buffers == needed_buffers, "internal error: sampler consumed more random buffers than the reference");
+    }
+
+    // fill one side of the sample pools with all samplers (core/solver.h:614-628)
+    void fill_pool(int side) {
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        cudaEvent_t begin, end;
+        GV_CHECK_CUDA(cudaEventCreate(&begin));
+        GV_CHECK_CUDA(cudaEventCreate(&end));
+        GV_CHECK_CUDA(cudaEventRecord(begin, sample_stream));
+        const uint64_t num_sample = pool_size();
+        const uint64_t work_load = (num_sample + num_sampler - 1) / num_sampler;
+        for (int i = 0; i < num_sampler; i++)
+            run_sampler(i, side, std::min(num_sample, work_load * i), std::min(num_sample, work_load * (i + 1)));
+        GV_CHECK_CUDA(cudaEventRecord(end, sample_stream));
+        GV_CHECK_CUDA(cudaEventSynchronize(end));
+        float ms = 0;
+        GV_CHECK_CUDA(cudaEventElapsedTime(&ms, begin, end));
+        stat_sample_seconds += ms * 1e-3;
+        cudaEventDestroy(begin);
+        cudaEventDestroy(end);
+    }
+
+    // ---- host <-> device block movement (replaces Memory::gather/scatter + to_device/to_host) ----
+    struct HostState {
+        std::vector<float> *matrix[3];
+    };
+    HostState vertex_state() { return {{&vertex_host, &vertex_m1_host, &vertex_m2_host}}; }
+    HostState context_state() { return {{&context_host, &context_m1_host, &context_m2_host}}; }
+
+    // load every resident block from the host matrices (load_partition/load_embedding, solver.h:1349-1495)
+    void load_blocks() {
+        const size_t total = size_t(graph->num_vertex()) * dim * sizeof(float);
+        DeviceArray staging;
+        staging.allocate(total);
+        slot_of_head.assign(num_partition, -1);
+        owner_of_head.assign(num_partition, 0);
+        free_slots.clear();
+        int next_slot = 0;
+        for (int h = 0; h < num_partition; h++) {
+            owner_of_head[h] = h % num_worker;
+            if (owner_of_head[h] == rank)
+                slot_of_head[h] = next_slot++;
+        }
+        for (int s = next_slot; s < int(vertex_slots.size()); s++)
+            free_slots.push_back(s);
+        HostState vertex = vertex_state(), context = context_state();
+        for (int s = 0; s < num_state; s++) {
+            GV_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, vertex.matrix[s]->data(), total, cudaMemcpyHostToDevice,
+                                          work_stream));
+            for (int h = 0; h < num_partition; h++)
+                if (slot_of_head[h] >= 0)
+                    GV_CHECK_ABI(gv_cuda_move_rows(vertex_slots[slot_of_head[h]].as<float>() + s * block_floats,
+                                                   staging.as<float>(), partition_ids[h].as<uint32_t>(),
+                                                   partitions[h].size(), dim, 1, work_stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+            GV_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, context.matrix[s]->data(), total, cudaMemcpyHostToDevice,
+                                          work_stream));
+            for (int g = 0; g < num_group; g++) {
+                const int t = g * num_worker + rank;
+                GV_CHECK_ABI(gv_cuda_move_rows(context_blocks[g].as<float>() + s * block_floats, staging.as<float>(),
+                                               partition_ids[t].as<uint32_t>(), partitions[t].size(), dim, 1,
+                                               work_stream));
+            }
+            GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+        }
+    }
+
+    // exchange wrapper: both directions optional
+    void exchange(const void *send, int dst, void *recv, int src, uint64_t bytes) {
+        require(exchange_fn != nullptr, "world_size > 1 needs gv_solver_set_exchange()");
+        if (exchange_fn(send, dst, recv, src, bytes, work_stream, exchange_ctx) != 0)
+            throw std::runtime_error("block exchange failed");
+    }
+
+    // the block of group g currently held by rank `holder` (vertex blocks migrate, context blocks do not)
+    int held_part(bool vertex_side, int g, int holder) const {
+        if (!vertex_side)
+            return g * num_worker + holder;
+        for (int h = g * num_worker; h < (g + 1) * num_worker; h++)
+            if (owner_of_head[h] == holder)
+                return h;
+        throw std::runtime_error("internal error: inconsistent block ownership");
+    }
+
+    // write every block back into the host matrices (write_back, core/solver.h:1498-1504).  With
+    // several ranks each group's blocks are passed around the ring so that every rank ends up
+    // with complete matrices behind its numpy views.
+    void write_back() {
+        const size_t total = size_t(graph->num_vertex()) * dim * sizeof(float);
+        DeviceArray staging, incoming;
+        staging.allocate(total);
+        const uint64_t block_bytes = block_floats * num_state * sizeof(float);
+        if (num_worker > 1)
+            incoming.allocate(block_bytes);
+        for (int side = 0; side < 2; side++) {
+            const bool vertex_side = side == 0;
+            HostState host = vertex_side ? vertex_state() : context_state();
+            for (int s = 0; s < num_state; s++) {
+                for (int g = 0; g < num_group; g++) {
+                    const int my_part = held_part(vertex_side, g, rank);
+                    const float *mine = vertex_side ? vertex_slots[slot_of_head[my_part]].as<float>()
+                                                    : context_blocks[g].as<float>();
+                    for (int d = 0; d < num_worker; d++) {
+                        const int from = (rank - d + num_worker) % num_worker;
+                        const float *block = mine;
+                        if (d > 0) {  // send mine d ranks ahead, receive the block held d ranks behind
+                            exchange(mine, (rank + d) % num_worker, incoming.ptr, from, block_bytes);
+                            block = incoming.as<float>();
+                        }
+                        const int part = held_part(vertex_side, g, from);
+                        GV_CHECK_ABI(gv_cuda_move_rows(staging.as<float>(), block + s * block_floats,
+                                                       partition_ids[part].as<uint32_t>(), partitions[part].size(),
+                                                       dim, 0, work_stream));
+                        GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+                    }
+                }
+                GV_CHECK_CUDA(cudaMemcpyAsync(host.matrix[s]->data(), staging.ptr, total, cudaMemcpyDeviceToHost,
+                                              work_stream));
+                GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+            }
+        }
+    }
+
+    // WorkerMixin::build_negative_sampler, core/solver.h:1264-1278 (tail partition, pow(degree, 0.75))
+    void build_negative_tables() {
+        for (int g = 0; g < num_group; g++) {
+            const int tail = g * num_worker + rank;
+            const auto &ids = partitions[tail];
+            std::vector<float> weights(ids.size());
+            for (size_t i = 0; i < ids.size(); i++)
+                weights[i] = std::pow(graph->vertex_weights[ids[i]], negative_sample_exponent);
+            std::vector<float> prob(ids.size());
+            std::vector<uint32_t> alias(ids.size());
+            build_alias<uint32_t>(weights.data(), weights.size(), prob.data(), alias.data());
+            std::vector<gv_alias_entry_t> table(ids.size());
+            for (size_t i = 0; i < ids.size(); i++)
+                table[i] = {prob[i], alias[i]};
+            negative_tables[g].upload(table, work_stream);
+            negative_counts[g] = uint32_t(ids.size());
+        }
+    }
+
+    // GraphSolver::init_embeddings, instance/graph.cuh:724-731
+    void init_embeddings() {
+        std::uniform_real_distribution<float> init(-0.5 / dim, 0.5 / dim);
+        for (auto &x : vertex_host)
+            x = init(g_engine);
+        std::fill(context_host.begin(), context_host.end(), 0.f);
+    }
+
+    // ---- GraphSolver::train prologue + SolverMixin::train up to the first pool fill ----
+    void train_begin(const std::string &_model, int _num_epoch, bool _resume, int _augmentation_step,
+                     int _random_walk_length, int _random_walk_batch_size, int _shuffle_base, float _p, float _q,
+                     int _positive_reuse, float _negative_sample_exponent, float _negative_weight,
+                     int _log_frequency) {
+        require(built, "The model must be built on a graph first");
+        require(!training, "train() is already running");
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        // instance/graph.cuh:774-789
+        augmentation_step = _augmentation_step;
+        random_walk_length = _random_walk_length;
+        random_walk_batch_size = _random_walk_batch_size;
+        shuffle_base = _shuffle_base;
+        p = _p;
+        q = _q;
+        if (augmentation_step == 0)
+            augmentation_step = int(std::log(double(kExpectedDegree)) /
+                                    std::log(float(graph->num_edge) / graph->num_vertex()));
+        if (shuffle_base == 0)
+            shuffle_base = augmentation_step;
+        // `model` still holds the PREVIOUS call's model here (graph.cuh:785 runs before solver.h:592)
+        if (model == "DeepWalk" || model == "node2vec")
+            shuffle_base = 1;
+        require(augmentation_step >= 1, "`augmentation_step` should be a positive integer");
+        require(augmentation_step <= random_walk_length,
+                "`random_walk_length` should be no less than `augmentation_step`");
+        // core/solver.h:588-611
+        require(_model == "DeepWalk" || _model == "LINE" || _model == "node2vec", "Invalid model `" + _model + "`");
+        model = _model;
+        num_epoch = _num_epoch;
+        resume = _resume;
+        positive_reuse = _positive_reuse;
+        negative_sample_exponent = _negative_sample_exponent;
+        negative_weight = _negative_weight;
+        log_frequency = std::max(1, _log_frequency);
+        require(random_walk_length >= 1 && random_walk_batch_size >= 1 && positive_reuse >= 1,
+                "invalid random walk / positive reuse parameters");
+        require(pool_size() % shuffle_base == 0 || augmentation_step == 1,
+                "Can't perform pseudo shuffle on " + std::to_string(pool_size()) + " elements by a shuffle base of " +
+                    std::to_string(shuffle_base) + ". Try setting the episode size to a multiple of the shuffle base");
+        if (log_enabled())
+            fprintf(stderr, "%s\n", info().c_str());
+        if (!resume) {
+            init_embeddings();
+            for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
+                std::fill(m->begin(), m->end(), 0.f);
+            batch_id = 0;
+        }
+        num_batch = int(batch_id + uint64_t(num_epoch) * graph->num_edge / batch_size);
+        prepare_sampling();
+        load_blocks();
+        build_negative_tables();
+        if (capture_negatives)
+            d_negatives_out.allocate(uint64_t(chunk_batches) * batch_size * std::max(1, num_negative) * 4);
+        stat_positive = stat_kernel_seconds = stat_train_seconds = stat_sample_seconds = 0;
+        stat_launches = 0;
+        previous_batch_loss = 0;
+        training = true;
+        fill_pool(pool_id ^ 1);
+    }
+
+    // WorkerMixin::train for one block, core/solver.h:1511-1557: positive_reuse * episode_size batches
+    void train_block(int head, int tail, int first_batch, int batch_stride) {
+        const int g = tail / num_worker;
+        float *vertex = vertex_slots[slot_of_head[head]].as<float>();
+        float *context = context_blocks[g].as<float>();
+        gv_matrices_t matrices;
+        matrices.dim = dim;
+        matrices.vertex = vertex;
+        matrices.context = context;
+        matrices.vertex_m1 = num_state >= 2 ? vertex + block_floats : nullptr;
+        matrices.context_m1 = num_state >= 2 ? context + block_floats : nullptr;
+        matrices.vertex_m2 = num_state >= 3 ? vertex + 2 * block_floats : nullptr;
+        matrices.context_m2 = num_state >= 3 ? context + 2 * block_floats : nullptr;
+        gv_device_optimizer_t device_optimizer = {optimizer.desc.type, optimizer.desc.weight_decay, optimizer.desc.a,
+                                                  optimizer.desc.b, optimizer.desc.epsilon};
+        const uint32_t *pool = pools[pool_id][head][g].as<uint32_t>();
+        const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2;
+        std::vector<float> lr(episode_size), loss(episode_size);
+        std::vector<cudaEvent_t> timers;
+        int buffer = 0;
+        for (int reuse = 0; reuse < positive_reuse; reuse++) {
+            for (int j = 0; j < episode_size; j++)
+                lr[j] = optimizer.lr_at(first_batch + (reuse * episode_size + j) * batch_stride, num_batch);
+            GV_CHECK_CUDA(cudaMemcpyAsync(d_lr.ptr, lr.data(), episode_size * sizeof(float), cudaMemcpyHostToDevice,
+                                          work_stream));
+            GV_CHECK_CUDA(cudaMemsetAsync(d_loss.ptr, 0, episode_size * sizeof(float), work_stream));
+            for (int j0 = 0; j0 < episode_size; j0 += chunk_batches, buffer ^= 1) {
+                const int count = std::min(chunk_batches, episode_size - j0);
+                // negatives: one curandGenerateUniformDouble(2 * B * k) per batch, like train_batch (solver.h:1536)
+                if (num_negative > 0) {
+                    GV_CHECK_CUDA(cudaStreamWaitEvent(random_stream, random_free[buffer], 0));
+                    for (int j = 0; j < count; j++)
+                        GV_CHECK_CURAND(curandGenerateUniformDouble(
+                            worker_generator, d_random[buffer].as<double>() + j * per_batch_random, per_batch_random));
+                    GV_CHECK_CUDA(cudaEventRecord(random_ready[buffer], random_stream));
+                    GV_CHECK_CUDA(cudaStreamWaitEvent(work_stream, random_ready[buffer], 0));
+                }
+                cudaEvent_t begin, end;
+                GV_CHECK_CUDA(cudaEventCreate(&begin));
+                GV_CHECK_CUDA(cudaEventCreate(&end));
+                GV_CHECK_CUDA(cudaEventRecord(begin, work_stream));
+                GV_CHECK_ABI(gv_cuda_train_block(
+                    &matrices, pool + uint64_t(j0) * batch_size * 2, uint64_t(count) * batch_size, num_negative,
+                    nullptr, d_random[buffer].as<double>(), negative_tables[g].as<gv_alias_entry_t>(),
+                    negative_counts[g], capture_negatives ? d_negatives_out.as<uint32_t>() : nullptr,
+                    &device_optimizer, d_lr.as<float>() + j0, batch_size, negative_weight, nullptr,
+                    d_loss.as<float>() + j0, 0, work_stream));
+                GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
+                GV_CHECK_CUDA(cudaEventRecord(random_free[buffer], work_stream));
+                timers.push_back(begin);
+                timers.push_back(end);
+                stat_launches++;
+                if (capture_negatives && reuse == positive_reuse - 1 && j0 + count == episode_size) {
+                    last_negatives.resize(size_t(batch_size) * num_negative);
+                    GV_CHECK_CUDA(cudaMemcpyAsync(last_negatives.data(),
+                                                  d_negatives_out.as<uint32_t>() +
+                                                      size_t(count - 1) * batch_size * num_negative,
+                                                  last_negatives.size() * 4, cudaMemcpyDeviceToHost, work_stream));
+                }
+            }
+            GV_CHECK_CUDA(cudaMemcpyAsync(loss.data(), d_loss.ptr, episode_size * sizeof(float),
+                                          cudaMemcpyDeviceToHost, work_stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+            // the reference logs, at batch b, the mean loss of the batch trained before it (appendix A.8)
+            for (int j = 0; j < episode_size; j++) {
+                const int this_batch = first_batch + (reuse * episode_size + j) * batch_stride;
+                if (this_batch % log_frequency == 0) {
+                    logged_loss.push_back(previous_batch_loss);
+                    if (log_enabled())
+                        fprintf(stderr, "Batch id: %d / %d\nloss = %g\n", this_batch, num_batch, previous_batch_loss);
+                }
+                previous_batch_loss = loss[j] / batch_size;
+            }
+        }
+        for (size_t i = 0; i < timers.size(); i += 2) {
+            float ms = 0;
+            GV_CHECK_CUDA(cudaEventElapsedTime(&ms, timers[i], timers[i + 1]));
+            stat_kernel_seconds += ms * 1e-3;
+            cudaEventDestroy(timers[i]);
+            cudaEventDestroy(timers[i + 1]);
+        }
+        stat_positive += double(positive_reuse) * episode_size * batch_size;
+    }
+
+    // one pass of the episode loop, core/solver.h:629-649
+    bool train_episode() {
+        require(training, "train_begin() has not been called");
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        if (batch_id >= num_batch)
+            return false;
+        pool_id ^= 1;
+        // the samplers fill the other pool while the worker trains on this one
+        std::exception_ptr sampler_error;
+        std::thread sampler([&]() {
+            try {
+                fill_pool(pool_id ^ 1);
+            } catch (...) {
+                sampler_error = std::current_exception();
+            }
+        });
+        std::exception_ptr worker_error;
+        try {
+            cudaEvent_t begin, end;
+            GV_CHECK_CUDA(cudaEventCreate(&begin));
+            GV_CHECK_CUDA(cudaEventCreate(&end));
+            GV_CHECK_CUDA(cudaEventRecord(begin, work_stream));
+            const auto schedule = make_schedule(num_partition, num_worker);
+            const int per_block = positive_reuse * episode_size;
+            for (const auto &step : schedule) {
+                const int width = int(step.size());
+                if (num_worker > 1)
+                    rotate_vertex_blocks(step);
+                // batch ids: the reference's workers share an atomic counter (solver.h:1520); we use the
+                // interleaving first_batch + j * width, which is what lock-step workers would draw.
+                train_block(step[rank].head, step[rank].tail, batch_id + rank, width);
+                batch_id += per_block * width;
+            }
+            GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
+            GV_CHECK_CUDA(cudaEventSynchronize(end));
+            float ms = 0;
+            GV_CHECK_CUDA(cudaEventElapsedTime(&ms, begin, end));
+            stat_train_seconds += ms * 1e-3;
+            cudaEventDestroy(begin);
+            cudaEventDestroy(end);
+        } catch (...) {
+            worker_error = std::current_exception();
+        }
+        sampler.join();
+        if (worker_error)
+            std::rethrow_exception(worker_error);
+        if (sampler_error)
+            std::rethrow_exception(sampler_error);
+        return true;
+    }
+
+    // Move the vertex blocks this step needs onto their workers.  Inside one group of
+    // num_worker head blocks the assignment is a permutation, so each rank sends at most one
+    // block and receives at most one (a ring shift for the default schedule).
+    void rotate_vertex_blocks(const std::vector<Assignment> &step) {
+        const int need = step[rank].head;
+        const int source = owner_of_head[need];
+        int give = -1, destination = -1;
+        for (int i = 0; i < num_worker; i++)
+            if (i != rank && owner_of_head[step[i].head] == rank) {
+                give = step[i].head;
+                destination = i;
+            }
+        const uint64_t bytes = block_floats * num_state * sizeof(float);
+        int incoming_slot = -1;
+        if (source != rank) {
+            require(!free_slots.empty(), "internal error: no free vertex slot");
+            incoming_slot = free_slots.back();
+            free_slots.pop_back();
+        }
+        if (give >= 0 || incoming_slot >= 0)
+            exchange(give >= 0 ? vertex_slots[slot_of_head[give]].ptr : nullptr, destination,
+                     incoming_slot >= 0 ? vertex_slots[incoming_slot].ptr : nullptr, incoming_slot >= 0 ? source : -1,
+                     bytes);
+        if (give >= 0) {
+            free_slots.push_back(slot_of_head[give]);
+            slot_of_head[give] = -1;
+        }
+        if (incoming_slot >= 0)
+            slot_of_head[need] = incoming_slot;
+        for (int i = 0; i < num_worker; i++)
+            owner_of_head[step[i].head] = i;
+    }
+
+    void train_end() {
+        require(training, "train_begin() has not been called");
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        write_back();
+        training = false;
+    }
+
+    void train(const std::string &_model, int _num_epoch, bool _resume, int _augmentation_step,
+               int _random_walk_length, int _random_walk_batch_size, int _shuffle_base, float _p, float _q,
+               int _positive_reuse, float _negative_sample_exponent, float _negative_weight, int _log_frequency) {
+        train_begin(_model, _num_epoch, _resume, _augmentation_step, _random_walk_length, _random_walk_batch_size,
+                    _shuffle_base, _p, _q, _positive_reuse, _negative_sample_exponent, _negative_weight,
+                    _log_frequency);
+        try {
+            while (train_episode())
+                ;
+        } catch (...) {
+            training = false;
+            throw;
+        }
+        train_end();
+    }
+
+    // SolverMixin::predict_numpy, core/solver.h:729-802.  Both matrices are uploaded in global-id
+    // order, so no bucketing by partition block is needed; rows are (v, c) like the reference.
+    void predict(const uint32_t *pairs, uint64_t num, float *logits) {
+        require(built, "The model must be built on a graph first");
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        const uint32_t n = graph->num_vertex();
+        std::vector<uint32_t> batch(num * 2);
+        for (uint64_t i = 0; i < num; i++) {
+            require(pairs[i * 2] < n && pairs[i * 2 + 1] < n, "predict: vertex id out of range");
+            batch[i * 2] = pairs[i * 2 + 1];  // device layout {tail, head}
+            batch[i * 2 + 1] = pairs[i * 2];
+        }
+        DeviceArray d_vertex, d_context, d_batch, d_logits;
+        d_vertex.upload(vertex_host, work_stream);
+        d_context.upload(context_host, work_stream);
+        d_batch.upload(batch, work_stream);
+        d_logits.allocate(std::max<uint64_t>(1, num) * sizeof(float));
+        GV_CHECK_ABI(gv_cuda_predict(dim, d_vertex.as<float>(), d_context.as<float>(), d_batch.as<uint32_t>(), num,
+                                     d_logits.as<float>(), work_stream));
+        GV_CHECK_CUDA(cudaMemcpyAsync(logits, d_logits.ptr, num * sizeof(float), cudaMemcpyDeviceToHost, work_stream));
+        GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+    }
+
+    // SolverMixin::clear + GraphSolver::clear: free everything but the host embeddings
+    void clear() {
+        require(!training, "clear() during training");
+        cudaSetDevice(device);
+        vertex_slots.clear();
+        context_blocks.clear();
+        negative_tables.clear();
+        partition_ids.clear();
+        for (int side = 0; side < 2; side++) {
+            pools[side].clear();
+            pool_pointers[side].release();
+        }
+        for (auto *a : {&d_offsets, &d_edge_u, &d_edge_v, &d_edge_prob, &d_edge_alias, &d_vertex_tables, &d_locations,
+                        &d_sampler_random, &d_chains, &d_fill, &d_last_walk, &d_fill_scratch, &d_random[0],
+                        &d_random[1], &d_lr, &d_loss, &d_negatives_out})
+            a->release();
+        for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
+            std::vector<float>().swap(*m);
+        partitions.clear();
+        sampling_ready = false;
+        built = false;
+    }
+
+    // SolverMixin::info, core/solver.h:468-516 + GraphSolver overrides, graph.cuh:733-752
+    std::string info() const {
+        auto yes_no = [](bool x) { return x ? "yes" : "no"; };
+        auto size_string = [](uint64_t size) {
+            std::stringstream ss;
+            ss.precision(3);
+            if (size >= (uint64_t(1) << 40))
+                ss << double(size) / (uint64_t(1) << 40) << " TiB";
+            else if (size >= (uint64_t(1) << 30))
+                ss << double(size) / (uint64_t(1) << 30) << " GiB";
+            else if (size >= (uint64_t(1) << 20))
+                ss << double(size) / (uint64_t(1) << 20) << " MiB";
+            else if (size >= (uint64_t(1) << 10))
+                ss << double(size) / (uint64_t(1) << 10) << " KiB";
+            else
+                ss << size << " B";
+            return ss.str();
+        };
+        std::stringstream ss;
+        ss << "GraphSolver<" << dim << ", float32, uint32>" << std::endl;
+        ss << "----------------- Resource -----------------" << std::endl;
+        ss << "#worker: " << num_worker << ", #sampler: " << num_sampler << ", #partition: " << num_partition
+           << std::endl;
+        ss << "tied weights: no, episode size: " << episode_size << std::endl;
+        ss << "gpu memory limit: " << size_string(gpu_memory_limit) << std::endl;
+        ss << "gpu memory cost: " << size_string(gpu_memory_cost) << std::endl;
+        ss << "----------------- Sampling -----------------" << std::endl;
+        if (model == "LINE")
+            ss << "augmentation step: " << augmentation_step << ", shuffle base: " << shuffle_base << std::endl;
+        if (model == "DeepWalk")
+            ss << "augmentation step: " << augmentation_step << std::endl;
+        if (model == "node2vec")
+            ss << "augmentation step: " << augmentation_step << ", p: " << p << ", q: " << q << std::endl;
+        ss << "random walk length: " << random_walk_length << std::endl;
+        ss << "random walk batch size: " << random_walk_batch_size << std::endl;
+        ss << "#negative: " << num_negative << ", negative sample exponent: " << negative_sample_exponent
+           << std::endl;
+        ss << "----------------- Training -----------------" << std::endl;
+        ss << "model: " << model << std::endl;
+        ss << optimizer.info() << std::endl;
+        ss << "#epoch: " << num_epoch << ", batch size: " << batch_size << std::endl;
+        ss << "resume: " << yes_no(resume) << std::endl;
+        ss << "positive reuse: " << positive_reuse << ", negative weight: " << negative_weight;
+        return ss.str();
+    }
+
+    std::string attributes() const {
+        std::stringstream ss;
+        ss.precision(9);
+        ss << "dim=" << dim << "\nnum_partition=" << num_partition << "\nnum_negative=" << num_negative
+           << "\nnegative_sample_exponent=" << negative_sample_exponent << "\nnegative_weight=" << negative_weight
+           << "\nmodel=" << model << "\nnum_epoch=" << num_epoch << "\nresume=" << int(resume)
+           << "\nepisode_size=" << episode_size << "\nbatch_size=" << batch_size
+           << "\naugmentation_step=" << augmentation_step << "\nrandom_walk_length=" << random_walk_length
+           << "\nrandom_walk_batch_size=" << random_walk_batch_size << "\nshuffle_base=" << shuffle_base
+           << "\np=" << p << "\nq=" << q << "\npositive_reuse=" << positive_reuse
+           << "\nlog_frequency=" << log_frequency << "\nnum_worker=" << num_worker
+           << "\nnum_sampler=" << num_sampler << "\ngpu_memory_limit=" << gpu_memory_limit
+           << "\ngpu_memory_cost=" << gpu_memory_cost << "\nnum_batch=" << num_batch << "\nbatch_id=" << batch_id
+           << "\npool_id=" << pool_id << "\npartition_size=" << partition_size << "\nrank=" << rank
+           << "\noptimizer_type=" << optimizer.type_name() << "\noptimizer_lr=" << optimizer.init_lr
+           << "\noptimizer_weight_decay=" << optimizer.desc.weight_decay << "\n";
+        return ss.str();
+    }
+};
+
+}  // namespace gv
+
+// =============================================================================
+// C ABI
+// =============================================================================
+using gv::Solver;
+
+struct gv_solver {
+    std::unique_ptr<Solver> solver;
+};
+
+#define GV_TRY try {
+#define GV_CATCH(ret)                  \
+    }                                  \
+    catch (const std::exception &e) {  \
+        gv::set_error(e.what());       \
+        return ret;                    \
+    }
+
+static int copy_string(const std::string &text, char *buffer, size_t capacity) {
+    if (buffer && capacity) {
+        strncpy(buffer, text.c_str(), capacity - 1);
+        buffer[capacity - 1] = 0;
+    }
+    return int(text.size());
+}
+
+extern "C" {
+
+void gv_reset_global_engine(uint32_t seed) {
+    gv::g_engine = std::mt19937(seed);
+}
+
+gv_solver_t *gv_solver_create(int dim, const int *device_ids, int num_device, int num_sampler_per_worker,
+                              uint64_t gpu_memory_limit, int rank, int world_size) {
+    GV_TRY
+    std::unique_ptr<Solver> solver(
+        new Solver(dim, device_ids, num_device, num_sampler_per_worker, gpu_memory_limit, rank, world_size));
+    gv_solver *handle = new gv_solver();
+    handle->solver = std::move(solver);
+    return handle;
+    GV_CATCH(nullptr)
+}
+
+void gv_solver_destroy(gv_solver_t *solver) {
+    delete solver;
+}
+
+int gv_solver_set_exchange(gv_solver_t *solver, gv_exchange_fn fn, void *ctx) {
+    solver->solver->exchange_fn = fn;
+    solver->solver->exchange_ctx = ctx;
+    return 0;
+}
+
+int gv_solver_set_option(gv_solver_t *solver, const char *name, int value) {
+    GV_TRY
+    if (std::string(name) == "capture_negatives")
+        solver->solver->capture_negatives = value != 0;
+    else
+        throw std::runtime_error(std::string("unknown option `") + name + "`");
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_build(gv_solver_t *solver, gv_graph_t *graph, const gv_optimizer_t *optimizer, int num_partition,
+                    int num_negative, int batch_size, int episode_size) {
+    GV_TRY
+    solver->solver->build(&gv_graph_ref(graph), optimizer, num_partition, num_negative, batch_size, episode_size);
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_train(gv_solver_t *solver, const char *model, int num_epoch, int resume, int augmentation_step,
+                    int random_walk_length, int random_walk_batch_size, int shuffle_base, float p, float q,
+                    int positive_reuse, float negative_sample_exponent, float negative_weight, int log_frequency) {
+    GV_TRY
+    solver->solver->train(model, num_epoch, resume != 0, augmentation_step, random_walk_length,
+                          random_walk_batch_size, shuffle_base, p, q, positive_reuse, negative_sample_exponent,
+                          negative_weight, log_frequency);
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_train_begin(gv_solver_t *solver, const char *model, int num_epoch, int resume, int augmentation_step,
+                          int random_walk_length, int random_walk_batch_size, int shuffle_base, float p, float q,
+                          int positive_reuse, float negative_sample_exponent, float negative_weight,
+                          int log_frequency) {
+    GV_TRY
+    solver->solver->train_begin(model, num_epoch, resume != 0, augmentation_step, random_walk_length,
+                                random_walk_batch_size, shuffle_base, p, q, positive_reuse, negative_sample_exponent,
+                                negative_weight, log_frequency);
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_train_episode(gv_solver_t *solver) {
+    GV_TRY
+    return solver->solver->train_episode() ? 1 : 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_train_end(gv_solver_t *solver) {
+    GV_TRY
+    solver->solver->train_end();
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_predict(gv_solver_t *solver, const uint32_t *pairs, uint64_t num, float *logits) {
+    GV_TRY
+    solver->solver->predict(pairs, num, logits);
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_solver_clear(gv_solver_t *solver) {
+    GV_TRY
+    solver->solver->clear();
+    return 0;
+    GV_CATCH(-1)
+}
+
+float *gv_solver_embeddings(gv_solver_t *solver, int which, uint64_t *rows, int *dim) {
+    Solver &s = *solver->solver;
+    if (rows)
+        *rows = s.graph ? s.vertex_host.size() / s.dim : 0;
+    if (dim)
+        *dim = s.dim;
+    return which == 0 ? s.vertex_host.data() : s.context_host.data();
+}
+
+int gv_solver_info(const gv_solver_t *solver, char *buffer, size_t capacity) {
+    return copy_string(solver->solver->info(), buffer, capacity);
+}
+
+int gv_solver_attributes(const gv_solver_t *solver, char *buffer, size_t capacity) {
+    return copy_string(solver->solver->attributes(), buffer, capacity);
+}
+
+int gv_solver_logged_loss(const gv_solver_t *solver, float *out, int capacity) {
+    const auto &loss = solver->solver->logged_loss;
+    for (int i = 0; i < capacity && i < int(loss.size()); i++)
+        out[i] = loss[i];
+    return int(loss.size());
+}
+
+int gv_solver_stats(const gv_solver_t *solver, double *out, int capacity) {
+    const Solver &s = *solver->solver;
+    const double values[] = {s.stat_positive, s.stat_kernel_seconds, s.stat_train_seconds, s.stat_sample_seconds,
+                             double(s.stat_launches.load())};
+    for (int i = 0; i < capacity && i < 5; i++)
+        out[i] = values[i];
+    return 5;
+}
+
+int gv_solver_locations(const gv_solver_t *solver, uint32_t *part_of, uint32_t *local_of) {
+    const auto &locations = solver->solver->locations;
+    for (size_t v = 0; v < locations.size(); v++) {
+        part_of[v] = locations[v].part;
+        local_of[v] = locations[v].local;
+    }
+    return 0;
+}
+
+int64_t gv_solver_pool(gv_solver_t *solver, int pool, int head_partition, int tail_partition, uint32_t *out) {
+    GV_TRY
+    Solver &s = *solver->solver;
+    if (pool < 0 || pool > 1 || head_partition < 0 || head_partition >= s.num_partition || tail_partition < 0 ||
+        tail_partition >= s.num_partition)
+        throw std::runtime_error("gv_solver_pool: index out of range");
+    if (!s.owns_tail(tail_partition))
+        return 0;
+    cudaSetDevice(s.device);
+    const auto &block = s.pools[pool][head_partition][tail_partition / s.num_worker];
+    if (out) {
+        if (cudaMemcpy(out, block.ptr, block.bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+            throw std::runtime_error("gv_solver_pool: copy failed");
+    }
+    return int64_t(s.pool_size());
+    GV_CATCH(-1)
+}
+
+int gv_solver_last_negatives(gv_solver_t *solver, uint32_t *out) {
+    const auto &negatives = solver->solver->last_negatives;
+    if (out && !negatives.empty())
+        memcpy(out, negatives.data(), negatives.size() * sizeof(uint32_t));
+    return int(negatives.size());
+}
+
+}  // extern "C"

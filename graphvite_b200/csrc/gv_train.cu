@@ -1,0 +1,497 @@
+// =============================================================================
+// gv_train.cu -- the negative-sampling SGD hot loop, hand-written for sm_100a.
+//
+// Replaces gpu::graph::train / train_1_moment / train_2_moment / predict
+// (reference include/instance/gpu/graph.cuh:36-279), LINE::forward/backward
+// (include/instance/model/graph.h:40-85), the optimizer update rules
+// (include/core/optimizer.h:161-210) and gpu::Sample
+// (include/base/alias_table.cuh:175-183).
+//
+// Design:
+//  * one warp owns one positive sample and its k negatives at a time; the d-dim
+//    row is spread over the lanes as float4 (128-bit LDG/STG; a 128-d fp32 row is
+//    exactly one 512-B warp-wide transaction), the vertex row lives in registers
+//    for the whole sample, dot products are butterfly warp-shuffle reductions and
+//    the Hogwild update is written back in place;
+//  * rows are loaded/stored with the .cg (L2-only) policy: a persistent kernel never
+//    flushes L1, and stale L1 copies of hub rows would otherwise hide other SMs'
+//    updates for the whole episode;
+//  * a warp takes 32 consecutive samples at a time: lane i loads sample i's
+//    {tail, head} pair (coalesced 256 B), draws its k negatives from the alias table
+//    (fused gpu::Sample) and parks the ids in shared memory, so index latency is paid
+//    once per 32 samples and every row address is known up front;
+//  * persistent grid: one launch consumes a whole pool block (any number of reference
+//    batches); the per-batch learning rate comes from a small array.
+// =============================================================================
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "gv_common.h"
+
+namespace gv {
+namespace device {
+
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+constexpr int kBlockThreads = 256;
+constexpr float kEpsilon = 1e-15f;  // util/common.h:28
+
+struct TrainParams {
+    float *vertex, *context, *vertex_m1, *context_m1, *vertex_m2, *context_m2;
+    const uint2 *pool;
+    unsigned long long num_sample;
+    int num_negative;
+    const uint32_t *negatives;
+    const double *random;
+    const gv_alias_entry_t *negative_table;
+    uint32_t negative_count;
+    uint32_t *negatives_out;
+    gv_device_optimizer_t optimizer;
+    const float *lr_per_batch;
+    uint32_t batch_size;
+    float negative_weight;
+    float *loss_per_sample, *loss_per_batch;
+};
+
+// -----------------------------------------------------------------------------
+// A d-dim fp32 row spread over a warp: pass p, lane l holds elements
+// [(p*32+l)*4, +4).  DIM must be a multiple of 4; lanes past the end hold zeros.
+// -----------------------------------------------------------------------------
+template<int DIM>
+struct Row {
+    static constexpr int kPass = (DIM + 127) / 128;
+    float4 x[kPass];
+};
+
+template<int DIM>
+__device__ __forceinline__ bool lane_active(int pass, int lane) {
+    return (DIM % 128 == 0) || ((pass * 32 + lane) * 4 < DIM);
+}
+
+template<int DIM>
+__device__ __forceinline__ void load_row(Row<DIM> &row, const float *base, int lane) {
+#pragma unroll
+    for (int p = 0; p < Row<DIM>::kPass; p++) {
+        if (lane_active<DIM>(p, lane))
+            row.x[p] = __ldcg(reinterpret_cast<const float4 *>(base) + p * 32 + lane);
+        else
+            row.x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template<int DIM>
+__device__ __forceinline__ void store_row(const Row<DIM> &row, float *base, int lane) {
+#pragma unroll
+    for (int p = 0; p < Row<DIM>::kPass; p++)
+        if (lane_active<DIM>(p, lane))
+            __stcg(reinterpret_cast<float4 *>(base) + p * 32 + lane, row.x[p]);
+}
+
+__device__ __forceinline__ float warp_sum(float value) {
+#pragma unroll
+    for (int delta = 16; delta > 0; delta >>= 1)
+        value += __shfl_xor_sync(kFullMask, value, delta);
+    return value;
+}
+
+template<int DIM>
+__device__ __forceinline__ float dot(const Row<DIM> &a, const Row<DIM> &b) {
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < Row<DIM>::kPass; p++) {
+        acc = fmaf(a.x[p].x, b.x[p].x, acc);
+        acc = fmaf(a.x[p].y, b.x[p].y, acc);
+        acc = fmaf(a.x[p].z, b.x[p].z, acc);
+        acc = fmaf(a.x[p].w, b.x[p].w, acc);
+    }
+    return warp_sum(acc);
+}
+
+// util/math.h:30-33
+__device__ __forceinline__ float sigmoid(float x) {
+    return x > 0 ? 1 / (1 + expf(-x)) : expf(x) / (expf(x) + 1);
+}
+
+// -----------------------------------------------------------------------------
+// core/optimizer.h:161-210 -- returns the step to subtract from `parameter`
+// -----------------------------------------------------------------------------
+template<int OPT>
+__device__ __forceinline__ float update(const gv_device_optimizer_t &o, float lr, float parameter, float gradient,
+                                        float &moment1, float &moment2, float weight) {
+    float regularized = weight * (gradient + o.weight_decay * parameter);
+    if (OPT == GV_OPT_SGD)
+        return lr * regularized;
+    if (OPT == GV_OPT_MOMENTUM) {
+        moment1 = o.a * moment1 + (1 - o.a) * regularized;
+        return lr * moment1;
+    }
+    if (OPT == GV_OPT_ADAGRAD) {
+        moment1 += regularized * regularized;
+        return lr * regularized / (sqrtf(moment1) + o.epsilon);
+    }
+    if (OPT == GV_OPT_RMSPROP) {
+        moment1 = o.a * moment1 + (1 - o.a) * regularized * regularized;
+        return lr * regularized / sqrtf(moment1 + o.epsilon);
+    }
+    moment1 = o.a * moment1 + (1 - o.a) * regularized;
+    moment2 = o.b * moment2 + (1 - o.b) * regularized * regularized;
+    return lr * moment1 / (sqrtf(moment2) + o.epsilon);
+}
+
+// LINE::backward, instance/model/graph.h:47-85: both updates read the pre-update v and c
+template<int DIM, int OPT>
+__device__ __forceinline__ void backward(const gv_device_optimizer_t &o, float lr, float gradient, float weight,
+                                         Row<DIM> &v, Row<DIM> &c, Row<DIM> &vm1, Row<DIM> &cm1, Row<DIM> &vm2,
+                                         Row<DIM> &cm2) {
+#pragma unroll
+    for (int p = 0; p < Row<DIM>::kPass; p++) {
+#define GV_ELEMENT(f)                                                                        \
+    {                                                                                        \
+        float vv = v.x[p].f, cc = c.x[p].f;                                                  \
+        v.x[p].f = vv - update<OPT>(o, lr, vv, gradient * cc, vm1.x[p].f, vm2.x[p].f, weight); \
+        c.x[p].f = cc - update<OPT>(o, lr, cc, gradient * vv, cm1.x[p].f, cm2.x[p].f, weight); \
+    }
+        GV_ELEMENT(x)
+        GV_ELEMENT(y)
+        GV_ELEMENT(z)
+        GV_ELEMENT(w)
+#undef GV_ELEMENT
+    }
+}
+
+// AliasTable::sample as called by gpu::Sample (base/alias_table.cuh:148-152,175-183):
+// both randoms are narrowed to float first; index = Index(double(rand1) * count).
+// cuRAND doubles lie in (0,1]: rand1 == 1 would index one past the table in the
+// reference; we clamp to count-1 and change no other outcome.
+__device__ __forceinline__ uint32_t alias_sample_narrowed(const gv_alias_entry_t *table, uint32_t count, double random1,
+                                                          double random2) {
+    float rand1 = float(random1), rand2 = float(random2);
+    uint32_t index = uint32_t(double(rand1) * double(count));
+    index = min(index, count - 1);
+    const uint2 entry = __ldg(reinterpret_cast<const uint2 *>(table) + index);
+    return rand2 < __uint_as_float(entry.x) ? index : entry.y;
+}
+
+// -----------------------------------------------------------------------------
+// The train kernel.  NM moment rows accompany every embedding row.
+// -----------------------------------------------------------------------------
+template<int DIM, int OPT>
+__global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams p) {
+    constexpr int NM = OPT == GV_OPT_SGD ? 0 : (OPT == GV_OPT_ADAM ? 2 : 1);
+    extern __shared__ uint32_t shared_ids[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int k = p.num_negative;
+    const int stride = k + 2;  // head, k negatives, positive tail
+    uint32_t *ids = shared_ids + warp_in_block * 32 * stride;
+
+    const unsigned long long num_chunk = (p.num_sample + 31) / 32;
+    const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const gv_device_optimizer_t o = p.optimizer;
+
+    for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+         chunk < num_chunk; chunk += num_warp) {
+        const unsigned long long base = chunk * 32;
+        const unsigned long long i = base + lane;
+        const bool valid = i < p.num_sample;
+        float lr_lane = 0.f;
+        uint32_t batch_lane = 0;
+        if (valid) {
+            const uint2 pair = __ldcs(p.pool + i);  // {tail, head}, streamed once
+            ids[lane * stride] = pair.y;
+            ids[lane * stride + 1 + k] = pair.x;
+            for (int s = 0; s < k; s++) {
+                const unsigned long long t = i * k + s;
+                uint32_t negative;
+                if (p.negatives)
+                    negative = __ldcs(p.negatives + t);
+                else {
+                    const double2 r = __ldcs(reinterpret_cast<const double2 *>(p.random) + t);
+                    negative = alias_sample_narrowed(p.negative_table, p.negative_count, r.x, r.y);
+                }
+                ids[lane * stride + 1 + s] = negative;
+                if (p.negatives_out)
+                    p.negatives_out[t] = negative;
+            }
+            batch_lane = uint32_t(i / p.batch_size);
+            lr_lane = __ldg(p.lr_per_batch + batch_lane);
+        }
+        __syncwarp();
+
+        const int count = int(min(32ull, p.num_sample - base));
+        float loss_lane = 0.f;
+        for (int t = 0; t < count; t++) {
+            const uint32_t *sample = ids + t * stride;
+            const uint32_t head = sample[0];
+            const float lr = __shfl_sync(kFullMask, lr_lane, t);
+
+            Row<DIM> v, vm1, vm2, c, cm1, cm2, c_next, cm1_next, cm2_next;
+            const size_t head_offset = size_t(head) * DIM;
+            uint32_t tail = sample[1];
+            // issue every independent load of this sample before the first use
+            load_row<DIM>(v, p.vertex + head_offset, lane);
+            load_row<DIM>(c, p.context + size_t(tail) * DIM, lane);
+            if (NM >= 1) {
+                load_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
+                load_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
+            }
+            if (NM >= 2) {
+                load_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
+                load_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
+            }
+            float sample_loss = 0.f;
+            for (int s = 0; s <= k; s++) {
+                // prefetch the next target's rows while this one is being processed
+                uint32_t tail_next = tail;
+                if (s < k) {
+                    tail_next = sample[2 + s];
+                    if (tail_next != tail) {
+                        load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane);
+                        if (NM >= 1)
+                            load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane);
+                        if (NM >= 2)
+                            load_row<DIM>(cm2_next, p.context_m2 + size_t(tail_next) * DIM, lane);
+                    }
+                }
+                // forward (LINE::forward) and the gradient of the logistic loss, gpu/graph.cuh:73-88
+                const float logit = dot<DIM>(v, c);
+                const float prob = sigmoid(logit);
+                float gradient, weight;
+                if (s == k) {
+                    gradient = prob - 1;
+                    weight = 1;
+                    sample_loss += weight * -logf(prob + kEpsilon);
+                } else {
+                    gradient = prob;
+                    weight = p.negative_weight;
+                    sample_loss += weight * -logf(1 - prob + kEpsilon);
+                }
+                backward<DIM, OPT>(o, lr, gradient, weight, v, c, vm1, cm1, vm2, cm2);
+                store_row<DIM>(c, p.context + size_t(tail) * DIM, lane);
+                if (NM >= 1)
+                    store_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
+                if (NM >= 2)
+                    store_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
+                if (s < k && tail_next != tail) {
+                    c = c_next;
+                    if (NM >= 1)
+                        cm1 = cm1_next;
+                    if (NM >= 2)
+                        cm2 = cm2_next;
+                }  // else: the same row again -- keep the just-updated registers
+                tail = tail_next;
+            }
+            store_row<DIM>(v, p.vertex + head_offset, lane);
+            if (NM >= 1)
+                store_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
+            if (NM >= 2)
+                store_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
+            sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
+            if (lane == t)
+                loss_lane = sample_loss;
+        }
+        if (p.loss_per_sample && valid)
+            p.loss_per_sample[i] = loss_lane;
+        if (p.loss_per_batch) {
+            // a 32-sample chunk may straddle batches: one reduction + atomic per distinct batch
+            unsigned remaining = __ballot_sync(kFullMask, valid);
+            while (remaining) {
+                const int leader = __ffs(remaining) - 1;
+                const uint32_t batch = __shfl_sync(kFullMask, batch_lane, leader);
+                const bool mine = valid && batch_lane == batch;
+                const float sum = warp_sum(mine ? loss_lane : 0.f);
+                if (lane == leader)
+                    atomicAdd(p.loss_per_batch + batch, sum);
+                remaining &= ~__ballot_sync(kFullMask, mine);
+            }
+        }
+        __syncwarp();  // ids[] is rewritten by the next chunk
+    }
+}
+
+// gpu::Sample, base/alias_table.cuh:175-183
+__global__ void __launch_bounds__(256) sample_negatives_kernel(const gv_alias_entry_t *table, uint32_t count,
+                                                               const double *random, unsigned long long num,
+                                                               uint32_t *out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < num; t += stride) {
+        const double2 r = __ldcs(reinterpret_cast<const double2 *>(random) + t);
+        out[t] = alias_sample_narrowed(table, count, r.x, r.y);
+    }
+}
+
+// gpu::graph::predict, instance/gpu/graph.cuh:250-279
+template<int DIM>
+__global__ void __launch_bounds__(kBlockThreads) predict_kernel(const float *vertex, const float *context,
+                                                                const uint2 *batch, unsigned long long num,
+                                                                float *logits) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < num;
+         i += num_warp) {
+        const uint2 pair = __ldg(batch + i);  // {tail, head}
+        Row<DIM> v, c;
+        load_row<DIM>(v, vertex + size_t(pair.y) * DIM, lane);
+        load_row<DIM>(c, context + size_t(pair.x) * DIM, lane);
+        const float logit = dot<DIM>(v, c);
+        if (lane == 0)
+            logits[i] = logit;
+    }
+}
+
+// -----------------------------------------------------------------------------
+// launch helpers
+// -----------------------------------------------------------------------------
+static int device_sm_count() {
+    int device = 0, sms = 0;
+    if (cudaGetDevice(&device) != cudaSuccess)
+        return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+        return 148;
+    return sms;
+}
+
+template<int DIM, int OPT>
+static int launch_train(const TrainParams &p, int num_warps, cudaStream_t stream) {
+    auto kernel = train_kernel<DIM, OPT>;
+    int threads = kBlockThreads;
+    int blocks;
+    if (num_warps > 0) {
+        threads = num_warps >= kBlockThreads / 32 ? kBlockThreads : num_warps * 32;
+        blocks = (num_warps * 32 + threads - 1) / threads;
+    }
+    const size_t shared_bytes = size_t(threads / 32) * 32 * (p.num_negative + 2) * sizeof(uint32_t);
+    if (shared_bytes > 200 * 1024)
+        return fail("num_negative too large for the train kernel's shared-memory staging");
+    if (shared_bytes > 48 * 1024)
+        GV_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shared_bytes)));
+    if (num_warps <= 0) {
+        int per_sm = 0;
+        GV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, shared_bytes));
+        if (per_sm < 1)
+            per_sm = 1;
+        blocks = device_sm_count() * per_sm;  // persistent: exactly one resident wave
+        const unsigned long long needed = ((p.num_sample + 31) / 32 + threads / 32 - 1) / (threads / 32);
+        if ((unsigned long long)blocks > needed)
+            blocks = int(needed);
+    }
+    if (blocks < 1)
+        blocks = 1;
+    kernel<<<blocks, threads, shared_bytes, stream>>>(p);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<int DIM>
+static int dispatch_optimizer(const TrainParams &p, int num_warps, cudaStream_t stream) {
+    switch (p.optimizer.type) {
+        case GV_OPT_SGD: return launch_train<DIM, GV_OPT_SGD>(p, num_warps, stream);
+        case GV_OPT_MOMENTUM: return launch_train<DIM, GV_OPT_MOMENTUM>(p, num_warps, stream);
+        case GV_OPT_ADAGRAD: return launch_train<DIM, GV_OPT_ADAGRAD>(p, num_warps, stream);
+        case GV_OPT_RMSPROP: return launch_train<DIM, GV_OPT_RMSPROP>(p, num_warps, stream);
+        case GV_OPT_ADAM: return launch_train<DIM, GV_OPT_ADAM>(p, num_warps, stream);
+    }
+    return fail("unknown optimizer type " + std::to_string(p.optimizer.type));
+}
+
+}  // namespace device
+}  // namespace gv
+
+using namespace gv;
+using namespace gv::device;
+
+extern "C" {
+
+int gv_cuda_train_block(const gv_matrices_t *m, const uint32_t *pool, uint64_t num_sample, int num_negative,
+                        const uint32_t *negatives, const double *random, const gv_alias_entry_t *negative_table,
+                        uint32_t negative_count, uint32_t *negatives_out, const gv_device_optimizer_t *optimizer,
+                        const float *lr_per_batch, uint32_t batch_size, float negative_weight,
+                        float *loss_per_sample, float *loss_per_batch, int num_warps, void *stream) {
+    if (!m || !pool || !optimizer || !lr_per_batch)
+        return fail("gv_cuda_train_block: null argument");
+    if (num_sample == 0)
+        return 0;
+    if (num_negative < 0 || batch_size == 0)
+        return fail("gv_cuda_train_block: invalid num_negative / batch_size");
+    if (!negatives && num_negative > 0 && (!random || !negative_table || negative_count == 0))
+        return fail("gv_cuda_train_block: need either `negatives` or (`random`, `negative_table`)");
+    int num_moment = optimizer->type == GV_OPT_SGD ? 0 : (optimizer->type == GV_OPT_ADAM ? 2 : 1);
+    if (!m->vertex || !m->context || (num_moment >= 1 && (!m->vertex_m1 || !m->context_m1)) ||
+        (num_moment >= 2 && (!m->vertex_m2 || !m->context_m2)))
+        return fail("gv_cuda_train_block: missing embedding / moment matrix");
+    TrainParams p;
+    p.vertex = m->vertex;
+    p.context = m->context;
+    p.vertex_m1 = m->vertex_m1;
+    p.context_m1 = m->context_m1;
+    p.vertex_m2 = m->vertex_m2;
+    p.context_m2 = m->context_m2;
+    p.pool = reinterpret_cast<const uint2 *>(pool);
+    p.num_sample = num_sample;
+    p.num_negative = num_negative;
+    p.negatives = negatives;
+    p.random = random;
+    p.negative_table = negative_table;
+    p.negative_count = negative_count;
+    p.negatives_out = negatives_out;
+    p.optimizer = *optimizer;
+    p.lr_per_batch = lr_per_batch;
+    p.batch_size = batch_size;
+    p.negative_weight = negative_weight;
+    p.loss_per_sample = loss_per_sample;
+    p.loss_per_batch = loss_per_batch;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (m->dim) {  // src/graphvite.cu:52-59 instantiates exactly these dimensions
+        case 32: return dispatch_optimizer<32>(p, num_warps, s);
+        case 64: return dispatch_optimizer<64>(p, num_warps, s);
+        case 96: return dispatch_optimizer<96>(p, num_warps, s);
+        case 128: return dispatch_optimizer<128>(p, num_warps, s);
+        case 256: return dispatch_optimizer<256>(p, num_warps, s);
+        case 512: return dispatch_optimizer<512>(p, num_warps, s);
+    }
+    return fail("unsupported embedding dimension " + std::to_string(m->dim) + " (32, 64, 96, 128, 256, 512)");
+}
+
+int gv_cuda_sample_negatives(const gv_alias_entry_t *table, uint32_t count, const double *random, uint64_t num,
+                             uint32_t *out, void *stream) {
+    if (num == 0)
+        return 0;
+    if (!table || !random || !out || count == 0)
+        return fail("gv_cuda_sample_negatives: null argument");
+    unsigned long long blocks = (num + 255) / 256;
+    const unsigned long long cap = (unsigned long long)device_sm_count() * 8;
+    if (blocks > cap)
+        blocks = cap;
+    sample_negatives_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, count, random, num, out);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gv_cuda_predict(int dim, const float *vertex, const float *context, const uint32_t *batch, uint64_t num,
+                    float *logits, void *stream) {
+    if (num == 0)
+        return 0;
+    if (!vertex || !context || !batch || !logits)
+        return fail("gv_cuda_predict: null argument");
+    unsigned long long blocks = (num + kBlockThreads / 32 - 1) / (kBlockThreads / 32);
+    const unsigned long long cap = (unsigned long long)device_sm_count() * 8;
+    if (blocks > cap)
+        blocks = cap;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint2 *pairs = reinterpret_cast<const uint2 *>(batch);
+    switch (dim) {
+        case 32: predict_kernel<32><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        case 64: predict_kernel<64><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        case 96: predict_kernel<96><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        case 128: predict_kernel<128><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        case 256: predict_kernel<256><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        case 512: predict_kernel<512><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        default: return fail("unsupported embedding dimension " + std::to_string(dim));
+    }
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

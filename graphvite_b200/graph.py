@@ -1,0 +1,134 @@
+"""Graphs -- mirrors graphvite.graph.Graph (reference include/bind.h:109-187 over
+include/instance/graph.cuh:62-277).  Only the node-embedding graph is in scope."""
+import ctypes
+
+from . import _lib
+from .base import cfg, dtype
+
+lib = _lib.lib
+
+
+class _NameMap(object):
+    """Read-only name -> id mapping backed by the native graph (bind.h:135)."""
+
+    def __init__(self, graph):
+        self._graph = graph
+
+    def __getitem__(self, name):
+        index = lib.gv_graph_name2id(self._graph._handle, str(name).encode())
+        if index < 0:
+            raise KeyError(name)
+        return index
+
+    def __contains__(self, name):
+        return lib.gv_graph_name2id(self._graph._handle, str(name).encode()) >= 0
+
+    def get(self, name, default=None):
+        index = lib.gv_graph_name2id(self._graph._handle, str(name).encode())
+        return default if index < 0 else index
+
+    def __len__(self):
+        return self._graph.num_vertex
+
+    def __iter__(self):
+        return iter(self._graph.id2name)
+
+    def keys(self):
+        return self._graph.id2name
+
+    def items(self):
+        return [(name, i) for i, name in enumerate(self._graph.id2name)]
+
+
+class Graph(object):
+    """Graph(index_type=dtype.uint32): normal graphs without attributes."""
+
+    def __init__(self, index_type=None):
+        index_type = cfg.index_type if index_type is None else index_type
+        if index_type != dtype.uint32:
+            raise ValueError("Can't find an instantiation of Graph with index_type = %s" % (index_type,))
+        self._handle = lib.gv_graph_create()
+        self._id2name = None
+
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            lib.gv_graph_destroy(handle)
+
+    # -- load overloads, bind.h:133-159 -------------------------------------------------
+    def load(self, *args, **kwargs):
+        """load(file_name, as_undirected=True, normalization=False, delimiters=' \\t\\r\\n', comment='#')
+        load(edge_list, as_undirected=True, normalization=False)
+        load(weighted_edge_list, as_undirected=True, normalization=False)"""
+        self._id2name = None
+        names = ["file_name", "as_undirected", "normalization", "delimiters", "comment"]
+        for alias in ("edge_list", "weighted_edge_list"):
+            if alias in kwargs:
+                kwargs["file_name"] = kwargs.pop(alias)
+        params = dict(zip(names, args))
+        for key, value in kwargs.items():
+            if key not in names or key in params:
+                raise TypeError("load(): incompatible function arguments")
+            params[key] = value
+        if "file_name" not in params:
+            raise TypeError("load(): incompatible function arguments")
+        source = params["file_name"]
+        as_undirected = bool(params.get("as_undirected", True))
+        normalization = bool(params.get("normalization", False))
+        if isinstance(source, (str, bytes)):
+            delimiters = params.get("delimiters", " \t\r\n")
+            comment = params.get("comment", "#")
+            path = source if isinstance(source, bytes) else source.encode()
+            _lib.check(lib.gv_graph_load_file(self._handle, path, int(as_undirected), int(normalization),
+                                              delimiters.encode(), comment.encode()))
+            return
+        if "delimiters" in params or "comment" in params:
+            raise TypeError("load(): incompatible function arguments")
+        edges = list(source)
+        count = len(edges)
+        u_names = (ctypes.c_char_p * count)(*[str(e[0]).encode() for e in edges])
+        v_names = (ctypes.c_char_p * count)(*[str(e[1]).encode() for e in edges])
+        weights = None
+        if count and len(edges[0]) == 3:
+            weights = (ctypes.c_float * count)(*[float(e[2]) for e in edges])
+        _lib.check(lib.gv_graph_load_edges(self._handle, u_names, v_names, weights, count, int(as_undirected),
+                                           int(normalization)))
+
+    def save(self, file_name, weighted=True, anonymous=False):
+        """save(file_name, weighted=True, anonymous=False): save the graph in edge-list format."""
+        _lib.check(lib.gv_graph_save(self._handle, file_name.encode(), int(weighted), int(anonymous)))
+
+    # -- read-only attributes, bind.h:128-135 --------------------------------------------
+    @property
+    def num_vertex(self):
+        return int(lib.gv_graph_num_vertex(self._handle))
+
+    @property
+    def num_edge(self):
+        return int(lib.gv_graph_num_edge(self._handle))
+
+    @property
+    def as_undirected(self):
+        return bool(lib.gv_graph_as_undirected(self._handle))
+
+    @property
+    def normalization(self):
+        return bool(lib.gv_graph_normalization(self._handle))
+
+    @property
+    def id2name(self):
+        if self._id2name is None or len(self._id2name) != self.num_vertex:
+            self._id2name = [lib.gv_graph_id2name(self._handle, i).decode() for i in range(self.num_vertex)]
+        return self._id2name
+
+    @property
+    def name2id(self):
+        return _NameMap(self)
+
+    def __repr__(self):
+        buffer = ctypes.create_string_buffer(4096)
+        lib.gv_graph_info(self._handle, buffer, len(buffer))
+        return buffer.value.decode()
+
+
+__all__ = ["Graph"]

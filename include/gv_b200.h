@@ -1,0 +1,266 @@
+/*
+ * gv_b200.h -- C ABI of the B200-native node-embedding trainer (libgv_b200.so).
+ *
+ * This is the drop-in boundary for the node-embedding hot path of
+ * DeepGraphLearning/graphvite v0.2.2.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference's include/).  All
+ * signatures are plain C: pointers, sizes and PODs; no C++ or torch types.
+ *
+ * Layers
+ *   gv_cuda_*   device layer: hand-written sm_100a kernels + launchers.  Pointers are
+ *               DEVICE pointers unless stated; `stream` is a cudaStream_t passed as void*.
+ *   gv_graph_*, gv_optimizer_*, gv_solver_*
+ *               host runtime (C++): what bind.h exposes as graphvite.graph.Graph,
+ *               graphvite.optimizer.* and graphvite.solver.GraphSolver.
+ *
+ * Error model: functions return 0 on success and a non-zero code on failure;
+ * gv_last_error() returns a thread-local message.  (The reference aborts the
+ * process through glog CHECK/LOG(FATAL), util/debug.h:27-38; a C ABI must not.)
+ */
+#ifndef GV_B200_H_
+#define GV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GV_VERSION "0.1.0"
+
+/* ---- enums / PODs -------------------------------------------------------- */
+
+/* core/optimizer.h:28-36 OptimizerType */
+enum { GV_OPT_SGD = 0, GV_OPT_MOMENTUM = 1, GV_OPT_ADAGRAD = 2, GV_OPT_RMSPROP = 3, GV_OPT_ADAM = 4 };
+/* core/optimizer.h:42-85 LRSchedule::type */
+enum { GV_SCHEDULE_CONSTANT = 0, GV_SCHEDULE_LINEAR = 1, GV_SCHEDULE_CUSTOM = 2 };
+/* instance/graph.cuh:620-622 available models */
+enum { GV_MODEL_DEEPWALK = 0, GV_MODEL_LINE = 1, GV_MODEL_NODE2VEC = 2 };
+
+/* Device-side view of core/optimizer.h Optimizer (the reference passes the whole C++
+ * object, std::string included, by value into its kernels; appendix A.14 of SURVEY.md). */
+typedef struct {
+    int type;            /* GV_OPT_* */
+    float weight_decay;
+    float a;             /* momentum | alpha | beta1 */
+    float b;             /* beta2 */
+    float epsilon;
+} gv_device_optimizer_t;
+
+/* Host-side optimizer description (core/optimizer.h:272-319 helper classes). */
+typedef struct {
+    int type;            /* GV_OPT_*; -1 = "Default" (solver default, core/solver.h:291-296) */
+    float lr;
+    float weight_decay;
+    float a, b, epsilon;
+    int schedule;        /* GV_SCHEDULE_* */
+    /* GV_SCHEDULE_CUSTOM: factor = fn(batch_id, num_batch, ctx) (LRSchedule::ScheduleFunction) */
+    float (*schedule_fn)(int batch_id, int num_batch, void *ctx);
+    void *schedule_ctx;
+} gv_optimizer_t;
+
+/* Row-major [rows][dim] fp32 matrices of one (head block, tail block) pair resident in HBM
+ * (base/vector.h Vector<dim,float>, base/memory.h Memory<Vector,Index>::device_ptr). */
+typedef struct {
+    int dim;
+    float *vertex, *context;           /* embeddings[0], embeddings[1] */
+    float *vertex_m1, *context_m1;     /* first moments  (NULL unless num_moment >= 1) */
+    float *vertex_m2, *context_m2;     /* second moments (NULL unless num_moment == 2) */
+} gv_matrices_t;
+
+/* One alias-table entry as laid out on the device: prob and alias of
+ * base/alias_table.cuh AliasTable<float, uint32> interleaved so one 8-byte load fetches both. */
+typedef struct {
+    float prob;
+    uint32_t alias;
+} gv_alias_entry_t;
+
+const char *gv_last_error(void);
+const char *gv_version(void);
+
+/* ---- device layer -------------------------------------------------------- */
+
+/* Replaces gpu::graph::train / train_1_moment / train_2_moment
+ * (instance/gpu/graph.cuh:36-242) + the per-batch loop of WorkerMixin::train
+ * (core/solver.h:1511-1557): ONE launch consumes `num_sample` positive samples
+ * (= any number of reference batches) from a device-resident pool block.
+ *
+ *   pool           [num_sample] pairs {tail_local, head_local} (std::tuple layout, appendix A.1)
+ *   negatives      [num_sample][num_negative] local tail ids, or NULL to draw them in-kernel:
+ *   random         [num_sample][num_negative][2] cuRAND doubles (core/solver.h:1536) and
+ *   negative_table the tail partition's alias table (replaces gpu::Sample,
+ *                  base/alias_table.cuh:175-183, including its double->float narrowing)
+ *   negatives_out  optional [num_sample][num_negative]: the ids the kernel drew (test hook)
+ *   lr_per_batch   [ceil(num_sample / batch_size)] learning rates (Optimizer::apply_schedule)
+ *   loss_per_sample optional [num_sample] (the reference's `loss` buffer, gpu/graph.cuh:91-92)
+ *   loss_per_batch  optional [num batches], ACCUMULATED (+=) sums of the per-sample loss
+ *   num_warps      0 = persistent grid sized to the device; 1 = single-warp deterministic order
+ */
+int gv_cuda_train_block(const gv_matrices_t *matrices, const uint32_t *pool, uint64_t num_sample, int num_negative,
+                        const uint32_t *negatives, const double *random, const gv_alias_entry_t *negative_table,
+                        uint32_t negative_count, uint32_t *negatives_out, const gv_device_optimizer_t *optimizer,
+                        const float *lr_per_batch, uint32_t batch_size, float negative_weight,
+                        float *loss_per_sample, float *loss_per_batch, int num_warps, void *stream);
+
+/* gpu::Sample (base/alias_table.cuh:175-183): out[t] = table.sample(float(random[2t]), float(random[2t+1])). */
+int gv_cuda_sample_negatives(const gv_alias_entry_t *table, uint32_t count, const double *random, uint64_t num,
+                             uint32_t *out, void *stream);
+
+/* gpu::graph::predict (instance/gpu/graph.cuh:250-279): logits[i] = <vertex[head], context[tail]>,
+ * batch = pairs {tail, head}. */
+int gv_cuda_predict(int dim, const float *vertex, const float *context, const uint32_t *batch, uint64_t num,
+                    float *logits, void *stream);
+
+/* One chain position as the samplers store it: head/tail_locations[v] (core/solver.h:399-410). */
+typedef struct {
+    uint32_t part;    /* partition id */
+    uint32_t local;   /* row inside the partition block */
+} gv_location_t;
+
+/* Device CSR of the flattened graph plus the sampler tables
+ * (core/graph.h:87-101 flatten(); instance/graph.cuh:645-653 vertex_edge_tables;
+ *  core/solver.h:123 edge_table).  All arrays are device pointers. */
+typedef struct {
+    uint32_t num_vertex;
+    uint64_t num_edge;                       /* directed edges after flatten() */
+    const uint64_t *offsets;                 /* [num_vertex + 1] flat_offsets (+ end) */
+    const uint32_t *edge_u, *edge_v;         /* [num_edge] endpoints in flatten() order */
+    const float *edge_prob;                  /* [num_edge] edge_table.prob_table */
+    const uint64_t *edge_alias;              /* [num_edge] edge_table.alias_table (Index = size_t) */
+    const gv_alias_entry_t *vertex_tables;   /* [num_edge] per-vertex alias tables at offsets[v]; may be NULL */
+    const gv_location_t *locations;          /* [num_vertex] head_locations == tail_locations */
+} gv_device_graph_t;
+
+/* Walk part of GraphSampler::sample_random_walk (instance/graph.cuh:400-425) for `num_walk`
+ * independent walks: walk w reads the cuRAND doubles random[2*L*w .. 2*L*(w+1)) in the
+ * reference's (right-to-left) argument order and writes the locations of its L+1 vertices to
+ * chains[j * num_walk + w], j = 0..L.  With walk_length == 1 this is the draw part of
+ * SamplerMixin::sample (core/solver.h:1026-1040): one alias-sampled edge per "walk".
+ * Walks must not hit dead ends (every vertex has an out-edge), see DESIGN.md. */
+int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, uint32_t num_walk, int walk_length,
+                        gv_location_t *chains, void *stream);
+
+/* Pool fill (instance/graph.cuh:427-447 / core/solver.h:1041-1053): expands the chains into positive
+ * pairs in stream order (walk-major, then j, then k = 1..augmentation_step) and appends each pair
+ * to block [head part][tail part] of one sampler's slice [start, end) until that slice is full,
+ * through the pseudo-shuffle map.  Stable: the r-th pair of a block in stream order lands at slice
+ * offset r.
+ *   pool_blocks   device array [P*P] of device pointers to the blocks (pairs {tail_local,
+ *                 head_local}); a NULL block is counted but not written (owned by another rank)
+ *   fill          device [P*P], in/out: pairs of this slice each block has been offered so far
+ *   last_walk     device scalar, in/out: max (first_walk + w) over walks that completed a block
+ *   scratch       device scratch of gv_cuda_fill_scratch_bytes(num_walk, P) bytes
+ */
+typedef struct {
+    int num_partition;
+    int walk_length;          /* chain length - 1; 1 for edge sampling */
+    int augmentation_step;
+    int shuffle_base;
+    uint64_t pool_size;       /* episode_size * batch_size */
+    uint64_t start, end;      /* this sampler's slice */
+} gv_fill_params_t;
+
+size_t gv_cuda_fill_scratch_bytes(uint32_t num_walk, int num_partition);
+int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
+                      uint64_t first_walk, uint32_t *const *pool_blocks, unsigned long long *fill,
+                      unsigned long long *last_walk, void *scratch, void *stream);
+
+/* Memory::gather / Memory::scatter (base/memory.h:194-217) on the device: rows of `dim` floats,
+ * dst[i] = src[ids[i]] when gather != 0, else dst[ids[i]] = src[i]. */
+int gv_cuda_move_rows(float *dst, const float *src, const uint32_t *ids, uint64_t num_row, int dim, int gather,
+                      void *stream);
+
+/* ---- host runtime: Graph (instance/graph.cuh:62-277, bind.h:109-187) ------------------- */
+
+typedef struct gv_graph gv_graph_t;
+
+gv_graph_t *gv_graph_create(void);
+void gv_graph_destroy(gv_graph_t *graph);
+/* Graph::load_file (instance/graph.cuh:163-201) */
+int gv_graph_load_file(gv_graph_t *graph, const char *file_name, int as_undirected, int normalization,
+                       const char *delimiters, const char *comment);
+/* Graph::load_edge_list / load_weighted_edge_list (instance/graph.cuh:209-252); weights may be NULL */
+int gv_graph_load_edges(gv_graph_t *graph, const char *const *u_names, const char *const *v_names,
+                        const float *weights, uint64_t num_edge, int as_undirected, int normalization);
+/* Graph::save (instance/graph.cuh:260-277) */
+int gv_graph_save(gv_graph_t *graph, const char *file_name, int weighted, int anonymous);
+uint64_t gv_graph_num_vertex(const gv_graph_t *graph);
+uint64_t gv_graph_num_edge(const gv_graph_t *graph);      /* counts input lines (graph.cuh:152) */
+int gv_graph_as_undirected(const gv_graph_t *graph);
+int gv_graph_normalization(const gv_graph_t *graph);
+const char *gv_graph_id2name(const gv_graph_t *graph, uint64_t id);
+int64_t gv_graph_name2id(const gv_graph_t *graph, const char *name); /* -1 if absent */
+/* GraphMixin::flatten (core/graph.h:87-101): returns #directed edges; arrays may be NULL */
+uint64_t gv_graph_flatten(gv_graph_t *graph, uint32_t *u, uint32_t *v, float *w, uint64_t *flat_offsets,
+                          float *vertex_weights);
+/* Graph::info() */
+int gv_graph_info(const gv_graph_t *graph, char *buffer, size_t capacity);
+
+/* AliasTable::build (base/alias_table.cuh:84-128); alias is uint64 (Index = size_t) */
+int gv_alias_build(const float *weights, uint64_t n, float *prob, uint64_t *alias);
+
+/* ---- host runtime: GraphSolver (instance/graph.cuh:587-813, core/solver.h, bind.h:383-513) ---- */
+
+typedef struct gv_solver gv_solver_t;
+
+/* GraphSolver(device_ids, num_sampler_per_worker, gpu_memory_limit) (bind.h:445-447).
+ * dim in {32,64,96,128,256,512} (src/graphvite.cu:52-59); 0 for the two autos.
+ * Distributed (one process per GPU): world_size > 1, `rank` in [0, world_size), exactly one
+ * device id; the caller then provides the block exchange with gv_solver_set_exchange(). */
+gv_solver_t *gv_solver_create(int dim, const int *device_ids, int num_device, int num_sampler_per_worker,
+                              uint64_t gpu_memory_limit, int rank, int world_size);
+void gv_solver_destroy(gv_solver_t *solver);
+
+/* Block exchange for world_size > 1 (replaces WorkerMixin::write_embedding/load_embedding through
+ * host memory, core/solver.h:1349-1428): send `bytes` from device pointer `send` to rank `dst` and
+ * receive into `recv` from rank `src`, on CUDA stream `stream`; either side may be a no-op
+ * (dst/src = -1).  Python wires this to torch.distributed NCCL P2P over NVLink. */
+typedef int (*gv_exchange_fn)(const void *send, int dst, void *recv, int src, uint64_t bytes, void *stream,
+                              void *ctx);
+int gv_solver_set_exchange(gv_solver_t *solver, gv_exchange_fn fn, void *ctx);
+
+/* SolverMixin::build (core/solver.h:287-466); num_partition / episode_size 0 = auto */
+int gv_solver_build(gv_solver_t *solver, gv_graph_t *graph, const gv_optimizer_t *optimizer, int num_partition,
+                    int num_negative, int batch_size, int episode_size);
+/* GraphSolver::train (instance/graph.cuh:770-793); augmentation_step / shuffle_base 0 = auto */
+int gv_solver_train(gv_solver_t *solver, const char *model, int num_epoch, int resume, int augmentation_step,
+                    int random_walk_length, int random_walk_batch_size, int shuffle_base, float p, float q,
+                    int positive_reuse, float negative_sample_exponent, float negative_weight, int log_frequency);
+/* SolverMixin::predict_numpy (core/solver.h:729-802); pairs = (v, c) global ids, HOST memory */
+int gv_solver_predict(gv_solver_t *solver, const uint32_t *pairs, uint64_t num, float *logits);
+/* SolverMixin::clear (core/solver.h:805-816) */
+int gv_solver_clear(gv_solver_t *solver);
+/* numpy views (bind.h:90-106,439-442): solver-owned HOST matrix [num_vertex][dim]; which 0 vertex, 1 context */
+float *gv_solver_embeddings(gv_solver_t *solver, int which, uint64_t *rows, int *dim);
+/* read-only attributes (bind.h:415-436) as "key=value" lines, and SolverMixin::info() */
+int gv_solver_info(const gv_solver_t *solver, char *buffer, size_t capacity);
+int gv_solver_attributes(const gv_solver_t *solver, char *buffer, size_t capacity);
+/* mean loss values the reference would LOG (core/solver.h:1541-1549), in order */
+int gv_solver_logged_loss(const gv_solver_t *solver, float *out, int capacity);
+/* throughput counters of the last train(): positives consumed and device seconds in the train kernels */
+int gv_solver_stats(const gv_solver_t *solver, double *out, int capacity);
+
+/* ---- test hooks (no reference counterpart: the reference's members are simply public) ------- */
+/* the process-wide engine core/solver.h:50: re-seed (5489 = default-constructed) */
+void gv_reset_global_engine(uint32_t seed);
+/* head_locations (core/solver.h:399-410) */
+int gv_solver_locations(const gv_solver_t *solver, uint32_t *part_of, uint32_t *local_of);
+/* copy one sample-pool block (pairs {tail, head}) to host; returns #pairs */
+int64_t gv_solver_pool(gv_solver_t *solver, int pool, int head_partition, int tail_partition, uint32_t *out);
+/* set-up of train() up to and including the first pool fill (core/solver.h:588-628), then single episodes */
+int gv_solver_train_begin(gv_solver_t *solver, const char *model, int num_epoch, int resume, int augmentation_step,
+                          int random_walk_length, int random_walk_batch_size, int shuffle_base, float p, float q,
+                          int positive_reuse, float negative_sample_exponent, float negative_weight,
+                          int log_frequency);
+int gv_solver_train_episode(gv_solver_t *solver);   /* 1 = trained one episode, 0 = done, <0 error */
+int gv_solver_train_end(gv_solver_t *solver);       /* write_back (core/solver.h:650-653) */
+/* options: "capture_negatives" = 1 keeps the negatives the train kernel drew for the last batch */
+int gv_solver_set_option(gv_solver_t *solver, const char *name, int value);
+/* negatives drawn for the last trained batch of this rank's worker, [batch_size][num_negative] */
+int gv_solver_last_negatives(gv_solver_t *solver, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GV_B200_H_ */
