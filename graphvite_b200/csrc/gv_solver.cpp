@@ -243,6 +243,7 @@ struct Solver {
     cudaEvent_t random_ready[2] = {nullptr, nullptr}, random_free[2] = {nullptr, nullptr};
     int chunk_batches = 1;
     bool capture_negatives = false;
+    int train_num_warps = 0;  // 0 = persistent grid; 1 = single warp (sequential, reproducible; tests)
     std::vector<uint32_t> last_negatives;
     std::vector<float> logged_loss;
     float previous_batch_loss = 0;  // mean loss of the batch trained before (what the reference logs)
@@ -871,7 +872,7 @@ struct Solver {
                     nullptr, d_random[buffer].as<double>(), negative_tables[g].as<gv_alias_entry_t>(),
                     negative_counts[g], capture_negatives ? d_negatives_out.as<uint32_t>() : nullptr,
                     &device_optimizer, d_lr.as<float>() + j0, batch_size, negative_weight, nullptr,
-                    d_loss.as<float>() + j0, 0, work_stream));
+                    d_loss.as<float>() + j0, train_num_warps, work_stream));
                 GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
                 GV_CHECK_CUDA(cudaEventRecord(random_free[buffer], work_stream));
                 timers.push_back(begin);
@@ -1186,6 +1187,8 @@ int gv_solver_set_option(gv_solver_t *solver, const char *name, int value) {
     GV_TRY
     if (std::string(name) == "capture_negatives")
         solver->solver->capture_negatives = value != 0;
+    else if (std::string(name) == "train_num_warps")
+        solver->solver->train_num_warps = value;
     else
         throw std::runtime_error(std::string("unknown option `") + name + "`");
     return 0;

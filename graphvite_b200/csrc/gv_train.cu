@@ -409,10 +409,10 @@ int gv_cuda_train_block(const gv_matrices_t *m, const uint32_t *pool, uint64_t n
                         uint32_t negative_count, uint32_t *negatives_out, const gv_device_optimizer_t *optimizer,
                         const float *lr_per_batch, uint32_t batch_size, float negative_weight,
                         float *loss_per_sample, float *loss_per_batch, int num_warps, void *stream) {
-    if (!m || !pool || !optimizer || !lr_per_batch)
-        return fail("gv_cuda_train_block: null argument");
     if (num_sample == 0)
         return 0;
+    if (!m || !pool || !optimizer || !lr_per_batch)
+        return fail("gv_cuda_train_block: null argument");
     if (num_negative < 0 || batch_size == 0)
         return fail("gv_cuda_train_block: invalid num_negative / batch_size");
     if (!negatives && num_negative > 0 && (!random || !negative_table || negative_count == 0))

@@ -255,7 +255,8 @@ int gv_solver_train_begin(gv_solver_t *solver, const char *model, int num_epoch,
                           int log_frequency);
 int gv_solver_train_episode(gv_solver_t *solver);   /* 1 = trained one episode, 0 = done, <0 error */
 int gv_solver_train_end(gv_solver_t *solver);       /* write_back (core/solver.h:650-653) */
-/* options: "capture_negatives" = 1 keeps the negatives the train kernel drew for the last batch */
+/* options: "capture_negatives" = 1 keeps the negatives the train kernel drew for the last batch;
+ * "train_num_warps" = 1 runs the train kernel on a single warp (sequential order, reproducible) */
 int gv_solver_set_option(gv_solver_t *solver, const char *name, int value);
 /* negatives drawn for the last trained batch of this rank's worker, [batch_size][num_negative] */
 int gv_solver_last_negatives(gv_solver_t *solver, uint32_t *out);

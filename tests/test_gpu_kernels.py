@@ -1,0 +1,173 @@
+"""GPU parity of the device layer (gv_cuda_*) against the oracle.  Tolerances: integer / index
+results are bit-exact; fp32 results follow the same algorithm with a different summation order
+(float4 lanes + butterfly instead of lane-strided + shfl_down tree), so they agree to ~1e-6;
+we assert rtol 2e-4 / atol 2e-6 after up to a few hundred dependent updates."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 2e-4, 2e-6
+DIMS = [32, 64, 96, 128, 256, 512]
+
+
+def make_problem(dim, n, k, rows_v, rows_c, seed, unique=False, moments=0):
+    rng = np.random.RandomState(seed)
+    vertex = ((rng.rand(rows_v, dim) - 0.5) * 0.6).astype(np.float32)
+    context = ((rng.rand(rows_c, dim) - 0.5) * 0.6).astype(np.float32)
+    ms = [np.abs(rng.randn(*shape)).astype(np.float32) * 0.01
+          for shape in ((rows_v, dim), (rows_c, dim), (rows_v, dim), (rows_c, dim))]
+    ms = [m if i // 2 < moments else None for i, m in enumerate(ms)]
+    if unique:
+        heads = rng.permutation(rows_v)[:n]
+        tails = rng.permutation(rows_c)[:n * (k + 1)].reshape(n, k + 1)
+    else:
+        heads = rng.randint(0, rows_v, n)
+        tails = rng.randint(0, rows_c, (n, k + 1))
+        if n > 8 and k >= 1:  # force the corner cases: duplicate rows inside a sample, repeated heads
+            tails[3, 0] = tails[3, k]
+            tails[5, :] = tails[5, 0]
+            heads[7] = heads[6]
+    batch = np.stack([tails[:, k], heads], axis=1).astype(np.uint32)
+    negatives = np.ascontiguousarray(tails[:, :k]).astype(np.uint32)
+    return vertex, context, ms, batch, negatives
+
+
+def oracle_run(dim, vertex, context, ms, batch, negatives, optimizer, negative_weight, lr, batch_size):
+    v, c = vertex.copy(), context.copy()
+    m = [x.copy() if x is not None else None for x in ms]
+    losses = []
+    for b, start in enumerate(range(0, batch.shape[0], batch_size)):
+        sl = slice(start, start + batch_size)
+        losses.append(O.train_batch(dim, v, c, m, batch[sl], negatives[sl], optimizer, negative_weight, lr=float(lr[b])))
+    return v, c, m, np.concatenate(losses)
+
+
+def compare(got, v, c, m, loss):
+    np.testing.assert_allclose(got["vertex"], v, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(got["context"], c, rtol=RTOL, atol=ATOL)
+    for name, expected in zip(["vm1", "cm1", "vm2", "cm2"], m):
+        if expected is not None:
+            np.testing.assert_allclose(got[name], expected, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(got["loss"], loss, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("dim", DIMS)
+@pytest.mark.parametrize("opt", list(O.OPTIMIZERS))
+def test_train_single_warp_with_collisions(dim, opt):
+    """one warp = the reference's per-sample order executed sequentially, collisions included"""
+    from gpu_util import run_train_block
+    optimizer = O.OPTIMIZERS[opt]
+    moments = 0 if opt == "SGD" else (2 if opt == "Adam" else 1)
+    n, k, batch_size = 257, 3, 100
+    vertex, context, ms, batch, negatives = make_problem(dim, n, k, 40, 50, seed=dim + len(opt), moments=moments)
+    lr = np.array([optimizer[1], optimizer[1] * 0.5, optimizer[1] * 0.25], dtype=np.float32)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr, batch_size)
+    got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr, batch_size=batch_size,
+                          num_warps=1)
+    compare(got, v, c, m, loss)
+    expected_batch = np.array([loss[i:i + batch_size].sum() for i in range(0, n, batch_size)])
+    np.testing.assert_allclose(got["batch_loss"], expected_batch, rtol=1e-4)
+
+
+@pytest.mark.parametrize("dim", [32, 128, 512])
+@pytest.mark.parametrize("opt", ["SGD", "Momentum", "Adam"])
+@pytest.mark.parametrize("k", [0, 1, 5])
+def test_train_full_grid_race_free(dim, opt, k):
+    """persistent grid on a batch whose rows are all distinct: no races, so order does not matter"""
+    from gpu_util import run_train_block
+    optimizer = O.OPTIMIZERS[opt]
+    moments = 0 if opt == "SGD" else (2 if opt == "Adam" else 1)
+    n = 3000
+    vertex, context, ms, batch, negatives = make_problem(dim, n, k, n, n * (k + 1), seed=k + dim, unique=True,
+                                                         moments=moments)
+    lr = np.full(3, optimizer[1], dtype=np.float32)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives.reshape(n, k), optimizer, 5.0, lr, 1000)
+    got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr, batch_size=1000)
+    compare(got, v, c, m, loss)
+
+
+def test_train_large_k_shared_memory_opt_in():
+    """k = 200 needs > 48 KB of dynamic shared memory for the id staging"""
+    from gpu_util import run_train_block
+    optimizer = O.OPTIMIZERS["SGD"]
+    dim, n, k = 64, 96, 200
+    vertex, context, ms, batch, negatives = make_problem(dim, n, k, 30, 400, seed=5)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, [optimizer[1]], n)
+    got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, num_warps=1)
+    compare(got, v, c, m, loss)
+
+
+def test_empty_launch_is_a_no_op():
+    from gpu_util import run_train_block
+    optimizer = O.OPTIMIZERS["SGD"]
+    vertex, context, ms, batch, negatives = make_problem(128, 4, 1, 8, 8, seed=1)
+    got = run_train_block(128, vertex, context, ms, batch[:0], negatives[:0], optimizer, 5.0)
+    np.testing.assert_array_equal(got["vertex"], vertex)
+    np.testing.assert_array_equal(got["context"], context)
+
+
+@pytest.mark.parametrize("count", [1, 37, 1000, 70001])
+def test_sample_negatives_bit_exact(count):
+    """gpu::Sample with its double->float narrowing, including rand1 that narrows to 1.0f"""
+    from gpu_util import sample_negatives
+    rng = np.random.RandomState(count)
+    weights = (rng.pareto(1.2, count) + 0.01).astype(np.float32)
+    prob, alias = O.alias_build(weights)
+    random = 1.0 - rng.rand(2 * 5000)  # (0, 1] like cuRAND
+    random[10] = 1.0
+    random[12] = 1.0 - 1e-9  # narrows to 1.0f: the reference reads one past the table; both sides clamp
+    expected = O.alias_sample(prob, alias, random, gpu_path=True)
+    got = sample_negatives(prob, alias.astype(np.uint32), random)
+    np.testing.assert_array_equal(got, expected.astype(np.uint32))
+
+
+def test_fused_negative_sampling_equals_two_step():
+    from gpu_util import run_train_block
+    rng = np.random.RandomState(9)
+    dim, n, k, rows = 128, 999, 2, 64
+    optimizer = O.OPTIMIZERS["SGD"]
+    vertex, context, ms, batch, _ = make_problem(dim, n, k, rows, rows, seed=3)
+    weights = (rng.pareto(1.5, rows) + 0.05).astype(np.float32)
+    prob, alias = O.alias_build(weights)
+    random = 1.0 - rng.rand(n * k * 2)
+    negatives = O.alias_sample(prob, alias, random, gpu_path=True).astype(np.uint32).reshape(n, k)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, [optimizer[1]], n)
+    got = run_train_block(dim, vertex, context, ms, batch, None, optimizer, 5.0, num_warps=1, random=random,
+                          negative_table=(prob, alias.astype(np.uint32)))
+    np.testing.assert_array_equal(got["negatives"].reshape(n, k), negatives)
+    compare(got, v, c, m, loss)
+
+
+@pytest.mark.parametrize("dim", DIMS)
+def test_predict(dim):
+    from gpu_util import predict
+    rng = np.random.RandomState(dim)
+    vertex = rng.randn(100, dim).astype(np.float32)
+    context = rng.randn(120, dim).astype(np.float32)
+    batch = np.stack([rng.randint(0, 120, 777), rng.randint(0, 100, 777)], axis=1).astype(np.uint32)
+    np.testing.assert_allclose(predict(dim, vertex, context, batch), O.predict_batch(dim, vertex, context, batch),
+                               rtol=1e-5, atol=1e-5)
+
+
+def test_move_rows_round_trip():
+    import ctypes
+    import torch
+    from graphvite_b200 import _lib
+    from gpu_util import dev, stream_pointer
+    rng = np.random.RandomState(0)
+    matrix = rng.randn(500, 96).astype(np.float32)
+    ids = rng.permutation(500)[:123].astype(np.uint32)
+    d_matrix, d_ids = dev(matrix), dev(ids)
+    d_block = torch.zeros(123, 96, device="cuda")
+    _lib.check(_lib.lib.gv_cuda_move_rows(d_block.data_ptr(), d_matrix.data_ptr(), d_ids.data_ptr(), 123, 96, 1,
+                                          stream_pointer()))
+    np.testing.assert_array_equal(d_block.cpu().numpy(), matrix[ids])
+    d_back = torch.zeros(500, 96, device="cuda")
+    _lib.check(_lib.lib.gv_cuda_move_rows(d_back.data_ptr(), d_block.data_ptr(), d_ids.data_ptr(), 123, 96, 0,
+                                          stream_pointer()))
+    expected = np.zeros_like(matrix)
+    expected[ids] = matrix[ids]
+    np.testing.assert_array_equal(d_back.cpu().numpy(), expected)

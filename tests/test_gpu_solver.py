@@ -1,0 +1,159 @@
+"""GPU parity of the host runtime + device samplers (gv_solver_*) against the oracle solver:
+sample pools and negative indices bit-exact for the default engine seed, embeddings within
+float tolerance in the single-warp (sequential) mode, and norms / loss in the Hogwild mode."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "line_p1": dict(dim=32, P=1, k=1, B=500, E=4, S=1, model="LINE", epochs=4, aug=2, L=5, wb=10, optimizer="SGD"),
+    "line_p2_s3": dict(dim=32, P=2, k=3, B=400, E=3, S=3, model="LINE", epochs=8, aug=3, L=7, wb=8,
+                       optimizer="SGD"),
+    "deepwalk_p1": dict(dim=128, P=1, k=2, B=300, E=5, S=2, model="DeepWalk", epochs=3, aug=4, L=9, wb=6,
+                        optimizer="SGD"),
+    "edge_p2": dict(dim=32, P=2, k=1, B=500, E=2, S=2, model="LINE", epochs=3, aug=1, L=5, wb=10, optimizer="SGD"),
+    "line_p3_adam": dict(dim=32, P=3, k=2, B=300, E=2, S=1, model="LINE", epochs=4, aug=2, L=6, wb=10,
+                         optimizer="Adam"),
+    "line_odd_walks": dict(dim=64, P=2, k=1, B=450, E=2, S=1, model="LINE", epochs=2, aug=2, L=3, wb=7,
+                           optimizer="Momentum"),
+}
+
+
+def make_product(cfg, toy_graph_file, single_warp):
+    import graphvite_b200 as gv
+    from graphvite_b200 import _lib
+    _lib.lib.gv_reset_global_engine(5489)
+    graph = gv.graph.Graph()
+    graph.load(toy_graph_file)
+    solver = gv.solver.GraphSolver(cfg["dim"], device_ids=[0], num_sampler_per_worker=cfg["S"])
+    _lib.check(_lib.lib.gv_solver_set_option(solver._handle, b"capture_negatives", 1))
+    if single_warp:
+        _lib.check(_lib.lib.gv_solver_set_option(solver._handle, b"train_num_warps", 1))
+    name = cfg["optimizer"]
+    otype, lr, wd, a, b, eps = O.OPTIMIZERS[name]
+    kwargs = {"SGD": {}, "Momentum": dict(momentum=a), "Adam": dict(beta1=a, beta2=b, epsilon=eps)}[name]
+    optimizer = getattr(gv.optimizer, name)(lr, wd, **kwargs)
+    solver.build(graph, optimizer, cfg["P"], cfg["k"], cfg["B"], cfg["E"])
+    return gv, _lib, graph, solver
+
+
+def make_oracle(cfg, toy_graph_file):
+    graph = O.OracleGraph(toy_graph_file)
+    solver = O.OracleSolver(graph, cfg["dim"], 1, cfg["S"])
+    solver.build(cfg["optimizer"], cfg["P"], cfg["k"], cfg["B"], cfg["E"])
+    return graph, solver
+
+
+def product_pool(_lib, solver, side, head, tail, size):
+    out = np.zeros((size, 2), dtype=np.uint32)
+    count = _lib.lib.gv_solver_pool(solver._handle, side, head, tail, out.ctypes.data)
+    assert count == size
+    return out
+
+
+def train_args(cfg):
+    return (cfg["model"].encode(), cfg["epochs"], 0, cfg["aug"], cfg["L"], cfg["wb"], 0, 1.0, 1.0, 1, 0.75, 5.0, 1000)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_solver_matches_oracle_step_by_step(case, toy_graph_file):
+    cfg = CASES[case]
+    gv, _lib, graph, solver = make_product(cfg, toy_graph_file, single_warp=True)
+    ograph, osolver = make_oracle(cfg, toy_graph_file)
+    # partition: head_locations bit-exact
+    n = graph.num_vertex
+    part_of, local_of = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+    _lib.lib.gv_solver_locations(solver._handle, part_of.ctypes.data, local_of.ctypes.data)
+    opart, olocal = osolver.locations()
+    np.testing.assert_array_equal(part_of, opart.astype(np.uint32))
+    np.testing.assert_array_equal(local_of, olocal)
+
+    _lib.check(_lib.lib.gv_solver_train_begin(solver._handle, *train_args(cfg)))
+    osolver.train_begin(cfg["model"], cfg["epochs"], False, cfg["aug"], cfg["L"], cfg["wb"])
+    info = osolver.info()
+    for key in ("num_partition", "episode_size", "batch_size", "augmentation_step", "shuffle_base", "num_batch"):
+        assert getattr(solver, key) == info[key], key
+    size = info["episode_size"] * info["batch_size"]
+    P = info["num_partition"]
+
+    def check_pools(side):
+        for h in range(P):
+            for t in range(P):
+                np.testing.assert_array_equal(product_pool(_lib, solver, side, h, t, size), osolver.pool(side, h, t),
+                                              err_msg="pool %d block (%d, %d)" % (side, h, t))
+
+    check_pools(1)  # the first fill goes to pool_id ^ 1 = 1
+    episodes = 0
+    while True:
+        status = _lib.lib.gv_solver_train_episode(solver._handle)
+        assert status >= 0, _lib.last_error()
+        more = osolver.train_episode()
+        assert (status == 1) == more
+        if not more:
+            break
+        episodes += 1
+        check_pools(osolver.info()["pool_id"] ^ 1)
+        negatives = np.zeros(cfg["B"] * cfg["k"], dtype=np.uint32)
+        assert _lib.lib.gv_solver_last_negatives(solver._handle, negatives.ctypes.data) == negatives.size
+        np.testing.assert_array_equal(negatives, osolver.last_negatives(cfg["B"], cfg["k"]))
+    assert episodes >= 1
+    _lib.check(_lib.lib.gv_solver_train_end(solver._handle))
+    assert solver.batch_id == osolver.info()["batch_id"]
+    # sequential mode: embeddings equal up to fp32 summation order
+    np.testing.assert_allclose(solver.vertex_embeddings, osolver.embeddings(0), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(solver.context_embeddings, osolver.embeddings(1), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(solver.logged_loss, osolver.logged_loss(), rtol=1e-3, atol=1e-6)
+    # predict on the written-back matrices
+    pairs = np.random.RandomState(3).randint(0, n, (500, 2)).astype(np.uint32)
+    np.testing.assert_allclose(solver.predict(pairs), osolver.predict(pairs), rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["line_p1", "deepwalk_p1", "line_p3_adam"])
+def test_hogwild_training_statistics(case, toy_graph_file):
+    """full persistent grid (racy, like the reference): norms within 2%, same pools"""
+    cfg = CASES[case]
+    gv, _lib, graph, solver = make_product(cfg, toy_graph_file, single_warp=False)
+    ograph, osolver = make_oracle(cfg, toy_graph_file)
+    solver.train(cfg["model"], cfg["epochs"], False, cfg["aug"], cfg["L"], cfg["wb"])
+    osolver.train(model=cfg["model"], num_epoch=cfg["epochs"], augmentation_step=cfg["aug"],
+                  random_walk_length=cfg["L"], random_walk_batch_size=cfg["wb"])
+    for which, view in ((0, solver.vertex_embeddings), (1, solver.context_embeddings)):
+        expected = np.linalg.norm(osolver.embeddings(which))
+        assert abs(np.linalg.norm(view) - expected) <= 0.02 * expected
+
+
+def test_resume_and_numpy_views(toy_graph_file):
+    cfg = CASES["line_p1"]
+    gv, _lib, graph, solver = make_product(cfg, toy_graph_file, single_warp=True)
+    solver.train("LINE", 2, False, 2, 5, 10)
+    first = np.array(solver.vertex_embeddings)
+    assert solver.batch_id == 6
+    view = solver.vertex_embeddings
+    view[0, :] = 0.25  # views alias solver memory (bind.h:90-106); resume starts from the edited matrix
+    solver.train("LINE", 2, True, 2, 5, 10)
+    assert solver.batch_id == 12
+    assert not np.allclose(first, solver.vertex_embeddings)
+    assert solver.vertex_embeddings.shape == (graph.num_vertex, cfg["dim"])
+    solver.clear()
+    assert solver.vertex_embeddings.shape == (graph.num_vertex, cfg["dim"])
+
+
+def test_errors_are_reported_not_fatal(toy_graph_file):
+    import graphvite_b200 as gv
+    graph = gv.graph.Graph()
+    graph.load(toy_graph_file)
+    solver = gv.solver.GraphSolver(32, device_ids=[0])
+    with pytest.raises(gv.GVError):
+        solver.train("LINE")  # not built
+    solver.build(graph, batch_size=500, episode_size=3)
+    with pytest.raises(gv.GVError):
+        solver.train("TransE", 1)  # invalid model
+    with pytest.raises(gv.GVError):
+        solver.train("LINE", 1, augmentation_step=50, random_walk_length=40)  # walk shorter than augmentation
+    with pytest.raises(ValueError):
+        gv.solver.GraphSolver(100)

@@ -1,0 +1,174 @@
+"""CPU-side checks of the product library: the C ABI exports every symbol include/gv_b200.h
+declares, and the host-side Graph / AliasTable builders agree with the oracle and the goldens.
+No compute entry point is called here (there is no GPU in this container)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "gv_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(gv_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gv_exchange_fn"}
+    from graphvite_b200 import _lib
+    library = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(library, name)]
+    assert not missing, "declared in gv_b200.h but not exported: %s" % missing
+    unbound = sorted(declared - set(_lib.SIGNATURES))
+    assert not unbound, "declared but not bound in graphvite_b200/_lib.py: %s" % unbound
+    assert len(declared) >= 40
+
+
+def test_missing_extension_fails_loudly(tmp_path, monkeypatch):
+    """the product never falls back to CPU / PyTorch code when the .so is absent"""
+    import importlib.util
+    source = os.path.join(ROOT, "graphvite_b200", "_lib.py")
+    fake = tmp_path / "_lib.py"
+    fake.write_text(open(source).read())
+    spec = importlib.util.spec_from_file_location("gv_fake_lib", str(fake))
+    module = importlib.util.module_from_spec(spec)
+    with pytest.raises(ImportError, match="mandatory"):
+        spec.loader.exec_module(module)
+
+
+def test_solver_without_gpu_reports_an_error():
+    import graphvite_b200 as gv
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(gv.GVError, match="CUDA"):
+        gv.solver.GraphSolver(128)
+
+
+@pytest.mark.parametrize("undirected", [True, False])
+@pytest.mark.parametrize("normalization", [False, True])
+def test_graph_matches_golden_and_oracle(golden_dir, toy_graph_file, undirected, normalization):
+    import graphvite_b200 as gv
+    from graphvite_b200 import _lib
+    golden = np.load("%s/graph_u%d_n%d.npz" % (golden_dir, undirected, normalization))
+    graph = gv.graph.Graph()
+    graph.load(toy_graph_file, as_undirected=undirected, normalization=normalization)
+    assert graph.num_vertex == golden["num_vertex"] and graph.num_edge == golden["num_edge"]
+    assert graph.as_undirected == undirected and graph.normalization == normalization
+    m = _lib.lib.gv_graph_flatten(graph._handle, None, None, None, None, None)
+    u, v = np.zeros(m, dtype=np.uint32), np.zeros(m, dtype=np.uint32)
+    w, offsets = np.zeros(m, dtype=np.float32), np.zeros(graph.num_vertex, dtype=np.uint64)
+    weights = np.zeros(graph.num_vertex, dtype=np.float32)
+    _lib.lib.gv_graph_flatten(graph._handle, u.ctypes.data, v.ctypes.data, w.ctypes.data, offsets.ctypes.data,
+                              weights.ctypes.data)
+    np.testing.assert_array_equal(u, golden["u"])
+    np.testing.assert_array_equal(v, golden["v"])
+    np.testing.assert_array_equal(w, golden["w"])
+    np.testing.assert_array_equal(weights, golden["vertex_weights"])
+    oracle = O.OracleGraph(toy_graph_file, undirected, normalization)
+    np.testing.assert_array_equal(offsets, oracle.flat()[3])
+    assert graph.id2name == oracle.id2name()
+    assert graph.name2id["n65"] == 0 and "nope" not in graph.name2id
+    assert "#vertex: %d, #edge: %d" % (graph.num_vertex, graph.num_edge) in repr(graph)
+
+
+def test_graph_edge_list_overloads_and_save(tmp_path):
+    import graphvite_b200 as gv
+    edges = [("a", "b"), ("b", "c"), ("c", "a"), ("c", "c"), ("a", "b")]
+    graph = gv.graph.Graph()
+    graph.load(edges)
+    assert (graph.num_vertex, graph.num_edge) == (3, 5)
+    weighted = gv.graph.Graph()
+    weighted.load([(u, v, 0.5 + i) for i, (u, v) in enumerate(edges)], as_undirected=False)
+    path = str(tmp_path / "saved.txt")
+    weighted.save(path)
+    lines = open(path).read().split("\n")
+    assert lines[0].split("\t")[:2] == ["a", "b"] and abs(float(lines[0].split("\t")[2]) - 0.5) < 1e-6
+    reloaded = gv.graph.Graph()
+    reloaded.load(path, as_undirected=False)
+    assert (reloaded.num_vertex, reloaded.num_edge) == (3, 5)
+    weighted.save(path, weighted=False, anonymous=True)
+    assert open(path).readline().strip() == "0\t1"
+    with pytest.raises(gv.GVError, match="doesn't exist"):
+        graph.load(str(tmp_path / "missing.txt"))
+    bad = tmp_path / "bad.txt"
+    bad.write_text("a b\nc\n")
+    with pytest.raises(gv.GVError, match="Invalid format at line 2"):
+        graph.load(str(bad))
+    with pytest.raises(gv.GVError, match="Invalid format at line 1"):
+        bad.write_text("a b 1 extra\n")
+        graph.load(str(bad))
+
+
+def test_graph_custom_delimiters_and_comments(tmp_path):
+    import graphvite_b200 as gv
+    path = tmp_path / "g.csv"
+    path.write_text("% header\nx,y,2.5\n\ny,z % tail\n")
+    graph = gv.graph.Graph()
+    graph.load(str(path), delimiters=",\n ", comment="%")
+    assert (graph.num_vertex, graph.num_edge) == (3, 2)
+    oracle = O.OracleGraph(str(path), True, False, ",\n ", "%")
+    assert graph.id2name == oracle.id2name()
+
+
+@pytest.mark.parametrize("count", [1, 2, 37, 1000, 50000])
+def test_alias_build_matches_oracle(count):
+    from graphvite_b200 import _lib
+    rng = np.random.RandomState(count)
+    for weights in (rng.pareto(1.3, count) + 1e-3, np.ones(count), rng.randint(1, 4, count)):
+        weights = weights.astype(np.float32)
+        prob, alias = np.zeros(count, dtype=np.float32), np.zeros(count, dtype=np.uint64)
+        _lib.check(_lib.lib.gv_alias_build(weights.ctypes.data, count, prob.ctypes.data, alias.ctypes.data))
+        oprob, oalias = O.alias_build(weights)
+        np.testing.assert_array_equal(prob, oprob)
+        np.testing.assert_array_equal(alias, oalias)
+
+
+def test_alias_build_matches_golden(golden_dir):
+    from graphvite_b200 import _lib
+    golden = np.load(golden_dir + "/alias.npz")
+    weights = golden["weights"]
+    prob, alias = np.zeros(len(weights), dtype=np.float32), np.zeros(len(weights), dtype=np.uint64)
+    _lib.check(_lib.lib.gv_alias_build(weights.ctypes.data, len(weights), prob.ctypes.data, alias.ctypes.data))
+    np.testing.assert_array_equal(prob, golden["prob"])
+    np.testing.assert_array_equal(alias, golden["alias"])
+    with pytest.raises(_lib.GVError, match="Invalid sampling distribution"):
+        _lib.check(_lib.lib.gv_alias_build(weights.ctypes.data, 0, prob.ctypes.data, alias.ctypes.data))
+
+
+def test_optimizer_surface():
+    import graphvite_b200 as gv
+    opt = gv.optimizer
+    assert opt.Optimizer(gv.auto).type == "Default"
+    assert isinstance(opt.Optimizer("Adam", lr=1e-3), opt.Adam)
+    with pytest.raises(ValueError):
+        opt.Optimizer("Nope")
+    sgd = opt.SGD()
+    assert (sgd.lr, sgd.weight_decay, sgd.schedule.type) == (1e-4, 0, "linear")
+    adam = opt.Adam()
+    assert (adam.beta1, adam.beta2, adam.epsilon) == (0.999, 0.99999, 1e-8)
+    assert opt.Momentum().momentum == 0.999 and opt.AdaGrad().epsilon == 1e-10
+    assert opt.RMSprop().alpha == 0.999 and opt.RMSprop().epsilon == 1e-8
+    assert opt.LRSchedule("linear")(50, 100) == 0.5 and opt.LRSchedule("constant")(50, 100) == 1
+    custom = opt.SGD(0.1, schedule=lambda batch_id, num_batch: 0.5)
+    descriptor = custom._descriptor()
+    assert descriptor.schedule == 2 and abs(descriptor.schedule_fn(3, 10, None) - 0.5) < 1e-7
+    with pytest.raises(ValueError):
+        opt.LRSchedule("cosine")
+    assert "optimizer: Adam" in repr(adam) and "beta1" in repr(adam)
+
+
+def test_link_prediction_auc_formula():
+    from graphvite_b200.application import link_prediction_auc
+    assert link_prediction_auc([0.9, 0.8, 0.1, 0.2], [1, 1, 0, 0]) == 1.0
+    assert link_prediction_auc([0.1, 0.2, 0.9, 0.8], [1, 1, 0, 0]) == 0.0
+    rng = np.random.RandomState(0)
+    scores, labels = rng.rand(2000), rng.randint(0, 2, 2000)
+    from sklearn.metrics import roc_auc_score
+    assert abs(link_prediction_auc(scores, labels) - roc_auc_score(labels, scores)) < 1e-9
