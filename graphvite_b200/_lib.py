@@ -102,6 +102,7 @@ SIGNATURES = {
     "gv_solver_logged_loss": (c_int, [c_void_p, c_void_p, c_int]),
     "gv_solver_stats": (c_int, [c_void_p, c_void_p, c_int]),
     # test hooks
+    "gv_schedule_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int]),
     "gv_reset_global_engine": (None, [c_uint32]),
     "gv_solver_locations": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gv_solver_pool": (c_int64, [c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -109,6 +110,8 @@ SIGNATURES = {
                                       c_float, c_int, c_float, c_float, c_int]),
     "gv_solver_train_episode": (c_int, [c_void_p]),
     "gv_solver_train_end": (c_int, [c_void_p]),
+    "gv_solver_train_step": (c_int, [c_void_p]),
+    "gv_solver_device_timer": (c_double, [c_void_p, c_int]),
     "gv_solver_last_negatives": (c_int, [c_void_p, c_void_p]),
 }
 

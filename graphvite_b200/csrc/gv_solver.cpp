@@ -185,6 +185,40 @@ static std::vector<std::vector<Assignment>> make_schedule(int num_partition, int
     return schedule;
 }
 
+// Which rank holds which vertex (head) block.  Context blocks never move (tail t lives on rank
+// t % W); inside one group of W head blocks every schedule step assigns the blocks to the ranks by
+// a permutation, so each rank gives away at most one block and receives at most one per step.
+struct Transfer {
+    int need, source;        // block this rank trains next and the rank holding it now
+    int give, destination;   // block another rank needs from this rank (-1: none) and that rank
+};
+
+struct BlockDirectory {
+    int num_partition = 0, num_worker = 1;
+    std::vector<int> owner;  // head block -> rank
+
+    void reset(int P, int W) {
+        num_partition = P;
+        num_worker = W;
+        owner.resize(P);
+        for (int h = 0; h < P; h++)
+            owner[h] = h % W;
+    }
+    Transfer plan(int rank, const std::vector<Assignment> &step) const {
+        Transfer t = {step[rank].head, owner[step[rank].head], -1, -1};
+        for (int i = 0; i < num_worker; i++)
+            if (i != rank && owner[step[i].head] == rank) {
+                t.give = step[i].head;
+                t.destination = i;
+            }
+        return t;
+    }
+    void commit(const std::vector<Assignment> &step) {
+        for (int i = 0; i < num_worker; i++)
+            owner[step[i].head] = i;
+    }
+};
+
 struct Solver {
     // ---- construction (SolverMixin ctor, core/solver.h:184-213) ----
     int dim, device, rank, world_size;
@@ -223,7 +257,7 @@ struct Solver {
     int num_state = 1;                             // 1 + num_moment matrices per block
     std::vector<DeviceArray> vertex_slots;         // each num_state * block_floats floats
     std::vector<int> slot_of_head;                 // head block -> local slot or -1
-    std::vector<int> owner_of_head;                // head block -> rank
+    BlockDirectory directory;                      // head block -> rank
     std::vector<int> free_slots;
     std::vector<DeviceArray> context_blocks;       // [num_group]
     std::vector<DeviceArray> negative_tables;      // [num_group] gv_alias_entry_t
@@ -250,6 +284,7 @@ struct Solver {
     // stats
     double stat_positive = 0, stat_kernel_seconds = 0, stat_train_seconds = 0, stat_sample_seconds = 0;
     std::atomic<unsigned long long> stat_launches{0};
+    cudaEvent_t timer_begin = nullptr, timer_end = nullptr;
 
     Solver(int _dim, const int *device_ids, int num_device, int num_sampler_per_worker, uint64_t memory_limit,
            int _rank, int _world_size)
@@ -319,6 +354,8 @@ struct Solver {
             if (random_free[i])
                 cudaEventDestroy(random_free[i]);
         }
+        if (sampler_thread.joinable())
+            sampler_thread.join();
         if (work_stream)
             cudaStreamDestroy(work_stream);
         if (sample_stream)
@@ -650,14 +687,12 @@ struct Solver {
         DeviceArray staging;
         staging.allocate(total);
         slot_of_head.assign(num_partition, -1);
-        owner_of_head.assign(num_partition, 0);
+        directory.reset(num_partition, num_worker);
         free_slots.clear();
         int next_slot = 0;
-        for (int h = 0; h < num_partition; h++) {
-            owner_of_head[h] = h % num_worker;
-            if (owner_of_head[h] == rank)
+        for (int h = 0; h < num_partition; h++)
+            if (directory.owner[h] == rank)
                 slot_of_head[h] = next_slot++;
-        }
         for (int s = next_slot; s < int(vertex_slots.size()); s++)
             free_slots.push_back(s);
         HostState vertex = vertex_state(), context = context_state();
@@ -694,7 +729,7 @@ struct Solver {
         if (!vertex_side)
             return g * num_worker + holder;
         for (int h = g * num_worker; h < (g + 1) * num_worker; h++)
-            if (owner_of_head[h] == holder)
+            if (directory.owner[h] == holder)
                 return h;
         throw std::runtime_error("internal error: inconsistent block ownership");
     }
@@ -823,6 +858,7 @@ struct Solver {
         stat_launches = 0;
         previous_batch_loss = 0;
         training = true;
+        step_in_episode = 0;
         fill_pool(pool_id ^ 1);
     }
 
@@ -910,39 +946,54 @@ struct Solver {
         stat_positive += double(positive_reuse) * episode_size * batch_size;
     }
 
-    // one pass of the episode loop, core/solver.h:629-649
-    bool train_episode() {
+    // ---- the episode loop, core/solver.h:629-649, cut into schedule steps (sub-episodes) ----
+    std::vector<std::vector<Assignment>> schedule;
+    size_t step_in_episode = 0;
+    std::thread sampler_thread;
+    std::exception_ptr sampler_error;
+
+    void finish_sampler() {
+        if (sampler_thread.joinable())
+            sampler_thread.join();
+        if (sampler_error) {
+            std::exception_ptr error = sampler_error;
+            sampler_error = nullptr;
+            std::rethrow_exception(error);
+        }
+    }
+
+    // One sub-episode: every worker trains one (head, tail) block.  Returns false when training is over.
+    bool train_step() {
         require(training, "train_begin() has not been called");
         GV_CHECK_CUDA(cudaSetDevice(device));
-        if (batch_id >= num_batch)
-            return false;
-        pool_id ^= 1;
-        // the samplers fill the other pool while the worker trains on this one
-        std::exception_ptr sampler_error;
-        std::thread sampler([&]() {
-            try {
-                fill_pool(pool_id ^ 1);
-            } catch (...) {
-                sampler_error = std::current_exception();
-            }
-        });
-        std::exception_ptr worker_error;
+        if (step_in_episode == 0) {
+            if (batch_id >= num_batch)
+                return false;
+            pool_id ^= 1;
+            schedule = make_schedule(num_partition, num_worker);
+            // the samplers fill the other pool while the workers train on this one
+            const int side = pool_id ^ 1;
+            sampler_thread = std::thread([this, side]() {
+                try {
+                    fill_pool(side);
+                } catch (...) {
+                    sampler_error = std::current_exception();
+                }
+            });
+        }
         try {
+            const auto &step = schedule[step_in_episode];
+            const int width = int(step.size());
             cudaEvent_t begin, end;
             GV_CHECK_CUDA(cudaEventCreate(&begin));
             GV_CHECK_CUDA(cudaEventCreate(&end));
             GV_CHECK_CUDA(cudaEventRecord(begin, work_stream));
-            const auto schedule = make_schedule(num_partition, num_worker);
-            const int per_block = positive_reuse * episode_size;
-            for (const auto &step : schedule) {
-                const int width = int(step.size());
-                if (num_worker > 1)
-                    rotate_vertex_blocks(step);
-                // batch ids: the reference's workers share an atomic counter (solver.h:1520); we use the
-                // interleaving first_batch + j * width, which is what lock-step workers would draw.
-                train_block(step[rank].head, step[rank].tail, batch_id + rank, width);
-                batch_id += per_block * width;
-            }
+            if (num_worker > 1)
+                rotate_vertex_blocks(step);
+            // batch ids: the reference's workers share an atomic counter (solver.h:1520); we use the
+            // interleaving first_batch + j * width, which is what lock-step workers would draw.
+            train_block(step[rank].head, step[rank].tail, batch_id + rank, width);
+            batch_id += positive_reuse * episode_size * width;
             GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
             GV_CHECK_CUDA(cudaEventSynchronize(end));
             float ms = 0;
@@ -951,13 +1002,23 @@ struct Solver {
             cudaEventDestroy(begin);
             cudaEventDestroy(end);
         } catch (...) {
-            worker_error = std::current_exception();
+            if (sampler_thread.joinable())
+                sampler_thread.join();
+            step_in_episode = 0;
+            throw;
         }
-        sampler.join();
-        if (worker_error)
-            std::rethrow_exception(worker_error);
-        if (sampler_error)
-            std::rethrow_exception(sampler_error);
+        if (++step_in_episode == schedule.size()) {
+            step_in_episode = 0;
+            finish_sampler();
+        }
+        return true;
+    }
+
+    bool train_episode() {
+        if (!train_step())
+            return false;
+        while (step_in_episode != 0)
+            train_step();
         return true;
     }
 
@@ -965,38 +1026,32 @@ struct Solver {
     // num_worker head blocks the assignment is a permutation, so each rank sends at most one
     // block and receives at most one (a ring shift for the default schedule).
     void rotate_vertex_blocks(const std::vector<Assignment> &step) {
-        const int need = step[rank].head;
-        const int source = owner_of_head[need];
-        int give = -1, destination = -1;
-        for (int i = 0; i < num_worker; i++)
-            if (i != rank && owner_of_head[step[i].head] == rank) {
-                give = step[i].head;
-                destination = i;
-            }
+        const Transfer t = directory.plan(rank, step);
         const uint64_t bytes = block_floats * num_state * sizeof(float);
         int incoming_slot = -1;
-        if (source != rank) {
+        if (t.source != rank) {
             require(!free_slots.empty(), "internal error: no free vertex slot");
             incoming_slot = free_slots.back();
             free_slots.pop_back();
         }
-        if (give >= 0 || incoming_slot >= 0)
-            exchange(give >= 0 ? vertex_slots[slot_of_head[give]].ptr : nullptr, destination,
-                     incoming_slot >= 0 ? vertex_slots[incoming_slot].ptr : nullptr, incoming_slot >= 0 ? source : -1,
-                     bytes);
-        if (give >= 0) {
-            free_slots.push_back(slot_of_head[give]);
-            slot_of_head[give] = -1;
+        if (t.give >= 0 || incoming_slot >= 0)
+            exchange(t.give >= 0 ? vertex_slots[slot_of_head[t.give]].ptr : nullptr, t.destination,
+                     incoming_slot >= 0 ? vertex_slots[incoming_slot].ptr : nullptr,
+                     incoming_slot >= 0 ? t.source : -1, bytes);
+        if (t.give >= 0) {
+            free_slots.push_back(slot_of_head[t.give]);
+            slot_of_head[t.give] = -1;
         }
         if (incoming_slot >= 0)
-            slot_of_head[need] = incoming_slot;
-        for (int i = 0; i < num_worker; i++)
-            owner_of_head[step[i].head] = i;
+            slot_of_head[t.need] = incoming_slot;
+        directory.commit(step);
     }
 
     void train_end() {
         require(training, "train_begin() has not been called");
         GV_CHECK_CUDA(cudaSetDevice(device));
+        while (step_in_episode != 0)  // never stop in the middle of an episode
+            train_step();
         write_back();
         training = false;
     }
@@ -1158,6 +1213,39 @@ static int copy_string(const std::string &text, char *buffer, size_t capacity) {
 
 extern "C" {
 
+// The block movement of `num_episode` episodes for every rank, from the code the solver itself runs:
+// out[((e * steps + s) * W + rank) * 6 + {0..5}] = head, tail, need-source, give, destination, #held
+int gv_schedule_plan(int num_partition, int num_worker, int num_episode, int *out, int capacity) {
+    GV_TRY
+    if (num_partition < num_worker || num_partition % num_worker != 0)
+        throw std::runtime_error("#partition must be a positive multiple of #worker");
+    const auto schedule = gv::make_schedule(num_partition, num_worker);
+    gv::BlockDirectory directory;
+    directory.reset(num_partition, num_worker);
+    const int width = int(schedule[0].size());
+    if (int(schedule.size()) * width * 6 * num_episode > capacity)
+        throw std::runtime_error("gv_schedule_plan: capacity too small");
+    int n = 0;
+    for (int e = 0; e < num_episode; e++)
+        for (const auto &step : schedule) {
+            std::vector<gv::Transfer> transfers;
+            for (int rank = 0; rank < width; rank++)
+                transfers.push_back(directory.plan(rank, step));
+            directory.commit(step);
+            for (int rank = 0; rank < width; rank++) {
+                int held = 0;
+                for (int owner : directory.owner)
+                    held += owner == rank;
+                const int values[6] = {step[rank].head, step[rank].tail, transfers[rank].source, transfers[rank].give,
+                                       transfers[rank].destination, held};
+                for (int v : values)
+                    out[n++] = v;
+            }
+        }
+    return int(schedule.size());
+    GV_CATCH(-1)
+}
+
 void gv_reset_global_engine(uint32_t seed) {
     gv::g_engine = std::mt19937(seed);
 }
@@ -1230,6 +1318,33 @@ int gv_solver_train_episode(gv_solver_t *solver) {
     GV_TRY
     return solver->solver->train_episode() ? 1 : 0;
     GV_CATCH(-1)
+}
+
+int gv_solver_train_step(gv_solver_t *solver) {
+    GV_TRY
+    return solver->solver->train_step() ? 1 : 0;
+    GV_CATCH(-1)
+}
+
+double gv_solver_device_timer(gv_solver_t *solver, int stop) {
+    GV_TRY
+    Solver &s = *solver->solver;
+    cudaSetDevice(s.device);
+    if (!s.timer_begin) {
+        cudaEventCreate(&s.timer_begin);
+        cudaEventCreate(&s.timer_end);
+    }
+    if (!stop) {
+        if (cudaEventRecord(s.timer_begin, s.work_stream) != cudaSuccess)
+            throw std::runtime_error("cudaEventRecord failed");
+        return 0;
+    }
+    float ms = 0;
+    if (cudaEventRecord(s.timer_end, s.work_stream) != cudaSuccess || cudaEventSynchronize(s.timer_end) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, s.timer_begin, s.timer_end) != cudaSuccess)
+        throw std::runtime_error("device timer failed");
+    return double(ms) * 1e-3;
+    GV_CATCH(-1.0)
 }
 
 int gv_solver_train_end(gv_solver_t *solver) {

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "gv_common.h"
@@ -52,6 +53,7 @@ struct TrainParams {
     uint32_t batch_size;
     float negative_weight;
     float *loss_per_sample, *loss_per_batch;
+    int flags;  // experiment switches: 1 = L1-cached row loads, 2 = no next-row prefetch
 };
 
 // -----------------------------------------------------------------------------
@@ -70,11 +72,12 @@ __device__ __forceinline__ bool lane_active(int pass, int lane) {
 }
 
 template<int DIM>
-__device__ __forceinline__ void load_row(Row<DIM> &row, const float *base, int lane) {
+__device__ __forceinline__ void load_row(Row<DIM> &row, const float *base, int lane, bool l1 = false) {
 #pragma unroll
     for (int p = 0; p < Row<DIM>::kPass; p++) {
         if (lane_active<DIM>(p, lane))
-            row.x[p] = __ldcg(reinterpret_cast<const float4 *>(base) + p * 32 + lane);
+            row.x[p] = l1 ? __ldca(reinterpret_cast<const float4 *>(base) + p * 32 + lane)
+                          : __ldcg(reinterpret_cast<const float4 *>(base) + p * 32 + lane);
         else
             row.x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
     const unsigned long long num_chunk = (p.num_sample + 31) / 32;
     const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const gv_device_optimizer_t o = p.optimizer;
+    const bool l1 = p.flags & 1, prefetch = !(p.flags & 2);
 
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
          chunk < num_chunk; chunk += num_warp) {
@@ -231,8 +235,8 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
             const size_t head_offset = size_t(head) * DIM;
             uint32_t tail = sample[1];
             // issue every independent load of this sample before the first use
-            load_row<DIM>(v, p.vertex + head_offset, lane);
-            load_row<DIM>(c, p.context + size_t(tail) * DIM, lane);
+            load_row<DIM>(v, p.vertex + head_offset, lane, l1);
+            load_row<DIM>(c, p.context + size_t(tail) * DIM, lane, l1);
             if (NM >= 1) {
                 load_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
                 load_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
@@ -247,8 +251,8 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                 uint32_t tail_next = tail;
                 if (s < k) {
                     tail_next = sample[2 + s];
-                    if (tail_next != tail) {
-                        load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane);
+                    if (tail_next != tail && prefetch) {
+                        load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane, l1);
                         if (NM >= 1)
                             load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane);
                         if (NM >= 2)
@@ -274,6 +278,13 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                     store_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
                 if (NM >= 2)
                     store_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
+                if (s < k && tail_next != tail && !prefetch) {
+                    load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane, l1);
+                    if (NM >= 1)
+                        load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane);
+                    if (NM >= 2)
+                        load_row<DIM>(cm2_next, p.context_m2 + size_t(tail_next) * DIM, lane);
+                }
                 if (s < k && tail_next != tail) {
                     c = c_next;
                     if (NM >= 1)
@@ -442,6 +453,8 @@ int gv_cuda_train_block(const gv_matrices_t *m, const uint32_t *pool, uint64_t n
     p.negative_weight = negative_weight;
     p.loss_per_sample = loss_per_sample;
     p.loss_per_batch = loss_per_batch;
+    static const int env_flags = getenv("GV_KERNEL_FLAGS") ? atoi(getenv("GV_KERNEL_FLAGS")) : 0;
+    p.flags = env_flags;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (m->dim) {  // src/graphvite.cu:52-59 instantiates exactly these dimensions
         case 32: return dispatch_optimizer<32>(p, num_warps, s);

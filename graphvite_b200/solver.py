@@ -40,6 +40,11 @@ class GraphSolver(object):
         self._optimizer = None
         self._descriptor = None  # keeps the ctypes schedule callback alive
         self._exchange = None
+        if world_size > 1:
+            import torch
+            from . import distributed
+            device = torch.device("cuda", device_ids[0] if device_ids else torch.cuda.current_device())
+            distributed.attach(self, device)
 
     def __del__(self):
         handle, self._handle = getattr(self, "_handle", None), None

@@ -242,6 +242,11 @@ int gv_solver_logged_loss(const gv_solver_t *solver, float *out, int capacity);
 int gv_solver_stats(const gv_solver_t *solver, double *out, int capacity);
 
 /* ---- test hooks (no reference counterpart: the reference's members are simply public) ------- */
+/* SolverMixin::get_schedule (core/solver.h:519-575) plus the vertex-block movement it implies:
+ * for `num_episode` episodes, out[((e * steps + s) * W + rank) * 6 + i] = head, tail, source rank of
+ * the head block, block given away (-1 none), its destination rank, #head blocks held afterwards.
+ * Returns the number of steps per episode. */
+int gv_schedule_plan(int num_partition, int num_worker, int num_episode, int *out, int capacity);
 /* the process-wide engine core/solver.h:50: re-seed (5489 = default-constructed) */
 void gv_reset_global_engine(uint32_t seed);
 /* head_locations (core/solver.h:399-410) */
@@ -254,6 +259,10 @@ int gv_solver_train_begin(gv_solver_t *solver, const char *model, int num_epoch,
                           int positive_reuse, float negative_sample_exponent, float negative_weight,
                           int log_frequency);
 int gv_solver_train_episode(gv_solver_t *solver);   /* 1 = trained one episode, 0 = done, <0 error */
+/* one schedule step (sub-episode): every worker trains one (head, tail) block; 1 / 0 / <0 like above */
+int gv_solver_train_step(gv_solver_t *solver);
+/* CUDA-event stopwatch on the solver's work stream: stop = 0 starts it, stop = 1 returns the seconds */
+double gv_solver_device_timer(gv_solver_t *solver, int stop);
 int gv_solver_train_end(gv_solver_t *solver);       /* write_back (core/solver.h:650-653) */
 /* options: "capture_negatives" = 1 keeps the negatives the train kernel drew for the last batch;
  * "train_num_warps" = 1 runs the train kernel on a single warp (sequential order, reproducible) */
