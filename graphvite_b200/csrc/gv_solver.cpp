@@ -487,6 +487,8 @@ struct Solver {
         const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2 * sizeof(double);
         chunk_batches = int(std::max<uint64_t>(1, std::min<uint64_t>(episode_size, (uint64_t(192) << 20) /
                                                                                     std::max<uint64_t>(1, per_batch_random))));
+        if (getenv("GV_CHUNK_BATCHES"))  // experiment: launch granularity in batches
+            chunk_batches = std::max(1, std::min(episode_size, atoi(getenv("GV_CHUNK_BATCHES"))));
         for (int i = 0; i < 2; i++)
             d_random[i].allocate(std::max<uint64_t>(16, per_batch_random * chunk_batches));
         d_lr.allocate(size_t(episode_size) * sizeof(float));
@@ -899,21 +901,35 @@ struct Solver {
                     GV_CHECK_CUDA(cudaEventRecord(random_ready[buffer], random_stream));
                     GV_CHECK_CUDA(cudaStreamWaitEvent(work_stream, random_ready[buffer], 0));
                 }
+                // The loss is only needed for a batch whose successor logs it (one in log_frequency,
+                // core/solver.h:1541-1549): those batches get their own launch of the LOSS kernel.
                 cudaEvent_t begin, end;
                 GV_CHECK_CUDA(cudaEventCreate(&begin));
                 GV_CHECK_CUDA(cudaEventCreate(&end));
                 GV_CHECK_CUDA(cudaEventRecord(begin, work_stream));
-                GV_CHECK_ABI(gv_cuda_train_block(
-                    &matrices, pool + uint64_t(j0) * batch_size * 2, uint64_t(count) * batch_size, num_negative,
-                    nullptr, d_random[buffer].as<double>(), negative_tables[g].as<gv_alias_entry_t>(),
-                    negative_counts[g], capture_negatives ? d_negatives_out.as<uint32_t>() : nullptr,
-                    &device_optimizer, d_lr.as<float>() + j0, batch_size, negative_weight, nullptr,
-                    d_loss.as<float>() + j0, train_num_warps, work_stream));
+                for (int j = j0; j < j0 + count;) {
+                    auto wants_loss = [&](int b) {
+                        return (first_batch + (reuse * episode_size + b + 1) * batch_stride) % log_frequency == 0;
+                    };
+                    const bool with_loss = wants_loss(j);
+                    int j1 = j + 1;
+                    while (!with_loss && j1 < j0 + count && !wants_loss(j1))
+                        j1++;
+                    GV_CHECK_ABI(gv_cuda_train_block(
+                        &matrices, pool + uint64_t(j) * batch_size * 2, uint64_t(j1 - j) * batch_size, num_negative,
+                        nullptr, d_random[buffer].as<double>() + uint64_t(j - j0) * per_batch_random,
+                        negative_tables[g].as<gv_alias_entry_t>(), negative_counts[g],
+                        capture_negatives ? d_negatives_out.as<uint32_t>() + uint64_t(j - j0) * batch_size * num_negative
+                                          : nullptr,
+                        &device_optimizer, d_lr.as<float>() + j, batch_size, negative_weight, nullptr,
+                        with_loss ? d_loss.as<float>() + j : nullptr, train_num_warps, work_stream));
+                    stat_launches++;
+                    j = j1;
+                }
                 GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
                 GV_CHECK_CUDA(cudaEventRecord(random_free[buffer], work_stream));
                 timers.push_back(begin);
                 timers.push_back(end);
-                stat_launches++;
                 if (capture_negatives && reuse == positive_reuse - 1 && j0 + count == episode_size) {
                     last_negatives.resize(size_t(batch_size) * num_negative);
                     GV_CHECK_CUDA(cudaMemcpyAsync(last_negatives.data(),
@@ -928,7 +944,7 @@ struct Solver {
             // the reference logs, at batch b, the mean loss of the batch trained before it (appendix A.8)
             for (int j = 0; j < episode_size; j++) {
                 const int this_batch = first_batch + (reuse * episode_size + j) * batch_stride;
-                if (this_batch % log_frequency == 0) {
+                if (this_batch % log_frequency == 0) {  // previous_batch_loss was computed for exactly this
                     logged_loss.push_back(previous_batch_loss);
                     if (log_enabled())
                         fprintf(stderr, "Batch id: %d / %d\nloss = %g\n", this_batch, num_batch, previous_batch_loss);

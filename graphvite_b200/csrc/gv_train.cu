@@ -53,7 +53,7 @@ struct TrainParams {
     uint32_t batch_size;
     float negative_weight;
     float *loss_per_sample, *loss_per_batch;
-    int flags;  // experiment switches: 1 = L1-cached row loads, 2 = no next-row prefetch
+    int flags;  // experiment switches: 1 = L1-cached (.ca) row loads, 4 = never use train_sgd_kernel
 };
 
 // -----------------------------------------------------------------------------
@@ -111,9 +111,15 @@ __device__ __forceinline__ float dot(const Row<DIM> &a, const Row<DIM> &b) {
     return warp_sum(acc);
 }
 
-// util/math.h:30-33
+// util/math.h:30-33: sigmoid(x) = x > 0 ? 1 / (1 + exp(-x)) : exp(x) / (exp(x) + 1).
+// Both branches share e = exp(-|x|) and r = 1 / (1 + e).  The training path uses the hardware
+// exponential and reciprocal (ex2.approx / rcp.approx, <= 2 ulp each): the kernel is issue-bound on
+// the precise libdevice sequences otherwise, and the difference (~1e-7 relative on the gradient) is
+// three orders of magnitude below the Hogwild noise of the algorithm itself.
 __device__ __forceinline__ float sigmoid(float x) {
-    return x > 0 ? 1 / (1 + expf(-x)) : expf(x) / (expf(x) + 1);
+    const float e = __expf(-fabsf(x));
+    const float r = __fdividef(1.f, 1.f + e);
+    return x > 0 ? r : e * r;
 }
 
 // -----------------------------------------------------------------------------
@@ -123,8 +129,6 @@ template<int OPT>
 __device__ __forceinline__ float update(const gv_device_optimizer_t &o, float lr, float parameter, float gradient,
                                         float &moment1, float &moment2, float weight) {
     float regularized = weight * (gradient + o.weight_decay * parameter);
-    if (OPT == GV_OPT_SGD)
-        return lr * regularized;
     if (OPT == GV_OPT_MOMENTUM) {
         moment1 = o.a * moment1 + (1 - o.a) * regularized;
         return lr * moment1;
@@ -137,16 +141,39 @@ __device__ __forceinline__ float update(const gv_device_optimizer_t &o, float lr
         moment1 = o.a * moment1 + (1 - o.a) * regularized * regularized;
         return lr * regularized / sqrtf(moment1 + o.epsilon);
     }
-    moment1 = o.a * moment1 + (1 - o.a) * regularized;
-    moment2 = o.b * moment2 + (1 - o.b) * regularized * regularized;
-    return lr * moment1 / (sqrtf(moment2) + o.epsilon);
+    if (OPT == GV_OPT_ADAM) {
+        moment1 = o.a * moment1 + (1 - o.a) * regularized;
+        moment2 = o.b * moment2 + (1 - o.b) * regularized * regularized;
+        return lr * moment1 / (sqrtf(moment2) + o.epsilon);
+    }
+    return lr * regularized;
 }
 
-// LINE::backward, instance/model/graph.h:47-85: both updates read the pre-update v and c
+// LINE::backward, instance/model/graph.h:47-85: both updates read the pre-update v and c.
+// SGD (optimizer.h:161-164): x -= lr * w * (g * y + wd * x)  ==  x * (1 - lr*w*wd) - (lr*w*g) * y,
+// two instructions per element instead of five.
 template<int DIM, int OPT>
 __device__ __forceinline__ void backward(const gv_device_optimizer_t &o, float lr, float gradient, float weight,
                                          Row<DIM> &v, Row<DIM> &c, Row<DIM> &vm1, Row<DIM> &cm1, Row<DIM> &vm2,
                                          Row<DIM> &cm2) {
+    if constexpr (OPT == GV_OPT_SGD) {
+        const float scale = lr * weight;
+        const float alpha = 1.f - scale * o.weight_decay, beta = scale * gradient;
+#pragma unroll
+        for (int p = 0; p < Row<DIM>::kPass; p++) {
+#define GV_ELEMENT(f)                                      \
+    {                                                      \
+        const float vv = v.x[p].f, cc = c.x[p].f;          \
+        v.x[p].f = fmaf(-beta, cc, alpha * vv);            \
+        c.x[p].f = fmaf(-beta, vv, alpha * cc);            \
+    }
+            GV_ELEMENT(x)
+            GV_ELEMENT(y)
+            GV_ELEMENT(z)
+            GV_ELEMENT(w)
+#undef GV_ELEMENT
+        }
+    } else {
 #pragma unroll
     for (int p = 0; p < Row<DIM>::kPass; p++) {
 #define GV_ELEMENT(f)                                                                        \
@@ -160,6 +187,7 @@ __device__ __forceinline__ void backward(const gv_device_optimizer_t &o, float l
         GV_ELEMENT(z)
         GV_ELEMENT(w)
 #undef GV_ELEMENT
+    }
     }
 }
 
@@ -177,11 +205,22 @@ __device__ __forceinline__ uint32_t alias_sample_narrowed(const gv_alias_entry_t
 }
 
 // -----------------------------------------------------------------------------
-// The train kernel.  NM moment rows accompany every embedding row.
+// The train kernel.  NM moment rows accompany every embedding row.  LOSS = false skips the two
+// logf per target (the reference logs the loss of one batch in log_frequency, core/solver.h:1541).
+//
+// Memory-level parallelism: all rows of a sample are requested before the first one is used (the
+// next target's context row is prefetched while the current one is processed), and for SGD the
+// first two rows of the NEXT sample are requested before the current sample is computed.  Rows a
+// sample is about to overwrite are never consumed stale by the same warp: equal ids reuse the
+// updated registers, and a prefetched row that the current sample turned out to write is reloaded.
+// A single warp therefore executes exactly the sequential semantics of the reference's per-sample
+// loop, which is what the parity tests check; across warps the updates race (Hogwild), as in the
+// reference.
 // -----------------------------------------------------------------------------
-template<int DIM, int OPT>
+template<int DIM, int OPT, bool LOSS>
 __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams p) {
     constexpr int NM = OPT == GV_OPT_SGD ? 0 : (OPT == GV_OPT_ADAM ? 2 : 1);
+    constexpr bool kCross = NM == 0 && Row<DIM>::kPass <= 2;  // cross-sample prefetch (register budget)
     extern __shared__ uint32_t shared_ids[];
 
     const int lane = threadIdx.x & 31;
@@ -193,7 +232,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
     const unsigned long long num_chunk = (p.num_sample + 31) / 32;
     const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const gv_device_optimizer_t o = p.optimizer;
-    const bool l1 = p.flags & 1, prefetch = !(p.flags & 2);
+    const bool l1 = p.flags & 1;
 
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
          chunk < num_chunk; chunk += num_warp) {
@@ -226,32 +265,53 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
 
         const int count = int(min(32ull, p.num_sample - base));
         float loss_lane = 0.f;
+        Row<DIM> v, vm1, vm2, c, cm1, cm2, c_next, cm1_next, cm2_next, v_ahead, c_ahead;
+        uint32_t head = ids[0], tail = ids[1];
+        if (kCross) {
+            load_row<DIM>(v_ahead, p.vertex + size_t(head) * DIM, lane, l1);
+            load_row<DIM>(c_ahead, p.context + size_t(tail) * DIM, lane, l1);
+        }
         for (int t = 0; t < count; t++) {
             const uint32_t *sample = ids + t * stride;
-            const uint32_t head = sample[0];
             const float lr = __shfl_sync(kFullMask, lr_lane, t);
-
-            Row<DIM> v, vm1, vm2, c, cm1, cm2, c_next, cm1_next, cm2_next;
             const size_t head_offset = size_t(head) * DIM;
-            uint32_t tail = sample[1];
-            // issue every independent load of this sample before the first use
-            load_row<DIM>(v, p.vertex + head_offset, lane, l1);
-            load_row<DIM>(c, p.context + size_t(tail) * DIM, lane, l1);
-            if (NM >= 1) {
-                load_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
-                load_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
+            // ---- this sample's first rows: already in flight (SGD) or requested now ----
+            uint32_t head_ahead = head, tail_ahead = tail;
+            const bool more = t + 1 < count;
+            if (kCross) {
+                v = v_ahead;
+                c = c_ahead;
+                if (more) {  // request the next sample's first two rows before computing this one
+                    head_ahead = sample[stride];
+                    tail_ahead = sample[stride + 1];
+                    if (head_ahead != head)
+                        load_row<DIM>(v_ahead, p.vertex + size_t(head_ahead) * DIM, lane, l1);
+                    load_row<DIM>(c_ahead, p.context + size_t(tail_ahead) * DIM, lane, l1);
+                }
+            } else {
+                load_row<DIM>(v, p.vertex + head_offset, lane, l1);
+                load_row<DIM>(c, p.context + size_t(tail) * DIM, lane, l1);
+                if (NM >= 1) {
+                    load_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
+                    load_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
+                }
+                if (NM >= 2) {
+                    load_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
+                    load_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
+                }
+                if (more) {
+                    head_ahead = sample[stride];
+                    tail_ahead = sample[stride + 1];
+                }
             }
-            if (NM >= 2) {
-                load_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
-                load_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
-            }
+            bool stale_ahead = false;  // did this sample write the context row prefetched for the next one?
             float sample_loss = 0.f;
             for (int s = 0; s <= k; s++) {
                 // prefetch the next target's rows while this one is being processed
                 uint32_t tail_next = tail;
                 if (s < k) {
                     tail_next = sample[2 + s];
-                    if (tail_next != tail && prefetch) {
+                    if (tail_next != tail) {
                         load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane, l1);
                         if (NM >= 1)
                             load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane);
@@ -266,11 +326,13 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                 if (s == k) {
                     gradient = prob - 1;
                     weight = 1;
-                    sample_loss += weight * -logf(prob + kEpsilon);
+                    if (LOSS)
+                        sample_loss += weight * -logf(prob + kEpsilon);
                 } else {
                     gradient = prob;
                     weight = p.negative_weight;
-                    sample_loss += weight * -logf(1 - prob + kEpsilon);
+                    if (LOSS)
+                        sample_loss += weight * -logf(1 - prob + kEpsilon);
                 }
                 backward<DIM, OPT>(o, lr, gradient, weight, v, c, vm1, cm1, vm2, cm2);
                 store_row<DIM>(c, p.context + size_t(tail) * DIM, lane);
@@ -278,13 +340,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                     store_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
                 if (NM >= 2)
                     store_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
-                if (s < k && tail_next != tail && !prefetch) {
-                    load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane, l1);
-                    if (NM >= 1)
-                        load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane);
-                    if (NM >= 2)
-                        load_row<DIM>(cm2_next, p.context_m2 + size_t(tail_next) * DIM, lane);
-                }
+                stale_ahead |= tail == tail_ahead;
                 if (s < k && tail_next != tail) {
                     c = c_next;
                     if (NM >= 1)
@@ -299,23 +355,188 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                 store_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
             if (NM >= 2)
                 store_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
-            sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
-            if (lane == t)
-                loss_lane = sample_loss;
+            if (LOSS) {
+                sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
+                if (lane == t)
+                    loss_lane = sample_loss;
+            }
+            if (kCross && more) {
+                if (head_ahead == head)
+                    v_ahead = v;  // same vertex again: continue from the updated registers
+                if (stale_ahead)  // program order: this load follows the store above in the same thread
+                    load_row<DIM>(c_ahead, p.context + size_t(tail_ahead) * DIM, lane, l1);
+            }
+            head = head_ahead;
+            tail = tail_ahead;
         }
-        if (p.loss_per_sample && valid)
-            p.loss_per_sample[i] = loss_lane;
-        if (p.loss_per_batch) {
-            // a 32-sample chunk may straddle batches: one reduction + atomic per distinct batch
-            unsigned remaining = __ballot_sync(kFullMask, valid);
-            while (remaining) {
-                const int leader = __ffs(remaining) - 1;
-                const uint32_t batch = __shfl_sync(kFullMask, batch_lane, leader);
-                const bool mine = valid && batch_lane == batch;
-                const float sum = warp_sum(mine ? loss_lane : 0.f);
-                if (lane == leader)
-                    atomicAdd(p.loss_per_batch + batch, sum);
-                remaining &= ~__ballot_sync(kFullMask, mine);
+        if (LOSS) {
+            if (p.loss_per_sample && valid)
+                p.loss_per_sample[i] = loss_lane;
+            if (p.loss_per_batch) {
+                // a 32-sample chunk may straddle batches: one reduction + atomic per distinct batch
+                unsigned remaining = __ballot_sync(kFullMask, valid);
+                while (remaining) {
+                    const int leader = __ffs(remaining) - 1;
+                    const uint32_t batch = __shfl_sync(kFullMask, batch_lane, leader);
+                    const bool mine = valid && batch_lane == batch;
+                    const float sum = warp_sum(mine ? loss_lane : 0.f);
+                    if (lane == leader)
+                        atomicAdd(p.loss_per_batch + batch, sum);
+                    remaining &= ~__ballot_sync(kFullMask, mine);
+                }
+            }
+        }
+        __syncwarp();  // ids[] is rewritten by the next chunk
+    }
+}
+
+// -----------------------------------------------------------------------------
+// SGD with a compile-time number of negatives (the shipped configs all use k = 1): the hot
+// kernel.  Same staging and the same per-sample semantics as train_kernel above, but ALL rows
+// of sample t+1 (vertex + K+1 context rows) are requested before sample t is computed, so a warp
+// keeps 2 * (K + 2) rows in flight and the load latency of a sample hides behind the whole
+// previous sample.  Rows that the current sample writes and the next one reads (same vertex, or
+// a context row in both) are forwarded register-to-register instead of being reloaded, which
+// keeps a single warp exactly sequential.
+// -----------------------------------------------------------------------------
+template<int DIM, int K>
+struct SampleRows {
+    Row<DIM> v;
+    Row<DIM> c[K + 1];
+    uint32_t head;
+    uint32_t tail[K + 1];
+};
+
+template<int DIM, int K>
+__device__ __forceinline__ void request_sample(SampleRows<DIM, K> &rows, const uint32_t *sample, const TrainParams &p,
+                                               int lane, bool l1) {
+    rows.head = sample[0];
+#pragma unroll
+    for (int s = 0; s <= K; s++)
+        rows.tail[s] = sample[1 + s];
+    load_row<DIM>(rows.v, p.vertex + size_t(rows.head) * DIM, lane, l1);
+#pragma unroll
+    for (int s = 0; s <= K; s++)
+        load_row<DIM>(rows.c[s], p.context + size_t(rows.tail[s]) * DIM, lane, l1);
+}
+
+template<int DIM, int K, bool LOSS>
+__device__ __forceinline__ float process_sample(SampleRows<DIM, K> &cur, SampleRows<DIM, K> &next, bool has_next,
+                                                float lr, const TrainParams &p, int lane) {
+    float sample_loss = 0.f;
+    Row<DIM> unused;
+#pragma unroll
+    for (int s = 0; s <= K; s++) {
+        // a row that an earlier target of this sample already updated: continue from those registers
+#pragma unroll
+        for (int e = 0; e < s; e++)
+            if (cur.tail[e] == cur.tail[s])
+                cur.c[s] = cur.c[e];
+        const float prob = sigmoid(dot<DIM>(cur.v, cur.c[s]));
+        float gradient, weight;
+        if (s == K) {
+            gradient = prob - 1;
+            weight = 1;
+            if (LOSS)
+                sample_loss += weight * -logf(prob + kEpsilon);
+        } else {
+            gradient = prob;
+            weight = p.negative_weight;
+            if (LOSS)
+                sample_loss += weight * -logf(1 - prob + kEpsilon);
+        }
+        backward<DIM, GV_OPT_SGD>(p.optimizer, lr, gradient, weight, cur.v, cur.c[s], unused, unused, unused, unused);
+        store_row<DIM>(cur.c[s], p.context + size_t(cur.tail[s]) * DIM, lane);
+    }
+    store_row<DIM>(cur.v, p.vertex + size_t(cur.head) * DIM, lane);
+    if (has_next) {  // forward what the next sample requested before these stores were issued
+        if (next.head == cur.head)
+            next.v = cur.v;
+#pragma unroll
+        for (int s = 0; s <= K; s++)
+#pragma unroll
+            for (int e = 0; e <= K; e++)
+                if (next.tail[s] == cur.tail[e])
+                    next.c[s] = cur.c[e];
+    }
+    return sample_loss / (1 + K * p.negative_weight);  // gpu/graph.cuh:91-92
+}
+
+template<int DIM, int K, bool LOSS>
+__global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainParams p) {
+    extern __shared__ uint32_t shared_ids[];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    constexpr int stride = K + 2;  // head, K negatives, positive tail
+    uint32_t *ids = shared_ids + warp_in_block * 32 * stride;
+    const unsigned long long num_chunk = (p.num_sample + 31) / 32;
+    const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const bool l1 = p.flags & 1;
+
+    for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+         chunk < num_chunk; chunk += num_warp) {
+        const unsigned long long base = chunk * 32;
+        const unsigned long long i = base + lane;
+        const bool valid = i < p.num_sample;
+        float lr_lane = 0.f;
+        uint32_t batch_lane = 0;
+        if (valid) {
+            const uint2 pair = __ldcs(p.pool + i);  // {tail, head}, streamed once
+            ids[lane * stride] = pair.y;
+            ids[lane * stride + 1 + K] = pair.x;
+#pragma unroll
+            for (int s = 0; s < K; s++) {
+                const unsigned long long t = i * K + s;
+                uint32_t negative;
+                if (p.negatives)
+                    negative = __ldcs(p.negatives + t);
+                else {
+                    const double2 r = __ldcs(reinterpret_cast<const double2 *>(p.random) + t);
+                    negative = alias_sample_narrowed(p.negative_table, p.negative_count, r.x, r.y);
+                }
+                ids[lane * stride + 1 + s] = negative;
+                if (p.negatives_out)
+                    p.negatives_out[t] = negative;
+            }
+            batch_lane = uint32_t(i / p.batch_size);
+            lr_lane = __ldg(p.lr_per_batch + batch_lane);
+        }
+        __syncwarp();
+
+        const int count = int(min(32ull, p.num_sample - base));
+        float loss_lane = 0.f;
+        SampleRows<DIM, K> a, b;
+        request_sample<DIM, K>(a, ids, p, lane, l1);
+        for (int t = 0; t < count; t += 2) {
+            bool more = t + 1 < count;
+            if (more)
+                request_sample<DIM, K>(b, ids + (t + 1) * stride, p, lane, l1);
+            float loss = process_sample<DIM, K, LOSS>(a, b, more, __shfl_sync(kFullMask, lr_lane, t), p, lane);
+            if (LOSS && lane == t)
+                loss_lane = loss;
+            if (!more)
+                break;
+            more = t + 2 < count;
+            if (more)
+                request_sample<DIM, K>(a, ids + (t + 2) * stride, p, lane, l1);
+            loss = process_sample<DIM, K, LOSS>(b, a, more, __shfl_sync(kFullMask, lr_lane, t + 1), p, lane);
+            if (LOSS && lane == t + 1)
+                loss_lane = loss;
+        }
+        if (LOSS) {
+            if (p.loss_per_sample && valid)
+                p.loss_per_sample[i] = loss_lane;
+            if (p.loss_per_batch) {
+                unsigned remaining = __ballot_sync(kFullMask, valid);
+                while (remaining) {
+                    const int leader = __ffs(remaining) - 1;
+                    const uint32_t batch = __shfl_sync(kFullMask, batch_lane, leader);
+                    const bool mine = valid && batch_lane == batch;
+                    const float sum = warp_sum(mine ? loss_lane : 0.f);
+                    if (lane == leader)
+                        atomicAdd(p.loss_per_batch + batch, sum);
+                    remaining &= ~__ballot_sync(kFullMask, mine);
+                }
             }
         }
         __syncwarp();  // ids[] is rewritten by the next chunk
@@ -364,9 +585,8 @@ static int device_sm_count() {
     return sms;
 }
 
-template<int DIM, int OPT>
-static int launch_train(const TrainParams &p, int num_warps, cudaStream_t stream) {
-    auto kernel = train_kernel<DIM, OPT>;
+static int launch_train(void (*kernel)(const TrainParams), const TrainParams &p, int num_warps,
+                        cudaStream_t stream) {
     int threads = kBlockThreads;
     int blocks;
     if (num_warps > 0) {
@@ -395,14 +615,36 @@ static int launch_train(const TrainParams &p, int num_warps, cudaStream_t stream
     return 0;
 }
 
+template<int DIM, int K>
+static int launch_sgd(const TrainParams &p, int num_warps, cudaStream_t stream) {
+    if (p.loss_per_sample || p.loss_per_batch)
+        return launch_train(train_sgd_kernel<DIM, K, true>, p, num_warps, stream);
+    return launch_train(train_sgd_kernel<DIM, K, false>, p, num_warps, stream);
+}
+
+template<int DIM, int OPT>
+static int dispatch_loss(const TrainParams &p, int num_warps, cudaStream_t stream) {
+    // the pipelined SGD kernel for the usual small k, when two samples' rows fit in registers
+    if (OPT == GV_OPT_SGD && Row<DIM>::kPass <= 2 && !(p.flags & 4)) {
+        switch (p.num_negative) {
+            case 1: return launch_sgd<DIM, 1>(p, num_warps, stream);
+            case 2: return launch_sgd<DIM, 2>(p, num_warps, stream);
+            case 3: return launch_sgd<DIM, 3>(p, num_warps, stream);
+        }
+    }
+    if (p.loss_per_sample || p.loss_per_batch)
+        return launch_train(train_kernel<DIM, OPT, true>, p, num_warps, stream);
+    return launch_train(train_kernel<DIM, OPT, false>, p, num_warps, stream);
+}
+
 template<int DIM>
 static int dispatch_optimizer(const TrainParams &p, int num_warps, cudaStream_t stream) {
     switch (p.optimizer.type) {
-        case GV_OPT_SGD: return launch_train<DIM, GV_OPT_SGD>(p, num_warps, stream);
-        case GV_OPT_MOMENTUM: return launch_train<DIM, GV_OPT_MOMENTUM>(p, num_warps, stream);
-        case GV_OPT_ADAGRAD: return launch_train<DIM, GV_OPT_ADAGRAD>(p, num_warps, stream);
-        case GV_OPT_RMSPROP: return launch_train<DIM, GV_OPT_RMSPROP>(p, num_warps, stream);
-        case GV_OPT_ADAM: return launch_train<DIM, GV_OPT_ADAM>(p, num_warps, stream);
+        case GV_OPT_SGD: return dispatch_loss<DIM, GV_OPT_SGD>(p, num_warps, stream);
+        case GV_OPT_MOMENTUM: return dispatch_loss<DIM, GV_OPT_MOMENTUM>(p, num_warps, stream);
+        case GV_OPT_ADAGRAD: return dispatch_loss<DIM, GV_OPT_ADAGRAD>(p, num_warps, stream);
+        case GV_OPT_RMSPROP: return dispatch_loss<DIM, GV_OPT_RMSPROP>(p, num_warps, stream);
+        case GV_OPT_ADAM: return dispatch_loss<DIM, GV_OPT_ADAM>(p, num_warps, stream);
     }
     return fail("unknown optimizer type " + std::to_string(p.optimizer.type));
 }

@@ -113,39 +113,61 @@ def test_solver_matches_oracle_step_by_step(case, toy_graph_file):
     np.testing.assert_allclose(solver.predict(pairs), osolver.predict(pairs), rtol=1e-3, atol=1e-5)
 
 
-def test_hogwild_training_on_a_mid_size_graph(tmp_path):
-    """Full persistent grid (racy, like the reference) on a 20k-vertex graph where collisions are
-    as rare as in real workloads: embedding norms within 2% of the sequential oracle, and the
-    positive edges score far above random pairs."""
+def test_hogwild_training_matches_the_reference_statistically(tmp_path):
+    """Full persistent grid (racy, like the reference's kernels) against the UNMODIFIED reference
+    (oracle/_ref/libgraphvite.so through its own pybind API) on a 20k-vertex power-law graph: both
+    lose hub updates to races, so they are compared with each other, not with the sequential oracle.
+    Tolerances: embedding L2 norms within 3 %, link-prediction AUC within 0.01 (run-to-run spread of
+    either implementation is ~0.5 % / 0.003 at this size)."""
+    import os
+    import sys
     import graphvite_b200 as gv
     from graphvite_b200 import _lib, datasets
     from graphvite_b200.application import link_prediction_auc
-    u, v = datasets.power_law_edges(20000, 100000, seed=5)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "libgraphvite.so")):
+        pytest.skip("oracle/_ref/libgraphvite.so is not built")
+    sys.path.insert(0, root)
+    import bench
+    u, v = datasets.power_law_edges(20000, 200000, seed=5)
     path = str(tmp_path / "mid.txt")
     datasets.write_edge_list(path, u, v)
+    train = dict(num_epoch=100, augmentation_step=2, random_walk_length=10, random_walk_batch_size=20)
+
     _lib.lib.gv_reset_global_engine(5489)
     graph = gv.graph.Graph()
     graph.load(path)
-    solver = gv.solver.GraphSolver(64, device_ids=[0])
-    solver.build(graph, gv.optimizer.SGD(0.025, 0.005), num_negative=1, batch_size=2000, episode_size=50)
-    solver.train("LINE", num_epoch=20, augmentation_step=2, random_walk_length=10, random_walk_batch_size=20)
-    ograph = O.OracleGraph(path)
-    osolver = O.OracleSolver(ograph, 64, 1, 1)
-    osolver.build("SGD", 0, 1, 2000, 50)
-    osolver.train(model="LINE", num_epoch=20, augmentation_step=2, random_walk_length=10, random_walk_batch_size=20)
-    assert solver.batch_id == osolver.info()["batch_id"]
-    for which, view in ((0, solver.vertex_embeddings), (1, solver.context_embeddings)):
-        expected = np.linalg.norm(osolver.embeddings(which))
-        assert abs(np.linalg.norm(view) - expected) <= 0.02 * expected, (which, np.linalg.norm(view), expected)
+    solver = gv.solver.GraphSolver(128, device_ids=[0])
+    solver.build(graph, gv.optimizer.SGD(0.025, 0.005), num_negative=1, batch_size=10000, episode_size=50)
+    solver.train("LINE", **train)
+
+    ref = bench.load_reference()
+    rgraph = ref.graph.Graph_j()
+    rgraph.load(path, True, False)
+    rsolver = ref.solver.GraphSolver_128_f_j([0], 4, 0)
+    rsolver.build(rgraph, ref.optimizer.SGD(0.025, 0.005), 0, 1, 10000, 50)
+    rsolver.train(model="LINE", log_frequency=1 << 30, **train)
+    assert graph.id2name == rgraph.id2name
+
     rng = np.random.RandomState(0)
     ids = np.array([graph.name2id[str(x)] for x in range(20000)], dtype=np.uint32)
-    positive = np.stack([ids[u[:5000]], ids[v[:5000]]], axis=1)
-    negative = rng.randint(0, 20000, (5000, 2)).astype(np.uint32)
-    scores = solver.predict(np.concatenate([positive, negative]))
-    auc = link_prediction_auc(scores, np.r_[np.ones(5000), np.zeros(5000)])
-    oracle_auc = link_prediction_auc(osolver.predict(np.concatenate([positive, negative])),
-                                     np.r_[np.ones(5000), np.zeros(5000)])
-    assert abs(auc - oracle_auc) < 0.01 and auc > 0.6, (auc, oracle_auc)
+    pairs = np.concatenate([np.stack([ids[u[:5000]], ids[v[:5000]]], axis=1),
+                            rng.randint(0, 20000, (5000, 2)).astype(np.uint32)])
+    labels = np.r_[np.ones(5000), np.zeros(5000)]
+    ours, theirs = {}, {}
+    for out, s in ((ours, solver), (theirs, rsolver)):
+        vertex, context = np.array(s.vertex_embeddings), np.array(s.context_embeddings)
+        out["vertex"] = float(np.linalg.norm(vertex))
+        out["context"] = float(np.linalg.norm(context))
+        # scored on the host: the reference's predict_numpy indexes pool_offsets out of bounds
+        # (core/solver.h:748-751 with id >= num_sampler) and may corrupt the heap
+        out["auc"] = link_prediction_auc(np.einsum("ij,ij->i", vertex[pairs[:, 0]], context[pairs[:, 1]]), labels)
+    np.testing.assert_allclose(solver.predict(pairs), np.einsum(
+        "ij,ij->i", solver.vertex_embeddings[pairs[:, 0]], solver.context_embeddings[pairs[:, 1]]), rtol=1e-4, atol=1e-5)
+    print("ours", ours, "reference", theirs)
+    assert abs(ours["vertex"] - theirs["vertex"]) <= 0.03 * theirs["vertex"], (ours, theirs)
+    assert abs(ours["context"] - theirs["context"]) <= 0.03 * theirs["context"], (ours, theirs)
+    assert abs(ours["auc"] - theirs["auc"]) <= 0.01 and ours["auc"] > 0.7, (ours, theirs)
 
 
 def test_resume_and_numpy_views(toy_graph_file):
