@@ -100,13 +100,13 @@ def measured_peak():
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def make_solver(cfg, path, rank, world, local_rank):
+def make_solver(cfg, path, rank, world, local_rank, num_partition=0):
     import graphvite_b200 as gv
     graph = gv.graph.Graph()
     graph.load(path, as_undirected=True)
     solver = gv.solver.GraphSolver(cfg["dim"], device_ids=[local_rank], rank=rank, world_size=world)
-    solver.build(graph, gv.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), num_negative=cfg["num_negative"],
-                 batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
+    solver.build(graph, gv.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), num_partition=num_partition,
+                 num_negative=cfg["num_negative"], batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
     return gv, graph, solver
 
 
@@ -138,7 +138,7 @@ def run_ours(args, cfg):
         path = graph_file(cfg["graph"])
     barrier()
     path = graph_file(cfg["graph"])
-    gv, graph, solver = make_solver(cfg, path, rank, world, local_rank)
+    gv, graph, solver = make_solver(cfg, path, rank, world, local_rank, args.partitions)
     lib, handle = _lib.lib, solver._handle
     edges_per_step = cfg["episode_size"] * cfg["batch_size"]  # per GPU
     kw = train_kwargs(cfg, 4000)  # config/graph/line_youtube.yaml; far more epochs than we will run
@@ -331,6 +331,7 @@ def main():
     parser.add_argument("--workload", default="youtube", choices=sorted(WORKLOADS))
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    parser.add_argument("--partitions", type=int, default=0, help="num_partition (0 = auto; diagnosis only)")
     args = parser.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -24,6 +24,7 @@ P = ctypes.POINTER
 
 SCHEDULE_FN = ctypes.CFUNCTYPE(c_float, c_int, c_int, c_void_p)
 EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_int, c_uint64, c_void_p, c_void_p)
+HOST_ALLGATHER_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_uint64, c_void_p)
 
 
 class OptimizerDesc(ctypes.Structure):
@@ -64,13 +65,21 @@ SIGNATURES = {
     "gv_cuda_train_block": (c_int, [P(Matrices), c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_uint32,
                                     c_void_p, P(DeviceOptimizer), c_void_p, c_uint32, c_float, c_void_p, c_void_p,
                                     c_int, c_void_p]),
+    "gv_cuda_set_tunable": (c_int, [c_char_p, ctypes.c_long]),
     "gv_cuda_sample_negatives": (c_int, [c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_void_p]),
     "gv_cuda_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
-    "gv_cuda_random_walk": (c_int, [P(DeviceGraph), c_void_p, c_uint32, c_int, c_void_p, c_void_p]),
+    "gv_cuda_random_walk": (c_int, [P(DeviceGraph), c_void_p, c_uint32, c_int, c_uint64, c_uint32, c_uint64,
+                                    c_void_p, c_void_p]),
     "gv_cuda_fill_scratch_bytes": (c_size_t, [c_uint32, c_int]),
     "gv_cuda_fill_pool": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "gv_cuda_move_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p]),
+    "gv_cuda_fill_count": (c_int, [P(FillParams), c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "gv_cuda_fill_scatter": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "gv_cuda_peer_control_bytes": (c_size_t, [c_int, c_int]),
+    "gv_cuda_peer_exchange": (c_int, [c_int, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     # graph
     "gv_graph_create": (c_void_p, []),
     "gv_graph_destroy": (None, [c_void_p]),
@@ -90,6 +99,7 @@ SIGNATURES = {
     "gv_solver_create": (c_void_p, [c_int, P(c_int), c_int, c_int, c_uint64, c_int, c_int]),
     "gv_solver_destroy": (None, [c_void_p]),
     "gv_solver_set_exchange": (c_int, [c_void_p, EXCHANGE_FN, c_void_p]),
+    "gv_solver_set_host_allgather": (c_int, [c_void_p, HOST_ALLGATHER_FN, c_void_p]),
     "gv_solver_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "gv_solver_build": (c_int, [c_void_p, c_void_p, P(OptimizerDesc), c_int, c_int, c_int, c_int]),
     "gv_solver_train": (c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,

@@ -33,12 +33,17 @@ __device__ __forceinline__ Count alias_index(double rand1, Count count) {
 }
 
 __global__ void __launch_bounds__(256) random_walk_kernel(const gv_device_graph_t g, const double *random,
-                                                          uint32_t num_walk, int walk_length,
+                                                          uint32_t num_walk, int walk_length, uint64_t first_walk,
+                                                          uint32_t walks_per_buffer, uint64_t buffer_doubles,
                                                           gv_location_t *chains) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= num_walk)
         return;
-    const double2 *r = reinterpret_cast<const double2 *>(random) + size_t(w) * walk_length;
+    // walk (first_walk + w) of the span: buffer (index / walks_per_buffer), slot (index % walks_per_buffer);
+    // the unused tail of a refill buffer (when 5e6 is not a multiple of 2L) is skipped like the reference does
+    const uint64_t walk = first_walk + w;
+    const double2 *r = reinterpret_cast<const double2 *>(random + (walk / walks_per_buffer) * buffer_doubles) +
+                       (walk % walks_per_buffer) * walk_length;
     uint2 *out = reinterpret_cast<uint2 *>(chains) + w;
     const uint2 *locations = reinterpret_cast<const uint2 *>(g.locations);
 
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256) fill_count_kernel(const FillParams p, con
 // pass 2: one CTA per block b: exclusive scan of counts[:, b] over the walks, seeded with fill[b];
 // bases saturate at the slice length (anything beyond is dropped anyway).
 __global__ void __launch_bounds__(1024) fill_scan_kernel(const FillParams p, uint32_t num_walk, uint32_t *counts,
-                                                         unsigned long long *fill) {
+                                                         const unsigned long long *seeds, unsigned long long *fill) {
     __shared__ unsigned long long partial[1024];
     const int num_block = p.num_partition * p.num_partition;
     const int b = blockIdx.x;
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(1024) fill_scan_kernel(const FillParams p, uin
         partial[threadIdx.x] += add;
         __syncthreads();
     }
-    const unsigned long long seed = fill[b];
+    const unsigned long long seed = seeds[b];
     unsigned long long running = seed + partial[threadIdx.x] - sum;
     for (uint32_t w = begin; w < end; w++) {
         const uint32_t count = counts[size_t(w) * num_block + b];
@@ -122,8 +127,89 @@ __global__ void __launch_bounds__(1024) fill_scan_kernel(const FillParams p, uin
         running += count;
     }
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1)
+    if (fill && threadIdx.x == blockDim.x - 1)
         fill[b] = seed + partial[threadIdx.x];
+}
+
+// totals[b] = pairs this set of walks offers to block b (one CTA per block)
+__global__ void __launch_bounds__(1024) fill_reduce_kernel(int num_block, uint32_t num_walk, const uint32_t *counts,
+                                                           unsigned long long *totals) {
+    __shared__ unsigned long long partial[1024];
+    const int b = blockIdx.x;
+    unsigned long long sum = 0;
+    for (uint32_t w = threadIdx.x; w < num_walk; w += blockDim.x)
+        sum += counts[size_t(w) * num_block + b];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    for (int offset = blockDim.x / 2; offset > 0; offset >>= 1) {
+        if (threadIdx.x < offset)
+            partial[threadIdx.x] += partial[threadIdx.x + offset];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        totals[b] = partial[0];
+}
+
+// ---- cross-rank stable partition over NVLink peer memory ----------------------------------------
+// Every rank walks a contiguous slice of a round's walks.  To keep the pools bit-identical to the
+// sequential reference, rank r's pairs of block b must land behind those of ranks < r: each rank
+// publishes its per-block totals into every peer's inbox (peer stores + a system-scope fence + a
+// flag), waits for all W flags of the round and derives its base offsets.  Control region of a rank:
+//   inbox [2][W][num_block + 1] u64 (last slot: walk index that completed a block), flags [2][W] u64.
+__device__ __forceinline__ unsigned long long *control_inbox(unsigned long long *control, int W, int num_block,
+                                                             int parity, int rank) {
+    return control + (size_t(parity) * W + rank) * (num_block + 1);
+}
+__device__ __forceinline__ unsigned long long *control_flag(unsigned long long *control, int W, int num_block,
+                                                            int parity, int rank) {
+    return control + size_t(2) * W * (num_block + 1) + size_t(parity) * W + rank;
+}
+
+__global__ void __launch_bounds__(512) peer_publish_kernel(int rank, int W, int num_block, int parity,
+                                                           unsigned long long round_id,
+                                                           const unsigned long long *totals,
+                                                           const unsigned long long *last_walk,
+                                                           unsigned long long *const *controls) {
+    for (int i = threadIdx.x; i < (num_block + 1) * W; i += blockDim.x) {
+        const int peer = i / (num_block + 1), slot = i % (num_block + 1);
+        const unsigned long long value = slot < num_block ? (totals ? totals[slot] : 0ull) : *last_walk;
+        control_inbox(controls[peer], W, num_block, parity, rank)[slot] = value;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < W) {
+        volatile unsigned long long *flag = control_flag(controls[threadIdx.x], W, num_block, parity, rank);
+        *flag = round_id;
+    }
+}
+
+__global__ void __launch_bounds__(512) peer_gather_kernel(int rank, int W, int num_block, int parity,
+                                                          unsigned long long round_id, unsigned long long *control,
+                                                          unsigned long long *fill, unsigned long long *bases,
+                                                          unsigned long long *last_walk) {
+    if (threadIdx.x < W) {
+        volatile unsigned long long *flag = control_flag(control, W, num_block, parity, threadIdx.x);
+        while (*flag != round_id)
+            __nanosleep(200);
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int b = threadIdx.x; b <= num_block; b += blockDim.x) {
+        unsigned long long before = 0, all = 0, latest = 0;
+        for (int r = 0; r < W; r++) {
+            const unsigned long long value =
+                *(volatile unsigned long long *)(control_inbox(control, W, num_block, parity, r) + b);
+            if (r < rank)
+                before += value;
+            all += value;
+            latest = max(latest, value);
+        }
+        if (b < num_block) {
+            bases[b] = fill[b] + before;
+            fill[b] += all;
+        } else
+            *last_walk = max(*last_walk, latest);
+    }
 }
 
 // pass 3: every walk re-emits its pairs in order and writes the ones that still fit
@@ -211,17 +297,19 @@ using namespace gv::device;
 extern "C" {
 
 int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, uint32_t num_walk, int walk_length,
+                        uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,
                         gv_location_t *chains, void *stream) {
     if (num_walk == 0)
         return 0;
-    if (!graph || !random || !chains || walk_length < 1)
+    if (!graph || !random || !chains || walk_length < 1 || walks_per_buffer == 0 ||
+        buffer_doubles < uint64_t(walks_per_buffer) * 2 * walk_length || buffer_doubles % 2 != 0)
         return fail("gv_cuda_random_walk: invalid argument");
     if (walk_length > 1 && !graph->vertex_tables)
         return fail("gv_cuda_random_walk: per-vertex alias tables are required for walk_length > 1");
     const int threads = 256;
     const uint32_t blocks = (num_walk + threads - 1) / threads;
-    random_walk_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(*graph, random, num_walk,
-                                                                                  walk_length, chains);
+    random_walk_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        *graph, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles, chains);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -273,9 +361,92 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
     uint32_t *counts = static_cast<uint32_t *>(scratch);
     fill_count_kernel<<<blocks, threads, 0, s>>>(p, c, num_walk, counts);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scan_kernel<<<p.num_partition * p.num_partition, 1024, 0, s>>>(p, num_walk, counts, fill);
+    fill_scan_kernel<<<p.num_partition * p.num_partition, 1024, 0, s>>>(p, num_walk, counts, fill, fill);
     GV_CUDA_OK(cudaGetLastError());
     fill_scatter_kernel<<<blocks, threads, 0, s>>>(p, c, num_walk, first_walk, counts, pool_blocks, last_walk);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+size_t gv_cuda_peer_control_bytes(int world_size, int num_partition) {
+    const size_t num_block = size_t(num_partition) * num_partition;
+    return (size_t(2) * world_size * (num_block + 1) + size_t(2) * world_size) * sizeof(unsigned long long);
+}
+
+static int make_fill_params(const gv_fill_params_t *params, FillParams &p) {
+    if (!params || params->num_partition < 1 || params->num_partition > 16)
+        return fail("fill: num_partition must be in [1, 16]");
+    if (params->shuffle_base < 1 || params->pool_size % params->shuffle_base != 0)
+        return fail("Can't perform pseudo shuffle: episode size must be a multiple of the shuffle base");
+    if (params->end < params->start || params->end > params->pool_size)
+        return fail("fill: invalid slice");
+    p.num_partition = params->num_partition;
+    p.walk_length = params->walk_length;
+    p.augmentation_step = params->augmentation_step;
+    p.shuffle_base = params->shuffle_base;
+    p.pool_size = params->pool_size;
+    p.start = params->start;
+    p.slice = params->end - params->start;
+    return 0;
+}
+
+int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk, void *scratch,
+                       unsigned long long *totals, void *stream) {
+    FillParams p;
+    if (make_fill_params(params, p))
+        return -1;
+    if (!chains || !scratch || !totals)
+        return fail("gv_cuda_fill_count: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int num_block = p.num_partition * p.num_partition;
+    if (num_walk == 0) {
+        GV_CUDA_OK(cudaMemsetAsync(totals, 0, num_block * sizeof(unsigned long long), s));
+        return 0;
+    }
+    uint32_t *counts = static_cast<uint32_t *>(scratch);
+    fill_count_kernel<<<(num_walk + 255) / 256, 256, 0, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk, counts);
+    GV_CUDA_OK(cudaGetLastError());
+    fill_reduce_kernel<<<num_block, 1024, 0, s>>>(num_block, num_walk, counts, totals);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
+                         uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
+                         unsigned long long *last_walk, void *scratch, void *stream) {
+    FillParams p;
+    if (make_fill_params(params, p))
+        return -1;
+    if (num_walk == 0)
+        return 0;
+    if (!chains || !scratch || !bases || !pool_blocks || !last_walk)
+        return fail("gv_cuda_fill_scatter: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint32_t *counts = static_cast<uint32_t *>(scratch);
+    fill_scan_kernel<<<p.num_partition * p.num_partition, 1024, 0, s>>>(p, num_walk, counts, bases, nullptr);
+    GV_CUDA_OK(cudaGetLastError());
+    fill_scatter_kernel<<<(num_walk + 255) / 256, 256, 0, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk,
+                                                              first_walk, counts, pool_blocks, last_walk);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gv_cuda_peer_exchange(int rank, int world_size, int num_partition, uint64_t round_id,
+                          const unsigned long long *totals, unsigned long long *const *controls,
+                          unsigned long long *control, unsigned long long *fill, unsigned long long *bases,
+                          unsigned long long *last_walk, void *stream) {
+    if (!controls || !control || !fill || !bases || !last_walk || world_size < 1 || world_size > 256)
+        return fail("gv_cuda_peer_exchange: invalid argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int num_block = num_partition * num_partition, parity = int(round_id & 1);
+    peer_publish_kernel<<<1, 512, 0, s>>>(rank, world_size, num_block, parity, round_id, totals, last_walk, controls);
+    GV_CUDA_OK(cudaGetLastError());
+    peer_gather_kernel<<<1, 512, 0, s>>>(rank, world_size, num_block, parity, round_id, control, fill, bases,
+                                         last_walk);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }

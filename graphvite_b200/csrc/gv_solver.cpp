@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -42,7 +43,7 @@ static const int kMinBatchSize = 10000;
 static const int kSamplePerVertex = 175;
 static const int kMinEpisodeSample = 20000000;
 static const int kExpectedDegree = 1600;
-static const uint64_t kMaxWalkChunk = 1 << 18;  // walks per sampler launch (bounds the scratch)
+static const int kSpanBuffers = 16;  // refill buffers generated and walked per sampler round
 
 #define GV_CHECK_CUDA(call)                                                                              \
     do {                                                                                                 \
@@ -68,6 +69,23 @@ static void require(bool condition, const std::string &message) {
     if (!condition)
         throw std::runtime_error(message);
 }
+
+static double now_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// GV_LOG=2: phase timings of train_begin() on stderr
+struct PhaseTimer {
+    double last = now_seconds();
+    bool on = getenv("GV_LOG") != nullptr && atoi(getenv("GV_LOG")) >= 2;
+    void mark(const char *what) {
+        if (on) {
+            const double t = now_seconds();
+            fprintf(stderr, "[gv] %-28s %8.3f s\n", what, t - last);
+            last = t;
+        }
+    }
+};
 
 static bool log_enabled() {
     static const bool on = getenv("GV_LOG") != nullptr && atoi(getenv("GV_LOG")) > 0;
@@ -227,9 +245,13 @@ struct Solver {
     std::vector<unsigned long long> sampler_seeds, worker_seeds;
     cudaStream_t work_stream = nullptr, sample_stream = nullptr, random_stream = nullptr;
     std::vector<curandGenerator_t> sampler_generators;
+    std::vector<uint64_t> sampler_buffers;  // refill buffers each sampler's stream has consumed so far
+    uint64_t walk_chunk = 1 << 18;           // walks per sampler launch (bounds chains + scratch)
     curandGenerator_t worker_generator = nullptr;
     gv_exchange_fn exchange_fn = nullptr;
     void *exchange_ctx = nullptr;
+    gv_host_allgather_fn host_allgather_fn = nullptr;
+    void *host_allgather_ctx = nullptr;
 
     // ---- build ----
     Graph *graph = nullptr;
@@ -263,8 +285,14 @@ struct Solver {
     std::vector<DeviceArray> negative_tables;      // [num_group] gv_alias_entry_t
     std::vector<uint32_t> negative_counts;
     std::vector<DeviceArray> partition_ids;        // [num_partition] global ids of each partition
-    std::vector<std::vector<DeviceArray>> pools[2];  // [head][group]
-    DeviceArray pool_pointers[2];                  // [P*P] block pointers (NULL if not owned)
+    // sample pools: one arena [side][head][group] of pool_size pairs + the peer control region.
+    // With partitioned sampling the arenas of all ranks are mapped into every rank (CUDA IPC).
+    DeviceArray pool_arena;
+    DeviceArray pool_pointers[2];                  // [P*P] block pointers (NULL: not reachable from here)
+    bool partitioned_sampling = false;
+    std::vector<void *> peer_arenas;               // [W] mapped arenas (own entry = pool_arena.ptr)
+    DeviceArray d_peer_controls, d_totals, d_bases;
+    uint64_t peer_round = 0;
     // device graph
     DeviceArray d_offsets, d_edge_u, d_edge_v, d_edge_prob, d_edge_alias, d_vertex_tables, d_locations;
     gv_device_graph_t device_graph;
@@ -323,7 +351,12 @@ struct Solver {
         for (int i = 0; i < num_worker; i++)
             worker_seeds.push_back(random_seed(g_engine));
         GV_CHECK_CUDA(cudaStreamCreateWithFlags(&work_stream, cudaStreamNonBlocking));
-        GV_CHECK_CUDA(cudaStreamCreateWithFlags(&sample_stream, cudaStreamNonBlocking));
+        {
+            // sampler kernels are short: let them run ahead of the queued train launches
+            int least = 0, greatest = 0;
+            GV_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            GV_CHECK_CUDA(cudaStreamCreateWithPriority(&sample_stream, cudaStreamNonBlocking, greatest));
+        }
         GV_CHECK_CUDA(cudaStreamCreateWithFlags(&random_stream, cudaStreamNonBlocking));
         for (int i = 0; i < num_sampler; i++) {
             curandGenerator_t generator;
@@ -331,6 +364,7 @@ struct Solver {
             GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(generator, sampler_seeds[i]));
             GV_CHECK_CURAND(curandSetStream(generator, sample_stream));
             sampler_generators.push_back(generator);
+            sampler_buffers.push_back(0);
         }
         GV_CHECK_CURAND(curandCreateGenerator(&worker_generator, CURAND_RNG_PSEUDO_DEFAULT));
         GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(worker_generator, worker_seeds[rank]));
@@ -344,6 +378,9 @@ struct Solver {
 
     ~Solver() {
         cudaSetDevice(device);
+        if (sampler_thread.joinable())
+            sampler_thread.join();
+        close_peers();
         for (auto g : sampler_generators)
             curandDestroyGenerator(g);
         if (worker_generator)
@@ -367,6 +404,21 @@ struct Solver {
     int num_moment() const { return optimizer.num_moment(); }
     uint64_t pool_size() const { return uint64_t(episode_size) * batch_size; }
     bool owns_tail(int tail) const { return tail % num_worker == rank; }
+    uint64_t pool_block_bytes() const { return pool_size() * 2 * sizeof(uint32_t); }
+    uint64_t pool_block_offset(int side, int head, int group) const {
+        return ((uint64_t(side) * num_partition + head) * num_group + group) * pool_block_bytes();
+    }
+    uint64_t control_offset() const { return pool_block_offset(2, 0, 0); }
+    uint32_t *pool_block(int side, int head, int group) const {
+        return reinterpret_cast<uint32_t *>(static_cast<char *>(pool_arena.ptr) + pool_block_offset(side, head, group));
+    }
+    void close_peers() {
+        for (int r = 0; r < int(peer_arenas.size()); r++)
+            if (r != rank && peer_arenas[r])
+                cudaIpcCloseMemHandle(peer_arenas[r]);
+        peer_arenas.clear();
+        partitioned_sampling = false;
+    }
 
     // bytes this rank keeps resident for a given partition count (our memory model; the
     // reference's gpu_memory_demand, core/solver.h:829-866, budgets ONE cached block pair)
@@ -467,25 +519,75 @@ struct Solver {
         for (int i = 0; i < num_partition; i++)
             partition_ids[i].upload(partitions[i], work_stream);
         d_locations.upload(locations, work_stream);
-        for (int side = 0; side < 2; side++) {
-            pools[side].clear();
-            pools[side].resize(num_partition);
-            std::vector<uint32_t *> pointers(size_t(num_partition) * num_partition, nullptr);
-            for (int h = 0; h < num_partition; h++) {
-                pools[side][h] = std::vector<DeviceArray>(num_group);
-                for (int g = 0; g < num_group; g++) {
-                    pools[side][h][g].allocate(pool_size() * 2 * sizeof(uint32_t));
-                    const int tail = g * num_worker + rank;
-                    pointers[size_t(h) * num_partition + tail] = pools[side][h][g].as<uint32_t>();
-                }
+        close_peers();
+        const size_t control_bytes = gv_cuda_peer_control_bytes(num_worker, num_partition);
+        pool_arena.allocate(control_offset() + control_bytes);
+        GV_CHECK_CUDA(cudaMemsetAsync(static_cast<char *>(pool_arena.ptr) + control_offset(), 0, control_bytes,
+                                      work_stream));
+        GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+        peer_arenas.assign(num_worker, nullptr);
+        peer_arenas[rank] = pool_arena.ptr;
+        if (num_worker > 1 && host_allgather_fn && !getenv("GV_REPLICATED_SAMPLING")) {
+            // trade CUDA IPC handles of the arenas: samplers are then partitioned over the ranks and
+            // scatter their pairs straight into the owners' pools (peer stores over NVLink)
+            cudaIpcMemHandle_t mine;
+            std::vector<cudaIpcMemHandle_t> all(num_worker);
+            bool ok = cudaIpcGetMemHandle(&mine, pool_arena.ptr) == cudaSuccess;
+            if (!ok)
+                memset(&mine, 0, sizeof(mine));
+            require(host_allgather_fn(&mine, all.data(), sizeof(mine), host_allgather_ctx) == 0,
+                    "host all-gather of the IPC handles failed");
+            for (int r = 0; r < num_worker && ok; r++)
+                if (r != rank)
+                    ok = cudaIpcOpenMemHandle(&peer_arenas[r], all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            // everybody must agree on the mode
+            int mine_ok = ok, all_ok[256] = {0};
+            require(num_worker <= 256, "too many workers");
+            require(host_allgather_fn(&mine_ok, all_ok, sizeof(int), host_allgather_ctx) == 0,
+                    "host all-gather failed");
+            for (int r = 0; r < num_worker; r++)
+                ok = ok && all_ok[r];
+            cudaGetLastError();
+            if (ok)
+                partitioned_sampling = true;
+            else {
+                for (int r = 0; r < num_worker; r++)
+                    if (r != rank && peer_arenas[r]) {
+                        cudaIpcCloseMemHandle(peer_arenas[r]);
+                        peer_arenas[r] = nullptr;
+                    }
+                if (log_enabled())
+                    fprintf(stderr, "CUDA IPC unavailable: falling back to replicated sampling\n");
             }
+        }
+        for (int side = 0; side < 2; side++) {
+            std::vector<uint32_t *> pointers(size_t(num_partition) * num_partition, nullptr);
+            for (int h = 0; h < num_partition; h++)
+                for (int t = 0; t < num_partition; t++) {
+                    const int owner = t % num_worker;
+                    if (peer_arenas[owner])
+                        pointers[size_t(h) * num_partition + t] = reinterpret_cast<uint32_t *>(
+                            static_cast<char *>(peer_arenas[owner]) + pool_block_offset(side, h, t / num_worker));
+                }
             pool_pointers[side].upload(pointers, work_stream);
+        }
+        if (partitioned_sampling) {
+            std::vector<unsigned long long *> controls(num_worker);
+            for (int r = 0; r < num_worker; r++)
+                controls[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(peer_arenas[r]) +
+                                                                     control_offset());
+            d_peer_controls.upload(controls, work_stream);
+            d_totals.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
+            d_bases.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
+            peer_round = 0;
         }
         negative_tables = std::vector<DeviceArray>(num_group);
         negative_counts.assign(num_group, 0);
         // worker scratch
         const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2 * sizeof(double);
-        chunk_batches = int(std::max<uint64_t>(1, std::min<uint64_t>(episode_size, (uint64_t(192) << 20) /
+        // one train launch consumes a chunk of batches: long enough to amortise the launch and the tail
+        // (16 batches = 1.6e6 edges ~ 1 ms), short enough that the samplers' kernels get SMs in between
+        chunk_batches = int(std::max<uint64_t>(1, std::min<uint64_t>(std::min(episode_size, 16), (uint64_t(192) << 20) /
                                                                                     std::max<uint64_t>(1, per_batch_random))));
         if (getenv("GV_CHUNK_BATCHES"))  // experiment: launch granularity in batches
             chunk_batches = std::max(1, std::min(episode_size, atoi(getenv("GV_CHUNK_BATCHES"))));
@@ -494,7 +596,6 @@ struct Solver {
         d_lr.allocate(size_t(episode_size) * sizeof(float));
         d_loss.allocate(size_t(episode_size) * sizeof(float));
         // sampler scratch
-        d_sampler_random.allocate(size_t(kRandBatchSize) * sizeof(double));
         d_fill.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
         d_last_walk.allocate(sizeof(unsigned long long));
         sampling_ready = false;
@@ -569,10 +670,13 @@ struct Solver {
             device_graph.vertex_tables = d_vertex_tables.as<gv_alias_entry_t>();
         }
         const int L = sample_mode == 0 ? 1 : random_walk_length;
-        const uint64_t walks_per_buffer = uint64_t(kRandBatchSize - 2 * L) / (2 * L) + 1;
-        const uint64_t chunk = std::min<uint64_t>(walks_per_buffer, kMaxWalkChunk);
-        d_chains.allocate(chunk * (L + 1) * sizeof(gv_location_t));
-        d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(chunk), num_partition));
+        // per launch: at most walk_chunk walks per rank (chains <= 256 MB, histogram scratch <= 256 MB)
+        walk_chunk = std::min<uint64_t>(uint64_t(1) << 20, (uint64_t(256) << 20) / (uint64_t(L + 1) * sizeof(gv_location_t)));
+        walk_chunk = std::min<uint64_t>(walk_chunk, (uint64_t(256) << 20) / (uint64_t(num_partition) * num_partition * 4));
+        walk_chunk = std::max<uint64_t>(walk_chunk, 1024);
+        d_chains.allocate(walk_chunk * (L + 1) * sizeof(gv_location_t));
+        d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(walk_chunk), num_partition));
+        d_sampler_random.allocate(size_t(kSpanBuffers) * kRandBatchSize * sizeof(double));
         sampling_ready = true;
     }
 
@@ -609,41 +713,84 @@ struct Solver {
         uint64_t buffers = 0, walks_done = 0;
         bool complete = false;
         unsigned long long last_walk = 0;
+        const uint64_t span_capacity = d_sampler_random.bytes / (size_t(kRandBatchSize) * sizeof(double));
+        const uint32_t share = partitioned_sampling ? num_worker : 1;
         while (!complete) {
-            // refill: the next kRandBatchSize doubles of this sampler's stream (solver.h:1015-1016,1028-1031)
-            GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
-                                                        d_sampler_random.as<double>(), kRandBatchSize));
-            buffers++;
-            uint64_t in_buffer = 0;
-            while (in_buffer < walks_per_buffer && !complete) {
-                // how many walks are still needed, judged from the emptiest block
-                uint64_t missing = 0;
-                for (int b = 0; b < num_block; b++)
-                    missing = std::max<uint64_t>(missing, slice - std::min<uint64_t>(slice, fill[b]));
-                uint64_t want = uint64_t(double(missing) * num_block / pairs_per_walk * 1.02) + 2 * walk_batch;
-                want = (want + walk_batch - 1) / walk_batch * walk_batch;
-                const uint32_t count = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, kMaxWalkChunk),
-                                                                   walks_per_buffer - in_buffer));
-                const double *random = d_sampler_random.as<double>() + in_buffer * 2 * L;
-                GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, random, count, L, d_chains.as<gv_location_t>(),
-                                                 sample_stream));
-                GV_CHECK_ABI(gv_cuda_fill_pool(&params, d_chains.as<gv_location_t>(), count, walks_done,
-                                               pool_pointers[side].as<uint32_t *>(),
-                                               d_fill.as<unsigned long long>(),
-                                               d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
-                                               sample_stream));
-                stat_launches += num_partition == 1 ? 3 : 4;
+            // walks still needed, judged from the emptiest block: the slowest block receives at most
+            // 1 / num_block of the pairs, so 97 % of this estimate is certainly needed -- that many whole
+            // refill buffers are generated and walked in one go; the remainder goes buffer by buffer
+            uint64_t missing = 0;
+            for (int b = 0; b < num_block; b++)
+                missing = std::max<uint64_t>(missing, slice - std::min<uint64_t>(slice, fill[b]));
+            const double estimate = double(missing) * num_block / pairs_per_walk;
+            const uint64_t span = std::max<uint64_t>(1, std::min<uint64_t>(span_capacity,
+                                                                          uint64_t(estimate * 0.97 / walks_per_buffer)));
+            // refill: the next kRandBatchSize doubles of this sampler's stream per buffer
+            // (solver.h:1015-1016,1028-1031), same call size as the reference
+            for (uint64_t j = 0; j < span; j++)
+                GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
+                                                            d_sampler_random.as<double>() + j * kRandBatchSize,
+                                                            kRandBatchSize));
+            buffers += span;
+            const uint64_t in_span = span * walks_per_buffer;
+            uint64_t done_in_span = 0;
+            while (done_in_span < in_span && !complete) {
+                uint64_t want = in_span - done_in_span;
+                if (span == 1) {  // finishing: stop as soon as possible (checked per batch of walks)
+                    missing = 0;
+                    for (int b = 0; b < num_block; b++)
+                        missing = std::max<uint64_t>(missing, slice - std::min<uint64_t>(slice, fill[b]));
+                    want = uint64_t(double(missing) * num_block / pairs_per_walk * 1.02) + 2 * walk_batch;
+                    want = (want + walk_batch - 1) / walk_batch * walk_batch;
+                }
+                const uint32_t count = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, walk_chunk * share),
+                                                                   in_span - done_in_span));
+                // this rank's slice of the round (everything unless the sampling is partitioned)
+                const uint32_t lo = uint32_t(uint64_t(count) * (partitioned_sampling ? rank : 0) / share);
+                const uint32_t hi = uint32_t(uint64_t(count) * (partitioned_sampling ? rank + 1 : 1) / share);
+                GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, d_sampler_random.as<double>(), hi - lo, L,
+                                                 done_in_span + lo, uint32_t(walks_per_buffer), kRandBatchSize,
+                                                 d_chains.as<gv_location_t>(), sample_stream));
+                if (!partitioned_sampling) {
+                    GV_CHECK_ABI(gv_cuda_fill_pool(&params, d_chains.as<gv_location_t>(), count, walks_done,
+                                                   pool_pointers[side].as<uint32_t *>(),
+                                                   d_fill.as<unsigned long long>(),
+                                                   d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
+                                                   sample_stream));
+                    stat_launches += num_partition == 1 ? 3 : 4;
+                } else {
+                    // stream order over the ranks is kept by exchanging per-block totals through peer
+                    // memory before anybody scatters
+                    GV_CHECK_ABI(gv_cuda_fill_count(&params, d_chains.as<gv_location_t>(), hi - lo,
+                                                    d_fill_scratch.ptr, d_totals.as<unsigned long long>(),
+                                                    sample_stream));
+                    peer_barrier(d_totals.as<unsigned long long>());
+                    GV_CHECK_ABI(gv_cuda_fill_scatter(&params, d_chains.as<gv_location_t>(), hi - lo, walks_done + lo,
+                                                      pool_pointers[side].as<uint32_t *>(),
+                                                      d_bases.as<unsigned long long>(),
+                                                      d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
+                                                      sample_stream));
+                    stat_launches += 7;
+                }
                 GV_CHECK_CUDA(cudaMemcpyAsync(fill.data(), d_fill.ptr, num_block * sizeof(unsigned long long),
                                               cudaMemcpyDeviceToHost, sample_stream));
                 GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk),
                                               cudaMemcpyDeviceToHost, sample_stream));
                 GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
-                in_buffer += count;
+                done_in_span += count;
                 walks_done += count;
                 complete = true;
                 for (int b = 0; b < num_block; b++)
                     complete = complete && fill[b] >= slice;
             }
+        }
+        if (partitioned_sampling) {
+            // every rank's last scatter has been issued: one more exchange acts as the barrier after which
+            // the pools are complete everywhere, and carries the walk index that completed the last block
+            peer_barrier(nullptr);
+            GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk), cudaMemcpyDeviceToHost,
+                                          sample_stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
         }
         // The reference stops at the end of the batch of walks that completed the last block; a
         // batch that runs past the current buffer pulls one more refill (only possible when
@@ -653,12 +800,43 @@ struct Solver {
         for (; buffers < needed_buffers; buffers++)
             GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
                                                         d_sampler_random.as<double>(), kRandBatchSize));
-        require(buffers == needed_buffers, "internal error: sampler consumed more random buffers than the reference");
+        if (buffers > needed_buffers) {
+            // a multi-buffer span overshot (a block filled faster than its 1 / num_block share allows --
+            // not expected): rebuild the generator and replay the stream up to where the reference stands
+            if (log_enabled())
+                fprintf(stderr, "sampler %d: over-generated %llu refill buffers, replaying the stream\n", sampler_id,
+                        (unsigned long long)(buffers - needed_buffers));
+            GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(sampler_generators[sampler_id],
+                                                               sampler_seeds[sampler_id]));
+            GV_CHECK_CURAND(curandSetGeneratorOffset(sampler_generators[sampler_id], 0));
+            for (uint64_t j = 0; j < sampler_buffers[sampler_id] + needed_buffers; j++)
+                GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
+                                                            d_sampler_random.as<double>(), kRandBatchSize));
+            buffers = needed_buffers;
+        }
+        sampler_buffers[sampler_id] += needed_buffers;
+    }
+
+    // one round of the peer exchange on the sample stream (gv_cuda_peer_exchange); totals == nullptr
+    // publishes zeros, i.e. a pure barrier
+    void peer_barrier(const unsigned long long *totals) {
+        GV_CHECK_ABI(gv_cuda_peer_exchange(rank, num_worker, num_partition, ++peer_round, totals,
+                                           d_peer_controls.as<unsigned long long *>(),
+                                           reinterpret_cast<unsigned long long *>(static_cast<char *>(pool_arena.ptr) +
+                                                                                  control_offset()),
+                                           d_fill.as<unsigned long long>(), d_bases.as<unsigned long long>(),
+                                           d_last_walk.as<unsigned long long>(), sample_stream));
     }
 
     // fill one side of the sample pools with all samplers (core/solver.h:614-628)
     void fill_pool(int side) {
         GV_CHECK_CUDA(cudaSetDevice(device));
+        if (partitioned_sampling) {
+            // nobody may write into a pool that some rank is still training on: every rank gets here
+            // only after it finished the previous episode, so a barrier over the ranks is enough
+            peer_barrier(nullptr);
+            GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+        }
         cudaEvent_t begin, end;
         GV_CHECK_CUDA(cudaEventCreate(&begin));
         GV_CHECK_CUDA(cudaEventCreate(&end));
@@ -844,6 +1022,7 @@ struct Solver {
                     std::to_string(shuffle_base) + ". Try setting the episode size to a multiple of the shuffle base");
         if (log_enabled())
             fprintf(stderr, "%s\n", info().c_str());
+        PhaseTimer phase;
         if (!resume) {
             init_embeddings();
             for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
@@ -851,9 +1030,13 @@ struct Solver {
             batch_id = 0;
         }
         num_batch = int(batch_id + uint64_t(num_epoch) * graph->num_edge / batch_size);
+        phase.mark("init embeddings");
         prepare_sampling();
+        phase.mark("sampler tables + graph upload");
         load_blocks();
+        phase.mark("embedding upload");
         build_negative_tables();
+        phase.mark("negative tables");
         if (capture_negatives)
             d_negatives_out.allocate(uint64_t(chunk_batches) * batch_size * std::max(1, num_negative) * 4);
         stat_positive = stat_kernel_seconds = stat_train_seconds = stat_sample_seconds = 0;
@@ -862,6 +1045,7 @@ struct Solver {
         training = true;
         step_in_episode = 0;
         fill_pool(pool_id ^ 1);
+        phase.mark("first pool fill");
     }
 
     // WorkerMixin::train for one block, core/solver.h:1511-1557: positive_reuse * episode_size batches
@@ -879,7 +1063,7 @@ struct Solver {
         matrices.context_m2 = num_state >= 3 ? context + 2 * block_floats : nullptr;
         gv_device_optimizer_t device_optimizer = {optimizer.desc.type, optimizer.desc.weight_decay, optimizer.desc.a,
                                                   optimizer.desc.b, optimizer.desc.epsilon};
-        const uint32_t *pool = pools[pool_id][head][g].as<uint32_t>();
+        const uint32_t *pool = pool_block(pool_id, head, g);
         const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2;
         std::vector<float> lr(episode_size), loss(episode_size);
         std::vector<cudaEvent_t> timers;
@@ -1119,13 +1303,13 @@ struct Solver {
         context_blocks.clear();
         negative_tables.clear();
         partition_ids.clear();
-        for (int side = 0; side < 2; side++) {
-            pools[side].clear();
+        close_peers();
+        pool_arena.release();
+        for (int side = 0; side < 2; side++)
             pool_pointers[side].release();
-        }
         for (auto *a : {&d_offsets, &d_edge_u, &d_edge_v, &d_edge_prob, &d_edge_alias, &d_vertex_tables, &d_locations,
                         &d_sampler_random, &d_chains, &d_fill, &d_last_walk, &d_fill_scratch, &d_random[0],
-                        &d_random[1], &d_lr, &d_loss, &d_negatives_out})
+                        &d_random[1], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases})
             a->release();
         for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
             std::vector<float>().swap(*m);
@@ -1287,6 +1471,12 @@ int gv_solver_set_exchange(gv_solver_t *solver, gv_exchange_fn fn, void *ctx) {
     return 0;
 }
 
+int gv_solver_set_host_allgather(gv_solver_t *solver, gv_host_allgather_fn fn, void *ctx) {
+    solver->solver->host_allgather_fn = fn;
+    solver->solver->host_allgather_ctx = ctx;
+    return 0;
+}
+
 int gv_solver_set_option(gv_solver_t *solver, const char *name, int value) {
     GV_TRY
     if (std::string(name) == "capture_negatives")
@@ -1435,9 +1625,9 @@ int64_t gv_solver_pool(gv_solver_t *solver, int pool, int head_partition, int ta
     if (!s.owns_tail(tail_partition))
         return 0;
     cudaSetDevice(s.device);
-    const auto &block = s.pools[pool][head_partition][tail_partition / s.num_worker];
     if (out) {
-        if (cudaMemcpy(out, block.ptr, block.bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        if (cudaMemcpy(out, s.pool_block(pool, head_partition, tail_partition / s.num_worker), s.pool_block_bytes(),
+                       cudaMemcpyDeviceToHost) != cudaSuccess)
             throw std::runtime_error("gv_solver_pool: copy failed");
     }
     return int64_t(s.pool_size());

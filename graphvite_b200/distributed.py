@@ -62,11 +62,45 @@ def make_exchange(device=None, group=None):
     return _lib.EXCHANGE_FN(exchange)
 
 
+_host_group = None
+
+
+def make_host_allgather():
+    """gv_host_allgather_fn over a gloo group (host buffers; used once per build() to trade the CUDA
+    IPC handles of the sample-pool arenas).  Must be created by all ranks collectively."""
+    import torch
+    import torch.distributed as dist
+    global _host_group
+    if dist.get_backend() == "gloo":
+        group = None
+    else:
+        if _host_group is None:
+            _host_group = dist.new_group(backend="gloo")
+        group = _host_group
+    world = dist.get_world_size()
+
+    def allgather(send, recv, nbytes, ctx):
+        try:
+            source = _as_tensor(send, nbytes, None).clone()
+            chunks = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(chunks, source, group=group)
+            _as_tensor(recv, nbytes * world, None).copy_(torch.cat(chunks))
+            return 0
+        except Exception:
+            traceback.print_exc(file=sys.stderr)
+            return -1
+
+    return _lib.HOST_ALLGATHER_FN(allgather)
+
+
 def attach(solver, device=None, group=None):
-    """Wire a GraphSolver created with world_size > 1 to the default process group."""
+    """Wire a GraphSolver created with world_size > 1 to the default process group: the NCCL block
+    exchange and the host all-gather that enables partitioned sampling over NVLink peer memory."""
     callback = make_exchange(device, group)
     _lib.check(_lib.lib.gv_solver_set_exchange(solver._handle, callback, None))
-    solver._exchange = callback
+    gather = make_host_allgather()
+    _lib.check(_lib.lib.gv_solver_set_host_allgather(solver._handle, gather, None))
+    solver._exchange = (callback, gather)
     return solver
 
 

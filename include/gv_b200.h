@@ -103,6 +103,10 @@ int gv_cuda_train_block(const gv_matrices_t *matrices, const uint32_t *pool, uin
                         const float *lr_per_batch, uint32_t batch_size, float negative_weight,
                         float *loss_per_sample, float *loss_per_batch, int num_warps, void *stream);
 
+/* Device-layer tunables: "hot_rows" = rows with a local id below this value are read through L1
+ * (default 128; rows are in degree order, so these are the hubs), "kernel_flags" = experiment bits. */
+int gv_cuda_set_tunable(const char *name, long value);
+
 /* gpu::Sample (base/alias_table.cuh:175-183): out[t] = table.sample(float(random[2t]), float(random[2t+1])). */
 int gv_cuda_sample_negatives(const gv_alias_entry_t *table, uint32_t count, const double *random, uint64_t num,
                              uint32_t *out, void *stream);
@@ -133,12 +137,15 @@ typedef struct {
 } gv_device_graph_t;
 
 /* Walk part of GraphSampler::sample_random_walk (instance/graph.cuh:400-425) for `num_walk`
- * independent walks: walk w reads the cuRAND doubles random[2*L*w .. 2*L*(w+1)) in the
- * reference's (right-to-left) argument order and writes the locations of its L+1 vertices to
- * chains[j * num_walk + w], j = 0..L.  With walk_length == 1 this is the draw part of
- * SamplerMixin::sample (core/solver.h:1026-1040): one alias-sampled edge per "walk".
+ * independent walks.  `random` holds consecutive refill buffers of `buffer_doubles` cuRAND doubles
+ * (kRandBatchSize = 5e6 in the reference, core/solver.h:52), each serving `walks_per_buffer` walks
+ * (the reference refills when rand_id > 5e6 - 2L, instance/graph.cuh:401).  Walk first_walk + w reads
+ * the 2*L doubles of its slot in the reference's (right-to-left) argument order and writes the
+ * locations of its L+1 vertices to chains[j * num_walk + w], j = 0..L.  With walk_length == 1 this is
+ * the draw part of SamplerMixin::sample (core/solver.h:1026-1040): one alias-sampled edge per "walk".
  * Walks must not hit dead ends (every vertex has an out-edge), see DESIGN.md. */
 int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, uint32_t num_walk, int walk_length,
+                        uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,
                         gv_location_t *chains, void *stream);
 
 /* Pool fill (instance/graph.cuh:427-447 / core/solver.h:1041-1053): expands the chains into positive
@@ -165,6 +172,27 @@ size_t gv_cuda_fill_scratch_bytes(uint32_t num_walk, int num_partition);
 int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
                       uint64_t first_walk, uint32_t *const *pool_blocks, unsigned long long *fill,
                       unsigned long long *last_walk, void *scratch, void *stream);
+
+/* The same pool fill split in two for sampling partitioned over several GPUs: every rank walks a
+ * slice of the walks; gv_cuda_fill_count leaves the per-walk histogram in `scratch` and the slice's
+ * per-block totals in `totals` [P*P]; the ranks exchange totals (gv_cuda_peer_exchange) and
+ * gv_cuda_fill_scatter appends the slice's pairs behind those of the lower ranks (`bases` [P*P] =
+ * slice offsets at which this rank's pairs start).  pool_blocks may point into peer GPUs' memory. */
+int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk, void *scratch,
+                       unsigned long long *totals, void *stream);
+int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
+                         uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
+                         unsigned long long *last_walk, void *scratch, void *stream);
+/* All-gather of the per-block totals through NVLink peer memory, fused with the prefix over ranks:
+ * publishes `totals` (NULL = zeros) and *last_walk into every rank's control region (`controls` [W]
+ * device pointers, peers mapped with CUDA IPC), waits until all W ranks published round `round_id`
+ * (strictly increasing), then bases[b] = fill[b] + sum_{r<rank} totals_r[b], fill[b] += sum_r totals_r[b],
+ * *last_walk = max over ranks.  Control regions are gv_cuda_peer_control_bytes() long and start zeroed. */
+size_t gv_cuda_peer_control_bytes(int world_size, int num_partition);
+int gv_cuda_peer_exchange(int rank, int world_size, int num_partition, uint64_t round_id,
+                          const unsigned long long *totals, unsigned long long *const *controls,
+                          unsigned long long *control, unsigned long long *fill, unsigned long long *bases,
+                          unsigned long long *last_walk, void *stream);
 
 /* Memory::gather / Memory::scatter (base/memory.h:194-217) on the device: rows of `dim` floats,
  * dst[i] = src[ids[i]] when gather != 0, else dst[ids[i]] = src[i]. */
@@ -219,6 +247,11 @@ void gv_solver_destroy(gv_solver_t *solver);
 typedef int (*gv_exchange_fn)(const void *send, int dst, void *recv, int src, uint64_t bytes, void *stream,
                               void *ctx);
 int gv_solver_set_exchange(gv_solver_t *solver, gv_exchange_fn fn, void *ctx);
+/* Host all-gather used once in build() to trade CUDA IPC handles of the sample-pool arenas, so that
+ * the samplers can be partitioned over the ranks and scatter pairs straight into the owner's pool
+ * over NVLink.  recv holds world_size * bytes.  Without it every rank samples all blocks itself. */
+typedef int (*gv_host_allgather_fn)(const void *send, void *recv, uint64_t bytes, void *ctx);
+int gv_solver_set_host_allgather(gv_solver_t *solver, gv_host_allgather_fn fn, void *ctx);
 
 /* SolverMixin::build (core/solver.h:287-466); num_partition / episode_size 0 = auto */
 int gv_solver_build(gv_solver_t *solver, gv_graph_t *graph, const gv_optimizer_t *optimizer, int num_partition,

@@ -33,6 +33,7 @@ def main():
     _lib.check(_lib.lib.gv_solver_set_option(solver._handle, b"train_num_warps", 1))
     solver.build(graph, gv.optimizer.SGD(0.025, 0.005), num_partition, cfg["k"], cfg["B"], cfg["E"])
     assert solver.num_partition == num_partition and solver.num_worker == world
+    print("rank %d sampling: %s" % (rank, "replicated" if os.environ.get("GV_REPLICATED_SAMPLING") else "partitioned"))
 
     ograph = O.OracleGraph(toy)
     osolver = O.OracleSolver(ograph, cfg["dim"], world, cfg["S"])

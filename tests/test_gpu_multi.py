@@ -19,14 +19,16 @@ def gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("world,partitions", [(2, 2), (2, 4), (4, 4), (8, 8)])
-def test_multi_gpu_matches_oracle(world, partitions):
+@pytest.mark.parametrize("world,partitions,replicated", [(2, 2, 0), (2, 4, 0), (2, 2, 1), (4, 4, 0), (8, 8, 0)])
+def test_multi_gpu_matches_oracle(world, partitions, replicated):
     if gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     env = dict(os.environ, GV_TEST_PARTITIONS=str(partitions))
+    if replicated:  # every rank samples all blocks itself (no CUDA IPC): the fallback path
+        env["GV_REPLICATED_SAMPLING"] = "1"
     command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                "--master-addr", "127.0.0.1", "--master-port", str(port),
                os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
