@@ -172,6 +172,14 @@ def run_ours(args, cfg):
     achieved = positives * per_edge / kernel_seconds / 1e9
     peak, peak_kind = measured_peak()
     launches = int(after["launches"] - before["launches"])
+    # DRAM bytes of one launch of the same kernel from the committed `ncu --set full` capture
+    traffic, traffic_note = None, "no ncu capture committed"
+    capture = os.path.join(ROOT, "profiles", "r01_train_kernel.json")
+    if os.path.exists(capture) and cfg["dim"] == 128 and cfg["num_negative"] == 1:
+        info = json.load(open(capture))
+        traffic = info["dram_bytes_per_launch"]
+        traffic_note = ("dram__bytes_read+write.sum per launch of %d edges (%.0f B/edge vs %d algorithmic), %s" %
+                        (info["edges_per_launch"], info["dram_bytes_per_edge"], per_edge, info["source"]))
 
     if args.no_e2e:
         if rank == 0:
@@ -215,8 +223,9 @@ def run_ours(args, cfg):
                    "l2": "working set (2 x %.0f MB embeddings + %.0f MB pool block) >> 126 MB L2, no flush needed" %
                          (matrix_bytes / 1e6, edges_per_step * 8 / 1e6)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_kind, "bytes_per_edge": per_edge,
-                     "kernel": "gv::device::train_kernel<128, SGD>",
+                     "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_kind,
+                     "bytes_per_edge": per_edge, "kernel": "gv::device::train_sgd_kernel<%d, %d>" % (cfg["dim"], cfg["num_negative"]),
+                     "algorithmic_bytes_per_launch": per_edge * 16 * cfg["batch_size"],
                      "kernel_edges_per_s": positives / kernel_seconds},
         "e2e": {"value": e2e_edges / e2e_seconds, "unit": "edges/s", "h2d_bytes_per_step": h2d / e2e_steps,
                 "d2h_bytes_per_step": d2h / e2e_steps, "seconds": e2e_seconds, "edges": e2e_edges,
