@@ -3,12 +3,15 @@ path needs (reference python/graphvite/application/application.py:41-187,265-453
 load / build / train / link_prediction / save_model / load_model, driven by the same keyword
 arguments as the reference's config/*.yaml sections.
 """
+import logging
 import pickle
 
 import numpy as np
 
 from . import graph as _graph, optimizer as _optimizer, solver as _solver
 from .base import auto
+
+logger = logging.getLogger(__name__)
 
 
 def link_prediction_auc(scores, labels):
@@ -23,6 +26,14 @@ def link_prediction_auc(scores, labels):
     if total == 0:
         raise ValueError("link prediction needs both positive and negative edges")
     return float(hit[y == 0].sum()) / total
+
+
+def Application(type, *args, **kwargs):
+    """Application(type, *args, **kwargs): factory of application.py:1371-1392; only the node-embedding
+    application ("graph") is in scope."""
+    if type == "graph":
+        return GraphApplication(*args, **kwargs)
+    raise ValueError("Unknown application `%s` (this build ships the node-embedding application `graph`)" % type)
 
 
 class GraphApplication(object):
@@ -41,9 +52,28 @@ class GraphApplication(object):
         self.solver = _solver.GraphSolver(dim, float_type, index_type, self.gpus[:1], num_sampler_per_worker,
                                           gpu_memory_limit, **kwargs)
 
+    def set_format(self, delimiters=" \t\r\n", comment="#"):
+        """application.py:64-76"""
+        self._format = dict(delimiters=delimiters, comment=comment)
+        return self
+
     def load(self, **kwargs):
+        fmt = getattr(self, "_format", None)
+        if fmt and "file_name" in kwargs:
+            kwargs = dict(fmt, **kwargs)
         self.graph.load(**kwargs)
         return self
+
+    def evaluate(self, task, **kwargs):
+        """application.py:107-129: dispatch on the task name"""
+        name = task.replace(" ", "_")
+        if name == "link_prediction":
+            result = self.link_prediction(**kwargs)
+        else:
+            raise ValueError("task `%s` is not available in this build (link prediction is)" % task)
+        for metric, value in sorted(result.items()):
+            logger.warning("%s: %g" % (metric, value))
+        return result
 
     def build(self, optimizer=auto, **kwargs):
         if isinstance(optimizer, dict):  # cmd.py:99-106: a dict becomes Optimizer(**dict)
@@ -121,4 +151,4 @@ class GraphApplication(object):
         return self
 
 
-__all__ = ["GraphApplication", "link_prediction_auc"]
+__all__ = ["Application", "GraphApplication", "link_prediction_auc"]

@@ -79,75 +79,80 @@ struct FillParams {
     unsigned long long pool_size, start, slice;  // slice = end - start
 };
 
-// pass 1: counts[w][b] = pairs of walk w that belong to block b
-__global__ void __launch_bounds__(256) fill_count_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk,
-                                                         uint32_t *counts) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= num_walk)
-        return;
-    const int num_block = p.num_partition * p.num_partition;
-    uint32_t *row = counts + size_t(w) * num_block;
-    for (int b = 0; b < num_block; b++)
-        row[b] = 0;
+// Stable partition of the pairs by block, two levels.  A CTA owns `T` consecutive walks (one per
+// thread) and keeps a histogram counters[b][thread] in shared memory (conflict-free: thread is the
+// fast index).
+//   fill_count_kernel   per-CTA totals per block              -> cta_counts[b][cta]
+//   fill_scan_kernel    exclusive scan over the CTAs per block -> cta_counts[b][cta] = slice offset of
+//                       the CTA's first pair of block b (seeded, saturating at the slice length)
+//   fill_scatter_kernel recounts, scans the threads of the CTA per block and emits the pairs in order
+__device__ __forceinline__ void count_walk_pairs(const FillParams &p, const uint2 *chains, uint32_t num_walk,
+                                                 uint32_t w, uint32_t *counters, int T) {
     for (int j = 0; j < p.walk_length; j++) {
         const uint32_t head_part = chains[size_t(j) * num_walk + w].x;
         for (int k = 1; k <= p.augmentation_step && j + k <= p.walk_length; k++) {
             const uint32_t tail_part = chains[size_t(j + k) * num_walk + w].x;
-            row[head_part * p.num_partition + tail_part]++;
+            counters[(head_part * p.num_partition + tail_part) * T + threadIdx.x]++;
         }
     }
 }
 
-// pass 2: one CTA per block b: exclusive scan of counts[:, b] over the walks, seeded with fill[b];
-// bases saturate at the slice length (anything beyond is dropped anyway).
-__global__ void __launch_bounds__(1024) fill_scan_kernel(const FillParams p, uint32_t num_walk, uint32_t *counts,
-                                                         const unsigned long long *seeds, unsigned long long *fill) {
+__global__ void fill_count_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk, uint32_t *cta_counts) {
+    extern __shared__ uint32_t counters[];
+    const int T = blockDim.x, num_block = p.num_partition * p.num_partition;
+    const uint32_t w = blockIdx.x * T + threadIdx.x;
+    for (int b = 0; b < num_block; b++)
+        counters[b * T + threadIdx.x] = 0;
+    if (w < num_walk)
+        count_walk_pairs(p, chains, num_walk, w, counters, T);
+    __syncthreads();
+    // one warp per block id: sum the T per-thread counts
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, num_warp = T >> 5;
+    for (int b = warp; b < num_block; b += num_warp) {
+        uint32_t sum = 0;
+        for (int t = lane; t < T; t += 32)
+            sum += counters[b * T + t];
+        for (int delta = 16; delta > 0; delta >>= 1)
+            sum += __shfl_xor_sync(0xFFFFFFFFu, sum, delta);
+        if (lane == 0)
+            cta_counts[size_t(b) * gridDim.x + blockIdx.x] = sum;
+    }
+}
+
+// one CTA per block id: exclusive scan of the per-CTA totals, seeded with seeds[b]
+__global__ void __launch_bounds__(1024) fill_scan_kernel(const FillParams p, uint32_t num_cta, uint32_t *cta_counts,
+                                                         const unsigned long long *seeds, unsigned long long *fill,
+                                                         unsigned long long *totals) {
     __shared__ unsigned long long partial[1024];
-    const int num_block = p.num_partition * p.num_partition;
     const int b = blockIdx.x;
-    const uint32_t per_thread = (num_walk + blockDim.x - 1) / blockDim.x;
-    const uint32_t begin = min(num_walk, threadIdx.x * per_thread), end = min(num_walk, begin + per_thread);
+    uint32_t *row = cta_counts + size_t(b) * num_cta;
+    const uint32_t per_thread = (num_cta + blockDim.x - 1) / blockDim.x;
+    const uint32_t begin = min(num_cta, threadIdx.x * per_thread), end = min(num_cta, begin + per_thread);
     unsigned long long sum = 0;
-    for (uint32_t w = begin; w < end; w++)
-        sum += counts[size_t(w) * num_block + b];
+    for (uint32_t c = begin; c < end; c++)
+        sum += row[c];
     partial[threadIdx.x] = sum;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partial sums
-    for (int offset = 1; offset < blockDim.x; offset <<= 1) {
+    for (int offset = 1; offset < blockDim.x; offset <<= 1) {  // Hillis-Steele inclusive scan
         unsigned long long add = threadIdx.x >= offset ? partial[threadIdx.x - offset] : 0;
         __syncthreads();
         partial[threadIdx.x] += add;
         __syncthreads();
     }
-    const unsigned long long seed = seeds[b];
+    const unsigned long long seed = seeds ? seeds[b] : 0;
     unsigned long long running = seed + partial[threadIdx.x] - sum;
-    for (uint32_t w = begin; w < end; w++) {
-        const uint32_t count = counts[size_t(w) * num_block + b];
-        counts[size_t(w) * num_block + b] = uint32_t(min(running, p.slice));
+    for (uint32_t c = begin; c < end; c++) {
+        const uint32_t count = row[c];
+        row[c] = uint32_t(min(running, p.slice));
         running += count;
     }
     __syncthreads();
-    if (fill && threadIdx.x == blockDim.x - 1)
-        fill[b] = seed + partial[threadIdx.x];
-}
-
-// totals[b] = pairs this set of walks offers to block b (one CTA per block)
-__global__ void __launch_bounds__(1024) fill_reduce_kernel(int num_block, uint32_t num_walk, const uint32_t *counts,
-                                                           unsigned long long *totals) {
-    __shared__ unsigned long long partial[1024];
-    const int b = blockIdx.x;
-    unsigned long long sum = 0;
-    for (uint32_t w = threadIdx.x; w < num_walk; w += blockDim.x)
-        sum += counts[size_t(w) * num_block + b];
-    partial[threadIdx.x] = sum;
-    __syncthreads();
-    for (int offset = blockDim.x / 2; offset > 0; offset >>= 1) {
-        if (threadIdx.x < offset)
-            partial[threadIdx.x] += partial[threadIdx.x + offset];
-        __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+        if (fill)
+            fill[b] = seed + partial[threadIdx.x];
+        if (totals)
+            totals[b] = partial[threadIdx.x];
     }
-    if (threadIdx.x == 0)
-        totals[b] = partial[0];
 }
 
 // ---- cross-rank stable partition over NVLink peer memory ----------------------------------------
@@ -212,16 +217,40 @@ __global__ void __launch_bounds__(512) peer_gather_kernel(int rank, int W, int n
     }
 }
 
-// pass 3: every walk re-emits its pairs in order and writes the ones that still fit
-__global__ void __launch_bounds__(256) fill_scatter_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk,
-                                                           unsigned long long first_walk, uint32_t *counts,
-                                                           uint32_t *const *pool_blocks,
-                                                           unsigned long long *last_walk) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+// every walk re-emits its pairs in order and writes the ones that still fit
+__global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk,
+                                    unsigned long long first_walk, const uint32_t *cta_bases,
+                                    uint32_t *const *pool_blocks, unsigned long long *last_walk) {
+    extern __shared__ uint32_t counters[];
+    const int T = blockDim.x, num_block = p.num_partition * p.num_partition;
+    const uint32_t w = blockIdx.x * T + threadIdx.x;
+    for (int b = 0; b < num_block; b++)
+        counters[b * T + threadIdx.x] = 0;
+    if (w < num_walk)
+        count_walk_pairs(p, chains, num_walk, w, counters, T);
+    __syncthreads();
+    // exclusive scan over the CTA's threads, one warp per block id, 4 consecutive threads per lane step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, num_warp = T >> 5;
+    const uint32_t slice = uint32_t(p.slice);
+    for (int b = warp; b < num_block; b += num_warp) {
+        uint32_t running = cta_bases[size_t(b) * gridDim.x + blockIdx.x];
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const uint32_t count = counters[b * T + t0 + lane];
+            uint32_t inclusive = count;
+            for (int delta = 1; delta < 32; delta <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inclusive, delta);
+                if (lane >= delta)
+                    inclusive += up;
+            }
+            const unsigned long long start = (unsigned long long)running + inclusive - count;
+            counters[b * T + t0 + lane] = uint32_t(min(start, (unsigned long long)slice));
+            const unsigned long long next = (unsigned long long)running + __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+            running = uint32_t(min(next, (unsigned long long)slice));
+        }
+    }
+    __syncthreads();
     if (w >= num_walk)
         return;
-    const int num_block = p.num_partition * p.num_partition;
-    uint32_t *row = counts + size_t(w) * num_block;
     const unsigned long long shuffle_stride = p.pool_size / p.shuffle_base;
     bool completed = false;
     for (int j = 0; j < p.walk_length; j++) {
@@ -229,16 +258,16 @@ __global__ void __launch_bounds__(256) fill_scatter_kernel(const FillParams p, c
         for (int k = 1; k <= p.augmentation_step && j + k <= p.walk_length; k++) {
             const uint2 tail = chains[size_t(j + k) * num_walk + w];
             const int b = head.x * p.num_partition + tail.x;
-            const unsigned long long in_slice = row[b];
-            if (in_slice < p.slice) {
-                row[b] = uint32_t(in_slice + 1);
+            const uint32_t in_slice = counters[b * T + threadIdx.x];
+            if (in_slice < slice) {
+                counters[b * T + threadIdx.x] = in_slice + 1;
                 const unsigned long long offset = p.start + in_slice;
                 // pseudo shuffle, instance/graph.cuh:440-441
                 const unsigned long long shuffled = offset % p.shuffle_base * shuffle_stride + offset / p.shuffle_base;
                 uint2 *block = reinterpret_cast<uint2 *>(pool_blocks[b]);
                 if (block)
                     block[shuffled] = make_uint2(tail.y, head.y);  // {tail_local, head_local}
-                completed |= in_slice + 1 == p.slice;
+                completed |= in_slice + 1 == slice;
             }
         }
     }
@@ -314,10 +343,19 @@ int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, ui
     return 0;
 }
 
+// CTA size of the histogram kernels: as many walks per CTA as 48 KB of counters allow
+static int fill_threads(int num_partition) {
+    const int num_block = num_partition * num_partition;
+    int threads = int((48 * 1024) / (size_t(num_block) * sizeof(uint32_t))) / 32 * 32;
+    return threads > 128 ? 128 : (threads < 32 ? 32 : threads);
+}
+
 size_t gv_cuda_fill_scratch_bytes(uint32_t num_walk, int num_partition) {
     if (num_partition <= 1)
         return 16;
-    return size_t(num_walk) * num_partition * num_partition * sizeof(uint32_t);
+    const int threads = fill_threads(num_partition);
+    const size_t num_cta = (size_t(num_walk) + threads - 1) / threads;
+    return num_cta * num_partition * num_partition * sizeof(uint32_t) + 256;
 }
 
 int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
@@ -358,12 +396,16 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
     }
     if (!scratch)
         return fail("gv_cuda_fill_pool: scratch required for num_partition > 1");
-    uint32_t *counts = static_cast<uint32_t *>(scratch);
-    fill_count_kernel<<<blocks, threads, 0, s>>>(p, c, num_walk, counts);
+    uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
+    const int num_block = p.num_partition * p.num_partition;
+    const int T = fill_threads(p.num_partition);
+    const uint32_t num_cta = (num_walk + T - 1) / T;
+    const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
+    fill_count_kernel<<<num_cta, T, shared, s>>>(p, c, num_walk, cta_counts);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scan_kernel<<<p.num_partition * p.num_partition, 1024, 0, s>>>(p, num_walk, counts, fill, fill);
+    fill_scan_kernel<<<num_block, 1024, 0, s>>>(p, num_cta, cta_counts, fill, fill, nullptr);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scatter_kernel<<<blocks, threads, 0, s>>>(p, c, num_walk, first_walk, counts, pool_blocks, last_walk);
+    fill_scatter_kernel<<<num_cta, T, shared, s>>>(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -407,12 +449,28 @@ int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chai
         GV_CUDA_OK(cudaMemsetAsync(totals, 0, num_block * sizeof(unsigned long long), s));
         return 0;
     }
-    uint32_t *counts = static_cast<uint32_t *>(scratch);
-    fill_count_kernel<<<(num_walk + 255) / 256, 256, 0, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk, counts);
+    uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
+    const int T = fill_threads(p.num_partition);
+    const uint32_t num_cta = (num_walk + T - 1) / T;
+    const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
+    fill_count_kernel<<<num_cta, T, shared, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk, cta_counts);
     GV_CUDA_OK(cudaGetLastError());
-    fill_reduce_kernel<<<num_block, 1024, 0, s>>>(num_block, num_walk, counts, totals);
+    // unseeded scan: cta_counts become offsets relative to the start of this rank's pairs; totals out
+    FillParams unbounded = p;
+    unbounded.slice = ~0ull;
+    fill_scan_kernel<<<num_block, 1024, 0, s>>>(unbounded, num_cta, cta_counts, nullptr, nullptr, totals);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// adds the rank's base offsets to the relative CTA offsets left by gv_cuda_fill_count (saturating)
+__global__ void fill_rebase_kernel(unsigned long long slice, uint32_t num_cta, uint32_t *cta_counts,
+                                   const unsigned long long *bases) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < num_cta) {
+        const unsigned long long value = bases[blockIdx.y] + cta_counts[size_t(blockIdx.y) * num_cta + c];
+        cta_counts[size_t(blockIdx.y) * num_cta + c] = uint32_t(value < slice ? value : slice);
+    }
 }
 
 int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
@@ -426,11 +484,15 @@ int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *ch
     if (!chains || !scratch || !bases || !pool_blocks || !last_walk)
         return fail("gv_cuda_fill_scatter: null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    uint32_t *counts = static_cast<uint32_t *>(scratch);
-    fill_scan_kernel<<<p.num_partition * p.num_partition, 1024, 0, s>>>(p, num_walk, counts, bases, nullptr);
+    uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
+    const int num_block = p.num_partition * p.num_partition;
+    const int T = fill_threads(p.num_partition);
+    const uint32_t num_cta = (num_walk + T - 1) / T;
+    const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
+    fill_rebase_kernel<<<dim3((num_cta + 255) / 256, num_block), 256, 0, s>>>(p.slice, num_cta, cta_counts, bases);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scatter_kernel<<<(num_walk + 255) / 256, 256, 0, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk,
-                                                              first_walk, counts, pool_blocks, last_walk);
+    fill_scatter_kernel<<<num_cta, T, shared, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk, first_walk,
+                                                   cta_counts, pool_blocks, last_walk);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -295,6 +295,7 @@ struct Solver {
     uint64_t peer_round = 0;
     // device graph
     DeviceArray d_offsets, d_edge_u, d_edge_v, d_edge_prob, d_edge_alias, d_vertex_tables, d_locations;
+    DeviceArray d_edge_tables, d_table_offsets;  // node2vec: one alias table per directed edge
     gv_device_graph_t device_graph;
     bool sampling_ready = false;
     int sample_mode = 0;
@@ -613,7 +614,7 @@ struct Solver {
         else if (model == "DeepWalk" || model == "LINE")
             sample_mode = 1;
         else
-            throw std::runtime_error("the node2vec second-order walker is not implemented in this build");
+            sample_mode = 2;
         const size_t m = graph->edge_u.size();
         require(m > 0, "The graph has no edges");
         // edge_table.build(graph->edge_weights), core/solver.h:255-256
@@ -669,6 +670,12 @@ struct Solver {
             d_vertex_tables.upload(tables, sample_stream);
             device_graph.vertex_tables = d_vertex_tables.as<gv_alias_entry_t>();
         }
+        if (sample_mode == 2)
+            build_node2vec_tables();
+        else {
+            d_edge_tables.release();
+            d_table_offsets.release();
+        }
         const int L = sample_mode == 0 ? 1 : random_walk_length;
         // per launch: at most walk_chunk walks per rank (chains <= 256 MB, histogram scratch <= 256 MB)
         walk_chunk = std::min<uint64_t>(uint64_t(1) << 20, (uint64_t(256) << 20) / (uint64_t(L + 1) * sizeof(gv_location_t)));
@@ -678,6 +685,50 @@ struct Solver {
         d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(walk_chunk), num_partition));
         d_sampler_random.allocate(size_t(kSpanBuffers) * kRandBatchSize * sizeof(double));
         sampling_ready = true;
+    }
+
+    // GraphSolver::build_edge_edge, instance/graph.cuh:656-677, on the device: one alias table per
+    // directed edge (u -> v) over the out-edges of v, Sigma deg^2 entries in one flat array.
+    void build_node2vec_tables() {
+        const size_t m = graph->edge_u.size();
+        std::vector<unsigned long long> table_offsets(m + 1, 0);
+        for (size_t e = 0; e < m; e++) {
+            const uint32_t v = graph->edge_v[e];
+            table_offsets[e + 1] = table_offsets[e] + (graph->offsets[v + 1] - graph->offsets[v]);
+        }
+        const unsigned long long total = table_offsets[m];
+        size_t free_bytes = 0, total_bytes = 0;
+        GV_CHECK_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+        const unsigned long long budget = std::min<unsigned long long>(total, 1ull << 27);  // entries per build batch
+        const unsigned long long needed = total * sizeof(gv_alias_entry_t) + budget * 8 + m * 8 + (m + 1) * 8;
+        require(needed + (1ull << 30) < free_bytes,
+                "node2vec needs " + std::to_string(needed >> 20) + " MiB of device memory for its per-edge alias tables "
+                "(sum of squared degrees = " + std::to_string(total) + " entries), only " +
+                std::to_string(free_bytes >> 20) + " MiB are free");
+        // neighbour lists sorted inside every vertex's CSR range, for the membership test
+        std::vector<uint32_t> sorted(graph->edge_v);
+        for (uint32_t v = 0; v < graph->num_vertex(); v++)
+            std::sort(sorted.begin() + graph->offsets[v], sorted.begin() + graph->offsets[v + 1]);
+        DeviceArray d_sorted, d_weights, d_little, d_large;
+        d_sorted.upload(sorted, sample_stream);
+        d_weights.upload(graph->edge_w, sample_stream);
+        d_table_offsets.upload(table_offsets, sample_stream);
+        d_edge_tables.allocate(total * sizeof(gv_alias_entry_t));
+        d_little.allocate(budget * sizeof(uint32_t));
+        d_large.allocate(budget * sizeof(uint32_t));
+        for (size_t first = 0; first < m;) {
+            size_t last = first;
+            while (last < m && table_offsets[last + 1] - table_offsets[first] <= budget)
+                last++;
+            require(last > first, "internal error: node2vec table larger than the build batch");
+            GV_CHECK_ABI(gv_cuda_node2vec_build(&device_graph, d_weights.as<float>(), d_sorted.as<uint32_t>(),
+                                                d_table_offsets.as<unsigned long long>(), first,
+                                                uint32_t(last - first), p, q, d_edge_tables.as<gv_alias_entry_t>(),
+                                                d_little.as<uint32_t>(), d_large.as<uint32_t>(), sample_stream));
+            stat_launches++;
+            first = last;
+        }
+        GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
     }
 
     // ---- one sampler's share of a pool (SamplerMixin::sample / GraphSampler::sample_random_walk) ----
@@ -748,9 +799,16 @@ struct Solver {
                 // this rank's slice of the round (everything unless the sampling is partitioned)
                 const uint32_t lo = uint32_t(uint64_t(count) * (partitioned_sampling ? rank : 0) / share);
                 const uint32_t hi = uint32_t(uint64_t(count) * (partitioned_sampling ? rank + 1 : 1) / share);
-                GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, d_sampler_random.as<double>(), hi - lo, L,
-                                                 done_in_span + lo, uint32_t(walks_per_buffer), kRandBatchSize,
-                                                 d_chains.as<gv_location_t>(), sample_stream));
+                if (sample_mode == 2)
+                    GV_CHECK_ABI(gv_cuda_biased_walk(&device_graph, d_edge_tables.as<gv_alias_entry_t>(),
+                                                     d_table_offsets.as<unsigned long long>(),
+                                                     d_sampler_random.as<double>(), hi - lo, L, done_in_span + lo,
+                                                     uint32_t(walks_per_buffer), kRandBatchSize,
+                                                     d_chains.as<gv_location_t>(), sample_stream));
+                else
+                    GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, d_sampler_random.as<double>(), hi - lo, L,
+                                                     done_in_span + lo, uint32_t(walks_per_buffer), kRandBatchSize,
+                                                     d_chains.as<gv_location_t>(), sample_stream));
                 if (!partitioned_sampling) {
                     GV_CHECK_ABI(gv_cuda_fill_pool(&params, d_chains.as<gv_location_t>(), count, walks_done,
                                                    pool_pointers[side].as<uint32_t *>(),
@@ -1309,7 +1367,8 @@ struct Solver {
             pool_pointers[side].release();
         for (auto *a : {&d_offsets, &d_edge_u, &d_edge_v, &d_edge_prob, &d_edge_alias, &d_vertex_tables, &d_locations,
                         &d_sampler_random, &d_chains, &d_fill, &d_last_walk, &d_fill_scratch, &d_random[0],
-                        &d_random[1], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases})
+                        &d_random[1], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_edge_tables,
+                        &d_table_offsets})
             a->release();
         for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
             std::vector<float>().swap(*m);

@@ -148,6 +148,24 @@ int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, ui
                         uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,
                         gv_location_t *chains, void *stream);
 
+/* node2vec.  GraphSolver::build_edge_edge (instance/graph.cuh:656-677): the alias table of directed
+ * edge e = (u -> v) covers the out-edges (v -> x) with weight w/p if x == u, w/q if u is not a
+ * neighbour of x, w otherwise; it has deg(v) entries and lives at tables[table_offsets[e]].  One
+ * launch builds the tables of edges [first_edge, first_edge + num_table) with the reference's FIFO
+ * pairing order (bit-identical tables); scratch_little / scratch_large hold
+ * table_offsets[first_edge + num_table] - table_offsets[first_edge] entries each.
+ * sorted_neighbors = edge_v sorted inside every vertex's CSR range (membership test). */
+int gv_cuda_node2vec_build(const gv_device_graph_t *graph, const float *edge_weights, const uint32_t *sorted_neighbors,
+                           const unsigned long long *table_offsets, uint64_t first_edge, uint32_t num_table, float p,
+                           float q, gv_alias_entry_t *tables, uint32_t *scratch_little, uint32_t *scratch_large,
+                           void *stream);
+/* Walk part of GraphSampler::sample_biased_random_walk (instance/graph.cuh:321-349); arguments as
+ * gv_cuda_random_walk, steps drawn from the table of the edge the walk arrived by. */
+int gv_cuda_biased_walk(const gv_device_graph_t *graph, const gv_alias_entry_t *tables,
+                        const unsigned long long *table_offsets, const double *random, uint32_t num_walk,
+                        int walk_length, uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,
+                        gv_location_t *chains, void *stream);
+
 /* Pool fill (instance/graph.cuh:427-447 / core/solver.h:1041-1053): expands the chains into positive
  * pairs in stream order (walk-major, then j, then k = 1..augmentation_step) and appends each pair
  * to block [head part][tail part] of one sampler's slice [start, end) until that slice is full,

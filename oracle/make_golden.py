@@ -80,6 +80,10 @@ SOLVER_CASES = {
                     optimizer="SGD"),
     "line_p3_adam": dict(dim=32, P=3, k=2, B=300, E=2, S=1, model="LINE", epochs=4, aug=2, L=6, wb=10, sb=0,
                          optimizer="Adam"),
+    "node2vec_p2": dict(dim=32, P=2, k=1, B=400, E=3, S=2, model="node2vec", epochs=5, aug=3, L=8, wb=10, sb=0,
+                        optimizer="SGD", p=0.5, q=2.0),
+    "node2vec_p1": dict(dim=32, P=1, k=2, B=500, E=2, S=1, model="node2vec", epochs=3, aug=2, L=5, wb=10, sb=0,
+                        optimizer="SGD", p=4.0, q=0.25),
 }
 
 
@@ -109,13 +113,19 @@ def make_toy_graph(path):
         fout.write("\n".join(lines) + "\n")
 
 
-def main(out_dir):
+def main(out_dir, only=None):
     os.makedirs(out_dir, exist_ok=True)
     lib = load_harness()
     toy = os.path.join(GOLDEN, "toy_graph.txt")
     if not os.path.exists(toy):
         make_toy_graph(toy)
 
+    if not only:
+        write_basics(lib, out_dir, toy)
+    write_solver_cases(lib, out_dir, toy, only)
+
+
+def write_basics(lib, out_dir, toy):
     # ---- process-wide engine + cuRAND stream ---------------------------------------------
     lib.ref_reset_engine()
     seeds = np.array([lib.ref_draw_seed() for _ in range(6)], dtype=np.uint64)
@@ -161,17 +171,22 @@ def main(out_dir):
             np.savez_compressed(os.path.join(out_dir, "graph_u%d_n%d.npz" % (undirected, normalization)),
                                 num_vertex=n, num_edge=lib.ref_graph_num_edge(g), u=u, v=v, w=w, vertex_weights=vw)
 
+
+
+def write_solver_cases(lib, out_dir, toy, only):
     # ---- solver runs ----------------------------------------------------------------------------
     graph = lib.ref_graph_load(toy.encode(), 1, 0)
     num_vertex = lib.ref_graph_num_vertex(graph)
     num_directed = lib.ref_graph_num_directed_edge(graph)
     for name, cfg in SOLVER_CASES.items():
+        if only and name not in only:
+            continue
         lib.ref_reset_engine()
         solver = lib.ref_solver_new(cfg["dim"], 1, cfg["S"], 4 << 30)
         otype, lr, wd, a, b, eps = OPTIMIZERS[cfg["optimizer"]]
         lib.ref_solver_build(solver, graph, otype, 1, lr, wd, a, b, eps, cfg["P"], cfg["k"], cfg["B"], cfg["E"])
         lib.ref_solver_train(solver, cfg["model"].encode(), cfg["epochs"], 0, cfg["aug"], cfg["L"], cfg["wb"],
-                             cfg["sb"], 1.0, 1.0, 1, 0.75, 5.0, 1000)
+                             cfg["sb"], cfg.get("p", 1.0), cfg.get("q", 1.0), 1, 0.75, 5.0, 1000)
         info = np.zeros(10, dtype=np.int32)
         lib.ref_solver_info(solver, ptr(info))
         P, E, B = int(info[0]), int(info[1]), int(info[2])
@@ -205,7 +220,7 @@ def main(out_dir):
         print("solver case", name, "info", info.tolist(), flush=True)
 
     # ---- the reference kernels on race-free batches ---------------------------------------------
-    for dim in (32, 128):
+    for dim in (() if only else (32, 128)):
         for oname, (otype, lr, wd, a, b, eps) in OPTIMIZERS.items():
             rng = np.random.RandomState(100 + dim + otype)
             n, k = 64, 2
@@ -233,4 +248,5 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"),
+         set(sys.argv[2:]) or None)

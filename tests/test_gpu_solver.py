@@ -21,6 +21,10 @@ CASES = {
                          optimizer="Adam"),
     "line_odd_walks": dict(dim=64, P=2, k=1, B=450, E=2, S=1, model="LINE", epochs=2, aug=2, L=3, wb=7,
                            optimizer="Momentum"),
+    "node2vec_p2": dict(dim=32, P=2, k=1, B=400, E=3, S=2, model="node2vec", epochs=5, aug=3, L=8, wb=10,
+                        optimizer="SGD", p=0.5, q=2.0),
+    "node2vec_p1": dict(dim=32, P=1, k=2, B=500, E=2, S=1, model="node2vec", epochs=3, aug=2, L=5, wb=10,
+                        optimizer="SGD", p=4.0, q=0.25),
 }
 
 
@@ -57,7 +61,8 @@ def product_pool(_lib, solver, side, head, tail, size):
 
 
 def train_args(cfg):
-    return (cfg["model"].encode(), cfg["epochs"], 0, cfg["aug"], cfg["L"], cfg["wb"], 0, 1.0, 1.0, 1, 0.75, 5.0, 1000)
+    return (cfg["model"].encode(), cfg["epochs"], 0, cfg["aug"], cfg["L"], cfg["wb"], 0, cfg.get("p", 1.0),
+            cfg.get("q", 1.0), 1, 0.75, 5.0, 1000)
 
 
 @pytest.mark.parametrize("case", list(CASES))
@@ -74,7 +79,8 @@ def test_solver_matches_oracle_step_by_step(case, toy_graph_file):
     np.testing.assert_array_equal(local_of, olocal)
 
     _lib.check(_lib.lib.gv_solver_train_begin(solver._handle, *train_args(cfg)))
-    osolver.train_begin(cfg["model"], cfg["epochs"], False, cfg["aug"], cfg["L"], cfg["wb"])
+    osolver.train_begin(cfg["model"], cfg["epochs"], False, cfg["aug"], cfg["L"], cfg["wb"], 0, cfg.get("p", 1.0),
+                        cfg.get("q", 1.0))
     info = osolver.info()
     for key in ("num_partition", "episode_size", "batch_size", "augmentation_step", "shuffle_base", "num_batch"):
         assert getattr(solver, key) == info[key], key
@@ -202,3 +208,43 @@ def test_errors_are_reported_not_fatal(toy_graph_file):
         solver.train("LINE", 1, augmentation_step=50, random_walk_length=40)  # walk shorter than augmentation
     with pytest.raises(ValueError):
         gv.solver.GraphSolver(100)
+
+
+def test_config_driven_run(tmp_path, toy_graph_file):
+    """`graphvite run config.yaml` semantics (cmd.py:140-163) on the toy graph: load, build, train,
+    link prediction with a filter file, save_model / load_model round trip"""
+    import yaml
+    import graphvite_b200 as gv
+    from graphvite_b200 import cmd
+    edges = [line.split("#")[0].split()[:2] for line in open(toy_graph_file)]
+    edges = [e for e in edges if len(e) == 2]
+    rng = np.random.RandomState(1)
+    test = tmp_path / "test.txt"
+    with open(test, "w") as fout:
+        for u, v in edges[:200]:
+            fout.write("%s\t%s\t1\n" % (u, v))
+        for _ in range(200):
+            fout.write("n%d\tn%d\t0\n" % (rng.randint(300), rng.randint(300)))
+    train = tmp_path / "train.txt"
+    with open(train, "w") as fout:
+        for u, v in edges[200:]:
+            fout.write("%s %s\n" % (u, v))
+    model = tmp_path / "model.pkl"
+    cfg = {"application": "graph", "resource": {"gpus": [0], "cpu_per_gpu": 3, "dim": 32},
+           "format": {"delimiters": " \t\r\n", "comment": "#"},
+           "graph": {"file_name": str(train), "as_undirected": True},
+           "build": {"optimizer": {"type": "SGD", "lr": 0.025, "weight_decay": 0.005}, "num_partition": "auto",
+                     "num_negative": 1, "batch_size": 500, "episode_size": 4},
+           "train": {"model": "LINE", "num_epoch": 300, "augmentation_step": 2, "random_walk_length": 5,
+                     "random_walk_batch_size": 10},
+           "evaluate": [{"task": "link prediction", "file_name": str(test), "filter_file": str(train)}],
+           "save": {"file_name": str(model)}}
+    path = tmp_path / "config.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    app, results = cmd.run_main(cmd.get_parser().parse_args(["run", str(path)]))
+    assert app.solver.num_sampler == 2  # cpu_per_gpu - 1 (application.py:283-286)
+    assert 0.55 < results[0]["AUC"] <= 1.0
+    other = gv.application.Application("graph", 32, gpus=[0])
+    other.load(file_name=str(train)).build(batch_size=500, episode_size=4).load_model(str(model))
+    np.testing.assert_array_equal(other.solver.vertex_embeddings, app.solver.vertex_embeddings)
+    assert abs(other.link_prediction(file_name=str(test), filter_file=str(train))["AUC"] - results[0]["AUC"]) < 1e-6

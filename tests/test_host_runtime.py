@@ -172,3 +172,36 @@ def test_link_prediction_auc_formula():
     scores, labels = rng.rand(2000), rng.randint(0, 2, 2000)
     from sklearn.metrics import roc_auc_score
     assert abs(link_prediction_auc(scores, labels) - roc_auc_score(labels, scores)) < 1e-9
+
+
+def test_yaml_config_loading(tmp_path):
+    """the reference's quick-start configuration loads unchanged except for the dataset placeholders"""
+    import yaml
+    from graphvite_b200 import cmd, optimizer, auto
+    reference = "/root/reference/config/demo/quick_start.yaml"
+    if os.path.exists(reference):
+        cfg = yaml.safe_load(open(reference))
+    else:  # the same content (config/demo/quick_start.yaml), for boxes without /root/reference
+        cfg = {"application": "graph", "resource": {"gpus": [0], "cpu_per_gpu": 8, "dim": 128},
+               "format": {"delimiters": " \t\r\n", "comment": "#"},
+               "graph": {"file_name": "<blogcatalog.train>", "as_undirected": True},
+               "build": {"optimizer": {"type": "SGD", "lr": 0.025, "weight_decay": 0.005}, "num_partition": "auto",
+                         "num_negative": 1, "batch_size": 100000, "episode_size": 500},
+               "train": {"model": "LINE", "num_epoch": 2000, "negative_weight": 5, "augmentation_step": 2,
+                         "random_walk_length": 40, "random_walk_batch_size": 100, "log_frequency": 1000},
+               "evaluate": [{"task": "link prediction", "file_name": "<blogcatalog.test>",
+                             "filter_file": "<blogcatalog.train>"}],
+               "save": {"file_name": "line_blogcatalog.pkl"}}
+    path = tmp_path / "quick_start.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    with pytest.raises(ValueError, match="dataset placeholder"):
+        cmd.load_config(str(path))
+    cfg["graph"]["file_name"] = "graph.txt"
+    cfg["evaluate"] = [{"task": "link prediction", "file_name": "test.txt", "filter_file": "graph.txt"}]
+    path.write_text(yaml.safe_dump(cfg))
+    loaded = cmd.load_config(str(path))
+    assert isinstance(loaded["build"]["optimizer"], optimizer.SGD)
+    assert loaded["build"]["optimizer"].weight_decay == 0.005
+    assert loaded["build"]["num_partition"] == auto and loaded["resource"]["dim"] == 128
+    args = cmd.get_parser().parse_args(["run", str(path), "--epoch", "3", "--no-eval"])
+    assert args.epoch == 3 and args.eval is False

@@ -9,7 +9,7 @@ import pytest
 
 import oracle_lib as O
 
-SOLVER_CASES = ["line_p1", "line_p2_s3", "deepwalk_p1", "edge_p2", "line_p3_adam"]
+SOLVER_CASES = ["line_p1", "line_p2_s3", "deepwalk_p1", "edge_p2", "line_p3_adam", "node2vec_p2", "node2vec_p1"]
 
 
 def load(golden_dir, name):
@@ -70,7 +70,8 @@ def test_solver_integer_state(golden_dir, toy_graph_file, case):
     solver = O.OracleSolver(graph, cfg["dim"], 1, cfg["S"])
     solver.build(cfg["optimizer"], cfg["P"], cfg["k"], cfg["B"], cfg["E"])
     solver.train(model=cfg["model"], num_epoch=cfg["epochs"], augmentation_step=cfg["aug"],
-                 random_walk_length=cfg["L"], random_walk_batch_size=cfg["wb"])
+                 random_walk_length=cfg["L"], random_walk_batch_size=cfg["wb"], p=cfg.get("p", 1.0),
+                 q=cfg.get("q", 1.0))
     assert list(solver.info().values()) == golden["info"].tolist()
     part_of, local_of = solver.locations()
     np.testing.assert_array_equal(part_of, golden["part_of"])
