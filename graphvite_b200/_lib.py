@@ -65,6 +65,13 @@ SIGNATURES = {
     "gv_cuda_train_block": (c_int, [P(Matrices), c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_uint32,
                                     c_void_p, P(DeviceOptimizer), c_void_p, c_uint32, c_float, c_void_p, c_void_p,
                                     c_int, c_void_p]),
+    "gv_rng_create": (c_void_p, [ctypes.c_ulonglong, c_void_p]),
+    "gv_rng_destroy": (None, [c_void_p]),
+    "gv_rng_generate": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+    "gv_rng_position": (c_uint64, [c_void_p]),
+    "gv_rng_state_bytes": (c_size_t, []),
+    "gv_rng_save": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gv_rng_restore": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gv_cuda_set_tunable": (c_int, [c_char_p, ctypes.c_long]),
     "gv_cuda_sample_negatives": (c_int, [c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_void_p]),
     "gv_cuda_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),

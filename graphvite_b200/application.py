@@ -69,8 +69,10 @@ class GraphApplication(object):
         name = task.replace(" ", "_")
         if name == "link_prediction":
             result = self.link_prediction(**kwargs)
+        elif name == "node_classification":
+            result = self.node_classification(**kwargs)
         else:
-            raise ValueError("task `%s` is not available in this build (link prediction is)" % task)
+            raise ValueError("task `%s` is not available in this build" % task)
         for metric, value in sorted(result.items()):
             logger.warning("%s: %g" % (metric, value))
         return result
@@ -128,6 +130,75 @@ class GraphApplication(object):
                     labels.append(int(y))
         scores = self.solver.predict(np.asarray(pairs, dtype=np.uint32).reshape(-1, 2))
         return {"AUC": link_prediction_auc(scores, labels)}
+
+    # application.py:293-351 + linear_classification (:456-533): one-vs-rest logistic regression on
+    # frozen vertex embeddings, top-k prediction with k = number of true labels, micro / macro F1
+    def node_classification(self, X=None, Y=None, file_name=None, portions=(0.02,), normalization=False, times=1,
+                            patience=100):
+        import torch
+        if file_name:
+            if not (X is None and Y is None):
+                raise ValueError("Evaluation data and file should not be provided at the same time")
+            X, Y = [], []
+            with open(file_name, "r") as fin:
+                for line in fin:
+                    tokens = line.split("#")[0].split()
+                    if tokens:
+                        x, y = tokens
+                        X.append(x)
+                        Y.append(y)
+        if X is None or Y is None:
+            raise ValueError("Either evaluation data (X, Y) or a file name should be provided")
+        name2id = self.graph.name2id
+        classes = {c: i for i, c in enumerate(np.unique(Y))}
+        rows = [(name2id[x], classes[y]) for x, y in zip(X, Y) if x in name2id]
+        nodes = np.unique([r[0] for r in rows])
+        position = {node: i for i, node in enumerate(nodes)}
+        labels = np.zeros((len(nodes), len(classes)), dtype=np.int64)
+        for node, cls in rows:
+            labels[position[node], cls] = 1
+        embeddings = np.array(self.solver.vertex_embeddings[nodes], dtype=np.float32)
+        if normalization:
+            embeddings = embeddings / np.linalg.norm(embeddings, axis=1, keepdims=True)
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        features = torch.as_tensor(embeddings, device=device)
+        targets = torch.as_tensor(labels, device=device)
+        metrics = {}
+        for portion in portions:
+            num_train = int(len(nodes) * portion)
+            macro, micro = [], []
+            for _ in range(times):
+                order = torch.as_tensor(np.random.permutation(len(nodes)), device=device)
+                train, test = order[:num_train], order[num_train:]
+                # one training example per (node, label) pair, like generate_one_vs_rest
+                pairs = targets[train].nonzero()
+                x = features[train][pairs[:, 0]]
+                y = torch.nn.functional.one_hot(pairs[:, 1], targets.shape[1]).float()
+                linear = torch.nn.Linear(features.shape[1], targets.shape[1]).to(device)
+                optimizer = torch.optim.SGD(linear.parameters(), lr=1, weight_decay=2e-5, momentum=0.9)
+                best_loss, best_epoch = float("inf"), -1
+                for epoch in range(100000):
+                    optimizer.zero_grad()
+                    loss = torch.nn.functional.binary_cross_entropy_with_logits(linear(x), y)
+                    loss.backward()
+                    optimizer.step()
+                    if loss.item() < best_loss:
+                        best_loss, best_epoch = loss.item(), epoch
+                    if epoch == best_epoch + patience:
+                        break
+                with torch.no_grad():
+                    logits = linear(features[test])
+                    truth = targets[test]
+                    count = truth.sum(dim=1, keepdim=True)
+                    ranked, _ = logits.sort(dim=1, descending=True)
+                    thresholds = ranked.gather(1, (count - 1).clamp(min=0))
+                    predictions = (logits >= thresholds).long()
+                    tp = (predictions & truth).sum(dim=0).float()
+                    macro.append((2 * tp / (truth.sum(dim=0) + predictions.sum(dim=0)).float()).mean().item())
+                    micro.append((2 * tp.sum() / (truth.sum() + predictions.sum()).float()).item())
+            metrics["macro-F1@%g%%" % (portion * 100)] = float(np.mean(macro))
+            metrics["micro-F1@%g%%" % (portion * 100)] = float(np.mean(micro))
+        return metrics
 
     # application.py:145-187 / 131-143
     def save_model(self, file_name, save_hyperparameter=False):

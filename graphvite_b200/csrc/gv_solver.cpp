@@ -14,7 +14,6 @@
 // One process drives one GPU; world_size processes form the reference's num_worker.
 // =============================================================================
 #include <cuda_runtime.h>
-#include <curand.h>
 
 #include <algorithm>
 #include <atomic>
@@ -51,13 +50,6 @@ static const int kSpanBuffers = 16;  // refill buffers generated and walked per 
         if (gv_e__ != cudaSuccess)                                                                       \
             throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(gv_e__) + " at " + \
                                      __FILE__ + ":" + std::to_string(__LINE__));                         \
-    } while (0)
-#define GV_CHECK_CURAND(call)                                                                      \
-    do {                                                                                           \
-        curandStatus_t gv_e__ = (call);                                                            \
-        if (gv_e__ != CURAND_STATUS_SUCCESS)                                                       \
-            throw std::runtime_error("CURAND error " + std::to_string(int(gv_e__)) + " at " +      \
-                                     __FILE__ + ":" + std::to_string(__LINE__));                   \
     } while (0)
 #define GV_CHECK_ABI(call)                              \
     do {                                                \
@@ -244,10 +236,11 @@ struct Solver {
     uint64_t gpu_memory_limit, gpu_memory_cost = 0;
     std::vector<unsigned long long> sampler_seeds, worker_seeds;
     cudaStream_t work_stream = nullptr, sample_stream = nullptr, random_stream = nullptr;
-    std::vector<curandGenerator_t> sampler_generators;
+    std::vector<gv_rng_t *> sampler_generators;  // one XORWOW stream per sampler (gv_rng.cu)
     std::vector<uint64_t> sampler_buffers;  // refill buffers each sampler's stream has consumed so far
     uint64_t walk_chunk = 1 << 18;           // walks per sampler launch (bounds chains + scratch)
-    curandGenerator_t worker_generator = nullptr;
+    gv_rng_t *worker_generator = nullptr;
+    DeviceArray d_rng_snapshot;
     gv_exchange_fn exchange_fn = nullptr;
     void *exchange_ctx = nullptr;
     gv_host_allgather_fn host_allgather_fn = nullptr;
@@ -359,17 +352,16 @@ struct Solver {
             GV_CHECK_CUDA(cudaStreamCreateWithPriority(&sample_stream, cudaStreamNonBlocking, greatest));
         }
         GV_CHECK_CUDA(cudaStreamCreateWithFlags(&random_stream, cudaStreamNonBlocking));
+        // the reference's cuRAND XORWOW streams (solver.h:950-953, 1247-1250), from our own generator
         for (int i = 0; i < num_sampler; i++) {
-            curandGenerator_t generator;
-            GV_CHECK_CURAND(curandCreateGenerator(&generator, CURAND_RNG_PSEUDO_DEFAULT));
-            GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(generator, sampler_seeds[i]));
-            GV_CHECK_CURAND(curandSetStream(generator, sample_stream));
+            gv_rng_t *generator = gv_rng_create(sampler_seeds[i], sample_stream);
+            require(generator != nullptr, gv_last_error());
             sampler_generators.push_back(generator);
             sampler_buffers.push_back(0);
         }
-        GV_CHECK_CURAND(curandCreateGenerator(&worker_generator, CURAND_RNG_PSEUDO_DEFAULT));
-        GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(worker_generator, worker_seeds[rank]));
-        GV_CHECK_CURAND(curandSetStream(worker_generator, random_stream));
+        worker_generator = gv_rng_create(worker_seeds[rank], random_stream);
+        require(worker_generator != nullptr, gv_last_error());
+        d_rng_snapshot.allocate(gv_rng_state_bytes());
         for (int i = 0; i < 2; i++) {
             GV_CHECK_CUDA(cudaEventCreateWithFlags(&random_ready[i], cudaEventDisableTiming));
             GV_CHECK_CUDA(cudaEventCreateWithFlags(&random_free[i], cudaEventDisableTiming));
@@ -383,9 +375,8 @@ struct Solver {
             sampler_thread.join();
         close_peers();
         for (auto g : sampler_generators)
-            curandDestroyGenerator(g);
-        if (worker_generator)
-            curandDestroyGenerator(worker_generator);
+            gv_rng_destroy(g);
+        gv_rng_destroy(worker_generator);
         for (int i = 0; i < 2; i++) {
             if (random_ready[i])
                 cudaEventDestroy(random_ready[i]);
@@ -760,6 +751,7 @@ struct Solver {
 
         GV_CHECK_CUDA(cudaMemsetAsync(d_fill.ptr, 0, d_fill.bytes, sample_stream));
         GV_CHECK_CUDA(cudaMemsetAsync(d_last_walk.ptr, 0, sizeof(unsigned long long), sample_stream));
+        GV_CHECK_ABI(gv_rng_save(sampler_generators[sampler_id], d_rng_snapshot.ptr, sample_stream));
         std::vector<unsigned long long> fill(num_block, 0);
         uint64_t buffers = 0, walks_done = 0;
         bool complete = false;
@@ -778,10 +770,9 @@ struct Solver {
                                                                           uint64_t(estimate * 0.97 / walks_per_buffer)));
             // refill: the next kRandBatchSize doubles of this sampler's stream per buffer
             // (solver.h:1015-1016,1028-1031), same call size as the reference
-            for (uint64_t j = 0; j < span; j++)
-                GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
-                                                            d_sampler_random.as<double>() + j * kRandBatchSize,
-                                                            kRandBatchSize));
+            GV_CHECK_ABI(gv_rng_generate(sampler_generators[sampler_id], d_sampler_random.as<double>(),
+                                         span * uint64_t(kRandBatchSize), sample_stream));
+            stat_launches++;
             buffers += span;
             const uint64_t in_span = span * walks_per_buffer;
             uint64_t done_in_span = 0;
@@ -856,20 +847,18 @@ struct Solver {
         const uint64_t executed = (last_walk / walk_batch + 1) * walk_batch;
         const uint64_t needed_buffers = (executed - 1) / walks_per_buffer + 1;
         for (; buffers < needed_buffers; buffers++)
-            GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
-                                                        d_sampler_random.as<double>(), kRandBatchSize));
+            GV_CHECK_ABI(gv_rng_generate(sampler_generators[sampler_id], d_sampler_random.as<double>(), kRandBatchSize,
+                                         sample_stream));
         if (buffers > needed_buffers) {
             // a multi-buffer span overshot (a block filled faster than its 1 / num_block share allows --
-            // not expected): rebuild the generator and replay the stream up to where the reference stands
+            // not expected): rewind the stream to the start of this call and replay what the reference consumed
             if (log_enabled())
-                fprintf(stderr, "sampler %d: over-generated %llu refill buffers, replaying the stream\n", sampler_id,
+                fprintf(stderr, "sampler %d: over-generated %llu refill buffers, rewinding the stream\n", sampler_id,
                         (unsigned long long)(buffers - needed_buffers));
-            GV_CHECK_CURAND(curandSetPseudoRandomGeneratorSeed(sampler_generators[sampler_id],
-                                                               sampler_seeds[sampler_id]));
-            GV_CHECK_CURAND(curandSetGeneratorOffset(sampler_generators[sampler_id], 0));
-            for (uint64_t j = 0; j < sampler_buffers[sampler_id] + needed_buffers; j++)
-                GV_CHECK_CURAND(curandGenerateUniformDouble(sampler_generators[sampler_id],
-                                                            d_sampler_random.as<double>(), kRandBatchSize));
+            GV_CHECK_ABI(gv_rng_restore(sampler_generators[sampler_id], d_rng_snapshot.ptr, sample_stream));
+            for (uint64_t j = 0; j < needed_buffers; j++)
+                GV_CHECK_ABI(gv_rng_generate(sampler_generators[sampler_id], d_sampler_random.as<double>(),
+                                             kRandBatchSize, sample_stream));
             buffers = needed_buffers;
         }
         sampler_buffers[sampler_id] += needed_buffers;
@@ -1137,9 +1126,10 @@ struct Solver {
                 // negatives: one curandGenerateUniformDouble(2 * B * k) per batch, like train_batch (solver.h:1536)
                 if (num_negative > 0) {
                     GV_CHECK_CUDA(cudaStreamWaitEvent(random_stream, random_free[buffer], 0));
-                    for (int j = 0; j < count; j++)
-                        GV_CHECK_CURAND(curandGenerateUniformDouble(
-                            worker_generator, d_random[buffer].as<double>() + j * per_batch_random, per_batch_random));
+                    // (the stream is positional: one call for the chunk == one call per batch)
+                    GV_CHECK_ABI(gv_rng_generate(worker_generator, d_random[buffer].as<double>(),
+                                                 uint64_t(count) * per_batch_random, random_stream));
+                    stat_launches++;
                     GV_CHECK_CUDA(cudaEventRecord(random_ready[buffer], random_stream));
                     GV_CHECK_CUDA(cudaStreamWaitEvent(work_stream, random_ready[buffer], 0));
                 }

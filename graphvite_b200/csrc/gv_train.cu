@@ -449,9 +449,13 @@ __device__ __forceinline__ float process_sample(SampleRows<DIM, K> &cur, SampleR
         backward<DIM, GV_OPT_SGD>(p.optimizer, lr, gradient, weight, cur.v, cur.c[s], unused, unused, unused, unused);
         store_row<DIM>(cur.c[s], p.context + size_t(cur.tail[s]) * DIM, lane);
     }
-    store_row<DIM>(cur.v, p.vertex + size_t(cur.head) * DIM, lane);
+    // consecutive samples of one walk often share the head (DeepWalk / node2vec: k = 1..augmentation_step
+    // with shuffle_base 1): the row is carried in registers and written once at the end of the run
+    const bool same_head = has_next && next.head == cur.head;
+    if (!same_head)
+        store_row<DIM>(cur.v, p.vertex + size_t(cur.head) * DIM, lane);
     if (has_next) {  // forward what the next sample requested before these stores were issued
-        if (next.head == cur.head)
+        if (same_head)
             next.v = cur.v;
 #pragma unroll
         for (int s = 0; s <= K; s++)
@@ -584,6 +588,9 @@ __global__ void __launch_bounds__(kBlockThreads) predict_kernel(const float *ver
 // here by the launch granularity (L1 is invalidated between launches).
 static uint32_t g_hot_rows = getenv("GV_HOT_ROWS") ? uint32_t(atol(getenv("GV_HOT_ROWS"))) : 128;
 static int g_kernel_flags = getenv("GV_KERNEL_FLAGS") ? atoi(getenv("GV_KERNEL_FLAGS")) : 0;
+// resident train CTAs per SM (0 = as many as fit).  One less than the maximum leaves registers and
+// thread slots for the samplers' kernels, which otherwise only run between train launches.
+static int g_blocks_per_sm = getenv("GV_TRAIN_BLOCKS_PER_SM") ? atoi(getenv("GV_TRAIN_BLOCKS_PER_SM")) : 0;
 
 // -----------------------------------------------------------------------------
 // launch helpers
@@ -613,6 +620,8 @@ static int launch_train(void (*kernel)(const TrainParams), const TrainParams &p,
     if (num_warps <= 0) {
         int per_sm = 0;
         GV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, shared_bytes));
+        if (g_blocks_per_sm > 0 && per_sm > g_blocks_per_sm)
+            per_sm = g_blocks_per_sm;
         if (per_sm < 1)
             per_sm = 1;
         blocks = device_sm_count() * per_sm;  // persistent: exactly one resident wave
@@ -727,6 +736,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_hot_rows = value < 0 ? 0u : uint32_t(value);
     else if (key == "kernel_flags")
         g_kernel_flags = int(value);
+    else if (key == "train_blocks_per_sm")
+        g_blocks_per_sm = int(value);
     else
         return fail("unknown tunable `" + key + "`");
     return 0;

@@ -103,6 +103,20 @@ int gv_cuda_train_block(const gv_matrices_t *matrices, const uint32_t *pool, uin
                         const float *lr_per_batch, uint32_t batch_size, float negative_weight,
                         float *loss_per_sample, float *loss_per_batch, int num_warps, void *stream);
 
+/* The reference's random stream: cuRAND XORWOW uniform doubles exactly as
+ * curandCreateGenerator(CURAND_RNG_PSEUDO_DEFAULT) + curandSetPseudoRandomGeneratorSeed(seed) +
+ * curandGenerateUniformDouble produce them (core/solver.h:950-953,966,1247-1250,1536), generated by
+ * our own kernel: stream position n = the (n / 4096)-th double of XORWOW subsequence n % 4096.
+ * Consecutive gv_rng_generate calls continue the stream; save / restore snapshot it on the device. */
+typedef struct gv_rng gv_rng_t;
+gv_rng_t *gv_rng_create(unsigned long long seed, void *stream);
+void gv_rng_destroy(gv_rng_t *rng);
+int gv_rng_generate(gv_rng_t *rng, double *out, uint64_t n, void *stream);
+uint64_t gv_rng_position(const gv_rng_t *rng);
+size_t gv_rng_state_bytes(void);
+int gv_rng_save(const gv_rng_t *rng, void *snapshot, void *stream);
+int gv_rng_restore(gv_rng_t *rng, const void *snapshot, void *stream);
+
 /* Device-layer tunables: "hot_rows" = rows with a local id below this value are read through L1
  * (default 128; rows are in degree order, so these are the hubs), "kernel_flags" = experiment bits. */
 int gv_cuda_set_tunable(const char *name, long value);

@@ -171,3 +171,49 @@ def test_move_rows_round_trip():
     expected = np.zeros_like(matrix)
     expected[ids] = matrix[ids]
     np.testing.assert_array_equal(d_back.cpu().numpy(), expected)
+
+
+def test_rng_reproduces_curand_stream(golden_dir):
+    """gv_rng (our XORWOW kernel) == cuRAND's device generator (golden from the reference harness) ==
+    cuRAND's host generator (oracle), for any call split; snapshots rewind it exactly."""
+    import ctypes
+    import torch
+    from graphvite_b200 import _lib
+    from gpu_util import stream_pointer
+    lib = _lib.lib
+    golden = np.load(golden_dir + "/curand.npz")
+
+    def generate(rng, n):
+        out = torch.zeros(n, dtype=torch.float64, device="cuda")
+        _lib.check(lib.gv_rng_generate(rng, out.data_ptr(), n, stream_pointer()))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    rng = lib.gv_rng_create(int(golden["seeds"][0]), stream_pointer())
+    assert rng
+    small = np.concatenate([generate(rng, int(n)) for n in golden["small_chunks"]])
+    np.testing.assert_array_equal(small, golden["small"])  # device cuRAND, same call sizes
+    assert lib.gv_rng_position(rng) == len(small)
+    lib.gv_rng_destroy(rng)
+
+    seed = int(golden["big_seed"])
+    rng = lib.gv_rng_create(seed, stream_pointer())
+    first = generate(rng, 5000000)
+    snapshot = torch.zeros(lib.gv_rng_state_bytes(), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.gv_rng_save(rng, snapshot.data_ptr(), stream_pointer()))
+    second = generate(rng, 5000000)
+    np.testing.assert_array_equal(first[:8192], golden["big_head"])
+    np.testing.assert_array_equal(np.r_[first[-2048:], second[:2048]], golden["big_mid"])
+    np.testing.assert_array_equal(second[-4096:], golden["big_tail"])
+    # odd splits of the same stretch, after rewinding
+    _lib.check(lib.gv_rng_restore(rng, snapshot.data_ptr(), stream_pointer()))
+    assert lib.gv_rng_position(rng) == 5000000
+    pieces = [generate(rng, n) for n in (1, 4095, 4097, 123457, 5000000 - 1 - 4095 - 4097 - 123457)]
+    np.testing.assert_array_equal(np.concatenate(pieces), second)
+    lib.gv_rng_destroy(rng)
+    # host cuRAND (the oracle's generator) for a fresh seed
+    expected = O.curand_uniform_double(987654321, [100000])
+    rng = lib.gv_rng_create(987654321, stream_pointer())
+    np.testing.assert_array_equal(generate(rng, 100000), expected)
+    assert expected.min() > 0 and expected.max() <= 1
+    lib.gv_rng_destroy(rng)

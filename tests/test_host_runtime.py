@@ -205,3 +205,25 @@ def test_yaml_config_loading(tmp_path):
     assert loaded["build"]["num_partition"] == auto and loaded["resource"]["dim"] == 128
     args = cmd.get_parser().parse_args(["run", str(path), "--epoch", "3", "--no-eval"])
     assert args.epoch == 3 and args.eval is False
+
+
+def test_node_classification_on_separable_embeddings():
+    """GraphApplication.node_classification (application.py:293-351): F1 == 1 when the classes are
+    linearly separable; unknown node names are dropped like name_map does"""
+    from graphvite_b200.application import GraphApplication
+
+    class FakeGraph(object):
+        name2id = {str(i): i for i in range(200)}
+
+    class FakeSolver(object):
+        rng = np.random.RandomState(0)
+        centers = rng.randn(4, 16) * 3
+        cls = rng.randint(0, 4, 200)
+        vertex_embeddings = (centers[cls] + 0.3 * rng.randn(200, 16)).astype(np.float32)
+
+    app = GraphApplication.__new__(GraphApplication)
+    app.graph, app.solver = FakeGraph(), FakeSolver()
+    X = [str(i) for i in range(200)] + ["unknown"]
+    Y = ["c%d" % c for c in FakeSolver.cls] + ["c0"]
+    result = app.node_classification(X=X, Y=Y, portions=(0.2,), times=2, patience=20)
+    assert result["macro-F1@20%"] > 0.95 and result["micro-F1@20%"] > 0.95
