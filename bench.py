@@ -184,7 +184,11 @@ def run_ours(args, cfg):
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": seconds / args.steps * 1e3, "roofline_gbs": achieved,
-                              "frac": achieved / peak, "gpu_launches": launches, "note": "profiling run, no e2e"}))
+                              "frac": achieved / peak, "gpu_launches": launches, "note": "profiling run, no e2e"}),
+                  flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # end to end through the public API: host graph + host embeddings in, host embeddings out
     del solver

@@ -295,8 +295,11 @@ struct Solver {
     // sampler scratch
     DeviceArray d_sampler_random, d_chains, d_fill, d_last_walk, d_fill_scratch;
     // worker scratch
-    DeviceArray d_random[2], d_lr, d_loss, d_negatives_out;
-    cudaEvent_t random_ready[2] = {nullptr, nullptr}, random_free[2] = {nullptr, nullptr};
+    // negatives' randoms are generated kRandomBuffers chunks ahead on a high-priority stream, so the
+    // (tiny) generator kernel slips into SM slots freed between train launches instead of delaying one
+    static const int kRandomBuffers = 4;
+    DeviceArray d_random[kRandomBuffers], d_lr, d_loss, d_negatives_out;
+    cudaEvent_t random_ready[kRandomBuffers] = {}, random_free[kRandomBuffers] = {};
     int chunk_batches = 1;
     bool capture_negatives = false;
     int train_num_warps = 0;  // 0 = persistent grid; 1 = single warp (sequential, reproducible; tests)
@@ -350,8 +353,9 @@ struct Solver {
             int least = 0, greatest = 0;
             GV_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
             GV_CHECK_CUDA(cudaStreamCreateWithPriority(&sample_stream, cudaStreamNonBlocking, greatest));
+            GV_CHECK_CUDA(cudaStreamCreateWithPriority(&random_stream, cudaStreamNonBlocking, greatest));
         }
-        GV_CHECK_CUDA(cudaStreamCreateWithFlags(&random_stream, cudaStreamNonBlocking));
+
         // the reference's cuRAND XORWOW streams (solver.h:950-953, 1247-1250), from our own generator
         for (int i = 0; i < num_sampler; i++) {
             gv_rng_t *generator = gv_rng_create(sampler_seeds[i], sample_stream);
@@ -362,7 +366,7 @@ struct Solver {
         worker_generator = gv_rng_create(worker_seeds[rank], random_stream);
         require(worker_generator != nullptr, gv_last_error());
         d_rng_snapshot.allocate(gv_rng_state_bytes());
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kRandomBuffers; i++) {
             GV_CHECK_CUDA(cudaEventCreateWithFlags(&random_ready[i], cudaEventDisableTiming));
             GV_CHECK_CUDA(cudaEventCreateWithFlags(&random_free[i], cudaEventDisableTiming));
         }
@@ -377,7 +381,7 @@ struct Solver {
         for (auto g : sampler_generators)
             gv_rng_destroy(g);
         gv_rng_destroy(worker_generator);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kRandomBuffers; i++) {
             if (random_ready[i])
                 cudaEventDestroy(random_ready[i]);
             if (random_free[i])
@@ -583,7 +587,7 @@ struct Solver {
                                                                                     std::max<uint64_t>(1, per_batch_random))));
         if (getenv("GV_CHUNK_BATCHES"))  // experiment: launch granularity in batches
             chunk_batches = std::max(1, std::min(episode_size, atoi(getenv("GV_CHUNK_BATCHES"))));
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < kRandomBuffers; i++)
             d_random[i].allocate(std::max<uint64_t>(16, per_batch_random * chunk_batches));
         d_lr.allocate(size_t(episode_size) * sizeof(float));
         d_loss.allocate(size_t(episode_size) * sizeof(float));
@@ -1121,7 +1125,7 @@ struct Solver {
             GV_CHECK_CUDA(cudaMemcpyAsync(d_lr.ptr, lr.data(), episode_size * sizeof(float), cudaMemcpyHostToDevice,
                                           work_stream));
             GV_CHECK_CUDA(cudaMemsetAsync(d_loss.ptr, 0, episode_size * sizeof(float), work_stream));
-            for (int j0 = 0; j0 < episode_size; j0 += chunk_batches, buffer ^= 1) {
+            for (int j0 = 0; j0 < episode_size; j0 += chunk_batches, buffer = (buffer + 1) % kRandomBuffers) {
                 const int count = std::min(chunk_batches, episode_size - j0);
                 // negatives: one curandGenerateUniformDouble(2 * B * k) per batch, like train_batch (solver.h:1536)
                 if (num_negative > 0) {
@@ -1357,7 +1361,7 @@ struct Solver {
             pool_pointers[side].release();
         for (auto *a : {&d_offsets, &d_edge_u, &d_edge_v, &d_edge_prob, &d_edge_alias, &d_vertex_tables, &d_locations,
                         &d_sampler_random, &d_chains, &d_fill, &d_last_walk, &d_fill_scratch, &d_random[0],
-                        &d_random[1], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_edge_tables,
+                        &d_random[1], &d_random[2], &d_random[3], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_edge_tables,
                         &d_table_offsets})
             a->release();
         for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})

@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
         Row<DIM> v, vm1, vm2, c, cm1, cm2, c_next, cm1_next, cm2_next, v_ahead, c_ahead;
         uint32_t head = ids[0], tail = ids[1];
         if (kCross) {
-            load_row<DIM>(v_ahead, p.vertex + size_t(head) * DIM, lane, l1);
-            load_row<DIM>(c_ahead, p.context + size_t(tail) * DIM, lane, l1);
+            load_row<DIM>(v_ahead, p.vertex + size_t(head) * DIM, lane, l1 || head < p.hot_rows);
+            load_row<DIM>(c_ahead, p.context + size_t(tail) * DIM, lane, l1 || tail < p.hot_rows);
         }
         for (int t = 0; t < count; t++) {
             const uint32_t *sample = ids + t * stride;
@@ -290,15 +290,15 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                     load_row<DIM>(c_ahead, p.context + size_t(tail_ahead) * DIM, lane, l1 || tail_ahead < p.hot_rows);
                 }
             } else {
-                load_row<DIM>(v, p.vertex + head_offset, lane, l1);
-                load_row<DIM>(c, p.context + size_t(tail) * DIM, lane, l1);
+                load_row<DIM>(v, p.vertex + head_offset, lane, l1 || head < p.hot_rows);
+                load_row<DIM>(c, p.context + size_t(tail) * DIM, lane, l1 || tail < p.hot_rows);
                 if (NM >= 1) {
-                    load_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
-                    load_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
+                    load_row<DIM>(vm1, p.vertex_m1 + head_offset, lane, head < p.hot_rows);
+                    load_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane, tail < p.hot_rows);
                 }
                 if (NM >= 2) {
-                    load_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
-                    load_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
+                    load_row<DIM>(vm2, p.vertex_m2 + head_offset, lane, head < p.hot_rows);
+                    load_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane, tail < p.hot_rows);
                 }
                 if (more) {
                     head_ahead = sample[stride];
@@ -313,11 +313,11 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                 if (s < k) {
                     tail_next = sample[2 + s];
                     if (tail_next != tail) {
-                        load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane, l1);
+                        load_row<DIM>(c_next, p.context + size_t(tail_next) * DIM, lane, l1 || tail_next < p.hot_rows);
                         if (NM >= 1)
-                            load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane);
+                            load_row<DIM>(cm1_next, p.context_m1 + size_t(tail_next) * DIM, lane, tail_next < p.hot_rows);
                         if (NM >= 2)
-                            load_row<DIM>(cm2_next, p.context_m2 + size_t(tail_next) * DIM, lane);
+                            load_row<DIM>(cm2_next, p.context_m2 + size_t(tail_next) * DIM, lane, tail_next < p.hot_rows);
                     }
                 }
                 // forward (LINE::forward) and the gradient of the logistic loss, gpu/graph.cuh:73-88
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                 if (head_ahead == head)
                     v_ahead = v;  // same vertex again: continue from the updated registers
                 if (stale_ahead)  // program order: this load follows the store above in the same thread
-                    load_row<DIM>(c_ahead, p.context + size_t(tail_ahead) * DIM, lane, l1);
+                    load_row<DIM>(c_ahead, p.context + size_t(tail_ahead) * DIM, lane, l1 || tail_ahead < p.hot_rows);
             }
             head = head_ahead;
             tail = tail_ahead;
