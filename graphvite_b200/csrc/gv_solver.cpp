@@ -378,6 +378,7 @@ struct Solver {
         if (sampler_thread.joinable())
             sampler_thread.join();
         close_peers();
+        unpin_host();
         for (auto g : sampler_generators)
             gv_rng_destroy(g);
         gv_rng_destroy(worker_generator);
@@ -395,6 +396,13 @@ struct Solver {
             cudaStreamDestroy(sample_stream);
         if (random_stream)
             cudaStreamDestroy(random_stream);
+    }
+
+    std::vector<void *> pinned_host;
+    void unpin_host() {
+        for (void *pointer : pinned_host)
+            cudaHostUnregister(pointer);
+        pinned_host.clear();
     }
 
     int num_moment() const { return optimizer.num_moment(); }
@@ -493,8 +501,15 @@ struct Solver {
                 locations[partitions[i][j]] = {uint32_t(i), j};
 
         const size_t total = size_t(graph->num_vertex()) * dim;
+        unpin_host();
         vertex_host.assign(total, 0.f);
         context_host.assign(total, 0.f);
+        // page-lock the matrices behind the numpy views: upload and write-back run at PCIe speed
+        for (auto *m : {&vertex_host, &context_host})
+            if (cudaHostRegister(m->data(), m->size() * sizeof(float), cudaHostRegisterDefault) == cudaSuccess)
+                pinned_host.push_back(m->data());
+            else
+                cudaGetLastError();
         const int nm = num_moment();
         vertex_m1_host.assign(nm >= 1 ? total : 0, 0.f);
         context_m1_host.assign(nm >= 1 ? total : 0, 0.f);
@@ -615,12 +630,26 @@ struct Solver {
         // edge_table.build(graph->edge_weights), core/solver.h:255-256
         std::vector<float> edge_prob(m);
         std::vector<uint64_t> edge_alias(m);
-        build_alias<uint64_t>(graph->edge_w.data(), m, edge_prob.data(), edge_alias.data());
+        // Vose over all directed edges is sequential (0.1 s for 1e7 edges): overlap it with the uploads
+        // and with the per-vertex tables below
+        std::exception_ptr edge_error;
+        std::thread edge_builder([&]() {
+            try {
+                build_alias<uint64_t>(graph->edge_w.data(), m, edge_prob.data(), edge_alias.data());
+            } catch (...) {
+                edge_error = std::current_exception();
+            }
+        });
+        struct Joiner {
+            std::thread &thread;
+            ~Joiner() {
+                if (thread.joinable())
+                    thread.join();
+            }
+        } joiner{edge_builder};
         d_offsets.upload(graph->offsets, sample_stream);
         d_edge_u.upload(graph->edge_u, sample_stream);
         d_edge_v.upload(graph->edge_v, sample_stream);
-        d_edge_prob.upload(edge_prob, sample_stream);
-        d_edge_alias.upload(edge_alias, sample_stream);
         device_graph.num_vertex = graph->num_vertex();
         device_graph.num_edge = m;
         device_graph.offsets = d_offsets.as<uint64_t>();
@@ -665,6 +694,13 @@ struct Solver {
             d_vertex_tables.upload(tables, sample_stream);
             device_graph.vertex_tables = d_vertex_tables.as<gv_alias_entry_t>();
         }
+        edge_builder.join();
+        if (edge_error)
+            std::rethrow_exception(edge_error);
+        d_edge_prob.upload(edge_prob, sample_stream);
+        d_edge_alias.upload(edge_alias, sample_stream);
+        device_graph.edge_prob = d_edge_prob.as<float>();
+        device_graph.edge_alias = d_edge_alias.as<uint64_t>();
         if (sample_mode == 2)
             build_node2vec_tables();
         else {
@@ -1074,20 +1110,33 @@ struct Solver {
         if (log_enabled())
             fprintf(stderr, "%s\n", info().c_str());
         PhaseTimer phase;
+        // init_embeddings draws |V| * dim floats from the process-wide mt19937 (inherently sequential,
+        // 0.4 s at Youtube size): it runs on its own thread while the sampler tables are built and uploaded
+        std::thread initializer;
         if (!resume) {
-            init_embeddings();
-            for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
-                std::fill(m->begin(), m->end(), 0.f);
+            initializer = std::thread([this]() {
+                init_embeddings();
+                for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
+                    std::fill(m->begin(), m->end(), 0.f);
+            });
             batch_id = 0;
         }
         num_batch = int(batch_id + uint64_t(num_epoch) * graph->num_edge / batch_size);
-        phase.mark("init embeddings");
-        prepare_sampling();
-        phase.mark("sampler tables + graph upload");
+        try {
+            prepare_sampling();
+            phase.mark("sampler tables + graph upload");
+            build_negative_tables();
+            phase.mark("negative tables");
+        } catch (...) {
+            if (initializer.joinable())
+                initializer.join();
+            throw;
+        }
+        if (initializer.joinable())
+            initializer.join();
+        phase.mark("init embeddings (rest)");
         load_blocks();
         phase.mark("embedding upload");
-        build_negative_tables();
-        phase.mark("negative tables");
         if (capture_negatives)
             d_negatives_out.allocate(uint64_t(chunk_batches) * batch_size * std::max(1, num_negative) * 4);
         stat_positive = stat_kernel_seconds = stat_train_seconds = stat_sample_seconds = 0;
