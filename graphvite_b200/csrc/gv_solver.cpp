@@ -291,7 +291,8 @@ struct Solver {
     DeviceArray d_edge_tables, d_table_offsets;  // node2vec: one alias table per directed edge
     gv_device_graph_t device_graph;
     bool sampling_ready = false;
-    int sample_mode = 0;
+    int sample_mode = 0, tables_mode = -1;
+    float tables_p = 0, tables_q = 0;
     // sampler scratch
     DeviceArray d_sampler_random, d_chains, d_fill, d_last_walk, d_fill_scratch;
     // worker scratch
@@ -627,6 +628,15 @@ struct Solver {
             sample_mode = 2;
         const size_t m = graph->edge_u.size();
         require(m > 0, "The graph has no edges");
+        // The tables depend on the graph, the kind of walk and (node2vec) p, q only: a later train() call
+        // on the same build() -- e.g. train, evaluate, train(resume=True) -- reuses what is resident.
+        // (The reference rebuilds them in every call, instance/graph.cuh:680-721.)
+        const bool reusable = sampling_ready && tables_mode == sample_mode && (sample_mode != 2 || (tables_p == p && tables_q == q));
+        if (reusable) {
+            allocate_sampler_scratch();
+            return;
+        }
+        sampling_ready = false;
         // edge_table.build(graph->edge_weights), core/solver.h:255-256
         std::vector<float> edge_prob(m);
         std::vector<uint64_t> edge_alias(m);
@@ -707,6 +717,15 @@ struct Solver {
             d_edge_tables.release();
             d_table_offsets.release();
         }
+        tables_mode = sample_mode;
+        tables_p = p;
+        tables_q = q;
+        allocate_sampler_scratch();
+        sampling_ready = true;
+    }
+
+    // chains / histogram scratch / refill buffers of the samplers (depend on the walk length and P)
+    void allocate_sampler_scratch() {
         const int L = sample_mode == 0 ? 1 : random_walk_length;
         // per launch: at most walk_chunk walks per rank (chains <= 256 MB, histogram scratch <= 256 MB)
         walk_chunk = std::min<uint64_t>(uint64_t(1) << 20, (uint64_t(256) << 20) / (uint64_t(L + 1) * sizeof(gv_location_t)));
@@ -715,7 +734,6 @@ struct Solver {
         d_chains.allocate(walk_chunk * (L + 1) * sizeof(gv_location_t));
         d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(walk_chunk), num_partition));
         d_sampler_random.allocate(size_t(kSpanBuffers) * kRandBatchSize * sizeof(double));
-        sampling_ready = true;
     }
 
     // GraphSolver::build_edge_edge, instance/graph.cuh:656-677, on the device: one alias table per
