@@ -335,6 +335,18 @@ def run_reference(args, cfg):
     }), flush=True)
 
 
+def start_watchdog(seconds):
+    """A hung collective must not hang the box: give up loudly after `seconds`."""
+    def expire():
+        sys.stderr.write("bench.py: no result after %d s, aborting\n" % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+    timer = threading.Timer(seconds, expire)
+    timer.daemon = True
+    timer.start()
+    return timer
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -345,7 +357,10 @@ def main():
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     parser.add_argument("--partitions", type=int, default=0, help="num_partition (0 = auto; diagnosis only)")
+    parser.add_argument("--watchdog", type=int, default=1500, help="abort after this many seconds (0 = never)")
     args = parser.parse_args()
+    if args.watchdog > 0:
+        start_watchdog(args.watchdog)
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)

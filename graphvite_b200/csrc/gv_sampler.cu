@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(1024) fill_scan_kernel(const FillParams p, uin
 // publishes its per-block totals into every peer's inbox (peer stores + a system-scope fence + a
 // flag), waits for all W flags of the round and derives its base offsets.  Control region of a rank:
 //   inbox [2][W][num_block + 1] u64 (last slot: walk index that completed a block), flags [2][W] u64.
+constexpr unsigned long long kPeerTimeoutNs = 120ull * 1000 * 1000 * 1000;  // 2 minutes
+
 __device__ __forceinline__ unsigned long long *control_inbox(unsigned long long *control, int W, int num_block,
                                                              int parity, int rank) {
     return control + (size_t(parity) * W + rank) * (num_block + 1);
@@ -192,13 +194,32 @@ __global__ void __launch_bounds__(512) peer_gather_kernel(int rank, int W, int n
                                                           unsigned long long round_id, unsigned long long *control,
                                                           unsigned long long *fill, unsigned long long *bases,
                                                           unsigned long long *last_walk) {
+    // wait for every rank's flag, but never hang the GPU: after kPeerTimeoutNs the round is abandoned and
+    // *last_walk is set to the all-ones marker, which the host turns into an error
+    __shared__ int timed_out;
+    if (threadIdx.x == 0)
+        timed_out = 0;
+    __syncthreads();
     if (threadIdx.x < W) {
         volatile unsigned long long *flag = control_flag(control, W, num_block, parity, threadIdx.x);
-        while (*flag != round_id)
+        unsigned long long begin, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(begin));
+        while (*flag != round_id) {
             __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - begin > kPeerTimeoutNs) {
+                timed_out = 1;
+                break;
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
+    if (timed_out) {
+        if (threadIdx.x == 0)
+            *last_walk = ~0ull;
+        return;
+    }
     for (int b = threadIdx.x; b <= num_block; b += blockDim.x) {
         unsigned long long before = 0, all = 0, latest = 0;
         for (int r = 0; r < W; r++) {

@@ -884,6 +884,7 @@ struct Solver {
                 GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk),
                                               cudaMemcpyDeviceToHost, sample_stream));
                 GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+                require(last_walk != ~0ull, "a peer rank did not reach the sampler exchange within 2 minutes");
                 done_in_span += count;
                 walks_done += count;
                 complete = true;
@@ -898,6 +899,7 @@ struct Solver {
             GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk), cudaMemcpyDeviceToHost,
                                           sample_stream));
             GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+            require(last_walk != ~0ull, "a peer rank did not reach the sampler exchange within 2 minutes");
         }
         // The reference stops at the end of the batch of walks that completed the last block; a
         // batch that runs past the current buffer pulls one more refill (only possible when
@@ -940,7 +942,11 @@ struct Solver {
             // nobody may write into a pool that some rank is still training on: every rank gets here
             // only after it finished the previous episode, so a barrier over the ranks is enough
             peer_barrier(nullptr);
+            unsigned long long marker = 0;
+            GV_CHECK_CUDA(cudaMemcpyAsync(&marker, d_last_walk.ptr, sizeof(marker), cudaMemcpyDeviceToHost,
+                                          sample_stream));
             GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+            require(marker != ~0ull, "a peer rank did not reach the sampler barrier within 2 minutes");
         }
         cudaEvent_t begin, end;
         GV_CHECK_CUDA(cudaEventCreate(&begin));

@@ -1,0 +1,118 @@
+"""Kernel-level parity of the pool fill (gv_cuda_fill_pool, gv_cuda_fill_count / _scatter) against a
+sequential restatement of the reference's append loop (instance/graph.cuh:427-447), bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def sequential_fill(chains, P, L, aug, shuffle_base, pool_size, start, end, fill, pools):
+    """the reference loop: walk-major, j, then k; append to block [hp][tp] while its slice has room"""
+    num_walk = chains.shape[1]
+    last = -1
+    for w in range(num_walk):
+        for j in range(L):
+            for k in range(1, aug + 1):
+                if j + k > L:
+                    break
+                hp, hl = chains[j, w]
+                tp, tl = chains[j + k, w]
+                b = hp * P + tp
+                offset = start + fill[b]
+                fill[b] += 1
+                if offset < end:
+                    shuffled = offset % shuffle_base * (pool_size // shuffle_base) + offset // shuffle_base
+                    pools[b][shuffled] = (tl, hl)
+                    if offset + 1 == end:
+                        last = max(last, w)
+    return last
+
+
+@pytest.mark.parametrize("P,L,aug,shuffle_base", [(1, 5, 2, 2), (2, 6, 3, 3), (3, 4, 4, 1), (4, 7, 2, 2), (8, 5, 5, 5),
+                                                  (16, 3, 2, 1), (2, 1, 1, 1)])
+def test_fill_pool_matches_sequential_append(P, L, aug, shuffle_base):
+    import torch
+    from graphvite_b200 import _lib
+    from gpu_util import stream_pointer
+    lib = _lib.lib
+    rng = np.random.RandomState(P * 100 + L)
+    num_block = P * P
+    pool_size = 600 * shuffle_base
+    start, end = 60 * shuffle_base, 60 * shuffle_base + 400
+    expected = [np.full((pool_size, 2), 0xFFFFFFFF, dtype=np.uint32) for _ in range(num_block)]
+    fill = np.zeros(num_block, dtype=np.int64)
+    d_pools = [torch.full((pool_size, 2), -1, dtype=torch.int32, device="cuda") for _ in range(num_block)]
+    if P > 1:
+        d_pools[num_block - 1] = None  # a block owned by "another rank": counted, never written
+    pointers = torch.tensor([p.data_ptr() if p is not None else 0 for p in d_pools], dtype=torch.int64, device="cuda")
+    d_fill = torch.zeros(num_block, dtype=torch.int64, device="cuda")
+    d_last = torch.zeros(1, dtype=torch.int64, device="cuda")
+    params = _lib.FillParams(P, L, aug, shuffle_base, pool_size, start, end)
+    first_walk, last_expected = 0, 0
+    for call, num_walk in enumerate([257, 1, 1000, 33]):
+        chains = np.zeros((L + 1, num_walk, 2), dtype=np.uint32)
+        chains[:, :, 0] = rng.randint(0, P, (L + 1, num_walk))
+        chains[:, :, 1] = rng.randint(0, 1000, (L + 1, num_walk))
+        last = sequential_fill(chains, P, L, aug, shuffle_base, pool_size, start, end, fill, expected)
+        if last >= 0:
+            last_expected = max(last_expected, first_walk + last)
+        d_chains = torch.from_numpy(chains.view(np.int32)).cuda()
+        scratch = torch.zeros(lib.gv_cuda_fill_scratch_bytes(num_walk, P) + 16, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.gv_cuda_fill_pool(ctypes.byref(params), d_chains.data_ptr(), num_walk, first_walk,
+                                         pointers.data_ptr(), d_fill.data_ptr(), d_last.data_ptr(),
+                                         scratch.data_ptr(), stream_pointer()))
+        torch.cuda.synchronize()
+        first_walk += num_walk
+        np.testing.assert_array_equal(d_fill.cpu().numpy(), fill)
+    for b in range(num_block - (1 if P > 1 else 0)):
+        got = d_pools[b].cpu().numpy().view(np.uint32)
+        np.testing.assert_array_equal(got, expected[b], err_msg="block %d" % b)
+    assert int(d_last.item()) == last_expected
+
+
+def test_partitioned_fill_equals_single_rank():
+    """count / exchange-by-hand / scatter over 3 'ranks' gives the pools of one sequential pass"""
+    import torch
+    from graphvite_b200 import _lib
+    from gpu_util import stream_pointer
+    lib = _lib.lib
+    rng = np.random.RandomState(5)
+    P, L, aug, shuffle_base = 3, 6, 3, 3
+    num_block, pool_size = P * P, 900
+    start, end = 30, 630
+    num_walk = 700
+    chains = np.zeros((L + 1, num_walk, 2), dtype=np.uint32)
+    chains[:, :, 0] = rng.randint(0, P, (L + 1, num_walk))
+    chains[:, :, 1] = rng.randint(0, 5000, (L + 1, num_walk))
+    expected = [np.full((pool_size, 2), 0xFFFFFFFF, dtype=np.uint32) for _ in range(num_block)]
+    fill = np.zeros(num_block, dtype=np.int64)
+    sequential_fill(chains, P, L, aug, shuffle_base, pool_size, start, end, fill, expected)
+
+    d_pools = [torch.full((pool_size, 2), -1, dtype=torch.int32, device="cuda") for _ in range(num_block)]
+    pointers = torch.tensor([p.data_ptr() for p in d_pools], dtype=torch.int64, device="cuda")
+    params = _lib.FillParams(P, L, aug, shuffle_base, pool_size, start, end)
+    bounds = [0, 200, 201, 700]
+    totals, state = [], []
+    for r in range(3):
+        lo, hi = bounds[r], bounds[r + 1]
+        part = np.ascontiguousarray(chains[:, lo:hi])
+        d_chains = torch.from_numpy(part.view(np.int32)).cuda()
+        scratch = torch.zeros(lib.gv_cuda_fill_scratch_bytes(hi - lo, P) + 16, dtype=torch.uint8, device="cuda")
+        d_totals = torch.zeros(num_block, dtype=torch.int64, device="cuda")
+        _lib.check(lib.gv_cuda_fill_count(ctypes.byref(params), d_chains.data_ptr(), hi - lo, scratch.data_ptr(),
+                                          d_totals.data_ptr(), stream_pointer()))
+        torch.cuda.synchronize()
+        totals.append(d_totals.cpu().numpy())
+        state.append((d_chains, scratch, lo, hi))
+    np.testing.assert_array_equal(sum(totals), fill)
+    d_last = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for r in range(3):
+        d_chains, scratch, lo, hi = state[r]
+        bases = torch.from_numpy(sum(totals[:r], np.zeros(num_block, dtype=np.int64))).cuda()
+        _lib.check(lib.gv_cuda_fill_scatter(ctypes.byref(params), d_chains.data_ptr(), hi - lo, lo, pointers.data_ptr(),
+                                            bases.data_ptr(), d_last.data_ptr(), scratch.data_ptr(), stream_pointer()))
+    torch.cuda.synchronize()
+    for b in range(num_block):
+        np.testing.assert_array_equal(d_pools[b].cpu().numpy().view(np.uint32), expected[b], err_msg="block %d" % b)
