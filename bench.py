@@ -186,11 +186,13 @@ def run_ours(args, cfg):
             print(json.dumps({"value": value, "ms_per_step": seconds / args.steps * 1e3, "roofline_gbs": achieved,
                               "frac": achieved / peak, "gpu_launches": launches, "note": "profiling run, no e2e"}),
                   flush=True)
+        solver.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
     # end to end through the public API: host graph + host embeddings in, host embeddings out
+    solver.close()  # collective teardown (IPC importers close before exporters free)
     del solver
     gv2, graph2, solver2 = make_solver(cfg, path, rank, world, local_rank)
     per_episode = edges_per_step * world * (solver2.num_partition // world) ** 2 * world  # edges per episode
@@ -246,6 +248,7 @@ def run_ours(args, cfg):
                                       "sample": "unavailable: %s" % error}
     if rank == 0:
         print(json.dumps(result), flush=True)
+    solver2.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

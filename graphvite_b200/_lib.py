@@ -111,6 +111,7 @@ SIGNATURES = {
     "gv_solver_destroy": (None, [c_void_p]),
     "gv_solver_set_exchange": (c_int, [c_void_p, EXCHANGE_FN, c_void_p]),
     "gv_solver_set_host_allgather": (c_int, [c_void_p, HOST_ALLGATHER_FN, c_void_p]),
+    "gv_solver_release_peers": (c_int, [c_void_p]),
     "gv_solver_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "gv_solver_build": (c_int, [c_void_p, c_void_p, P(OptimizerDesc), c_int, c_int, c_int, c_int]),
     "gv_solver_train": (c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,

@@ -422,6 +422,8 @@ struct Solver {
             if (r != rank && peer_arenas[r])
                 cudaIpcCloseMemHandle(peer_arenas[r]);
         peer_arenas.clear();
+        if (partitioned_sampling)
+            built = false;  // the pool pointer tables referenced the peers: build() again before training
         partitioned_sampling = false;
     }
 
@@ -436,7 +438,9 @@ struct Solver {
         demand += uint64_t(2) * P * groups * episode * batch_size * 8;             // both sample pools
         demand += uint64_t(graph->log_u.size()) * (4 + 4 + 4 + 8 + 8);              // CSR + edge/vertex tables
         demand += uint64_t(graph->num_vertex()) * (8 + 8 + 8);                     // offsets, locations, negatives
-        demand += uint64_t(kRandBatchSize) * 8 + uint64_t(2) * 256 * 1024 * 1024;  // random buffers
+        demand += uint64_t(kSpanBuffers) * kRandBatchSize * 8;                     // samplers' refill buffers
+        demand += uint64_t(kRandomBuffers) * 16 * batch_size * std::max(1, num_negative) * 16;  // negatives' randoms
+        demand += uint64_t(2) * 256 * 1024 * 1024;                                 // walk chains + fill scratch
         demand += uint64_t(graph->num_vertex()) * dim * sizeof(float);             // staging for load / write-back
         return demand;
     }
@@ -1601,6 +1605,20 @@ int gv_solver_set_host_allgather(gv_solver_t *solver, gv_host_allgather_fn fn, v
     solver->solver->host_allgather_fn = fn;
     solver->solver->host_allgather_ctx = ctx;
     return 0;
+}
+
+// Unmap the other ranks' pool arenas.  CUDA requires every importer of an IPC allocation to close it
+// before the exporter frees it, so a multi-rank teardown is: release_peers on every rank, a barrier,
+// then destroy / clear / rebuild.
+int gv_solver_release_peers(gv_solver_t *solver) {
+    GV_TRY
+    Solver &s = *solver->solver;
+    if (s.training)
+        throw std::runtime_error("release_peers() during training");
+    cudaSetDevice(s.device);
+    s.close_peers();
+    return 0;
+    GV_CATCH(-1)
 }
 
 int gv_solver_set_option(gv_solver_t *solver, const char *name, int value) {

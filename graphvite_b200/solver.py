@@ -36,6 +36,7 @@ class GraphSolver(object):
         if not self._handle:
             raise _lib.GVError(_lib.last_error())
         self.dim = dim
+        self._world_size = int(world_size)
         self._graph = None       # the solver borrows the graph (core/solver.h:289): keep it alive
         self._optimizer = None
         self._descriptor = None  # keeps the ctypes schedule callback alive
@@ -45,6 +46,19 @@ class GraphSolver(object):
             from . import distributed
             device = torch.device("cuda", device_ids[0] if device_ids else torch.cuda.current_device())
             distributed.attach(self, device)
+
+    def close(self):
+        """Free the solver now.  With world_size > 1 this is a COLLECTIVE call (every rank, same order):
+        the ranks first unmap each other's sample pools, synchronise, and only then free their own."""
+        handle, self._handle = getattr(self, "_handle", None), None
+        if not handle:
+            return
+        if self._world_size > 1:
+            import torch.distributed as dist
+            lib.gv_solver_release_peers(handle)
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier()
+        lib.gv_solver_destroy(handle)
 
     def __del__(self):
         handle, self._handle = getattr(self, "_handle", None), None
@@ -59,6 +73,11 @@ class GraphSolver(object):
             raise TypeError("build(): incompatible function arguments (graph must be a Graph)")
         optimizer = as_optimizer(optimizer)
         descriptor = optimizer._descriptor()
+        if self._world_size > 1 and self._graph is not None:
+            # rebuilding frees the sample pools other ranks have mapped: unmap everywhere first
+            import torch.distributed as dist
+            _lib.check(lib.gv_solver_release_peers(self._handle))
+            dist.barrier()
         _lib.check(lib.gv_solver_build(self._handle, graph._handle, ctypes.byref(descriptor), int(num_partition),
                                        int(num_negative), int(batch_size), int(episode_size)))
         self._graph, self._optimizer, self._descriptor = graph, optimizer, descriptor

@@ -284,6 +284,10 @@ int gv_solver_set_exchange(gv_solver_t *solver, gv_exchange_fn fn, void *ctx);
  * over NVLink.  recv holds world_size * bytes.  Without it every rank samples all blocks itself. */
 typedef int (*gv_host_allgather_fn)(const void *send, void *recv, uint64_t bytes, void *ctx);
 int gv_solver_set_host_allgather(gv_solver_t *solver, gv_host_allgather_fn fn, void *ctx);
+/* Unmap the peers' arenas (collective teardown: every rank calls this, then a barrier, then
+ * gv_solver_destroy / gv_solver_build; CUDA IPC memory must be closed by all importers before the
+ * exporter frees it).  The solver needs build() again before it can train. */
+int gv_solver_release_peers(gv_solver_t *solver);
 
 /* SolverMixin::build (core/solver.h:287-466); num_partition / episode_size 0 = auto */
 int gv_solver_build(gv_solver_t *solver, gv_graph_t *graph, const gv_optimizer_t *optimizer, int num_partition,

@@ -71,6 +71,7 @@ def main():
     # every rank ends with the complete matrices
     np.testing.assert_allclose(solver.vertex_embeddings, osolver.embeddings(0), rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(solver.context_embeddings, osolver.embeddings(1), rtol=1e-3, atol=1e-5)
+    solver.close()
     dist.barrier()
     print("rank %d ok: %d episodes, %d partitions" % (rank, episodes, num_partition), flush=True)
     dist.destroy_process_group()
