@@ -1,6 +1,8 @@
 """Optimizers -- mirrors graphvite.optimizer (reference python/graphvite/optimizer.py and the
 pybind classes in include/bind.h:757-999, whose C++ definitions are include/core/optimizer.h:42-319).
 """
+from numpy import float32 as _f32
+
 from . import _lib
 from .base import auto
 
@@ -22,7 +24,9 @@ class LRSchedule(object):
                 raise ValueError("Invalid schedule `%s`" % type)
             self.type = type
             if type == "linear":
-                self.schedule_function = lambda batch_id, num_batch: max(1 - float(batch_id) / num_batch, 1e-4)
+                # single precision like LRSchedule::linear_schedule (core/optimizer.h:77-79)
+                self.schedule_function = lambda batch_id, num_batch: float(
+                    max(_f32(1) - _f32(batch_id) / _f32(num_batch), _f32(1e-4)))
             else:
                 self.schedule_function = lambda batch_id, num_batch: 1
 
