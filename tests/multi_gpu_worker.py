@@ -1,4 +1,4 @@
-"""Worker of tests/test_gpu_multi.py: one rank of a world_size-N GraphSolver on the toy graph in
+"""Worker of tests/test_gpu_w_multi.py: one rank of a world_size-N GraphSolver on the toy graph in
 single-warp (sequential) mode, checked against the oracle emulating N workers."""
 import os
 import sys
