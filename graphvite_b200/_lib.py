@@ -106,6 +106,23 @@ SIGNATURES = {
     "gv_graph_flatten": (c_uint64, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gv_graph_info": (c_int, [c_void_p, c_char_p, c_size_t]),
     "gv_alias_build": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p]),
+    # knowledge graph
+    "gv_kgraph_create": (c_void_p, []),
+    "gv_kgraph_destroy": (None, [c_void_p]),
+    "gv_kgraph_load_file": (c_int, [c_void_p, c_char_p, c_int, c_char_p, c_char_p]),
+    "gv_kgraph_load_triplets": (c_int, [c_void_p, P(c_char_p), P(c_char_p), P(c_char_p), P(c_float), c_uint64,
+                                        c_int]),
+    "gv_kgraph_save": (c_int, [c_void_p, c_char_p, c_int]),
+    "gv_kgraph_num_vertex": (c_uint64, [c_void_p]),
+    "gv_kgraph_num_edge": (c_uint64, [c_void_p]),
+    "gv_kgraph_num_relation": (c_uint64, [c_void_p]),
+    "gv_kgraph_normalization": (c_int, [c_void_p]),
+    "gv_kgraph_id2entity": (c_char_p, [c_void_p, c_uint64]),
+    "gv_kgraph_id2relation": (c_char_p, [c_void_p, c_uint64]),
+    "gv_kgraph_entity2id": (c_int64, [c_void_p, c_char_p]),
+    "gv_kgraph_relation2id": (c_int64, [c_void_p, c_char_p]),
+    "gv_kgraph_flatten": (c_uint64, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gv_kgraph_info": (c_int, [c_void_p, c_char_p, c_size_t]),
     # solver
     "gv_solver_create": (c_void_p, [c_int, P(c_int), c_int, c_int, c_uint64, c_int, c_int]),
     "gv_solver_destroy": (None, [c_void_p]),

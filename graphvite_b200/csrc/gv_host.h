@@ -48,6 +48,40 @@ struct Graph {
     std::string info() const;
 };
 
+// graphvite::KnowledgeGraph<uint32> (reference include/instance/knowledge_graph.cuh:67-284)
+struct KnowledgeGraph {
+    std::unordered_map<std::string, uint32_t> entity2id, relation2id;
+    std::vector<std::string> id2entity, id2relation;
+    std::vector<float> vertex_weights;  // summed weight of the triplets an entity heads
+    std::vector<uint32_t> degrees;      // number of triplets an entity heads
+    uint64_t num_edge = 0;
+    bool normalization = false;
+
+    // append-only triplet log in insertion order
+    std::vector<uint32_t> log_h, log_t, log_r;
+    std::vector<float> log_w;
+    // flatten(): CSR by head entity, insertion order inside an entity
+    bool flattened = false;
+    std::vector<uint64_t> offsets;  // [num_vertex + 1]
+    std::vector<uint32_t> edge_h, edge_t, edge_r;
+    std::vector<float> edge_w;
+
+    uint32_t num_vertex() const { return uint32_t(id2entity.size()); }
+    uint32_t num_relation() const { return uint32_t(id2relation.size()); }
+    void clear();
+    uint32_t intern_entity(const std::string &name);
+    uint32_t intern_relation(const std::string &name);
+    void add_edge(const std::string &h_name, const std::string &r_name, const std::string &t_name, float w);
+    void flatten();
+    void normalize();
+    void load_file(const char *file_name, bool normalized, const char *delimiters, const char *comment);
+    void load_triplets(const char *const *h_names, const char *const *r_names, const char *const *t_names,
+                       const float *weights, uint64_t count, bool normalized);
+    void save(const char *file_name, bool anonymous);
+    std::string info() const;
+};
+
 }  // namespace gv
 
 gv::Graph &gv_graph_ref(gv_graph_t *graph);
+gv::KnowledgeGraph &gv_kgraph_ref(gv_kgraph_t *graph);

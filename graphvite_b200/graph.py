@@ -1,5 +1,6 @@
 """Graphs -- mirrors graphvite.graph.Graph (reference include/bind.h:109-187 over
-include/instance/graph.cuh:62-277).  Only the node-embedding graph is in scope."""
+include/instance/graph.cuh:62-277) and graphvite.graph.KnowledgeGraph (bind.h:237-314 over
+include/instance/knowledge_graph.cuh:67-284)."""
 import ctypes
 
 from . import _lib
@@ -9,35 +10,37 @@ lib = _lib.lib
 
 
 class _NameMap(object):
-    """Read-only name -> id mapping backed by the native graph (bind.h:135)."""
+    """Read-only name -> id mapping backed by the native graph (bind.h:135,265-266)."""
 
-    def __init__(self, graph):
+    def __init__(self, graph, lookup=None, names="id2name"):
         self._graph = graph
+        self._lookup = lookup or lib.gv_graph_name2id
+        self._names = names
 
     def __getitem__(self, name):
-        index = lib.gv_graph_name2id(self._graph._handle, str(name).encode())
+        index = self._lookup(self._graph._handle, str(name).encode())
         if index < 0:
             raise KeyError(name)
         return index
 
     def __contains__(self, name):
-        return lib.gv_graph_name2id(self._graph._handle, str(name).encode()) >= 0
+        return self._lookup(self._graph._handle, str(name).encode()) >= 0
 
     def get(self, name, default=None):
-        index = lib.gv_graph_name2id(self._graph._handle, str(name).encode())
+        index = self._lookup(self._graph._handle, str(name).encode())
         return default if index < 0 else index
 
     def __len__(self):
-        return self._graph.num_vertex
+        return len(getattr(self._graph, self._names))
 
     def __iter__(self):
-        return iter(self._graph.id2name)
+        return iter(getattr(self._graph, self._names))
 
     def keys(self):
-        return self._graph.id2name
+        return getattr(self._graph, self._names)
 
     def items(self):
-        return [(name, i) for i, name in enumerate(self._graph.id2name)]
+        return [(name, i) for i, name in enumerate(getattr(self._graph, self._names))]
 
 
 class Graph(object):
@@ -131,4 +134,105 @@ class Graph(object):
         return buffer.value.decode()
 
 
-__all__ = ["Graph"]
+class KnowledgeGraph(object):
+    """KnowledgeGraph(index_type=dtype.uint32): knowledge graphs (triplets `head relation tail [weight]`)."""
+
+    def __init__(self, index_type=None):
+        index_type = cfg.index_type if index_type is None else index_type
+        if index_type != dtype.uint32:
+            raise ValueError("Can't find an instantiation of KnowledgeGraph with index_type = %s" % (index_type,))
+        self._handle = lib.gv_kgraph_create()
+        self._names = None
+
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            lib.gv_kgraph_destroy(handle)
+
+    # -- load overloads, bind.h:273-299 ---------------------------------------------------
+    def load(self, *args, **kwargs):
+        """load(file_name, normalization=False, delimiters=' \\t\\r\\n', comment='#')
+        load(triplet_list, normalization=False)
+        load(weighted_triplet_list, normalization=False)"""
+        self._names = None
+        names = ["file_name", "normalization", "delimiters", "comment"]
+        for alias in ("triplet_list", "weighted_triplet_list"):
+            if alias in kwargs:
+                kwargs["file_name"] = kwargs.pop(alias)
+        params = dict(zip(names, args))
+        for key, value in kwargs.items():
+            if key not in names or key in params:
+                raise TypeError("load(): incompatible function arguments")
+            params[key] = value
+        if "file_name" not in params or len(args) > len(names):
+            raise TypeError("load(): incompatible function arguments")
+        source = params["file_name"]
+        normalization = bool(params.get("normalization", False))
+        if isinstance(source, (str, bytes)):
+            delimiters = params.get("delimiters", " \t\r\n")
+            comment = params.get("comment", "#")
+            path = source if isinstance(source, bytes) else source.encode()
+            _lib.check(lib.gv_kgraph_load_file(self._handle, path, int(normalization), delimiters.encode(),
+                                               comment.encode()))
+            return
+        if "delimiters" in params or "comment" in params:
+            raise TypeError("load(): incompatible function arguments")
+        triplets = list(source)
+        count = len(triplets)
+        columns = [(ctypes.c_char_p * count)(*[str(t[i]).encode() for t in triplets]) for i in range(3)]
+        weights = None
+        if count and len(triplets[0]) == 4:
+            weights = (ctypes.c_float * count)(*[float(t[3]) for t in triplets])
+        _lib.check(lib.gv_kgraph_load_triplets(self._handle, columns[0], columns[1], columns[2], weights, count,
+                                               int(normalization)))
+
+    def save(self, file_name, anonymous=False):
+        """save(file_name, anonymous=False): save the graph in triplet-list format (head, tail, relation)."""
+        _lib.check(lib.gv_kgraph_save(self._handle, file_name.encode(), int(anonymous)))
+
+    # -- read-only attributes, bind.h:261-268 ------------------------------------------------
+    @property
+    def num_vertex(self):
+        return int(lib.gv_kgraph_num_vertex(self._handle))
+
+    @property
+    def num_edge(self):
+        return int(lib.gv_kgraph_num_edge(self._handle))
+
+    @property
+    def num_relation(self):
+        return int(lib.gv_kgraph_num_relation(self._handle))
+
+    @property
+    def normalization(self):
+        return bool(lib.gv_kgraph_normalization(self._handle))
+
+    def _name_lists(self):
+        if self._names is None or len(self._names[0]) != self.num_vertex or len(self._names[1]) != self.num_relation:
+            self._names = ([lib.gv_kgraph_id2entity(self._handle, i).decode() for i in range(self.num_vertex)],
+                           [lib.gv_kgraph_id2relation(self._handle, i).decode() for i in range(self.num_relation)])
+        return self._names
+
+    @property
+    def id2entity(self):
+        return self._name_lists()[0]
+
+    @property
+    def id2relation(self):
+        return self._name_lists()[1]
+
+    @property
+    def entity2id(self):
+        return _NameMap(self, lib.gv_kgraph_entity2id, "id2entity")
+
+    @property
+    def relation2id(self):
+        return _NameMap(self, lib.gv_kgraph_relation2id, "id2relation")
+
+    def __repr__(self):
+        buffer = ctypes.create_string_buffer(4096)
+        lib.gv_kgraph_info(self._handle, buffer, len(buffer))
+        return buffer.value.decode()
+
+
+__all__ = ["Graph", "KnowledgeGraph"]

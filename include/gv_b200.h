@@ -257,6 +257,37 @@ uint64_t gv_graph_flatten(gv_graph_t *graph, uint32_t *u, uint32_t *v, float *w,
 /* Graph::info() */
 int gv_graph_info(const gv_graph_t *graph, char *buffer, size_t capacity);
 
+/* ---- host runtime: KnowledgeGraph (instance/knowledge_graph.cuh:67-284, bind.h:237-314) ---------
+ * Entities and relations get ids in order of first appearance (head, relation, tail of each line). */
+
+typedef struct gv_kgraph gv_kgraph_t;
+
+gv_kgraph_t *gv_kgraph_create(void);
+void gv_kgraph_destroy(gv_kgraph_t *graph);
+/* KnowledgeGraph::load_file (instance/knowledge_graph.cuh:177-213): `head relation tail [weight]` per line */
+int gv_kgraph_load_file(gv_kgraph_t *graph, const char *file_name, int normalization, const char *delimiters,
+                        const char *comment);
+/* load_triplet_list / load_weighted_triplet_list (instance/knowledge_graph.cuh:220-260); weights may be NULL */
+int gv_kgraph_load_triplets(gv_kgraph_t *graph, const char *const *h_names, const char *const *r_names,
+                            const char *const *t_names, const float *weights, uint64_t num_triplet,
+                            int normalization);
+/* KnowledgeGraph::save (instance/knowledge_graph.cuh:267-283): columns head, tail, relation.  The
+ * reference takes the third column from the edge weight by mistake (:275); we write the relation. */
+int gv_kgraph_save(gv_kgraph_t *graph, const char *file_name, int anonymous);
+uint64_t gv_kgraph_num_vertex(const gv_kgraph_t *graph);
+uint64_t gv_kgraph_num_edge(const gv_kgraph_t *graph);
+uint64_t gv_kgraph_num_relation(const gv_kgraph_t *graph);
+int gv_kgraph_normalization(const gv_kgraph_t *graph);
+const char *gv_kgraph_id2entity(const gv_kgraph_t *graph, uint64_t id);
+const char *gv_kgraph_id2relation(const gv_kgraph_t *graph, uint64_t id);
+int64_t gv_kgraph_entity2id(const gv_kgraph_t *graph, const char *name);   /* -1 if absent */
+int64_t gv_kgraph_relation2id(const gv_kgraph_t *graph, const char *name); /* -1 if absent */
+/* GraphMixin::flatten (core/graph.h:87-101) with the relation attribute: returns #triplets; arrays may be NULL */
+uint64_t gv_kgraph_flatten(gv_kgraph_t *graph, uint32_t *h, uint32_t *t, uint32_t *r, float *w,
+                           uint64_t *flat_offsets, float *vertex_weights);
+/* KnowledgeGraph::info() */
+int gv_kgraph_info(const gv_kgraph_t *graph, char *buffer, size_t capacity);
+
 /* AliasTable::build (base/alias_table.cuh:84-128); alias is uint64 (Index = size_t) */
 int gv_alias_build(const float *weights, uint64_t n, float *prob, uint64_t *alias);
 
