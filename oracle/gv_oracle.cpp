@@ -26,115 +26,9 @@
 //   * libstdc++ std::mt19937 / uniform_int_distribution / uniform_real_distribution /
 //     std::sort / std::pow -- we call the very same library functions.
 // =============================================================================
-#include <curand.h>
-
-#include <algorithm>
-#include <climits>
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <memory>
-#include <queue>
-#include <random>
-#include <stdexcept>
-#include <string>
-#include <unordered_map>
-#include <unordered_set>
-#include <vector>
+#include "gv_oracle_common.h"
 
 namespace oracle {
-
-typedef uint32_t Index;
-
-// core/solver.h:51-57
-static const int kMaxPartition = 16;
-static const int kRandBatchSize = 5000000;
-static const int kSamplePerVertex = 175;
-static const int kMinEpisodeSample = 20000000;
-// instance/graph.cuh:56
-static const int kExpectedDegree = 1600;
-// util/common.h:28
-static const float kEpsilon = 1e-15f;
-
-static void fail(const std::string &msg) {
-    throw std::runtime_error(msg);
-}
-
-// -----------------------------------------------------------------------------
-// R1: process-wide engine, core/solver.h:50 (default-constructed mt19937)
-// -----------------------------------------------------------------------------
-static std::mt19937 &global_engine() {
-    static std::mt19937 seed;
-    return seed;
-}
-
-// -----------------------------------------------------------------------------
-// R2/R3: AliasTable, base/alias_table.cuh:84-152
-// -----------------------------------------------------------------------------
-template<class I>
-struct AliasTable {
-    std::vector<float> prob;
-    std::vector<I> alias;
-    I count = 0;
-
-    // base/alias_table.cuh:84-128
-    void build(const std::vector<float> &weights) {
-        count = weights.size();
-        if (count == 0)
-            fail("Invalid sampling distribution");
-        prob = weights;
-        alias.assign(count, 0);
-        double norm = 0;  // :92 "single precision may cause considerable truncation error"
-        for (size_t i = 0; i < count; i++)
-            norm += prob[i];
-        norm = norm / count;
-        for (size_t i = 0; i < count; i++)
-            prob[i] = float(double(prob[i]) / norm);  // float /= double
-
-        std::queue<I> large, little;
-        for (size_t i = 0; i < count; i++) {
-            if (prob[i] < 1)
-                little.push(i);
-            else
-                large.push(i);
-        }
-        while (!little.empty() && !large.empty()) {
-            I i = little.front(), j = large.front();
-            little.pop();
-            large.pop();
-            alias[i] = j;
-            float t = prob[i] + prob[j];
-            prob[j] = t - 1;
-            if (prob[j] < 1)
-                little.push(j);
-            else
-                large.push(j);
-        }
-        while (!little.empty()) {
-            I i = little.front();
-            little.pop();
-            alias[i] = i;
-        }
-        while (!large.empty()) {
-            I i = large.front();
-            large.pop();
-            alias[i] = i;
-        }
-    }
-
-    // base/alias_table.cuh:148-152.  cuRAND doubles lie in (0,1], so rand1*count can
-    // equal count (an out-of-bounds read in the reference); we clamp to count-1 and
-    // change no other outcome.
-    I sample(double rand1, double rand2) const {
-        I index = I(rand1 * count);
-        if (index >= count)
-            index = count - 1;
-        float p = float(rand2);
-        return p < prob[index] ? index : alias[index];
-    }
-};
 
 // -----------------------------------------------------------------------------
 // R5: Graph, instance/graph.cuh:62-277 and core/graph.h:87-101
@@ -253,23 +147,6 @@ struct Graph {
 };
 
 // -----------------------------------------------------------------------------
-// R6: partition, core/solver.h:873-887 (unstable std::sort: tie order is libstdc++'s)
-// -----------------------------------------------------------------------------
-static std::vector<std::vector<Index>> partition(const std::vector<float> &weights, int num_partition) {
-    std::vector<Index> indexes(weights.size());
-    for (Index i = 0; i < indexes.size(); i++)
-        indexes[i] = i;
-    std::sort(indexes.begin(), indexes.end(), [&weights](Index x, Index y) { return weights[x] > weights[y]; });
-    std::vector<std::vector<Index>> parts(num_partition);
-    for (Index i = 0; i < indexes.size(); i++) {
-        int part_id = i % (num_partition * 2);
-        part_id = std::min(part_id, num_partition * 2 - 1 - part_id);
-        parts[part_id].push_back(indexes[i]);
-    }
-    return parts;
-}
-
-// -----------------------------------------------------------------------------
 // R7: get_schedule, core/solver.h:519-575 (non-tied branch; GraphSolver never ties)
 // -----------------------------------------------------------------------------
 static std::vector<std::vector<std::pair<int, int>>> get_schedule(int num_partition, int num_worker) {
@@ -285,74 +162,6 @@ static std::vector<std::vector<std::pair<int, int>>> get_schedule(int num_partit
                 schedule.push_back(assignment);
             }
     return schedule;
-}
-
-// -----------------------------------------------------------------------------
-// R20: optimizer, core/optimizer.h:42-85,132-134,161-210
-// -----------------------------------------------------------------------------
-enum OptimizerType { kSGD = 0, kMomentum, kAdaGrad, kRMSprop, kAdam };
-enum ScheduleType { kConstant = 0, kLinear = 1 };
-
-struct Optimizer {
-    int type = kSGD;
-    int schedule = kLinear;
-    float init_lr = 0.025f, lr = 0.025f, weight_decay = 0.005f;
-    float a = 0, b = 0;  // momentum | alpha | beta1, beta2
-    float epsilon = 0;
-
-    int num_moment() const {
-        return type == kSGD ? 0 : (type == kAdam ? 2 : 1);
-    }
-    // optimizer.h:77-85,132-134
-    void apply_schedule(int batch_id, int num_batch) {
-        float factor = 1;
-        if (schedule == kLinear)
-            factor = std::max(1 - float(batch_id) / num_batch, 1e-4f);
-        lr = init_lr * factor;
-    }
-    // optimizer.h:161-164
-    float sgd_update(float parameter, float gradient, float weight) const {
-        return lr * weight * (gradient + weight_decay * parameter);
-    }
-    // optimizer.h:171-175
-    float momentum_update(float parameter, float gradient, float &moment1, float weight) const {
-        float regularized = weight * (gradient + weight_decay * parameter);
-        moment1 = a * moment1 + (1 - a) * regularized;
-        return lr * moment1;
-    }
-    // optimizer.h:182-186
-    float adagrad_update(float parameter, float gradient, float &moment1, float weight) const {
-        float regularized = weight * (gradient + weight_decay * parameter);
-        moment1 += regularized * regularized;
-        return lr * regularized / (sqrtf(moment1) + epsilon);
-    }
-    // optimizer.h:193-197
-    float rmsprop_update(float parameter, float gradient, float &moment1, float weight) const {
-        float regularized = weight * (gradient + weight_decay * parameter);
-        moment1 = a * moment1 + (1 - a) * regularized * regularized;
-        return lr * regularized / sqrtf(moment1 + epsilon);
-    }
-    // optimizer.h:203-210 (no bias correction)
-    float adam_update(float parameter, float gradient, float &moment1, float &moment2, float weight) const {
-        float regularized = weight * (gradient + weight_decay * parameter);
-        moment1 = a * moment1 + (1 - a) * regularized;
-        moment2 = b * moment2 + (1 - b) * regularized * regularized;
-        return lr * moment1 / (sqrtf(moment2) + epsilon);
-    }
-    float update(float parameter, float gradient, float *m1, float *m2, float weight) const {
-        switch (type) {
-            case kSGD: return sgd_update(parameter, gradient, weight);
-            case kMomentum: return momentum_update(parameter, gradient, *m1, weight);
-            case kAdaGrad: return adagrad_update(parameter, gradient, *m1, weight);
-            case kRMSprop: return rmsprop_update(parameter, gradient, *m1, weight);
-            default: return adam_update(parameter, gradient, *m1, *m2, weight);
-        }
-    }
-};
-
-// util/math.h:30-33
-static float sigmoid(float x) {
-    return x > 0 ? 1 / (1 + expf(-x)) : expf(x) / (expf(x) + 1);
 }
 
 // -----------------------------------------------------------------------------
@@ -425,27 +234,6 @@ static float train_sample(const Matrices &m, const Optimizer &opt, Index head_id
 }
 
 // -----------------------------------------------------------------------------
-// cuRAND host generator wrapper (XORWOW, same seeding calls as core/solver.h:950-953)
-// -----------------------------------------------------------------------------
-struct RandomStream {
-    curandGenerator_t generator = nullptr;
-    RandomStream(unsigned long long seed) {
-        if (curandCreateGeneratorHost(&generator, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
-            fail("curandCreateGeneratorHost failed");
-        curandSetPseudoRandomGeneratorSeed(generator, seed);
-    }
-    ~RandomStream() {
-        if (generator)
-            curandDestroyGenerator(generator);
-    }
-    RandomStream(const RandomStream &) = delete;
-    void generate(double *out, size_t n) {
-        if (curandGenerateUniformDouble(generator, out, n) != CURAND_STATUS_SUCCESS)
-            fail("curandGenerateUniformDouble failed");
-    }
-};
-
-// -----------------------------------------------------------------------------
 // Solver = SolverMixin + GraphSolver + samplers + workers, restated sequentially.
 // -----------------------------------------------------------------------------
 struct Solver {
@@ -480,6 +268,9 @@ struct Solver {
     std::vector<float> vertex_m1, context_m1, vertex_m2, context_m2;
 
     std::vector<float> last_loss;               // per-sample loss of the last trained batch
+    // each worker's loss buffer lives as long as the worker and is never cleared between blocks
+    // (core/solver.h:1326,1541-1549): the loss logged at a block's first batch is the previous block's last
+    std::vector<std::vector<float>> worker_loss;
     std::vector<Index> last_negative_batch;     // negatives of the last trained batch (local ids)
     std::vector<float> logged_loss;             // what the reference would LOG at each log point
     int sample_mode = 0;                        // 0 edge, 1 random walk, 2 biased random walk
@@ -549,6 +340,7 @@ struct Solver {
         vertex_m2.assign(nm >= 2 ? vertex_embeddings.size() : 0, 0);
         context_m2.assign(nm >= 2 ? vertex_embeddings.size() : 0, 0);
         // core/solver.h:960-967: each sampler generates its first buffer in build()
+        worker_loss.clear();
         sampler_random.resize(num_sampler);
         pool_id = 0;
     }
@@ -835,7 +627,11 @@ struct Solver {
         std::vector<double> random(size_t(batch_size) * num_negative * 2);
         std::vector<Index> targets(num_negative + 1);
         Optimizer opt = optimizer;
-        last_loss.assign(batch_size, 0);
+        if ((int)worker_loss.size() != num_worker)
+            worker_loss.assign(num_worker, std::vector<float>());
+        if ((int)worker_loss[worker_id].size() != batch_size)
+            worker_loss[worker_id].assign(batch_size, 0);
+        last_loss = worker_loss[worker_id];
         last_negative_batch.assign(size_t(batch_size) * num_negative, 0);
         for (int reuse = 0; reuse < positive_reuse; reuse++)
             for (int j = 0; j < episode_size; j++) {
@@ -860,6 +656,7 @@ struct Solver {
                                                 negative_weight);
                 }
             }
+        worker_loss[worker_id] = last_loss;
         scatter(v, vertex_embeddings, head_ids);
         scatter(c, context_embeddings, tail_ids);
         if (nm >= 1) {
@@ -909,6 +706,7 @@ struct Solver {
 using namespace oracle;
 
 static thread_local std::string g_error;
+void og_set_error(const std::string &message) { g_error = message; }  // used by gv_oracle_kg.cpp
 #define ORACLE_TRY try {
 #define ORACLE_CATCH(ret)            \
     }                                \

@@ -25,8 +25,8 @@ OPTIMIZERS = {
 
 def _build():
     path = os.path.join(ORACLE_DIR, "liboracle.so")
-    source = os.path.join(ORACLE_DIR, "gv_oracle.cpp")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(source):
+    sources = [os.path.join(ORACLE_DIR, name) for name in ("gv_oracle.cpp", "gv_oracle_kg.cpp", "gv_oracle_common.h")]
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(source) for source in sources):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
     return path
 
