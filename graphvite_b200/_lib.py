@@ -51,6 +51,13 @@ class DeviceGraph(ctypes.Structure):
                 ("vertex_tables", c_void_p), ("locations", c_void_p)]
 
 
+class KgMatrices(ctypes.Structure):
+    """gv_kg_matrices_t"""
+    _fields_ = [("dim", c_int), ("num_head", c_uint32), ("head", c_void_p), ("tail", c_void_p),
+                ("relation", c_void_p), ("head_m1", c_void_p), ("tail_m1", c_void_p), ("relation_m1", c_void_p),
+                ("head_m2", c_void_p), ("tail_m2", c_void_p), ("relation_m2", c_void_p)]
+
+
 class FillParams(ctypes.Structure):
     """gv_fill_params_t"""
     _fields_ = [("num_partition", c_int), ("walk_length", c_int), ("augmentation_step", c_int),
@@ -84,6 +91,10 @@ SIGNATURES = {
     "gv_cuda_fill_scratch_bytes": (c_size_t, [c_uint32, c_int]),
     "gv_cuda_fill_pool": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    "gv_cuda_kg_train_block": (c_int, [P(KgMatrices), c_int, c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_uint32,
+                                       c_void_p, P(DeviceOptimizer), c_void_p, c_uint32, c_float, c_float, c_float,
+                                       c_void_p, c_void_p, c_int, c_void_p]),
+    "gv_cuda_kg_predict": (c_int, [P(KgMatrices), c_int, c_void_p, c_uint64, c_float, c_void_p, c_void_p]),
     "gv_cuda_move_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p]),
     "gv_cuda_fill_count": (c_int, [P(FillParams), c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_fill_scatter": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,

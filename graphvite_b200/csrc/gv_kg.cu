@@ -1,0 +1,798 @@
+// =============================================================================
+// gv_kg.cu -- knowledge-graph embedding kernels, hand-written for sm_100a.
+//
+// Replaces gpu::knowledge_graph::train / train_1_moment / train_2_moment / predict (reference
+// include/instance/gpu/knowledge_graph.cuh:38-366) for the models TransE, DistMult, ComplEx, SimplE
+// and RotatE (include/instance/model/knowledge_graph.h:34-575) with the update rules of
+// include/core/optimizer.h:161-210 and the uniform negative draw of gpu::Sample
+// (include/base/alias_table.cuh:148-152,175-183 over the all-ones table of
+// instance/knowledge_graph.cuh:316-319).
+//
+// STATUS: compiles for sm_100a; NOT yet run on a GPU (written after the round's GPU budget was spent).
+//
+// Design.  One positive sample = 1 + k targets that share the relation row and, each, either the
+// positive head or the positive tail.  The reference walks the targets with one warp and
+// read-modify-writes head, tail and relation rows (plus moments) in global memory for every target:
+// ~7.8 MB per positive at d = 2048, k = 64 with Adam.  Here a *group* of dim / E threads (E = 2, 4 or 8
+// contiguous floats per thread; 256 threads at d = 2048) owns the sample and keeps the relation row,
+// the positive head row and the positive tail row -- with their moments -- in registers across all
+// targets; only the negative rows travel: read once for the self-adversarial normaliser, then one
+// read-modify-write with their moments.  That is ~3.6 MB per positive, with identical sequential
+// semantics inside the group (rows that alias a cached row are served from the registers; a target
+// whose head and tail are the same row of the same matrix takes an in-order slow path).  Groups race
+// against each other Hogwild-style exactly like the reference's warps.
+// The logit is a group-wide sum: butterfly shuffles inside a warp, one shared-memory hop (double
+// buffered, a single named barrier) across the warps of a group.
+// =============================================================================
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "gv_common.h"
+
+namespace gv {
+namespace device {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr float kEps = 1e-15f;  // util/common.h:28
+constexpr int kCtaThreads = 256;
+
+struct KgParams {
+    int dim;
+    uint32_t num_head;
+    int shared;  // head and tail blocks are the same memory
+    float *head, *tail, *relation;
+    float *head_m1, *tail_m1, *relation_m1;
+    float *head_m2, *tail_m2, *relation_m2;
+    const uint32_t *batch;  // [n][3] {relation, tail, head}
+    unsigned long long num_sample;
+    int num_negative;
+    const uint32_t *negatives;
+    const double *random;
+    uint32_t negative_count;
+    uint32_t *negatives_out;
+    gv_device_optimizer_t optimizer;
+    const float *lr_per_batch;
+    uint32_t batch_size;
+    float relation_lr_multiplier, margin_or_l3, temperature;
+    float *loss_per_sample, *loss_per_batch;
+};
+
+// ---- N contiguous floats per thread, moved with the widest aligned vector type ----------------
+template<int N>
+__device__ __forceinline__ void load_vec(float (&dst)[N], const float *src) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src) + i);
+            dst[i * 4] = v.x, dst[i * 4 + 1] = v.y, dst[i * 4 + 2] = v.z, dst[i * 4 + 3] = v.w;
+        }
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; i++) {
+            const float2 v = __ldcg(reinterpret_cast<const float2 *>(src) + i);
+            dst[i * 2] = v.x, dst[i * 2 + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            dst[i] = __ldcg(src + i);
+    }
+}
+
+template<int N>
+__device__ __forceinline__ void store_vec(float *dst, const float (&src)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; i++)
+            __stcg(reinterpret_cast<float4 *>(dst) + i,
+                   make_float4(src[i * 4], src[i * 4 + 1], src[i * 4 + 2], src[i * 4 + 3]));
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; i++)
+            __stcg(reinterpret_cast<float2 *>(dst) + i, make_float2(src[i * 2], src[i * 2 + 1]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            __stcg(dst + i, src[i]);
+    }
+}
+
+// a thread's slice of one row and of its NM moment rows
+template<int N, int NM>
+struct Slice {
+    float v[N];
+    float m1[NM >= 1 ? N : 1];
+    float m2[NM >= 2 ? N : 1];
+};
+
+template<int N, int NM>
+__device__ __forceinline__ void load_slice(Slice<N, NM> &s, const float *v, const float *m1, const float *m2,
+                                           size_t offset, bool active) {
+    if (active) {
+        load_vec<N>(s.v, v + offset);
+        if constexpr (NM >= 1)
+            load_vec<N>(s.m1, m1 + offset);
+        if constexpr (NM >= 2)
+            load_vec<N>(s.m2, m2 + offset);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            s.v[i] = 0.f;
+    }
+}
+
+template<int N, int NM>
+__device__ __forceinline__ void store_slice(const Slice<N, NM> &s, float *v, float *m1, float *m2, size_t offset,
+                                            bool active) {
+    if (!active)
+        return;
+    store_vec<N>(v + offset, s.v);
+    if constexpr (NM >= 1)
+        store_vec<N>(m1 + offset, s.m1);
+    if constexpr (NM >= 2)
+        store_vec<N>(m2 + offset, s.m2);
+}
+
+// ---- optimizers, core/optimizer.h:161-210: the step to subtract from `parameter` --------------
+struct Opt {
+    int type;
+    float lr, wd, a, b, eps;
+};
+
+template<int NM>
+__device__ __forceinline__ float step(const Opt &o, float parameter, float gradient, float &m1, float &m2,
+                                      float weight) {
+    if constexpr (NM == 0)
+        return o.lr * weight * (gradient + o.wd * parameter);
+    const float regularized = weight * (gradient + o.wd * parameter);
+    if constexpr (NM == 2) {
+        m1 = o.a * m1 + (1 - o.a) * regularized;
+        m2 = o.b * m2 + (1 - o.b) * regularized * regularized;
+        return o.lr * m1 / (sqrtf(m2) + o.eps);
+    }
+    if (o.type == GV_OPT_MOMENTUM) {
+        m1 = o.a * m1 + (1 - o.a) * regularized;
+        return o.lr * m1;
+    }
+    if (o.type == GV_OPT_ADAGRAD) {
+        m1 += regularized * regularized;
+        return o.lr * regularized / (sqrtf(m1) + o.eps);
+    }
+    m1 = o.a * m1 + (1 - o.a) * regularized * regularized;  // RMSprop
+    return o.lr * regularized / sqrtf(m1 + o.eps);
+}
+
+// util/math.h:30-44 (precise exponentials: the loss and the adversarial weights are compared with the reference)
+__device__ __forceinline__ float sigmoid(float x) {
+    return x > 0 ? 1 / (1 + expf(-x)) : expf(x) / (expf(x) + 1);
+}
+__device__ __forceinline__ float safe_exp(float x) {
+    return expf(fminf(fmaxf(x, -80.f), 80.f));
+}
+
+// ---- per-model slice geometry --------------------------------------------------------------------
+// entity rows: E floats per thread at offset c * E.  Relation VALUES: RotatE keeps dim/2 phases, the
+// thread owning pairs [c*E/2, (c+1)*E/2) reads them at offset c * E/2; every other model uses the
+// entity geometry.  Relation MOMENTS: RotatE and ComplEx index them by pair (ComplEx updates the same
+// moment for the real and the imaginary part, model/knowledge_graph.h:302-306,336-340).
+template<int E, int MODEL>
+struct Geometry {
+    static constexpr int RV = MODEL == GV_KG_ROTATE ? E / 2 : E;
+    static constexpr int RM = (MODEL == GV_KG_ROTATE || MODEL == GV_KG_COMPLEX) ? E / 2 : E;
+};
+
+template<int E, int MODEL, int NM>
+struct Relation {
+    float v[Geometry<E, MODEL>::RV];
+    float m1[NM >= 1 ? Geometry<E, MODEL>::RM : 1];
+    float m2[NM >= 2 ? Geometry<E, MODEL>::RM : 1];
+};
+
+// Model::forward restricted to a thread's slice (model/knowledge_graph.h:44-49,117-123,208-223,359-366,
+// 453-468); the caller sums over the group and applies `margin - sum` for TransE / RotatE.
+template<int E, int MODEL>
+__device__ __forceinline__ float partial_logit(const float (&h)[E], const float (&t)[E],
+                                               const float (&r)[Geometry<E, MODEL>::RV]) {
+    float output = 0.f;
+    if constexpr (MODEL == GV_KG_TRANSE) {
+#pragma unroll
+        for (int i = 0; i < E; i++)
+            output += fabsf(h[i] + r[i] - t[i]);
+    } else if constexpr (MODEL == GV_KG_DISTMULT) {
+#pragma unroll
+        for (int i = 0; i < E; i++)
+            output += h[i] * r[i] * t[i];
+    } else if constexpr (MODEL == GV_KG_SIMPLE) {
+#pragma unroll
+        for (int i = 0; i < E; i++)
+            output += h[i] * r[i] * t[i ^ 1];
+    } else if constexpr (MODEL == GV_KG_COMPLEX) {
+#pragma unroll
+        for (int i = 0; i < E / 2; i++) {
+            const float product_re = h[i * 2] * r[i * 2] - h[i * 2 + 1] * r[i * 2 + 1];
+            const float product_im = h[i * 2] * r[i * 2 + 1] + h[i * 2 + 1] * r[i * 2];
+            output += product_re * t[i * 2] + product_im * t[i * 2 + 1];
+        }
+    } else {  // RotatE
+#pragma unroll
+        for (int i = 0; i < E / 2; i++) {
+            float r_re, r_im;
+            sincosf(r[i], &r_im, &r_re);
+            const float distance_re = h[i * 2] * r_re - h[i * 2 + 1] * r_im - t[i * 2];
+            const float distance_im = h[i * 2] * r_im + h[i * 2 + 1] * r_re - t[i * 2 + 1];
+            output += sqrtf(distance_re * distance_re + distance_im * distance_im);
+        }
+    }
+    return output;
+}
+
+// Model::backward on a thread's slices, statement order of the reference kept
+// (model/knowledge_graph.h:51-108,125-190,225-340,368-433,470-575).  ALIAS: head and tail are the SAME
+// row of the same matrix; every tail access then goes to the head slice (and its moments), which
+// reproduces the reference's two successive read-modify-writes of one memory location.
+template<int E, int MODEL, int NM, bool ALIAS>
+__device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Relation<E, MODEL, NM> &R, const Opt &o,
+                                         float margin_or_l3, float gradient, float relation_lr_multiplier,
+                                         float weight) {
+    Slice<E, NM> &T = ALIAS ? H : Tin;
+    if constexpr (MODEL == GV_KG_TRANSE) {
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+            const float h = H.v[i], t = T.v[i], r = R.v[i];
+            const float s = h + r - t > 0 ? 1.f : -1.f;
+            H.v[i] -= step<NM>(o, h, -gradient * s, H.m1[NM >= 1 ? i : 0], H.m2[NM >= 2 ? i : 0], weight);
+            T.v[i] -= step<NM>(o, t, gradient * s, T.m1[NM >= 1 ? i : 0], T.m2[NM >= 2 ? i : 0], weight);
+            R.v[i] -= relation_lr_multiplier *
+                      step<NM>(o, r, -gradient * s, R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+        }
+    } else if constexpr (MODEL == GV_KG_DISTMULT || MODEL == GV_KG_SIMPLE) {
+        const float l3 = margin_or_l3 * 3;
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+            const int j = MODEL == GV_KG_SIMPLE ? (i ^ 1) : i;
+            const float h = H.v[i], t = T.v[j], r = R.v[i];
+            H.v[i] -= step<NM>(o, h, gradient * r * t + l3 * fabsf(h) * h, H.m1[NM >= 1 ? i : 0],
+                               H.m2[NM >= 2 ? i : 0], weight);
+            T.v[j] -= step<NM>(o, t, gradient * h * r + l3 * fabsf(t) * t, T.m1[NM >= 1 ? j : 0],
+                               T.m2[NM >= 2 ? j : 0], weight);
+            R.v[i] -= relation_lr_multiplier * step<NM>(o, r, gradient * h * t + l3 * fabsf(r) * r,
+                                                        R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+        }
+    } else if constexpr (MODEL == GV_KG_COMPLEX) {
+        const float l3 = margin_or_l3 * 3;
+#pragma unroll
+        for (int i = 0; i < E / 2; i++) {
+            const int re = i * 2, im = i * 2 + 1;
+            const float h_re = H.v[re], h_im = H.v[im], t_re = T.v[re], t_im = T.v[im];
+            const float r_re = R.v[re], r_im = R.v[im];
+            const float h_re_grad = gradient * (r_re * t_re + r_im * t_im);
+            const float h_im_grad = gradient * (-r_im * t_re + r_re * t_im);
+            H.v[re] -= step<NM>(o, h_re, h_re_grad + l3 * fabsf(h_re) * h_re, H.m1[NM >= 1 ? re : 0],
+                                H.m2[NM >= 2 ? re : 0], weight);
+            H.v[im] -= step<NM>(o, h_im, h_im_grad + l3 * fabsf(h_im) * h_im, H.m1[NM >= 1 ? im : 0],
+                                H.m2[NM >= 2 ? im : 0], weight);
+            const float t_re_grad = gradient * (h_re * r_re - h_im * r_im);
+            const float t_im_grad = gradient * (h_re * r_im + h_im * r_re);
+            T.v[re] -= step<NM>(o, t_re, t_re_grad + l3 * fabsf(t_re) * t_re, T.m1[NM >= 1 ? re : 0],
+                                T.m2[NM >= 2 ? re : 0], weight);
+            T.v[im] -= step<NM>(o, t_im, t_im_grad + l3 * fabsf(t_im) * t_im, T.m1[NM >= 1 ? im : 0],
+                                T.m2[NM >= 2 ? im : 0], weight);
+            const float r_re_grad = gradient * (h_re * t_re + h_im * t_im);
+            const float r_im_grad = gradient * (-h_im * t_re + h_re * t_im);
+            R.v[re] -= relation_lr_multiplier * step<NM>(o, r_re, r_re_grad + l3 * fabsf(r_re) * r_re,
+                                                         R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+            R.v[im] -= relation_lr_multiplier * step<NM>(o, r_im, r_im_grad + l3 * fabsf(r_im) * r_im,
+                                                         R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+        }
+    } else {  // RotatE
+#pragma unroll
+        for (int i = 0; i < E / 2; i++) {
+            const int re = i * 2, im = i * 2 + 1;
+            const float phase = R.v[i];
+            float r_re, r_im;
+            sincosf(phase, &r_im, &r_re);
+            const float h_re = H.v[re], h_im = H.v[im], t_re = T.v[re], t_im = T.v[im];
+            const float distance_re = h_re * r_re - h_im * r_im - t_re;
+            const float distance_im = h_re * r_im + h_im * r_re - t_im;
+            const float grad = gradient / (sqrtf(distance_re * distance_re + distance_im * distance_im) + kEps);
+            const float head_re_grad = -grad * (distance_re * r_re + distance_im * r_im);
+            const float head_im_grad = -grad * (-distance_re * r_im + distance_im * r_re);
+            H.v[re] -= step<NM>(o, h_re, head_re_grad, H.m1[NM >= 1 ? re : 0], H.m2[NM >= 2 ? re : 0], weight);
+            H.v[im] -= step<NM>(o, h_im, head_im_grad, H.m1[NM >= 1 ? im : 0], H.m2[NM >= 2 ? im : 0], weight);
+            T.v[re] -= step<NM>(o, t_re, grad * distance_re, T.m1[NM >= 1 ? re : 0], T.m2[NM >= 2 ? re : 0], weight);
+            T.v[im] -= step<NM>(o, t_im, grad * distance_im, T.m1[NM >= 1 ? im : 0], T.m2[NM >= 2 ? im : 0], weight);
+            const float relation_grad = -grad * (distance_re * (h_re * -r_im + h_im * -r_re) +
+                                                 distance_im * (h_re * r_re + h_im * -r_im));
+            R.v[i] -= relation_lr_multiplier *
+                      step<NM>(o, phase, relation_grad, R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+        }
+    }
+}
+
+// ---- a group of threads that owns one sample --------------------------------------------------------
+struct Group {
+    int threads;       // multiple of 32
+    int id_in_cta;     // named-barrier id - 1
+    int warps;         // threads / 32
+    int lane, warp;    // of this thread inside the group
+    float *scratch;    // [2][warps]
+    int parity;
+
+    __device__ __forceinline__ void sync() const {
+        if (warps == 1)
+            __syncwarp();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(id_in_cta + 1), "r"(threads) : "memory");
+    }
+    // sum over the group, the same value in every thread
+    __device__ __forceinline__ float sum(float value) {
+#pragma unroll
+        for (int delta = 16; delta > 0; delta >>= 1)
+            value += __shfl_xor_sync(kFull, value, delta);
+        if (warps == 1)
+            return value;
+        float *slot = scratch + parity * warps;
+        if (lane == 0)
+            slot[warp] = value;
+        sync();
+        float total = 0.f;
+        for (int w = 0; w < warps; w++)
+            total += slot[w];
+        parity ^= 1;  // the next sum uses the other buffer: one barrier per sum is enough
+        return total;
+    }
+};
+
+template<int MODEL>
+__device__ __forceinline__ float finish_logit(float sum, float margin_or_l3) {
+    return (MODEL == GV_KG_TRANSE || MODEL == GV_KG_ROTATE) ? margin_or_l3 - sum : sum;
+}
+
+// gpu::Sample over the all-ones alias table: prob == 1 and alias[i] == i, so the draw is the index
+__device__ __forceinline__ uint32_t uniform_negative(uint32_t count, double random1) {
+    const float rand1 = float(random1);
+    const uint32_t index = uint32_t(double(rand1) * double(count));
+    return min(index, count - 1);
+}
+
+// -----------------------------------------------------------------------------
+// The train kernel.  E floats per thread, NM moments per row.
+// Dynamic shared memory per group: 2 * warps floats (sums) + num_negative ids.
+// -----------------------------------------------------------------------------
+template<int E, int MODEL, int NM>
+__global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p) {
+    extern __shared__ __align__(16) unsigned char shared_bytes[];
+    using G = Geometry<E, MODEL>;
+    const int chunks = p.dim / E;                       // active threads of a group
+    const int group_threads = (chunks + 31) / 32 * 32;  // blockDim.x is a multiple of this
+    const int groups_per_cta = blockDim.x / group_threads;
+    Group g;
+    g.threads = group_threads;
+    g.warps = group_threads / 32;
+    g.id_in_cta = threadIdx.x / group_threads;
+    const int c = threadIdx.x % group_threads;
+    g.lane = c & 31;
+    g.warp = c >> 5;
+    g.parity = 0;
+    const size_t per_group = size_t(2) * g.warps * sizeof(float) + size_t(p.num_negative) * sizeof(uint32_t);
+    unsigned char *mine = shared_bytes + per_group * g.id_in_cta;
+    g.scratch = reinterpret_cast<float *>(mine);
+    uint32_t *negative_ids = reinterpret_cast<uint32_t *>(mine + size_t(2) * g.warps * sizeof(float));
+    const bool active = c < chunks;
+    const size_t slice = size_t(c) * E;                 // offset of this thread inside an entity row
+    const size_t relation_value = size_t(c) * G::RV, relation_moment = size_t(c) * G::RM;
+    const size_t dim = p.dim;
+    const int k = p.num_negative;
+    const bool adversarial = p.temperature > kEps;
+
+    Opt o;
+    o.type = p.optimizer.type;
+    o.wd = p.optimizer.weight_decay;
+    o.a = p.optimizer.a;
+    o.b = p.optimizer.b;
+    o.eps = p.optimizer.epsilon;
+
+    const unsigned long long first = (unsigned long long)blockIdx.x * groups_per_cta + g.id_in_cta;
+    const unsigned long long stride = (unsigned long long)gridDim.x * groups_per_cta;
+    for (unsigned long long sample = first; sample < p.num_sample; sample += stride) {
+        const uint32_t relation_id = __ldg(p.batch + sample * 3);
+        const uint32_t positive_tail = __ldg(p.batch + sample * 3 + 1);
+        const uint32_t positive_head = __ldg(p.batch + sample * 3 + 2);
+        o.lr = __ldg(p.lr_per_batch + sample / p.batch_size);
+
+        // the sample's negatives: given, or drawn from the random stream like train_batch does
+        for (int s = c; s < k; s += group_threads) {
+            const unsigned long long t = sample * k + s;
+            uint32_t negative;
+            if (p.negatives)
+                negative = __ldcs(p.negatives + t);
+            else
+                negative = uniform_negative(p.negative_count, __ldcs(p.random + t * 2));
+            negative_ids[s] = negative;
+            if (p.negatives_out)
+                p.negatives_out[t] = negative;
+        }
+        g.sync();
+
+        // cached rows: relation, positive head, positive tail (+ moments)
+        Relation<E, MODEL, NM> R;
+        {
+            const size_t base = size_t(relation_id) * dim;
+            if (active) {
+                load_vec<G::RV>(R.v, p.relation + base + relation_value);
+                if constexpr (NM >= 1)
+                    load_vec<G::RM>(R.m1, p.relation_m1 + base + relation_moment);
+                if constexpr (NM >= 2)
+                    load_vec<G::RM>(R.m2, p.relation_m2 + base + relation_moment);
+            } else {
+#pragma unroll
+                for (int i = 0; i < G::RV; i++)
+                    R.v[i] = 0.f;
+            }
+        }
+        // a self loop inside one block: the two cached rows would be the same memory -- do not cache
+        const bool cached = !(p.shared && positive_head == positive_tail);
+        Slice<E, NM> PH, PT;
+        if (cached) {
+            load_slice<E, NM>(PH, p.head, p.head_m1, p.head_m2, size_t(positive_head) * dim + slice, active);
+            load_slice<E, NM>(PT, p.tail, p.tail_m1, p.tail_m2, size_t(positive_tail) * dim + slice, active);
+        }
+
+        // ids of target s (s == k: the positive triple)
+        auto target = [&](int s, uint32_t &head_id, uint32_t &tail_id) {
+            head_id = positive_head;
+            tail_id = positive_tail;
+            if (s < k) {
+                const uint32_t negative = negative_ids[s];
+                if (negative < p.num_head)
+                    head_id = negative;
+                else
+                    tail_id = negative - p.num_head;
+            }
+        };
+
+        // pass 1: normaliser of the self-adversarial weights (gpu/knowledge_graph.cuh:59-77)
+        float bias = 0.f, normalizer = 0.f;
+        if (adversarial)
+            for (int s = 0; s < k; s++) {
+                uint32_t head_id, tail_id;
+                target(s, head_id, tail_id);
+                float partial = 0.f;
+                if (active) {
+                    float h[E], t[E];
+                    if (cached && head_id == positive_head) {
+#pragma unroll
+                        for (int i = 0; i < E; i++)
+                            h[i] = PH.v[i];
+                    } else
+                        load_vec<E>(h, p.head + size_t(head_id) * dim + slice);
+                    if (cached && tail_id == positive_tail) {
+#pragma unroll
+                        for (int i = 0; i < E; i++)
+                            t[i] = PT.v[i];
+                    } else
+                        load_vec<E>(t, p.tail + size_t(tail_id) * dim + slice);
+                    partial = partial_logit<E, MODEL>(h, t, R.v);
+                }
+                const float logit = finish_logit<MODEL>(g.sum(partial), p.margin_or_l3);
+                if (s == 0)
+                    bias = logit;
+                normalizer += safe_exp((logit - bias) / p.temperature);
+            }
+
+        // pass 2: negatives first, the positive triple last (gpu/knowledge_graph.cuh:79-118)
+        float sample_loss = 0.f;
+        for (int s = 0; s <= k; s++) {
+            uint32_t head_id, tail_id;
+            target(s, head_id, tail_id);
+            const bool head_cached = cached && head_id == positive_head;
+            const bool tail_cached = cached && tail_id == positive_tail;
+            const bool alias = p.shared && head_id == tail_id;  // one row of one matrix in both roles
+            const size_t head_offset = size_t(head_id) * dim + slice, tail_offset = size_t(tail_id) * dim + slice;
+            // Work on copies WH / WT so that every register array keeps static indexing; a cached row is
+            // copied in and back (register moves).  A target that aliases never has both rows cached (a
+            // cached pair is never a self loop); if one of them is cached, that slice IS the row.
+            Slice<E, NM> WH, WT;
+            const int head_source = head_cached ? 1 : ((alias && tail_cached) ? 2 : 0);  // 0 global, 1 PH, 2 PT
+            if (head_source == 1)
+                WH = PH;
+            else if (head_source == 2)
+                WH = PT;
+            else
+                load_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, active);
+            if (!alias) {
+                if (tail_cached)
+                    WT = PT;
+                else
+                    load_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, active);
+            }
+
+            float partial = 0.f;
+            if (active)
+                partial = alias ? partial_logit<E, MODEL>(WH.v, WH.v, R.v) : partial_logit<E, MODEL>(WH.v, WT.v, R.v);
+            const float logit = finish_logit<MODEL>(g.sum(partial), p.margin_or_l3);
+            const float prob = sigmoid(logit);
+            float gradient, weight;
+            if (s == k) {
+                gradient = prob - 1;
+                weight = 1;
+                sample_loss += weight * -logf(prob + kEps);
+            } else {
+                gradient = prob;
+                if (adversarial)
+                    weight = fminf(safe_exp((logit - bias) / p.temperature) / normalizer, 1.f);
+                else
+                    weight = float(1.0 / k);
+                sample_loss += weight * -logf(1 - prob + kEps);
+            }
+            if (active) {
+                if (alias)
+                    backward<E, MODEL, NM, true>(WH, WH, R, o, p.margin_or_l3, gradient, p.relation_lr_multiplier,
+                                                 weight);
+                else
+                    backward<E, MODEL, NM, false>(WH, WT, R, o, p.margin_or_l3, gradient, p.relation_lr_multiplier,
+                                                  weight);
+            }
+            if (head_source == 1)
+                PH = WH;
+            else if (head_source == 2)
+                PT = WH;
+            else
+                store_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, active);
+            if (!alias) {
+                if (tail_cached)
+                    PT = WT;
+                else
+                    store_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, active);
+            }
+        }
+
+        // write the cached rows back
+        if (cached) {
+            store_slice<E, NM>(PH, p.head, p.head_m1, p.head_m2, size_t(positive_head) * dim + slice, active);
+            store_slice<E, NM>(PT, p.tail, p.tail_m1, p.tail_m2, size_t(positive_tail) * dim + slice, active);
+        }
+        if (active) {
+            const size_t base = size_t(relation_id) * dim;
+            store_vec<G::RV>(p.relation + base + relation_value, R.v);
+            if constexpr (NM >= 1)
+                store_vec<G::RM>(p.relation_m1 + base + relation_moment, R.m1);
+            if constexpr (NM >= 2)
+                store_vec<G::RM>(p.relation_m2 + base + relation_moment, R.m2);
+        }
+        if (c == 0) {
+            const float loss = sample_loss / 2;
+            if (p.loss_per_sample)
+                p.loss_per_sample[sample] = loss;
+            if (p.loss_per_batch)
+                atomicAdd(p.loss_per_batch + sample / p.batch_size, loss);
+        }
+        g.sync();  // negative_ids are rewritten by the next sample
+    }
+}
+
+// gpu::knowledge_graph::predict, instance/gpu/knowledge_graph.cuh:341-366: batch rows {relation, tail, head}
+template<int E, int MODEL>
+__global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *head, const float *tail,
+                                                                 const float *relation, int dim_, const uint32_t *batch,
+                                                                 unsigned long long num_sample, float margin,
+                                                                 float *logits) {
+    extern __shared__ __align__(16) unsigned char shared_bytes[];
+    using G = Geometry<E, MODEL>;
+    const int chunks = dim_ / E;
+    const int group_threads = (chunks + 31) / 32 * 32;
+    const int groups_per_cta = blockDim.x / group_threads;
+    Group g;
+    g.threads = group_threads;
+    g.warps = group_threads / 32;
+    g.id_in_cta = threadIdx.x / group_threads;
+    const int c = threadIdx.x % group_threads;
+    g.lane = c & 31;
+    g.warp = c >> 5;
+    g.parity = 0;
+    g.scratch = reinterpret_cast<float *>(shared_bytes) + size_t(2) * g.warps * g.id_in_cta;
+    const bool active = c < chunks;
+    const size_t dim = dim_;
+    for (unsigned long long sample = (unsigned long long)blockIdx.x * groups_per_cta + g.id_in_cta; sample < num_sample;
+         sample += (unsigned long long)gridDim.x * groups_per_cta) {
+        const uint32_t relation_id = __ldg(batch + sample * 3);
+        const uint32_t tail_id = __ldg(batch + sample * 3 + 1);
+        const uint32_t head_id = __ldg(batch + sample * 3 + 2);
+        float partial = 0.f;
+        if (active) {
+            float h[E], t[E], r[G::RV];
+            load_vec<E>(h, head + size_t(head_id) * dim + size_t(c) * E);
+            load_vec<E>(t, tail + size_t(tail_id) * dim + size_t(c) * E);
+            load_vec<G::RV>(r, relation + size_t(relation_id) * dim + size_t(c) * G::RV);
+            partial = partial_logit<E, MODEL>(h, t, r);
+        }
+        const float logit = finish_logit<MODEL>(g.sum(partial), margin);
+        if (c == 0)
+            logits[sample] = logit;
+    }
+}
+
+int floats_per_thread(int dim) {
+    if (dim % 8 == 0 && dim >= 256)
+        return 8;
+    if (dim % 4 == 0 && dim >= 64)
+        return 4;
+    return 2;
+}
+
+template<int E, int MODEL>
+cudaError_t launch_train_nm(const KgParams &p, int num_moment, dim3 grid, dim3 block, size_t shared, cudaStream_t s) {
+    if (num_moment == 0)
+        kg_train_kernel<E, MODEL, 0><<<grid, block, shared, s>>>(p);
+    else if (num_moment == 1)
+        kg_train_kernel<E, MODEL, 1><<<grid, block, shared, s>>>(p);
+    else
+        kg_train_kernel<E, MODEL, 2><<<grid, block, shared, s>>>(p);
+    return cudaGetLastError();
+}
+
+template<int E>
+cudaError_t launch_train(const KgParams &p, int model, int num_moment, dim3 grid, dim3 block, size_t shared,
+                         cudaStream_t s) {
+    switch (model) {
+        case GV_KG_TRANSE: return launch_train_nm<E, GV_KG_TRANSE>(p, num_moment, grid, block, shared, s);
+        case GV_KG_DISTMULT: return launch_train_nm<E, GV_KG_DISTMULT>(p, num_moment, grid, block, shared, s);
+        case GV_KG_COMPLEX: return launch_train_nm<E, GV_KG_COMPLEX>(p, num_moment, grid, block, shared, s);
+        case GV_KG_SIMPLE: return launch_train_nm<E, GV_KG_SIMPLE>(p, num_moment, grid, block, shared, s);
+        default: return launch_train_nm<E, GV_KG_ROTATE>(p, num_moment, grid, block, shared, s);
+    }
+}
+
+template<int E>
+cudaError_t launch_predict(int model, const float *head, const float *tail, const float *relation, int dim,
+                           const uint32_t *batch, unsigned long long n, float margin, float *logits, dim3 grid,
+                           dim3 block, size_t shared, cudaStream_t s) {
+#define GV_PREDICT(M) kg_predict_kernel<E, M><<<grid, block, shared, s>>>(head, tail, relation, dim, batch, n, margin, logits)
+    switch (model) {
+        case GV_KG_TRANSE: GV_PREDICT(GV_KG_TRANSE); break;
+        case GV_KG_DISTMULT: GV_PREDICT(GV_KG_DISTMULT); break;
+        case GV_KG_COMPLEX: GV_PREDICT(GV_KG_COMPLEX); break;
+        case GV_KG_SIMPLE: GV_PREDICT(GV_KG_SIMPLE); break;
+        default: GV_PREDICT(GV_KG_ROTATE);
+    }
+#undef GV_PREDICT
+    return cudaGetLastError();
+}
+
+int check_geometry(const char *who, int dim, int model, int &E, int &group_threads) {
+    if (model < GV_KG_TRANSE || model > GV_KG_ROTATE)
+        return fail(std::string(who) + ": unknown model");
+    if (dim < 2 || dim % 2 != 0 || dim > 2048)
+        return fail(std::string(who) + ": dim must be even and at most 2048");
+    E = floats_per_thread(dim);
+    if (dim % E != 0)
+        return fail(std::string(who) + ": dim must be a multiple of " + std::to_string(E));
+    group_threads = (dim / E + 31) / 32 * 32;
+    if (group_threads > kCtaThreads)
+        return fail(std::string(who) + ": dim too large for one CTA");
+    return 0;
+}
+
+}  // namespace
+
+}  // namespace device
+}  // namespace gv
+
+using namespace gv;
+using namespace gv::device;
+
+extern "C" {
+
+int gv_cuda_kg_train_block(const gv_kg_matrices_t *m, int model, const uint32_t *batch, uint64_t num_sample,
+                           int num_negative, const uint32_t *negatives, const double *random, uint32_t negative_count,
+                           uint32_t *negatives_out, const gv_device_optimizer_t *optimizer, const float *lr_per_batch,
+                           uint32_t batch_size, float relation_lr_multiplier, float margin_or_l3,
+                           float adversarial_temperature, float *loss_per_sample, float *loss_per_batch, int num_group,
+                           void *stream) {
+    if (num_sample == 0)
+        return 0;
+    if (!m || !batch || !optimizer || !lr_per_batch || !m->head || !m->tail || !m->relation || batch_size == 0)
+        return fail("gv_cuda_kg_train_block: null argument");
+    if (num_negative < 0 || (num_negative > 0 && !negatives && (!random || negative_count == 0)))
+        return fail("gv_cuda_kg_train_block: negatives need either ids or a random stream and a count");
+    int E, group_threads;
+    if (check_geometry("gv_cuda_kg_train_block", m->dim, model, E, group_threads))
+        return -1;
+    const int type = optimizer->type;
+    const int num_moment = type == GV_OPT_SGD ? 0 : (type == GV_OPT_ADAM ? 2 : 1);
+    if (type < GV_OPT_SGD || type > GV_OPT_ADAM)
+        return fail("gv_cuda_kg_train_block: unknown optimizer");
+    if ((num_moment >= 1 && (!m->head_m1 || !m->tail_m1 || !m->relation_m1)) ||
+        (num_moment >= 2 && (!m->head_m2 || !m->tail_m2 || !m->relation_m2)))
+        return fail("gv_cuda_kg_train_block: moment matrices missing for this optimizer");
+    KgParams p;
+    p.dim = m->dim;
+    p.num_head = m->num_head;
+    p.shared = m->head == m->tail;
+    p.head = m->head, p.tail = m->tail, p.relation = m->relation;
+    p.head_m1 = m->head_m1, p.tail_m1 = m->tail_m1, p.relation_m1 = m->relation_m1;
+    p.head_m2 = m->head_m2, p.tail_m2 = m->tail_m2, p.relation_m2 = m->relation_m2;
+    p.batch = batch;
+    p.num_sample = num_sample;
+    p.num_negative = num_negative;
+    p.negatives = negatives;
+    p.random = random;
+    p.negative_count = negative_count;
+    p.negatives_out = negatives_out;
+    p.optimizer = *optimizer;
+    p.lr_per_batch = lr_per_batch;
+    p.batch_size = batch_size;
+    p.relation_lr_multiplier = relation_lr_multiplier;
+    p.margin_or_l3 = margin_or_l3;
+    p.temperature = adversarial_temperature;
+    p.loss_per_sample = loss_per_sample;
+    p.loss_per_batch = loss_per_batch;
+
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int device = 0, num_sm = 0;
+    GV_CUDA_OK(cudaGetDevice(&device));
+    GV_CUDA_OK(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, device));
+    // num_group == 1: one group, samples in order (the parity tests); 0: fill the device
+    const int groups_per_cta = num_group == 1 ? 1 : kCtaThreads / group_threads;
+    const dim3 block(groups_per_cta * group_threads);
+    const size_t per_group = size_t(2) * (group_threads / 32) * sizeof(float) + size_t(num_negative) * sizeof(uint32_t);
+    const size_t shared = per_group * groups_per_cta;
+    if (shared > 48 * 1024)
+        return fail("gv_cuda_kg_train_block: too many negatives per sample for the shared-memory id buffer");
+    unsigned long long ctas = (num_sample + groups_per_cta - 1) / groups_per_cta;
+    if (num_group == 1)
+        ctas = 1;
+    else if (num_group > 1)
+        ctas = std::min<unsigned long long>(ctas, (unsigned long long)(num_group + groups_per_cta - 1) / groups_per_cta);
+    else
+        ctas = std::min<unsigned long long>(ctas, (unsigned long long)num_sm * 2);
+    const dim3 grid((unsigned)ctas);
+    cudaError_t status;
+    if (E == 8)
+        status = launch_train<8>(p, model, num_moment, grid, block, shared, s);
+    else if (E == 4)
+        status = launch_train<4>(p, model, num_moment, grid, block, shared, s);
+    else
+        status = launch_train<2>(p, model, num_moment, grid, block, shared, s);
+    GV_CUDA_OK(status);
+    return 0;
+}
+
+int gv_cuda_kg_predict(const gv_kg_matrices_t *m, int model, const uint32_t *batch, uint64_t num_sample, float margin,
+                       float *logits, void *stream) {
+    if (num_sample == 0)
+        return 0;
+    if (!m || !batch || !logits || !m->head || !m->tail || !m->relation)
+        return fail("gv_cuda_kg_predict: null argument");
+    int E, group_threads;
+    if (check_geometry("gv_cuda_kg_predict", m->dim, model, E, group_threads))
+        return -1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int device = 0, num_sm = 0;
+    GV_CUDA_OK(cudaGetDevice(&device));
+    GV_CUDA_OK(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, device));
+    const int groups_per_cta = kCtaThreads / group_threads;
+    const dim3 block(groups_per_cta * group_threads);
+    const size_t shared = size_t(2) * (group_threads / 32) * sizeof(float) * groups_per_cta;
+    const unsigned long long ctas =
+        std::min<unsigned long long>((num_sample + groups_per_cta - 1) / groups_per_cta, (unsigned long long)num_sm * 8);
+    const dim3 grid((unsigned)ctas);
+    cudaError_t status;
+    if (E == 8)
+        status = launch_predict<8>(model, m->head, m->tail, m->relation, m->dim, batch, num_sample, margin, logits, grid,
+                                   block, shared, s);
+    else if (E == 4)
+        status = launch_predict<4>(model, m->head, m->tail, m->relation, m->dim, batch, num_sample, margin, logits, grid,
+                                   block, shared, s);
+    else
+        status = launch_predict<2>(model, m->head, m->tail, m->relation, m->dim, batch, num_sample, margin, logits, grid,
+                                   block, shared, s);
+    GV_CUDA_OK(status);
+    return 0;
+}
+
+}  // extern "C"

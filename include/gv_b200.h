@@ -37,6 +37,8 @@ enum { GV_OPT_SGD = 0, GV_OPT_MOMENTUM = 1, GV_OPT_ADAGRAD = 2, GV_OPT_RMSPROP =
 enum { GV_SCHEDULE_CONSTANT = 0, GV_SCHEDULE_LINEAR = 1, GV_SCHEDULE_CUSTOM = 2 };
 /* instance/graph.cuh:620-622 available models */
 enum { GV_MODEL_DEEPWALK = 0, GV_MODEL_LINE = 1, GV_MODEL_NODE2VEC = 2 };
+/* instance/knowledge_graph.cuh:575-577 available models (QuatE is not implemented) */
+enum { GV_KG_TRANSE = 0, GV_KG_DISTMULT = 1, GV_KG_COMPLEX = 2, GV_KG_SIMPLE = 3, GV_KG_ROTATE = 4 };
 
 /* Device-side view of core/optimizer.h Optimizer (the reference passes the whole C++
  * object, std::string included, by value into its kernels; appendix A.14 of SURVEY.md). */
@@ -225,6 +227,37 @@ int gv_cuda_peer_exchange(int rank, int world_size, int num_partition, uint64_t 
                           const unsigned long long *totals, unsigned long long *const *controls,
                           unsigned long long *control, unsigned long long *fill, unsigned long long *bases,
                           unsigned long long *last_walk, void *stream);
+
+/* Knowledge-graph train / predict kernels (instance/gpu/knowledge_graph.cuh:38-366 with the models of
+ * instance/model/knowledge_graph.h).  NOT yet validated on a GPU.
+ *   matrices   head and tail entity blocks [rows][dim] (the SAME pointers when the two partitions
+ *              coincide, core/solver.h:1351-1355) and the relation matrix [num_relation][dim]
+ *              (RotatE uses the first dim/2 floats of a row as phases); moments as the optimizer needs
+ *   num_head   rows of the head block: a negative id below it replaces the head, otherwise id - num_head
+ *              replaces the tail (gpu/knowledge_graph.cuh:64-71)
+ *   batch      device [n][3] {relation, tail_local, head_local} (the reference's tuple byte order)
+ *   negatives  device [n][k] ids, or NULL to draw them from `random` (2 doubles per negative, consumed
+ *              like WorkerMixin::train_batch + gpu::Sample) uniformly over negative_count ids
+ *   loss_*     optional: per-sample loss (sample_loss / 2) and its per-batch sum (atomicAdd)
+ *   num_group  0 = fill the device; 1 = one thread group, samples in order (deterministic)
+ */
+typedef struct {
+    int dim;
+    uint32_t num_head;
+    float *head, *tail, *relation;
+    float *head_m1, *tail_m1, *relation_m1;
+    float *head_m2, *tail_m2, *relation_m2;
+} gv_kg_matrices_t;
+
+int gv_cuda_kg_train_block(const gv_kg_matrices_t *matrices, int model, const uint32_t *batch, uint64_t num_sample,
+                           int num_negative, const uint32_t *negatives, const double *random, uint32_t negative_count,
+                           uint32_t *negatives_out, const gv_device_optimizer_t *optimizer, const float *lr_per_batch,
+                           uint32_t batch_size, float relation_lr_multiplier, float margin_or_l3,
+                           float adversarial_temperature, float *loss_per_sample, float *loss_per_batch, int num_group,
+                           void *stream);
+/* logits[i] = Model::forward(head[batch[i].head], tail[batch[i].tail], relation[batch[i].relation], margin) */
+int gv_cuda_kg_predict(const gv_kg_matrices_t *matrices, int model, const uint32_t *batch, uint64_t num_sample,
+                       float margin, float *logits, void *stream);
 
 /* Memory::gather / Memory::scatter (base/memory.h:194-217) on the device: rows of `dim` floats,
  * dst[i] = src[ids[i]] when gather != 0, else dst[ids[i]] = src[i]. */
