@@ -30,6 +30,7 @@
 #include <string>
 
 #include "gv_common.h"
+#include "gv_device.cuh"
 
 namespace gv {
 namespace device {
@@ -326,7 +327,7 @@ struct Group {
         if (warps == 1)
             __syncwarp();
         else
-            asm volatile("bar.sync %0, %1;" ::"r"(id_in_cta + 1), "r"(threads) : "memory");
+            gv_named_barrier(id_in_cta + 1, threads);
     }
     // sum over the group, the same value in every thread
     __device__ __forceinline__ float sum(float value) {
@@ -365,7 +366,7 @@ __device__ __forceinline__ uint32_t uniform_negative(uint32_t count, double rand
 // -----------------------------------------------------------------------------
 template<int E, int MODEL, int NM>
 __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p) {
-    extern __shared__ __align__(16) unsigned char shared_bytes[];
+    GV_DYNAMIC_SHARED(unsigned char, shared_bytes);
     using G = Geometry<E, MODEL>;
     const int chunks = p.dim / E;                       // active threads of a group
     const int group_threads = (chunks + 31) / 32 * 32;  // blockDim.x is a multiple of this
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *he
                                                                  const float *relation, int dim_, const uint32_t *batch,
                                                                  unsigned long long num_sample, float margin,
                                                                  float *logits) {
-    extern __shared__ __align__(16) unsigned char shared_bytes[];
+    GV_DYNAMIC_SHARED(unsigned char, shared_bytes);
     using G = Geometry<E, MODEL>;
     const int chunks = dim_ / E;
     const int group_threads = (chunks + 31) / 32 * 32;
@@ -627,11 +628,11 @@ int floats_per_thread(int dim) {
 template<int E, int MODEL>
 cudaError_t launch_train_nm(const KgParams &p, int num_moment, dim3 grid, dim3 block, size_t shared, cudaStream_t s) {
     if (num_moment == 0)
-        kg_train_kernel<E, MODEL, 0><<<grid, block, shared, s>>>(p);
+        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 0>)(p);
     else if (num_moment == 1)
-        kg_train_kernel<E, MODEL, 1><<<grid, block, shared, s>>>(p);
+        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 1>)(p);
     else
-        kg_train_kernel<E, MODEL, 2><<<grid, block, shared, s>>>(p);
+        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 2>)(p);
     return cudaGetLastError();
 }
 
@@ -651,7 +652,7 @@ template<int E>
 cudaError_t launch_predict(int model, const float *head, const float *tail, const float *relation, int dim,
                            const uint32_t *batch, unsigned long long n, float margin, float *logits, dim3 grid,
                            dim3 block, size_t shared, cudaStream_t s) {
-#define GV_PREDICT(M) kg_predict_kernel<E, M><<<grid, block, shared, s>>>(head, tail, relation, dim, batch, n, margin, logits)
+#define GV_PREDICT(M) GV_LAUNCH(grid, block, shared, s, kg_predict_kernel<E, M>)(head, tail, relation, dim, batch, n, margin, logits)
     switch (model) {
         case GV_KG_TRANSE: GV_PREDICT(GV_KG_TRANSE); break;
         case GV_KG_DISTMULT: GV_PREDICT(GV_KG_DISTMULT); break;

@@ -18,6 +18,7 @@
 #include <string>
 
 #include "gv_common.h"
+#include "gv_device.cuh"
 
 namespace gv {
 namespace device {
@@ -165,7 +166,7 @@ int gv_cuda_node2vec_build(const gv_device_graph_t *graph, const float *edge_wei
         return 0;
     if (!graph || !edge_weights || !sorted_neighbors || !table_offsets || !tables || !scratch_little || !scratch_large)
         return fail("gv_cuda_node2vec_build: null argument");
-    node2vec_build_kernel<<<(num_table + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    GV_LAUNCH((num_table + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), node2vec_build_kernel)(
         *graph, edge_weights, sorted_neighbors, table_offsets, first_edge, num_table, p, q, tables, scratch_little,
         scratch_large);
     GV_CUDA_OK(cudaGetLastError());
@@ -181,7 +182,7 @@ int gv_cuda_biased_walk(const gv_device_graph_t *graph, const gv_alias_entry_t *
     if (!graph || !tables || !table_offsets || !random || !chains || walk_length < 1 || walks_per_buffer == 0 ||
         buffer_doubles < uint64_t(walks_per_buffer) * 2 * walk_length || buffer_doubles % 2 != 0)
         return fail("gv_cuda_biased_walk: invalid argument");
-    biased_walk_kernel<<<(num_walk + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    GV_LAUNCH((num_walk + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), biased_walk_kernel)(
         *graph, tables, table_offsets, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles,
         chains);
     GV_CUDA_OK(cudaGetLastError());

@@ -19,6 +19,7 @@
 #include <string>
 
 #include "gv_common.h"
+#include "gv_device.cuh"
 
 namespace gv {
 namespace device {
@@ -98,7 +99,7 @@ __device__ __forceinline__ void count_walk_pairs(const FillParams &p, const uint
 }
 
 __global__ void fill_count_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk, uint32_t *cta_counts) {
-    extern __shared__ uint32_t counters[];
+    GV_DYNAMIC_SHARED(uint32_t, counters);
     const int T = blockDim.x, num_block = p.num_partition * p.num_partition;
     const uint32_t w = blockIdx.x * T + threadIdx.x;
     for (int b = 0; b < num_block; b++)
@@ -203,10 +204,10 @@ __global__ void __launch_bounds__(512) peer_gather_kernel(int rank, int W, int n
     if (threadIdx.x < W) {
         volatile unsigned long long *flag = control_flag(control, W, num_block, parity, threadIdx.x);
         unsigned long long begin, now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(begin));
+        begin = gv_global_timer_ns();
         while (*flag != round_id) {
             __nanosleep(200);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            now = gv_global_timer_ns();
             if (now - begin > kPeerTimeoutNs) {
                 timed_out = 1;
                 break;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(512) peer_gather_kernel(int rank, int W, int n
 __global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk,
                                     unsigned long long first_walk, const uint32_t *cta_bases,
                                     uint32_t *const *pool_blocks, unsigned long long *last_walk) {
-    extern __shared__ uint32_t counters[];
+    GV_DYNAMIC_SHARED(uint32_t, counters);
     const int T = blockDim.x, num_block = p.num_partition * p.num_partition;
     const uint32_t w = blockIdx.x * T + threadIdx.x;
     for (int b = 0; b < num_block; b++)
@@ -358,7 +359,7 @@ int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, ui
         return fail("gv_cuda_random_walk: per-vertex alias tables are required for walk_length > 1");
     const int threads = 256;
     const uint32_t blocks = (num_walk + threads - 1) / threads;
-    random_walk_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+    GV_LAUNCH(blocks, threads, 0, static_cast<cudaStream_t>(stream), random_walk_kernel)(
         *graph, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles, chains);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
@@ -408,10 +409,10 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
         // every walk is full length, so pair (w, j, k) sits at stream index w * pairs_per_walk + f(j, k);
         // fill[0] is read on the device and advanced by a 1-thread kernel behind the fill (same stream)
         const uint32_t per_walk = pairs_per_walk(p.walk_length, p.augmentation_step);
-        fill_direct_kernel<<<blocks, threads, 0, s>>>(p, c, num_walk, first_walk, per_walk, fill, pool_blocks,
+        GV_LAUNCH(blocks, threads, 0, s, fill_direct_kernel)(p, c, num_walk, first_walk, per_walk, fill, pool_blocks,
                                                       last_walk);
         GV_CUDA_OK(cudaGetLastError());
-        fill_advance_kernel<<<1, 1, 0, s>>>(fill, (unsigned long long)num_walk * per_walk);
+        GV_LAUNCH(1, 1, 0, s, fill_advance_kernel)(fill, (unsigned long long)num_walk * per_walk);
         GV_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -422,11 +423,11 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
     const int T = fill_threads(p.num_partition);
     const uint32_t num_cta = (num_walk + T - 1) / T;
     const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
-    fill_count_kernel<<<num_cta, T, shared, s>>>(p, c, num_walk, cta_counts);
+    GV_LAUNCH(num_cta, T, shared, s, fill_count_kernel)(p, c, num_walk, cta_counts);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scan_kernel<<<num_block, 1024, 0, s>>>(p, num_cta, cta_counts, fill, fill, nullptr);
+    GV_LAUNCH(num_block, 1024, 0, s, fill_scan_kernel)(p, num_cta, cta_counts, fill, fill, nullptr);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scatter_kernel<<<num_cta, T, shared, s>>>(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk);
+    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -474,12 +475,12 @@ int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chai
     const int T = fill_threads(p.num_partition);
     const uint32_t num_cta = (num_walk + T - 1) / T;
     const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
-    fill_count_kernel<<<num_cta, T, shared, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk, cta_counts);
+    GV_LAUNCH(num_cta, T, shared, s, fill_count_kernel)(p, reinterpret_cast<const uint2 *>(chains), num_walk, cta_counts);
     GV_CUDA_OK(cudaGetLastError());
     // unseeded scan: cta_counts become offsets relative to the start of this rank's pairs; totals out
     FillParams unbounded = p;
     unbounded.slice = ~0ull;
-    fill_scan_kernel<<<num_block, 1024, 0, s>>>(unbounded, num_cta, cta_counts, nullptr, nullptr, totals);
+    GV_LAUNCH(num_block, 1024, 0, s, fill_scan_kernel)(unbounded, num_cta, cta_counts, nullptr, nullptr, totals);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -510,9 +511,9 @@ int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *ch
     const int T = fill_threads(p.num_partition);
     const uint32_t num_cta = (num_walk + T - 1) / T;
     const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
-    fill_rebase_kernel<<<dim3((num_cta + 255) / 256, num_block), 256, 0, s>>>(p.slice, num_cta, cta_counts, bases);
+    GV_LAUNCH(dim3((num_cta + 255) / 256, num_block), 256, 0, s, fill_rebase_kernel)(p.slice, num_cta, cta_counts, bases);
     GV_CUDA_OK(cudaGetLastError());
-    fill_scatter_kernel<<<num_cta, T, shared, s>>>(p, reinterpret_cast<const uint2 *>(chains), num_walk, first_walk,
+    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, reinterpret_cast<const uint2 *>(chains), num_walk, first_walk,
                                                    cta_counts, pool_blocks, last_walk);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
@@ -526,9 +527,9 @@ int gv_cuda_peer_exchange(int rank, int world_size, int num_partition, uint64_t 
         return fail("gv_cuda_peer_exchange: invalid argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int num_block = num_partition * num_partition, parity = int(round_id & 1);
-    peer_publish_kernel<<<1, 512, 0, s>>>(rank, world_size, num_block, parity, round_id, totals, last_walk, controls);
+    GV_LAUNCH(1, 512, 0, s, peer_publish_kernel)(rank, world_size, num_block, parity, round_id, totals, last_walk, controls);
     GV_CUDA_OK(cudaGetLastError());
-    peer_gather_kernel<<<1, 512, 0, s>>>(rank, world_size, num_block, parity, round_id, control, fill, bases,
+    GV_LAUNCH(1, 512, 0, s, peer_gather_kernel)(rank, world_size, num_block, parity, round_id, control, fill, bases,
                                          last_walk);
     GV_CUDA_OK(cudaGetLastError());
     return 0;

@@ -30,6 +30,7 @@
 #include <string>
 
 #include "gv_common.h"
+#include "gv_device.cuh"
 
 namespace gv {
 namespace device {
@@ -118,8 +119,8 @@ __device__ __forceinline__ float dot(const Row<DIM> &a, const Row<DIM> &b) {
 // the precise libdevice sequences otherwise, and the difference (~1e-7 relative on the gradient) is
 // three orders of magnitude below the Hogwild noise of the algorithm itself.
 __device__ __forceinline__ float sigmoid(float x) {
-    const float e = __expf(-fabsf(x));
-    const float r = __fdividef(1.f, 1.f + e);
+    const float e = gv_fast_exp(-fabsf(x));
+    const float r = gv_fast_divide(1.f, 1.f + e);
     return x > 0 ? r : e * r;
 }
 
@@ -222,7 +223,7 @@ template<int DIM, int OPT, bool LOSS>
 __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams p) {
     constexpr int NM = OPT == GV_OPT_SGD ? 0 : (OPT == GV_OPT_ADAM ? 2 : 1);
     constexpr bool kCross = NM == 0 && Row<DIM>::kPass <= 2;  // cross-sample prefetch (register budget)
-    extern __shared__ uint32_t shared_ids[];
+    GV_DYNAMIC_SHARED(uint32_t, shared_ids);
 
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
@@ -469,7 +470,7 @@ __device__ __forceinline__ float process_sample(SampleRows<DIM, K> &cur, SampleR
 
 template<int DIM, int K, bool LOSS>
 __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainParams p) {
-    extern __shared__ uint32_t shared_ids[];
+    GV_DYNAMIC_SHARED(uint32_t, shared_ids);
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     constexpr int stride = K + 2;  // head, K negatives, positive tail
@@ -631,7 +632,7 @@ static int launch_train(void (*kernel)(const TrainParams), const TrainParams &p,
     }
     if (blocks < 1)
         blocks = 1;
-    kernel<<<blocks, threads, shared_bytes, stream>>>(p);
+    GV_LAUNCH(blocks, threads, shared_bytes, stream, kernel)(p);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -753,7 +754,7 @@ int gv_cuda_sample_negatives(const gv_alias_entry_t *table, uint32_t count, cons
     const unsigned long long cap = (unsigned long long)device_sm_count() * 8;
     if (blocks > cap)
         blocks = cap;
-    sample_negatives_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, count, random, num, out);
+    GV_LAUNCH(int(blocks), 256, 0, static_cast<cudaStream_t>(stream), sample_negatives_kernel)(table, count, random, num, out);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -771,12 +772,12 @@ int gv_cuda_predict(int dim, const float *vertex, const float *context, const ui
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const uint2 *pairs = reinterpret_cast<const uint2 *>(batch);
     switch (dim) {
-        case 32: predict_kernel<32><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
-        case 64: predict_kernel<64><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
-        case 96: predict_kernel<96><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
-        case 128: predict_kernel<128><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
-        case 256: predict_kernel<256><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
-        case 512: predict_kernel<512><<<int(blocks), kBlockThreads, 0, s>>>(vertex, context, pairs, num, logits); break;
+        case 32: GV_LAUNCH(int(blocks), kBlockThreads, 0, s, predict_kernel<32>)(vertex, context, pairs, num, logits); break;
+        case 64: GV_LAUNCH(int(blocks), kBlockThreads, 0, s, predict_kernel<64>)(vertex, context, pairs, num, logits); break;
+        case 96: GV_LAUNCH(int(blocks), kBlockThreads, 0, s, predict_kernel<96>)(vertex, context, pairs, num, logits); break;
+        case 128: GV_LAUNCH(int(blocks), kBlockThreads, 0, s, predict_kernel<128>)(vertex, context, pairs, num, logits); break;
+        case 256: GV_LAUNCH(int(blocks), kBlockThreads, 0, s, predict_kernel<256>)(vertex, context, pairs, num, logits); break;
+        case 512: GV_LAUNCH(int(blocks), kBlockThreads, 0, s, predict_kernel<512>)(vertex, context, pairs, num, logits); break;
         default: return fail("unsupported embedding dimension " + std::to_string(dim));
     }
     GV_CUDA_OK(cudaGetLastError());

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "gv_common.h"
+#include "gv_device.cuh"
 
 namespace gv {
 namespace device {
@@ -42,7 +43,7 @@ int gv_cuda_move_rows(float *dst, const float *src, const uint32_t *ids, uint64_
     unsigned long long blocks = (num_row + 7) / 8;
     if (blocks > 148 * 16)
         blocks = 148 * 16;
-    gv::device::move_rows_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, ids, num_row,
+    GV_LAUNCH(int(blocks), 256, 0, static_cast<cudaStream_t>(stream), gv::device::move_rows_kernel)(dst, src, ids, num_row,
                                                                                              dim, gather != 0);
     GV_CUDA_OK(cudaGetLastError());
     return 0;

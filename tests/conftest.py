@@ -8,6 +8,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
+# GV_EMULATE=1 (child runs of tests/test_emulated_kernels.py only): import the package from tests/emu/_pkg,
+# i.e. the unmodified Python files next to a libgv_b200.so built from the product's sources for the host
+# on top of tests/emu's CUDA emulation.  Test infrastructure like the oracle; never a product path.
+EMULATED = os.environ.get("GV_EMULATE") == "1"
+if EMULATED:
+    import subprocess
+    subprocess.check_call(["make", "-j8", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu", "_pkg"))
+
 
 def _ensure_built():
     """The shared objects are git-ignored build products: compile them once if a fresh checkout has

@@ -1,6 +1,7 @@
 """Helpers that drive the C ABI of libgv_b200 with torch-owned device memory (tests, smoke, bench).
 PyTorch is plumbing here: it owns the device buffers and the stream; the kernels are ours."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -9,14 +10,38 @@ from graphvite_b200 import _lib
 
 lib = _lib.lib
 
+# GV_EMULATE=1 (set by tests/test_emulated_kernels.py for its child pytest runs): the package on sys.path
+# is tests/emu/_pkg, whose libgv_b200.so is the product's sources compiled for the host on top of the CUDA
+# emulation in tests/emu -- "device" memory is then host memory and torch only lends CPU tensors.
+EMULATED = os.environ.get("GV_EMULATE") == "1"
+DEVICE = "cpu" if EMULATED else "cuda"
+
+
+def to_device(tensor):
+    """torch tensor -> the device the kernels run on (a private copy in both modes)."""
+    return tensor.clone() if EMULATED else tensor.cuda()
+
+
+def zeros(*shape, dtype=torch.float32):
+    return torch.zeros(*shape, dtype=dtype, device=DEVICE)
+
+
+def full(shape, value, dtype):
+    return torch.full(shape, value, dtype=dtype, device=DEVICE)
+
+
+def synchronize():
+    if not EMULATED:
+        synchronize()
+
 
 def dev(array, dtype=None):
-    """numpy -> cuda tensor (keeps unsigned data by viewing it as the signed type of equal width)."""
+    """numpy -> device tensor (keeps unsigned data by viewing it as the signed type of equal width)."""
     array = np.ascontiguousarray(array if dtype is None else array.astype(dtype))
     views = {np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}
     if array.dtype in views:
         array = array.view(views[array.dtype])
-    return torch.from_numpy(array).cuda()
+    return to_device(torch.from_numpy(array))
 
 
 def host(tensor, dtype):
@@ -24,6 +49,8 @@ def host(tensor, dtype):
 
 
 def stream_pointer():
+    if EMULATED:
+        return None
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -56,8 +83,8 @@ def run_train_block(dim, vertex, context, moments, batch, negatives, optimizer, 
         setattr(matrices, field, tensor.data_ptr() if tensor is not None else None)
     d_batch = dev(batch, np.uint32)
     d_lr = dev(np.asarray(lr, dtype=np.float32))
-    d_loss = torch.zeros(max(1, n), dtype=torch.float32, device="cuda") if per_sample_loss else None
-    d_batch_loss = torch.zeros(num_batch, dtype=torch.float32, device="cuda")
+    d_loss = torch.zeros(max(1, n), dtype=torch.float32, device=DEVICE) if per_sample_loss else None
+    d_batch_loss = torch.zeros(num_batch, dtype=torch.float32, device=DEVICE)
     device_optimizer = _lib.DeviceOptimizer(otype, wd, a, b, eps)
     if negatives is not None:
         k = negatives.size // n if n else 0
@@ -67,9 +94,9 @@ def run_train_block(dim, vertex, context, moments, batch, negatives, optimizer, 
         k = len(random) // (2 * n)
         d_negatives = None
         d_random = dev(np.asarray(random, dtype=np.float64))
-        d_table = torch.from_numpy(alias_entries(prob, alias).view(np.int64)).cuda()
+        d_table = to_device(torch.from_numpy(alias_entries(prob, alias).view(np.int64)))
         count = len(prob)
-        d_out = torch.zeros(n * k, dtype=torch.int32, device="cuda")
+        d_out = torch.zeros(n * k, dtype=torch.int32, device=DEVICE)
     _lib.check(lib.gv_cuda_train_block(
         ctypes.byref(matrices), d_batch.data_ptr(), n, k,
         d_negatives.data_ptr() if d_negatives is not None else None,
@@ -78,7 +105,7 @@ def run_train_block(dim, vertex, context, moments, batch, negatives, optimizer, 
         d_out.data_ptr() if d_out is not None else None,
         ctypes.byref(device_optimizer), d_lr.data_ptr(), batch_size, float(negative_weight),
         d_loss.data_ptr() if d_loss is not None else None, d_batch_loss.data_ptr(), num_warps, stream_pointer()))
-    torch.cuda.synchronize()
+    synchronize()
     result = {"vertex": d_vertex.cpu().numpy(), "context": d_context.cpu().numpy(),
               "loss": d_loss.cpu().numpy()[:n] if d_loss is not None else None,
               "batch_loss": d_batch_loss.cpu().numpy()}
@@ -91,20 +118,20 @@ def run_train_block(dim, vertex, context, moments, batch, negatives, optimizer, 
 
 def sample_negatives(prob, alias, random):
     n = len(random) // 2
-    d_table = torch.from_numpy(alias_entries(prob, alias).view(np.int64)).cuda()
+    d_table = to_device(torch.from_numpy(alias_entries(prob, alias).view(np.int64)))
     d_random = dev(np.asarray(random, dtype=np.float64))
-    d_out = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(n, dtype=torch.int32, device=DEVICE)
     _lib.check(lib.gv_cuda_sample_negatives(d_table.data_ptr(), len(prob), d_random.data_ptr(), n, d_out.data_ptr(),
                                             stream_pointer()))
-    torch.cuda.synchronize()
+    synchronize()
     return host(d_out, np.uint32)
 
 
 def predict(dim, vertex, context, batch):
     d_vertex, d_context, d_batch = dev(vertex), dev(context), dev(batch, np.uint32)
     n = batch.shape[0]
-    d_logits = torch.zeros(n, dtype=torch.float32, device="cuda")
+    d_logits = torch.zeros(n, dtype=torch.float32, device=DEVICE)
     _lib.check(lib.gv_cuda_predict(dim, d_vertex.data_ptr(), d_context.data_ptr(), d_batch.data_ptr(), n,
                                    d_logits.data_ptr(), stream_pointer()))
-    torch.cuda.synchronize()
+    synchronize()
     return d_logits.cpu().numpy()

@@ -155,17 +155,18 @@ def test_predict(dim):
 def test_move_rows_round_trip():
     import ctypes
     import torch
+    import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import dev, stream_pointer
     rng = np.random.RandomState(0)
     matrix = rng.randn(500, 96).astype(np.float32)
     ids = rng.permutation(500)[:123].astype(np.uint32)
     d_matrix, d_ids = dev(matrix), dev(ids)
-    d_block = torch.zeros(123, 96, device="cuda")
+    d_block = torch.zeros(123, 96, device=gpu_util.DEVICE)
     _lib.check(_lib.lib.gv_cuda_move_rows(d_block.data_ptr(), d_matrix.data_ptr(), d_ids.data_ptr(), 123, 96, 1,
                                           stream_pointer()))
     np.testing.assert_array_equal(d_block.cpu().numpy(), matrix[ids])
-    d_back = torch.zeros(500, 96, device="cuda")
+    d_back = torch.zeros(500, 96, device=gpu_util.DEVICE)
     _lib.check(_lib.lib.gv_cuda_move_rows(d_back.data_ptr(), d_block.data_ptr(), d_ids.data_ptr(), 123, 96, 0,
                                           stream_pointer()))
     expected = np.zeros_like(matrix)
@@ -178,15 +179,16 @@ def test_rng_reproduces_curand_stream(golden_dir):
     cuRAND's host generator (oracle), for any call split; snapshots rewind it exactly."""
     import ctypes
     import torch
+    import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import stream_pointer
     lib = _lib.lib
     golden = np.load(golden_dir + "/curand.npz")
 
     def generate(rng, n):
-        out = torch.zeros(n, dtype=torch.float64, device="cuda")
+        out = torch.zeros(n, dtype=torch.float64, device=gpu_util.DEVICE)
         _lib.check(lib.gv_rng_generate(rng, out.data_ptr(), n, stream_pointer()))
-        torch.cuda.synchronize()
+        gpu_util.synchronize()
         return out.cpu().numpy()
 
     rng = lib.gv_rng_create(int(golden["seeds"][0]), stream_pointer())
@@ -199,7 +201,7 @@ def test_rng_reproduces_curand_stream(golden_dir):
     seed = int(golden["big_seed"])
     rng = lib.gv_rng_create(seed, stream_pointer())
     first = generate(rng, 5000000)
-    snapshot = torch.zeros(lib.gv_rng_state_bytes(), dtype=torch.uint8, device="cuda")
+    snapshot = torch.zeros(lib.gv_rng_state_bytes(), dtype=torch.uint8, device=gpu_util.DEVICE)
     _lib.check(lib.gv_rng_save(rng, snapshot.data_ptr(), stream_pointer()))
     second = generate(rng, 5000000)
     np.testing.assert_array_equal(first[:8192], golden["big_head"])

@@ -34,6 +34,7 @@ def sequential_fill(chains, P, L, aug, shuffle_base, pool_size, start, end, fill
                                                   (16, 3, 2, 1), (2, 1, 1, 1)])
 def test_fill_pool_matches_sequential_append(P, L, aug, shuffle_base):
     import torch
+    import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import stream_pointer
     lib = _lib.lib
@@ -43,12 +44,12 @@ def test_fill_pool_matches_sequential_append(P, L, aug, shuffle_base):
     start, end = 60 * shuffle_base, 60 * shuffle_base + 400
     expected = [np.full((pool_size, 2), 0xFFFFFFFF, dtype=np.uint32) for _ in range(num_block)]
     fill = np.zeros(num_block, dtype=np.int64)
-    d_pools = [torch.full((pool_size, 2), -1, dtype=torch.int32, device="cuda") for _ in range(num_block)]
+    d_pools = [torch.full((pool_size, 2), -1, dtype=torch.int32, device=gpu_util.DEVICE) for _ in range(num_block)]
     if P > 1:
         d_pools[num_block - 1] = None  # a block owned by "another rank": counted, never written
-    pointers = torch.tensor([p.data_ptr() if p is not None else 0 for p in d_pools], dtype=torch.int64, device="cuda")
-    d_fill = torch.zeros(num_block, dtype=torch.int64, device="cuda")
-    d_last = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pointers = torch.tensor([p.data_ptr() if p is not None else 0 for p in d_pools], dtype=torch.int64, device=gpu_util.DEVICE)
+    d_fill = torch.zeros(num_block, dtype=torch.int64, device=gpu_util.DEVICE)
+    d_last = torch.zeros(1, dtype=torch.int64, device=gpu_util.DEVICE)
     params = _lib.FillParams(P, L, aug, shuffle_base, pool_size, start, end)
     first_walk, last_expected = 0, 0
     for call, num_walk in enumerate([257, 1, 1000, 33]):
@@ -58,12 +59,12 @@ def test_fill_pool_matches_sequential_append(P, L, aug, shuffle_base):
         last = sequential_fill(chains, P, L, aug, shuffle_base, pool_size, start, end, fill, expected)
         if last >= 0:
             last_expected = max(last_expected, first_walk + last)
-        d_chains = torch.from_numpy(chains.view(np.int32)).cuda()
-        scratch = torch.zeros(lib.gv_cuda_fill_scratch_bytes(num_walk, P) + 16, dtype=torch.uint8, device="cuda")
+        d_chains = gpu_util.to_device(torch.from_numpy(chains.view(np.int32)))
+        scratch = torch.zeros(lib.gv_cuda_fill_scratch_bytes(num_walk, P) + 16, dtype=torch.uint8, device=gpu_util.DEVICE)
         _lib.check(lib.gv_cuda_fill_pool(ctypes.byref(params), d_chains.data_ptr(), num_walk, first_walk,
                                          pointers.data_ptr(), d_fill.data_ptr(), d_last.data_ptr(),
                                          scratch.data_ptr(), stream_pointer()))
-        torch.cuda.synchronize()
+        gpu_util.synchronize()
         first_walk += num_walk
         np.testing.assert_array_equal(d_fill.cpu().numpy(), fill)
     for b in range(num_block - (1 if P > 1 else 0)):
@@ -75,6 +76,7 @@ def test_fill_pool_matches_sequential_append(P, L, aug, shuffle_base):
 def test_partitioned_fill_equals_single_rank():
     """count / exchange-by-hand / scatter over 3 'ranks' gives the pools of one sequential pass"""
     import torch
+    import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import stream_pointer
     lib = _lib.lib
@@ -90,29 +92,29 @@ def test_partitioned_fill_equals_single_rank():
     fill = np.zeros(num_block, dtype=np.int64)
     sequential_fill(chains, P, L, aug, shuffle_base, pool_size, start, end, fill, expected)
 
-    d_pools = [torch.full((pool_size, 2), -1, dtype=torch.int32, device="cuda") for _ in range(num_block)]
-    pointers = torch.tensor([p.data_ptr() for p in d_pools], dtype=torch.int64, device="cuda")
+    d_pools = [torch.full((pool_size, 2), -1, dtype=torch.int32, device=gpu_util.DEVICE) for _ in range(num_block)]
+    pointers = torch.tensor([p.data_ptr() for p in d_pools], dtype=torch.int64, device=gpu_util.DEVICE)
     params = _lib.FillParams(P, L, aug, shuffle_base, pool_size, start, end)
     bounds = [0, 200, 201, 700]
     totals, state = [], []
     for r in range(3):
         lo, hi = bounds[r], bounds[r + 1]
         part = np.ascontiguousarray(chains[:, lo:hi])
-        d_chains = torch.from_numpy(part.view(np.int32)).cuda()
-        scratch = torch.zeros(lib.gv_cuda_fill_scratch_bytes(hi - lo, P) + 16, dtype=torch.uint8, device="cuda")
-        d_totals = torch.zeros(num_block, dtype=torch.int64, device="cuda")
+        d_chains = gpu_util.to_device(torch.from_numpy(part.view(np.int32)))
+        scratch = torch.zeros(lib.gv_cuda_fill_scratch_bytes(hi - lo, P) + 16, dtype=torch.uint8, device=gpu_util.DEVICE)
+        d_totals = torch.zeros(num_block, dtype=torch.int64, device=gpu_util.DEVICE)
         _lib.check(lib.gv_cuda_fill_count(ctypes.byref(params), d_chains.data_ptr(), hi - lo, scratch.data_ptr(),
                                           d_totals.data_ptr(), stream_pointer()))
-        torch.cuda.synchronize()
+        gpu_util.synchronize()
         totals.append(d_totals.cpu().numpy())
         state.append((d_chains, scratch, lo, hi))
     np.testing.assert_array_equal(sum(totals), fill)
-    d_last = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_last = torch.zeros(1, dtype=torch.int64, device=gpu_util.DEVICE)
     for r in range(3):
         d_chains, scratch, lo, hi = state[r]
-        bases = torch.from_numpy(sum(totals[:r], np.zeros(num_block, dtype=np.int64))).cuda()
+        bases = gpu_util.to_device(torch.from_numpy(sum(totals[:r], np.zeros(num_block, dtype=np.int64))))
         _lib.check(lib.gv_cuda_fill_scatter(ctypes.byref(params), d_chains.data_ptr(), hi - lo, lo, pointers.data_ptr(),
                                             bases.data_ptr(), d_last.data_ptr(), scratch.data_ptr(), stream_pointer()))
-    torch.cuda.synchronize()
+    gpu_util.synchronize()
     for b in range(num_block):
         np.testing.assert_array_equal(d_pools[b].cpu().numpy().view(np.uint32), expected[b], err_msg="block %d" % b)

@@ -24,6 +24,7 @@ def run_kg_train(model, dim, head, tail, relation, moments, batch, negatives, op
     """Runs gv_cuda_kg_train_block on copies; tail=None means one shared entity matrix.  moments =
     dict(name -> array) for hm1, tm1, rm1, hm2, tm2, rm2 (tm* ignored when shared)."""
     import torch
+    import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import dev, host, stream_pointer
     otype, olr, wd, a, b, eps = optimizer
@@ -51,16 +52,16 @@ def run_kg_train(model, dim, head, tail, relation, moments, batch, negatives, op
     else:
         k = len(random) // (2 * n)
         d_negatives, d_random = None, dev(np.asarray(random, dtype=np.float64))
-        d_out = torch.zeros(n * k, dtype=torch.int32, device="cuda")
+        d_out = torch.zeros(n * k, dtype=torch.int32, device=gpu_util.DEVICE)
     d_lr = dev(np.asarray(lr, dtype=np.float32))
-    d_loss = torch.zeros(max(1, n), dtype=torch.float32, device="cuda")
-    d_batch_loss = torch.zeros(num_batch, dtype=torch.float32, device="cuda")
+    d_loss = torch.zeros(max(1, n), dtype=torch.float32, device=gpu_util.DEVICE)
+    d_batch_loss = torch.zeros(num_batch, dtype=torch.float32, device=gpu_util.DEVICE)
     device_optimizer = _lib.DeviceOptimizer(otype, wd, a, b, eps)
     _lib.check(_lib.lib.gv_cuda_kg_train_block(
         ctypes.byref(m), MODEL_IDS[model], d_batch.data_ptr(), n, k, pointer(d_negatives), pointer(d_random),
         negative_count, pointer(d_out), ctypes.byref(device_optimizer), d_lr.data_ptr(), batch_size, rlm, margin_or_l3,
         temperature, d_loss.data_ptr(), d_batch_loss.data_ptr(), num_group, stream_pointer()))
-    torch.cuda.synchronize()
+    gpu_util.synchronize()
     result = {name: (tensor.cpu().numpy() if tensor is not None else None) for name, tensor in d.items()}
     result["loss"] = d_loss.cpu().numpy()[:n]
     result["batch_loss"] = d_batch_loss.cpu().numpy()
@@ -207,6 +208,7 @@ def test_fused_uniform_negative_sampling_is_bit_exact():
 @pytest.mark.parametrize("model", K.MODELS)
 def test_predict(model, dim):
     import torch
+    import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import dev, stream_pointer
     rng = np.random.RandomState(dim)
@@ -214,12 +216,12 @@ def test_predict(model, dim):
     relation = ((rng.rand(6, dim) - 0.5) * 2).astype(np.float32)
     batch = np.stack([rng.randint(0, 6, 300), rng.randint(0, 50, 300), rng.randint(0, 50, 300)], axis=1).astype(np.uint32)
     d_entity, d_relation, d_batch = dev(entity), dev(relation), dev(batch, np.uint32)
-    logits = torch.zeros(300, dtype=torch.float32, device="cuda")
+    logits = torch.zeros(300, dtype=torch.float32, device=gpu_util.DEVICE)
     m = _lib.KgMatrices(dim, 50, d_entity.data_ptr(), d_entity.data_ptr(), d_relation.data_ptr(), None, None, None, None,
                         None, None)
     _lib.check(_lib.lib.gv_cuda_kg_predict(ctypes.byref(m), MODEL_IDS[model], d_batch.data_ptr(), 300, 6.0,
                                            logits.data_ptr(), stream_pointer()))
-    torch.cuda.synchronize()
+    gpu_util.synchronize()
     expected = np.array([K.forward(model, entity[h], entity[t], relation[r], 6.0) for r, t, h in batch], dtype=np.float32)
     np.testing.assert_allclose(logits.cpu().numpy(), expected, rtol=1e-4, atol=1e-4)
 
