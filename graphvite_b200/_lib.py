@@ -25,6 +25,7 @@ P = ctypes.POINTER
 SCHEDULE_FN = ctypes.CFUNCTYPE(c_float, c_int, c_int, c_void_p)
 EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_int, c_uint64, c_void_p, c_void_p)
 HOST_ALLGATHER_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_uint64, c_void_p)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_uint64, c_void_p, c_void_p)
 
 
 class OptimizerDesc(ctypes.Structure):
@@ -58,10 +59,17 @@ class KgMatrices(ctypes.Structure):
                 ("head_m2", c_void_p), ("tail_m2", c_void_p), ("relation_m2", c_void_p)]
 
 
+class DeviceKGraph(ctypes.Structure):
+    """gv_device_kgraph_t (device pointers)"""
+    _fields_ = [("num_edge", c_uint64), ("edge_h", c_void_p), ("edge_t", c_void_p), ("edge_r", c_void_p),
+                ("edge_prob", c_void_p), ("edge_alias", c_void_p), ("locations", c_void_p)]
+
+
 class FillParams(ctypes.Structure):
     """gv_fill_params_t"""
     _fields_ = [("num_partition", c_int), ("walk_length", c_int), ("augmentation_step", c_int),
-                ("shuffle_base", c_int), ("pool_size", c_uint64), ("start", c_uint64), ("end", c_uint64)]
+                ("shuffle_base", c_int), ("pool_size", c_uint64), ("start", c_uint64), ("end", c_uint64),
+                ("attributes", c_void_p)]
 
 
 # every symbol include/gv_b200.h declares: name -> (restype, argtypes)
@@ -95,6 +103,9 @@ SIGNATURES = {
                                        c_void_p, P(DeviceOptimizer), c_void_p, c_uint32, c_float, c_float, c_float,
                                        c_void_p, c_void_p, c_int, c_void_p]),
     "gv_cuda_kg_predict": (c_int, [P(KgMatrices), c_int, c_void_p, c_uint64, c_float, c_void_p, c_void_p]),
+    "gv_cuda_kg_draw": (c_int, [P(DeviceKGraph), c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "gv_cuda_kg_relation_delta": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
+    "gv_cuda_kg_relation_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "gv_cuda_move_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p]),
     "gv_cuda_fill_count": (c_int, [P(FillParams), c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_fill_scatter": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
@@ -151,6 +162,30 @@ SIGNATURES = {
     "gv_solver_attributes": (c_int, [c_void_p, c_char_p, c_size_t]),
     "gv_solver_logged_loss": (c_int, [c_void_p, c_void_p, c_int]),
     "gv_solver_stats": (c_int, [c_void_p, c_void_p, c_int]),
+    # knowledge-graph solver
+    "gv_kg_solver_create": (c_void_p, [c_int, P(c_int), c_int, c_int, c_uint64, c_int, c_int]),
+    "gv_kg_solver_destroy": (None, [c_void_p]),
+    "gv_kg_solver_set_exchange": (c_int, [c_void_p, EXCHANGE_FN, c_void_p]),
+    "gv_kg_solver_set_allreduce": (c_int, [c_void_p, ALLREDUCE_FN, c_void_p]),
+    "gv_kg_solver_set_option": (c_int, [c_void_p, c_char_p, c_int]),
+    "gv_kg_solver_build": (c_int, [c_void_p, c_void_p, P(OptimizerDesc), c_int, c_int, c_int, c_int]),
+    "gv_kg_solver_train": (c_int, [c_void_p, c_char_p, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float,
+                                   c_int]),
+    "gv_kg_solver_train_begin": (c_int, [c_void_p, c_char_p, c_int, c_int, c_float, c_float, c_float, c_int, c_int,
+                                         c_float, c_int]),
+    "gv_kg_solver_train_episode": (c_int, [c_void_p]),
+    "gv_kg_solver_train_end": (c_int, [c_void_p]),
+    "gv_kg_solver_predict": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+    "gv_kg_solver_clear": (c_int, [c_void_p]),
+    "gv_kg_solver_embeddings": (P(c_float), [c_void_p, c_int, P(c_uint64), P(c_int)]),
+    "gv_kg_solver_info": (c_int, [c_void_p, c_char_p, c_size_t]),
+    "gv_kg_solver_attributes": (c_int, [c_void_p, c_char_p, c_size_t]),
+    "gv_kg_solver_logged_loss": (c_int, [c_void_p, c_void_p, c_int]),
+    "gv_kg_solver_stats": (c_int, [c_void_p, c_void_p, c_int]),
+    "gv_kg_solver_locations": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gv_kg_solver_pool": (c_int64, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "gv_kg_solver_last_negatives": (c_int, [c_void_p, c_void_p]),
+    "gv_kg_schedule": (c_int, [c_int, c_int, c_void_p, c_int]),
     # test hooks
     "gv_schedule_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int]),
     "gv_reset_global_engine": (None, [c_uint32]),

@@ -1,0 +1,178 @@
+// Internal C++ declarations shared by the solvers of libgv_b200 (gv_solver.cpp, gv_kg_solver.cpp): the
+// process-wide engine, SolverMixin's constants, RAII device memory, the optimizer descriptor with its
+// learning-rate schedule, and SolverMixin::partition.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gv_host.h"
+
+namespace gv {
+
+// core/solver.h:50-57 and instance/graph.cuh:56
+extern std::mt19937 g_engine;  // defined in gv_solver.cpp; shared by every solver of the process
+static const int kMaxPartition = 16;
+static const int kRandBatchSize = 5000000;
+static const int kMinBatchSize = 10000;
+static const int kSamplePerVertex = 175;
+static const int kMinEpisodeSample = 20000000;
+static const int kExpectedDegree = 1600;
+static const int kSpanBuffers = 16;  // refill buffers generated and walked per sampler round
+
+#define GV_CHECK_CUDA(call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t gv_e__ = (call);                                                                     \
+        if (gv_e__ != cudaSuccess)                                                                       \
+            throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(gv_e__) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                         \
+    } while (0)
+#define GV_CHECK_ABI(call)                              \
+    do {                                                \
+        if ((call) != 0)                                \
+            throw std::runtime_error(gv_last_error()); \
+    } while (0)
+
+inline void require(bool condition, const std::string &message) {
+    if (!condition)
+        throw std::runtime_error(message);
+}
+
+inline double now_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// GV_LOG=2: phase timings of train_begin() on stderr
+struct PhaseTimer {
+    double last = now_seconds();
+    bool on = getenv("GV_LOG") != nullptr && atoi(getenv("GV_LOG")) >= 2;
+    void mark(const char *what) {
+        if (on) {
+            const double t = now_seconds();
+            fprintf(stderr, "[gv] %-28s %8.3f s\n", what, t - last);
+            last = t;
+        }
+    }
+};
+
+inline bool log_enabled() {
+    static const bool on = getenv("GV_LOG") != nullptr && atoi(getenv("GV_LOG")) > 0;
+    return on;
+}
+
+// RAII device allocation
+struct DeviceArray {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    DeviceArray() {}
+    DeviceArray(const DeviceArray &) = delete;
+    DeviceArray &operator=(const DeviceArray &) = delete;
+    ~DeviceArray() { release(); }
+    void release() {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    void allocate(size_t n) {
+        if (n == bytes && ptr)
+            return;
+        release();
+        if (n) {
+            GV_CHECK_CUDA(cudaMalloc(&ptr, n));
+            bytes = n;
+        }
+    }
+    template<class T>
+    T *as() const { return static_cast<T *>(ptr); }
+    template<class T>
+    void upload(const std::vector<T> &host, cudaStream_t stream = 0) {
+        allocate(host.size() * sizeof(T));
+        if (!host.empty()) {
+            GV_CHECK_CUDA(cudaMemcpyAsync(ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+};
+
+// core/optimizer.h:42-134
+struct HostOptimizer {
+    gv_optimizer_t desc;
+    float init_lr = 0;
+    std::string type_name() const {
+        static const char *names[] = {"SGD", "Momentum", "AdaGrad", "RMSprop", "Adam"};
+        return desc.type < 0 ? "Default" : names[desc.type];
+    }
+    int num_moment() const { return desc.type <= GV_OPT_SGD ? 0 : (desc.type == GV_OPT_ADAM ? 2 : 1); }
+    // LRSchedule::operator() + Optimizer::apply_schedule, core/optimizer.h:65-79,132-134
+    float lr_at(int batch_id, int num_batch) const {
+        float factor = 1;
+        if (desc.schedule == GV_SCHEDULE_LINEAR)
+            factor = std::max(1 - float(batch_id) / num_batch, 1e-4f);
+        else if (desc.schedule == GV_SCHEDULE_CUSTOM && desc.schedule_fn)
+            factor = desc.schedule_fn(batch_id, num_batch, desc.schedule_ctx);
+        return init_lr * factor;
+    }
+    std::string info() const {  // Optimizer::info, core/optimizer.h:137-155
+        static const char *schedules[] = {"constant", "linear", "custom"};
+        std::stringstream ss;
+        ss << "optimizer: " << type_name() << std::endl;
+        ss << "learning rate: " << init_lr << ", lr schedule: " << schedules[desc.schedule] << std::endl;
+        ss << "weight decay: " << desc.weight_decay;
+        if (desc.type == GV_OPT_MOMENTUM)
+            ss << std::endl << "momentum: " << desc.a;
+        if (desc.type == GV_OPT_ADAGRAD)
+            ss << std::endl << "epsilon: " << desc.epsilon;
+        if (desc.type == GV_OPT_RMSPROP)
+            ss << std::endl << "alpha: " << desc.a << ", epsilon: " << desc.epsilon;
+        if (desc.type == GV_OPT_ADAM)
+            ss << std::endl << "beta1: " << desc.a << ", beta2: " << desc.b << ", epsilon: " << desc.epsilon;
+        return ss.str();
+    }
+};
+
+// SolverMixin::partition, core/solver.h:873-887.  std::sort is unstable: the order of equal
+// weights is whatever libstdc++'s introsort leaves, so the very same call is made here.
+inline std::vector<std::vector<uint32_t>> partition_vertices(const std::vector<float> &weights, int num_partition) {
+    std::vector<uint32_t> order(weights.size());
+    for (uint32_t i = 0; i < order.size(); i++)
+        order[i] = i;
+    std::sort(order.begin(), order.end(), [&weights](uint32_t x, uint32_t y) { return weights[x] > weights[y]; });
+    std::vector<std::vector<uint32_t>> parts(num_partition);
+    const uint32_t period = num_partition * 2;
+    for (uint32_t i = 0; i < order.size(); i++) {
+        uint32_t slot = i % period;  // zig-zag deal: 0 1 .. P-1 P-1 .. 1 0
+        if (slot >= uint32_t(num_partition))
+            slot = period - 1 - slot;
+        parts[slot].push_back(order[i]);
+    }
+    return parts;
+}
+
+// pretty::size_string, util/io.h
+inline std::string size_string(uint64_t size) {
+    std::stringstream ss;
+    ss.precision(3);
+    if (size >= (uint64_t(1) << 40))
+        ss << double(size) / (uint64_t(1) << 40) << " TiB";
+    else if (size >= (uint64_t(1) << 30))
+        ss << double(size) / (uint64_t(1) << 30) << " GiB";
+    else if (size >= (uint64_t(1) << 20))
+        ss << double(size) / (uint64_t(1) << 20) << " MiB";
+    else if (size >= (uint64_t(1) << 10))
+        ss << double(size) / (uint64_t(1) << 10) << " KiB";
+    else
+        ss << size << " B";
+    return ss.str();
+}
+
+}  // namespace gv

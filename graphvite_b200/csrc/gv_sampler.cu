@@ -78,7 +78,21 @@ __global__ void __launch_bounds__(256) random_walk_kernel(const gv_device_graph_
 struct FillParams {
     int num_partition, walk_length, augmentation_step, shuffle_base;
     unsigned long long pool_size, start, slice;  // slice = end - start
+    const uint32_t *attributes;                  // knowledge graphs: relation of every sampled edge, else null
 };
+
+// one pool entry: a pair {tail_local, head_local}, or with attributes a triplet {relation, tail_local,
+// head_local} (the byte order of the reference's std::tuple<Index, Index[, Index]>)
+__device__ __forceinline__ void write_entry(const FillParams &p, uint32_t *block, unsigned long long position,
+                                            uint32_t walk, uint32_t tail_local, uint32_t head_local) {
+    if (p.attributes) {
+        uint32_t *entry = block + position * 3;
+        entry[0] = p.attributes[walk];
+        entry[1] = tail_local;
+        entry[2] = head_local;
+    } else
+        reinterpret_cast<uint2 *>(block)[position] = make_uint2(tail_local, head_local);
+}
 
 // Stable partition of the pairs by block, two levels.  A CTA owns `T` consecutive walks (one per
 // thread) and keeps a histogram counters[b][thread] in shared memory (conflict-free: thread is the
@@ -286,9 +300,9 @@ __global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uin
                 const unsigned long long offset = p.start + in_slice;
                 // pseudo shuffle, instance/graph.cuh:440-441
                 const unsigned long long shuffled = offset % p.shuffle_base * shuffle_stride + offset / p.shuffle_base;
-                uint2 *block = reinterpret_cast<uint2 *>(pool_blocks[b]);
+                uint32_t *block = pool_blocks[b];
                 if (block)
-                    block[shuffled] = make_uint2(tail.y, head.y);  // {tail_local, head_local}
+                    write_entry(p, block, shuffled, w, tail.y, head.y);
                 completed |= in_slice + 1 == slice;
             }
         }
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(256) fill_direct_kernel(const FillParams p, co
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= num_walk)
         return;
-    uint2 *block = reinterpret_cast<uint2 *>(pool_blocks[0]);
+    uint32_t *block = pool_blocks[0];
     const unsigned long long shuffle_stride = p.pool_size / p.shuffle_base;
     unsigned long long in_slice = fill[0] + (unsigned long long)w * pairs_per_walk;
     bool completed = false;
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(256) fill_direct_kernel(const FillParams p, co
             const unsigned long long offset = p.start + in_slice;
             const unsigned long long shuffled = offset % p.shuffle_base * shuffle_stride + offset / p.shuffle_base;
             if (block)
-                block[shuffled] = make_uint2(tail.y, head.y);
+                write_entry(p, block, shuffled, w, tail.y, head.y);
             completed |= in_slice + 1 == p.slice;
         }
     }
@@ -401,6 +415,9 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
     p.pool_size = params->pool_size;
     p.start = params->start;
     p.slice = params->end - params->start;
+    p.attributes = params->attributes;
+    if (p.attributes && (p.walk_length != 1 || p.augmentation_step != 1))
+        return fail("gv_cuda_fill_pool: attributes need walk_length == 1 (edge sampling)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const uint2 *c = reinterpret_cast<const uint2 *>(chains);
     const int threads = 256;
@@ -455,6 +472,9 @@ static int make_fill_params(const gv_fill_params_t *params, FillParams &p) {
     p.pool_size = params->pool_size;
     p.start = params->start;
     p.slice = params->end - params->start;
+    p.attributes = params->attributes;
+    if (p.attributes && (p.walk_length != 1 || p.augmentation_step != 1))
+        return fail("fill: attributes need walk_length == 1 (edge sampling)");
     return 0;
 }
 

@@ -104,6 +104,52 @@ def attach(solver, device=None, group=None):
     return solver
 
 
+def make_allreduce(device=None, group=None):
+    """Build the gv_allreduce_fn callback: sum `count` floats in place over all ranks (the relation deltas of
+    the knowledge-graph solver).  `device` = torch device of this rank, or None for host buffers (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    def allreduce(pointer, count, stream, ctx):
+        try:
+            def run():
+                tensor = _as_tensor(pointer, count * 4, device).view(torch.float32)
+                dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+            if device is None:
+                run()
+            else:
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=device)):
+                    run()
+            return 0
+        except Exception:
+            traceback.print_exc(file=sys.stderr)
+            return -1
+
+    return _lib.ALLREDUCE_FN(allreduce)
+
+
+def attach_knowledge_graph(solver, device=None, group=None):
+    """Wire a KnowledgeGraphSolver created with world_size > 1 to the default process group: entity blocks
+    move by NCCL send / recv, relation deltas are summed by an NCCL all-reduce, both on the solver's stream."""
+    exchange = make_exchange(device, group)
+    reduce = make_allreduce(device, group)
+    _lib.check(_lib.lib.gv_kg_solver_set_exchange(solver._handle, exchange, None))
+    _lib.check(_lib.lib.gv_kg_solver_set_allreduce(solver._handle, reduce, None))
+    solver._exchange = (exchange, reduce)
+    return solver
+
+
+def kg_schedule(num_partition, num_worker):
+    """SolverMixin::get_schedule for tied weights as an int array [steps, worker, 2] = (head, tail) partition."""
+    capacity = (num_partition * num_partition * 4 + 16) * num_worker * 2
+    out = np.zeros(capacity, dtype=np.int32)
+    steps = _lib.lib.gv_kg_schedule(num_partition, num_worker, out.ctypes.data, capacity)
+    if steps < 0:
+        raise _lib.GVError(_lib.last_error())
+    width = 1 if num_partition == 1 else num_worker
+    return out[:steps * width * 2].reshape(steps, width, 2)
+
+
 def schedule_plan(num_partition, num_worker, num_episode=1):
     """The (head, tail, source, give, destination, held) table of gv_schedule_plan as an int array
     [episode * steps, worker, 6]."""

@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _lib
 from .base import auto, cfg, dtype
-from .graph import Graph
+from .graph import Graph, KnowledgeGraph
 from .optimizer import as_optimizer
 
 lib = _lib.lib
@@ -166,10 +166,152 @@ class GraphSolver(object):
         return dict(zip(["positives", "kernel_seconds", "train_seconds", "sample_seconds", "launches"], out))
 
 
+class KnowledgeGraphSolver(object):
+    """KnowledgeGraphSolver(dim, float_type=dtype.float32, index_type=dtype.uint32, device_ids=[],
+    num_sampler_per_worker=auto, gpu_memory_limit=auto)
+
+    Knowledge graph embedding solver (reference include/bind.h:516-639 over
+    include/instance/knowledge_graph.cuh:531-677).  Models: TransE, DistMult, ComplEx, SimplE, RotatE.
+    Extra keyword arguments (not in the reference): rank, world_size for one-process-per-GPU runs.
+    """
+
+    def __init__(self, dim, float_type=None, index_type=None, device_ids=(), num_sampler_per_worker=auto,
+                 gpu_memory_limit=auto, rank=0, world_size=1):
+        float_type = cfg.float_type if float_type is None else float_type
+        index_type = cfg.index_type if index_type is None else index_type
+        if dim not in _KG_DIMS or float_type != dtype.float32 or index_type != dtype.uint32:
+            raise ValueError("Can't find an instantiation of KnowledgeGraphSolver with dim = %s, float_type = %s, "
+                             "index_type = %s" % (dim, float_type, index_type))
+        device_ids = list(device_ids)
+        ids = (ctypes.c_int * max(1, len(device_ids)))(*device_ids)
+        self._handle = lib.gv_kg_solver_create(int(dim), ids, len(device_ids), int(num_sampler_per_worker),
+                                               int(gpu_memory_limit), int(rank), int(world_size))
+        if not self._handle:
+            raise _lib.GVError(_lib.last_error())
+        self.dim = dim
+        self._world_size = int(world_size)
+        self._graph = None
+        self._optimizer = None
+        self._descriptor = None
+        self._exchange = None
+        if world_size > 1:
+            import torch
+            from . import distributed
+            device = torch.device("cuda", device_ids[0] if device_ids else torch.cuda.current_device())
+            distributed.attach_knowledge_graph(self, device)
+
+    def close(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            lib.gv_kg_solver_destroy(handle)
+
+    __del__ = close
+
+    # -- bind.h:579-594 -------------------------------------------------------------------
+    def build(self, graph, optimizer=auto, num_partition=auto, num_negative=64, batch_size=100000,
+              episode_size=auto):
+        """build(graph, optimizer=auto, num_partition=auto, num_negative=64, batch_size=100000, episode_size=auto)"""
+        if not isinstance(graph, KnowledgeGraph):
+            raise TypeError("build(): incompatible function arguments (graph must be a KnowledgeGraph)")
+        optimizer = as_optimizer(optimizer)
+        descriptor = optimizer._descriptor()
+        _lib.check(lib.gv_kg_solver_build(self._handle, graph._handle, ctypes.byref(descriptor), int(num_partition),
+                                          int(num_negative), int(batch_size), int(episode_size)))
+        self._graph, self._optimizer, self._descriptor = graph, optimizer, descriptor
+
+    # -- bind.h:596-619 -------------------------------------------------------------------
+    def train(self, model="RotatE", num_epoch=2000, resume=False, relation_lr_multiplier=1, margin=12,
+              l3_regularization=2e-3, sample_batch_size=2000, positive_reuse=1, adversarial_temperature=2,
+              log_frequency=100):
+        """train(model='RotatE', num_epoch=2000, resume=False, relation_lr_multiplier=1, margin=12,
+        l3_regularization=2e-3, sample_batch_size=2000, positive_reuse=1, adversarial_temperature=2,
+        log_frequency=100)"""
+        _lib.check(lib.gv_kg_solver_train(self._handle, model.encode(), int(num_epoch), int(bool(resume)),
+                                          float(relation_lr_multiplier), float(margin), float(l3_regularization),
+                                          int(sample_batch_size), int(positive_reuse), float(adversarial_temperature),
+                                          int(log_frequency)))
+
+    # -- bind.h:621-629 -------------------------------------------------------------------
+    def predict(self, samples):
+        """predict(samples): logits for an (?, 3) array of triplets ordered (h, t, r)."""
+        samples = np.ascontiguousarray(samples, dtype=np.uint32)
+        if samples.ndim != 2 or samples.shape[1] != 3:
+            raise _lib.GVError("Expect an array with shape (?, 3), but shape (%s) is found" %
+                               ", ".join(str(x) for x in samples.shape))
+        logits = np.empty(samples.shape[0], dtype=np.float32)
+        _lib.check(lib.gv_kg_solver_predict(self._handle, samples.ctypes.data, samples.shape[0], logits.ctypes.data))
+        return logits
+
+    def clear(self):
+        """clear(): free CPU and GPU memory, except the embeddings on CPU."""
+        _lib.check(lib.gv_kg_solver_clear(self._handle))
+
+    # -- numpy views, bind.h:569-572 ----------------------------------------------------------
+    def _view(self, which):
+        rows, dim = ctypes.c_uint64(), ctypes.c_int()
+        pointer = lib.gv_kg_solver_embeddings(self._handle, which, ctypes.byref(rows), ctypes.byref(dim))
+        if rows.value == 0:
+            return np.zeros((0, dim.value), dtype=np.float32)
+        return np.ctypeslib.as_array(pointer, shape=(rows.value, dim.value))
+
+    @property
+    def entity_embeddings(self):
+        """Entity embeddings (2D numpy view of solver-owned memory, mutable)."""
+        return self._view(0)
+
+    @property
+    def relation_embeddings(self):
+        """Relation embeddings (2D numpy view; RotatE uses the first dim / 2 entries of a row as phases)."""
+        return self._view(1)
+
+    def _attributes(self):
+        buffer = ctypes.create_string_buffer(4096)
+        lib.gv_kg_solver_attributes(self._handle, buffer, len(buffer))
+        return dict(line.split("=", 1) for line in buffer.value.decode().splitlines() if "=" in line)
+
+    optimizer = property(lambda self: self._optimizer)
+    model = property(lambda self: self._attributes()["model"])
+    resume = property(lambda self: bool(int(self._attributes()["resume"])))
+
+    def __getattr__(self, name):
+        if name in _KG_INT_ATTRIBUTES:
+            return int(self._attributes()[name])
+        if name in _KG_FLOAT_ATTRIBUTES:
+            return float(self._attributes()[name])
+        raise AttributeError("'KnowledgeGraphSolver' object has no attribute '%s'" % name)
+
+    def __repr__(self):
+        buffer = ctypes.create_string_buffer(8192)
+        lib.gv_kg_solver_info(self._handle, buffer, len(buffer))
+        return buffer.value.decode()
+
+    @property
+    def logged_loss(self):
+        """Mean batch losses in the order the reference would LOG them (core/solver.h:1541-1549)."""
+        count = lib.gv_kg_solver_logged_loss(self._handle, None, 0)
+        out = np.zeros(count, dtype=np.float32)
+        lib.gv_kg_solver_logged_loss(self._handle, out.ctypes.data, count)
+        return out
+
+    @property
+    def stats(self):
+        out = np.zeros(5, dtype=np.float64)
+        lib.gv_kg_solver_stats(self._handle, out.ctypes.data, 5)
+        return dict(zip(["positives", "kernel_seconds", "train_seconds", "sample_seconds", "launches"], out))
+
+
+_KG_DIMS = (32, 64, 96, 128, 256, 512, 1024, 2048)  # src/graphvite.cu:61-70
+_KG_INT_ATTRIBUTES = {"num_partition", "num_negative", "sample_batch_size", "num_epoch", "episode_size", "batch_size",
+                      "positive_reuse", "log_frequency", "num_worker", "num_sampler", "gpu_memory_limit",
+                      "gpu_memory_cost", "num_batch", "batch_id", "pool_id", "partition_size", "rank",
+                      "assignment_offset", "shuffle_partition"}
+_KG_FLOAT_ATTRIBUTES = {"negative_sample_exponent", "relation_lr_multiplier", "margin", "l3_regularization",
+                        "adversarial_temperature"}
+
 _INT_ATTRIBUTES = {"num_partition", "num_negative", "num_epoch", "episode_size", "batch_size", "augmentation_step",
                    "random_walk_length", "random_walk_batch_size", "shuffle_base", "positive_reuse", "log_frequency",
                    "num_worker", "num_sampler", "gpu_memory_limit", "gpu_memory_cost", "num_batch", "batch_id",
                    "pool_id", "partition_size", "rank"}
 _FLOAT_ATTRIBUTES = {"negative_sample_exponent", "negative_weight", "p", "q"}
 
-__all__ = ["GraphSolver"]
+__all__ = ["GraphSolver", "KnowledgeGraphSolver"]

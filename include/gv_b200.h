@@ -200,6 +200,11 @@ typedef struct {
     int shuffle_base;
     uint64_t pool_size;       /* episode_size * batch_size */
     uint64_t start, end;      /* this sampler's slice */
+    /* knowledge graphs (SamplerMixin::sample with KnowledgeGraphSampler::get_attributes,
+     * instance/knowledge_graph.cuh:300-302): device [num_walk] relation of every sampled edge, or NULL.
+     * When set (walk_length must be 1) pool entries are 12-byte triplets {relation, tail_local, head_local}
+     * -- the reference's std::tuple<Index, Index, Index> byte order -- instead of 8-byte pairs. */
+    const uint32_t *attributes;
 } gv_fill_params_t;
 
 size_t gv_cuda_fill_scratch_bytes(uint32_t num_walk, int num_partition);
@@ -258,6 +263,26 @@ int gv_cuda_kg_train_block(const gv_kg_matrices_t *matrices, int model, const ui
 /* logits[i] = Model::forward(head[batch[i].head], tail[batch[i].tail], relation[batch[i].relation], margin) */
 int gv_cuda_kg_predict(const gv_kg_matrices_t *matrices, int model, const uint32_t *batch, uint64_t num_sample,
                        float margin, float *logits, void *stream);
+
+/* Positive-sample draw of the knowledge-graph sampler (SamplerMixin::sample, core/solver.h:1036-1044, with
+ * KnowledgeGraphSampler::get_attributes, instance/knowledge_graph.cuh:300-302): draw d consumes
+ * random[2d] (accept, narrowed to float) and random[2d+1] (index) like edge_table.sample(random[r++],
+ * random[r++]) does under gcc; chains [2][num_draw] receive the (partition, local row) of head and tail,
+ * relations [num_draw] the edge's relation.  Feed both to gv_cuda_fill_pool (walk_length 1, attributes). */
+typedef struct {
+    uint64_t num_edge;
+    const uint32_t *edge_h, *edge_t, *edge_r;   /* flatten() order */
+    const float *edge_prob;                     /* AliasTable<float, size_t> over the triplet weights */
+    const uint64_t *edge_alias;
+    const gv_location_t *locations;             /* entity -> (partition, local row); tied head / tail */
+} gv_device_kgraph_t;
+int gv_cuda_kg_draw(const gv_device_kgraph_t *graph, const double *random, uint32_t num_draw, gv_location_t *chains,
+                    uint32_t *relations, void *stream);
+/* Write-back of the global relation matrix (WorkerMixin::write_embedding for kGlobal, core/solver.h:1413-1420:
+ * global -= loaded - trained), split so that several workers' deltas can be summed in between:
+ * delta = global - work;  [all-reduce(sum) of delta over the ranks];  global -= delta, work = global. */
+int gv_cuda_kg_relation_delta(const float *global, const float *work, float *delta, uint64_t n, void *stream);
+int gv_cuda_kg_relation_apply(float *global, float *work, const float *delta, uint64_t n, void *stream);
 
 /* Memory::gather / Memory::scatter (base/memory.h:194-217) on the device: rows of `dim` floats,
  * dst[i] = src[ids[i]] when gather != 0, else dst[ids[i]] = src[i]. */
@@ -373,6 +398,60 @@ int gv_solver_attributes(const gv_solver_t *solver, char *buffer, size_t capacit
 int gv_solver_logged_loss(const gv_solver_t *solver, float *out, int capacity);
 /* throughput counters of the last train(): positives consumed and device seconds in the train kernels */
 int gv_solver_stats(const gv_solver_t *solver, double *out, int capacity);
+
+/* ---- host runtime: KnowledgeGraphSolver (instance/knowledge_graph.cuh:531-677, core/solver.h,
+ * bind.h:516-639).  Same conventions as gv_solver_*: one process drives one GPU, world_size processes form
+ * the reference's num_worker.  Entity embeddings are ONE matrix used for heads and tails (tied weights,
+ * protocols kHeadPartition|kInPlace / kTailPartition|kInPlace|kSharedWithPredecessor); the relation matrix is
+ * global: every worker trains a private copy and the copies are reconciled by summing their deltas after
+ * every schedule step (the caller-provided all-reduce, NCCL over NVLink), which replaces the reference's
+ * scatter_sub through host memory. */
+typedef struct gv_kg_solver gv_kg_solver_t;
+
+/* dim even, <= 2048 (the reference instantiates 32..2048, src/graphvite.cu:61-70); 0 for the two autos */
+gv_kg_solver_t *gv_kg_solver_create(int dim, const int *device_ids, int num_device, int num_sampler_per_worker,
+                                    uint64_t gpu_memory_limit, int rank, int world_size);
+void gv_kg_solver_destroy(gv_kg_solver_t *solver);
+/* world_size > 1: entity blocks move between the ranks through `exchange` (see gv_solver_set_exchange) and
+ * the relation deltas are summed in place over all ranks by `allreduce` (count floats, device memory, on
+ * `stream`) */
+typedef int (*gv_allreduce_fn)(void *buffer, uint64_t count, void *stream, void *ctx);
+int gv_kg_solver_set_exchange(gv_kg_solver_t *solver, gv_exchange_fn fn, void *ctx);
+int gv_kg_solver_set_allreduce(gv_kg_solver_t *solver, gv_allreduce_fn fn, void *ctx);
+/* SolverMixin::build; optimizer type -1 = Adam(5e-5, 0) (knowledge_graph.cuh:557-559); minimum
+ * #partition is 1 for one worker, 2 * #worker otherwise (tied weights, core/solver.h:266-277) */
+int gv_kg_solver_build(gv_kg_solver_t *solver, gv_kgraph_t *graph, const gv_optimizer_t *optimizer, int num_partition,
+                       int num_negative, int batch_size, int episode_size);
+/* KnowledgeGraphSolver::train (knowledge_graph.cuh:666-677) */
+int gv_kg_solver_train(gv_kg_solver_t *solver, const char *model, int num_epoch, int resume,
+                       float relation_lr_multiplier, float margin, float l3_regularization, int sample_batch_size,
+                       int positive_reuse, float adversarial_temperature, int log_frequency);
+/* SolverMixin::predict_numpy: triplets = HOST [n][3] global ids ordered (head, tail, relation) (bind.h:621-629) */
+int gv_kg_solver_predict(gv_kg_solver_t *solver, const uint32_t *triplets, uint64_t num, float *logits);
+int gv_kg_solver_clear(gv_kg_solver_t *solver);
+/* numpy views (bind.h:569-572): which 0 = entity_embeddings [num_vertex][dim], 1 = relation_embeddings
+ * [num_relation][dim] (RotatE uses the first dim / 2 floats of a row) */
+float *gv_kg_solver_embeddings(gv_kg_solver_t *solver, int which, uint64_t *rows, int *dim);
+int gv_kg_solver_info(const gv_kg_solver_t *solver, char *buffer, size_t capacity);
+int gv_kg_solver_attributes(const gv_kg_solver_t *solver, char *buffer, size_t capacity);
+int gv_kg_solver_logged_loss(const gv_kg_solver_t *solver, float *out, int capacity);
+int gv_kg_solver_stats(const gv_kg_solver_t *solver, double *out, int capacity);
+/* test hooks, as for gv_solver_*: staged training, pools ({relation, tail_local, head_local} triplets),
+ * partition of the entities, the negatives drawn for the last batch, and the tied-weight schedule
+ * (SolverMixin::get_schedule, core/solver.h:519-561: out[(step * W + worker) * 2 + {0, 1}] = head, tail
+ * partition; returns #steps).  Options: "capture_negatives", "train_num_groups" (1 = one thread group,
+ * samples in order: deterministic), "shuffle_partition" (-1 = the reference's rule, 0 / 1 forces it). */
+int gv_kg_solver_train_begin(gv_kg_solver_t *solver, const char *model, int num_epoch, int resume,
+                             float relation_lr_multiplier, float margin, float l3_regularization,
+                             int sample_batch_size, int positive_reuse, float adversarial_temperature,
+                             int log_frequency);
+int gv_kg_solver_train_episode(gv_kg_solver_t *solver);
+int gv_kg_solver_train_end(gv_kg_solver_t *solver);
+int gv_kg_solver_set_option(gv_kg_solver_t *solver, const char *name, int value);
+int gv_kg_solver_locations(const gv_kg_solver_t *solver, uint32_t *part_of, uint32_t *local_of);
+int64_t gv_kg_solver_pool(gv_kg_solver_t *solver, int pool, int head_partition, int tail_partition, uint32_t *out);
+int gv_kg_solver_last_negatives(gv_kg_solver_t *solver, uint32_t *out);
+int gv_kg_schedule(int num_partition, int num_worker, int *out, int capacity);
 
 /* ---- test hooks (no reference counterpart: the reference's members are simply public) ------- */
 /* SolverMixin::get_schedule (core/solver.h:519-575) plus the vertex-block movement it implies:

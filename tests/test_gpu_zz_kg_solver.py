@@ -1,0 +1,194 @@
+"""GPU parity of the knowledge-graph host runtime (gv_kg_solver_*) against the oracle's KGSolver
+(oracle/gv_oracle_kg.cpp): partition, sample pools and negative indices bit-exact for the default engine
+seed; entity / relation embeddings, logged loss and predict within float tolerance (rtol 1e-3) in the
+one-group (sequential) mode.  The same file runs on the CPU under tests/emu (test_emulated_kernels.py).
+
+The oracle's solver half is parity-unpinned until oracle/make_golden_kg.py has recorded the reference on a
+GPU (see its header); what this file pins is product == oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_kg_lib as K
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOY_KG = os.path.join(ROOT, "tests", "golden", "toy_kg.txt")
+
+# dim, P, k, B (batch), E (episode), S (samplers), model, epochs, optimizer, sample batch, extra train kwargs
+CASES = {
+    "rotate_adam_p1": dict(dim=32, P=1, k=4, B=100, E=3, S=1, model="RotatE", epochs=1, optimizer="Adam", sb=64,
+                           train=dict(margin=6.0, adversarial_temperature=2.0)),
+    "transe_sgd_p1_s2": dict(dim=32, P=1, k=3, B=120, E=2, S=2, model="TransE", epochs=1, optimizer="SGD", sb=50,
+                             train=dict(margin=8.0, adversarial_temperature=0.0)),
+    "distmult_adagrad_p2": dict(dim=64, P=2, k=2, B=80, E=2, S=1, model="DistMult", epochs=2, optimizer="AdaGrad",
+                                sb=40, train=dict(l3_regularization=1e-3, adversarial_temperature=1.0)),
+    "complex_sgd_p4": dict(dim=32, P=4, k=2, B=60, E=2, S=3, model="ComplEx", epochs=2, optimizer="SGD", sb=32,
+                           train=dict(l3_regularization=2e-3, relation_lr_multiplier=0.5)),
+    "simple_momentum_p2": dict(dim=32, P=2, k=3, B=90, E=1, S=2, model="SimplE", epochs=2, optimizer="Momentum",
+                               sb=77, train=dict(adversarial_temperature=0.5, positive_reuse=2)),
+    "rotate_rmsprop_p2": dict(dim=96, P=2, k=2, B=70, E=2, S=1, model="RotatE", epochs=2, optimizer="RMSprop",
+                              sb=25, train=dict(margin=9.0, log_frequency=3)),
+}
+
+
+def optimizer_of(gv, name):
+    otype, lr, wd, a, b, eps = O.OPTIMIZERS[name]
+    kwargs = {"SGD": {}, "Momentum": dict(momentum=a), "AdaGrad": dict(epsilon=eps),
+              "RMSprop": dict(alpha=a, epsilon=eps), "Adam": dict(beta1=a, beta2=b, epsilon=eps)}[name]
+    return getattr(gv.optimizer, name)(lr, wd, **kwargs)
+
+
+def make_pair(cfg):
+    import graphvite_b200 as gv
+    from graphvite_b200 import _lib
+    _lib.lib.gv_reset_global_engine(5489)
+    graph = gv.graph.KnowledgeGraph()
+    graph.load(TOY_KG)
+    solver = gv.solver.KnowledgeGraphSolver(cfg["dim"], device_ids=[0], num_sampler_per_worker=cfg["S"])
+    _lib.check(_lib.lib.gv_kg_solver_set_option(solver._handle, b"capture_negatives", 1))
+    _lib.check(_lib.lib.gv_kg_solver_set_option(solver._handle, b"train_num_groups", 1))
+    solver.build(graph, optimizer_of(gv, cfg["optimizer"]), cfg["P"], cfg["k"], cfg["B"], cfg["E"])
+    ograph = K.OracleKnowledgeGraph(TOY_KG)
+    osolver = K.OracleKGSolver(ograph, cfg["dim"], 1, cfg["S"])
+    osolver.build(cfg["optimizer"], cfg["P"], cfg["k"], cfg["B"], cfg["E"])
+    return gv, _lib, graph, solver, ograph, osolver
+
+
+def train_kwargs(cfg):
+    kwargs = dict(model=cfg["model"], num_epoch=cfg["epochs"], resume=False, relation_lr_multiplier=1.0, margin=12.0,
+                  l3_regularization=2e-3, sample_batch_size=cfg["sb"], positive_reuse=1, adversarial_temperature=2.0,
+                  log_frequency=2)
+    kwargs.update(cfg["train"])
+    return kwargs
+
+
+def product_begin(_lib, solver, kw):
+    _lib.check(_lib.lib.gv_kg_solver_train_begin(
+        solver._handle, kw["model"].encode(), kw["num_epoch"], int(kw["resume"]), kw["relation_lr_multiplier"],
+        kw["margin"], kw["l3_regularization"], kw["sample_batch_size"], kw["positive_reuse"],
+        kw["adversarial_temperature"], kw["log_frequency"]))
+
+
+def product_pool(_lib, solver, side, head, tail, size):
+    out = np.zeros((size, 3), dtype=np.uint32)
+    assert _lib.lib.gv_kg_solver_pool(solver._handle, side, head, tail, out.ctypes.data) == size
+    return out
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_kg_solver_matches_oracle_step_by_step(case):
+    cfg = CASES[case]
+    gv, _lib, graph, solver, ograph, osolver = make_pair(cfg)
+    n = graph.num_vertex
+    part_of, local_of = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+    _lib.lib.gv_kg_solver_locations(solver._handle, part_of.ctypes.data, local_of.ctypes.data)
+    opart, olocal = osolver.locations()
+    np.testing.assert_array_equal(part_of, opart.astype(np.uint32))
+    np.testing.assert_array_equal(local_of, olocal)
+
+    kw = train_kwargs(cfg)
+    product_begin(_lib, solver, kw)
+    osolver.train_begin(**kw)
+    info = osolver.info()
+    for key in ("num_partition", "episode_size", "batch_size", "num_batch", "shuffle_partition"):
+        assert getattr(solver, key) == info[key], key
+    # identical initial embeddings: the same engine, the same draws
+    size = info["episode_size"] * info["batch_size"]
+    P = info["num_partition"]
+
+    def check_pools(side):
+        for h in range(P):
+            for t in range(P):
+                np.testing.assert_array_equal(product_pool(_lib, solver, side, h, t, size), osolver.pool(side, h, t),
+                                              err_msg="pool %d block (%d, %d)" % (side, h, t))
+
+    check_pools(1)
+    episodes = 0
+    while True:
+        status = _lib.lib.gv_kg_solver_train_episode(solver._handle)
+        assert status >= 0, _lib.last_error()
+        more = osolver.train_episode()
+        assert (status == 1) == more
+        if not more:
+            break
+        episodes += 1
+        oinfo = osolver.info()
+        check_pools(oinfo["pool_id"] ^ 1)
+        assert solver.assignment_offset == oinfo["assignment_offset"]
+        negatives = np.zeros(cfg["B"] * cfg["k"], dtype=np.uint32)
+        assert _lib.lib.gv_kg_solver_last_negatives(solver._handle, negatives.ctypes.data) == negatives.size
+        np.testing.assert_array_equal(negatives, osolver.last_negatives())
+    assert episodes >= 1
+    _lib.check(_lib.lib.gv_kg_solver_train_end(solver._handle))
+    assert solver.batch_id == osolver.info()["batch_id"]
+    np.testing.assert_allclose(solver.entity_embeddings, osolver.entity_embeddings, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(solver.relation_embeddings, osolver.relation_embeddings, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(solver.logged_loss, osolver.logged_loss(), rtol=1e-3, atol=1e-6)
+    triplets = np.stack([np.random.RandomState(3).randint(0, n, 400), np.random.RandomState(4).randint(0, n, 400),
+                         np.random.RandomState(5).randint(0, graph.num_relation, 400)], axis=1).astype(np.uint32)
+    np.testing.assert_allclose(solver.predict(triplets), osolver.predict(triplets), rtol=1e-3, atol=1e-4)
+
+
+def test_second_train_call_resumes_and_keeps_the_workers_relation_moments():
+    """train(); train(resume=True); train(resume=False) on one build(): the entity moments follow `resume`, the
+    worker-resident relation moments and the loss buffer survive every call (core/solver.h:1326,1378-1385)."""
+    cfg = CASES["rotate_adam_p1"]
+    gv, _lib, graph, solver, ograph, osolver = make_pair(cfg)
+    kw = train_kwargs(cfg)
+    for resume in (False, True, False):
+        kw["resume"] = resume
+        product_begin(_lib, solver, kw)
+        osolver.train_begin(**kw)
+        while _lib.lib.gv_kg_solver_train_episode(solver._handle) == 1:
+            assert osolver.train_episode()
+        assert not osolver.train_episode()
+        _lib.check(_lib.lib.gv_kg_solver_train_end(solver._handle))
+        np.testing.assert_allclose(solver.entity_embeddings, osolver.entity_embeddings, rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(solver.relation_embeddings, osolver.relation_embeddings, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(solver.logged_loss, osolver.logged_loss(), rtol=1e-3, atol=1e-6)
+
+
+def test_full_grid_training_learns_the_toy_graph():
+    """Every thread group of the device at once (Hogwild, like the reference's warps): true triplets must end up
+    scoring far above corrupted ones."""
+    import graphvite_b200 as gv
+    graph = gv.graph.KnowledgeGraph()
+    graph.load(TOY_KG)
+    solver = gv.solver.KnowledgeGraphSolver(64, device_ids=[0])
+    solver.build(graph, gv.optimizer.Adam(5e-3), num_negative=8, batch_size=256, episode_size=2)
+    solver.train("RotatE", num_epoch=60, margin=6.0, sample_batch_size=100, log_frequency=50)
+    ograph = K.OracleKnowledgeGraph(TOY_KG)
+    h, t, r, _, _ = ograph.flat()
+    true = np.stack([h, t, r], axis=1).astype(np.uint32)
+    rng = np.random.RandomState(0)
+    corrupted = true.copy()
+    corrupted[:, 1] = rng.randint(0, graph.num_vertex, len(true))
+    positive, negative = solver.predict(true), solver.predict(corrupted)
+    assert np.isfinite(positive).all() and np.isfinite(negative).all()
+    assert positive.mean() > negative.mean() + 1.0
+    assert "KnowledgeGraphSolver<64" in repr(solver) and "tied weights: yes" in repr(solver)
+
+
+def test_error_paths():
+    import graphvite_b200 as gv
+    from graphvite_b200 import _lib
+    graph = gv.graph.KnowledgeGraph()
+    graph.load(TOY_KG)
+    with pytest.raises(ValueError):
+        gv.solver.KnowledgeGraphSolver(100)
+    solver = gv.solver.KnowledgeGraphSolver(32, device_ids=[0])
+    with pytest.raises(_lib.GVError, match="must be built"):
+        solver.train("RotatE", num_epoch=1)
+    solver.build(graph, num_negative=2, batch_size=50, episode_size=1)
+    assert solver.optimizer.type in ("Default", "Adam")
+    with pytest.raises(_lib.GVError, match="multiple of 2"):
+        solver.build(graph, num_partition=3, num_negative=2, batch_size=50, episode_size=1)
+    solver.build(graph, num_negative=2, batch_size=50, episode_size=1)
+    with pytest.raises(_lib.GVError, match="Invalid model"):
+        solver.train("LINE", num_epoch=1)
+    with pytest.raises(_lib.GVError, match="shape"):
+        solver.predict(np.zeros((4, 2), dtype=np.uint32))
