@@ -397,6 +397,16 @@ struct KGSolver {
     int num_epoch = 0, sample_batch_size = 2000, positive_reuse = 1, log_frequency = 100;
     float relation_lr_multiplier = 1, margin = 12, l3_regularization = 2e-3f, adversarial_temperature = 2;
     bool resume = false, shuffle_partition = false;
+    // Switches of the MULTI-worker emulation (the reference is nondeterministic there; with one worker they
+    // change nothing the product is compared on):
+    //  shuffle_override >= 0  forces shuffle_partition (the product never rotates tail partitions with several
+    //                         workers: the rotated steps make two reference workers train copies of one partition)
+    //  synchronous_relation   all workers write their relation deltas back before any worker loads the matrix
+    //                         for the next step -- one legal interleaving of the reference's concurrent
+    //                         "write back, then load" per worker (core/solver.h:1436-1500), and the one an
+    //                         all-reduce of the deltas implements
+    int shuffle_override = -1;
+    bool synchronous_relation = false;
     int batch_id = 0, num_batch = 0, pool_id = 0, assignment_offset = 0;
 
     std::vector<unsigned long long> sampler_seeds, worker_seeds;
@@ -459,6 +469,8 @@ struct KGSolver {
         if (num_partition < min_partition)
             fail("#partition should be no less than " + std::to_string(min_partition));
         shuffle_partition = optimizer.num_moment() > 0;  // :385
+        if (shuffle_override >= 0)
+            shuffle_partition = shuffle_override != 0;
         assignment_offset = 0;
         partitions = partition(graph->vertex_weights, num_partition);
         locations.resize(graph->num_vertex);
@@ -734,6 +746,9 @@ struct KGSolver {
         auto schedule = get_schedule();
         int per_block = positive_reuse * episode_size;
         for (auto &assignment : schedule) {
+            if (synchronous_relation)
+                for (auto &w : workers)
+                    write_relation(w);
             for (int i = 0; i < (int)assignment.size(); i++)
                 train_block(i, assignment[i].first, (assignment[i].second + assignment_offset) % num_partition,
                             batch_id + i, (int)assignment.size());
@@ -902,6 +917,12 @@ int og_kg_solver_build(void *s, void *graph, int opt_type, int schedule, float l
     ((KGSolver *)s)->build((KGraph *)graph, opt, num_partition, num_negative, batch_size, episode_size);
     return 0;
     KG_CATCH(-1)
+}
+
+// see KGSolver::shuffle_override / synchronous_relation; call before build()
+void og_kg_solver_set_emulation(void *s, int shuffle_override, int synchronous_relation) {
+    ((KGSolver *)s)->shuffle_override = shuffle_override;
+    ((KGSolver *)s)->synchronous_relation = synchronous_relation != 0;
 }
 
 int og_kg_solver_train_begin(void *s, const char *model, int num_epoch, int resume, float relation_lr_multiplier,

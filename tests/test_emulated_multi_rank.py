@@ -1,0 +1,34 @@
+"""world_size > 1 on a machine without GPUs: tests/multi_rank_worker.py under the CUDA emulation of tests/emu
+(GV_EMULATE=1), one process per emulated device over gloo.  The ranks run the product's own multi-GPU code
+paths -- block directory and NCCL-shaped exchange of the node-embedding solver; entity-block movement,
+tied-weight schedule and relation all-reduce of the knowledge-graph solver -- and compare pools (bit-exact) and
+embeddings (rtol 1e-3) with the oracle's N-worker emulation.  On real GPUs the same worker runs over NCCL
+(tests/test_gpu_w_multi.py)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [("graph", 2, 2, ""), ("graph", 2, 4, ""), ("kg", 2, 4, "SGD"), ("kg", 2, 4, "Adam"), ("kg", 4, 8, "Adam")]
+
+
+@pytest.mark.parametrize("solver,world,partitions,optimizer", CASES,
+                         ids=["%s-w%d-p%d%s" % (s, w, p, "-" + o if o else "") for s, w, p, o in CASES])
+def test_multi_rank_under_emulation(solver, world, partitions, optimizer):
+    subprocess.check_call(["make", "-j8", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, GV_EMULATE="1", GV_EMU_BACKTRACE="1", GV_TEST_SOLVER=solver,
+               GV_TEST_PARTITIONS=str(partitions), GV_TEST_OPTIMIZER=optimizer or "SGD", OMP_NUM_THREADS="1")
+    command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(port),
+               os.path.join(ROOT, "tests", "multi_rank_worker.py")]
+    result = subprocess.run(command, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert result.returncode == 0, result.stdout[-6000:]
+    for rank in range(world):
+        assert "rank %d ok" % rank in result.stdout
