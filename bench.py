@@ -23,7 +23,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 # config/graph/line_youtube.yaml
 YOUTUBE = dict(dim=128, lr=0.025, weight_decay=0.005, num_negative=1, batch_size=100000, episode_size=500,

@@ -33,7 +33,9 @@ def Application(type, *args, **kwargs):
     application ("graph") is in scope."""
     if type == "graph":
         return GraphApplication(*args, **kwargs)
-    raise ValueError("Unknown application `%s` (this build ships the node-embedding application `graph`)" % type)
+    if type in ("knowledge graph", "knowledge_graph"):
+        return KnowledgeGraphApplication(*args, **kwargs)
+    raise ValueError("Unknown application `%s` (this build ships `graph` and `knowledge graph`)" % type)
 
 
 class GraphApplication(object):
@@ -222,4 +224,239 @@ class GraphApplication(object):
         return self
 
 
-__all__ = ["Application", "GraphApplication", "link_prediction_auc"]
+class KnowledgeGraphApplication(object):
+    """KnowledgeGraphApplication(dim, gpus=[], cpu_per_gpu=auto, gpu_memory_limit=auto, float_type, index_type)
+    (application.py:576-1067): load / build / train / link_prediction / entity_prediction / save_model /
+    load_model for TransE, DistMult, ComplEx, SimplE and RotatE.  Triplets are scored with the solver's own
+    predict kernel (the reference's "graphvite" backend, application.py:828-853)."""
+
+    SAMPLE_PER_DIMENSION = 7  # application.py:626
+
+    def __init__(self, dim, gpus=(), cpu_per_gpu=auto, gpu_memory_limit=auto, float_type=None, index_type=None,
+                 **kwargs):
+        self.dim = dim
+        self.gpus = list(gpus)
+        self.cpu_per_gpu = cpu_per_gpu
+        self.gpu_memory_limit = gpu_memory_limit
+        self.graph = _graph.KnowledgeGraph(index_type)
+        num_sampler_per_worker = auto if cpu_per_gpu == auto else cpu_per_gpu - 1  # application.py:632-638
+        self.solver = _solver.KnowledgeGraphSolver(dim, float_type, index_type, self.gpus[:1], num_sampler_per_worker,
+                                                   gpu_memory_limit, **kwargs)
+
+    def set_format(self, delimiters=" \t\r\n", comment="#"):
+        self._format = dict(delimiters=delimiters, comment=comment)
+        return self
+
+    def load(self, **kwargs):
+        fmt = getattr(self, "_format", None)
+        if fmt and "file_name" in kwargs:
+            kwargs = dict(fmt, **kwargs)
+        self.graph.load(**kwargs)
+        return self
+
+    def build(self, optimizer=auto, **kwargs):
+        if isinstance(optimizer, dict):
+            optimizer = _optimizer.Optimizer(**optimizer)
+        self.solver.build(self.graph, optimizer, **kwargs)
+        return self
+
+    def train(self, **kwargs):
+        self.solver.train(**kwargs)
+        return self
+
+    def evaluate(self, task, **kwargs):
+        name = task.replace(" ", "_")
+        if name == "link_prediction":
+            result = self.link_prediction(**kwargs)
+        elif name == "entity_prediction":
+            return self.entity_prediction(**kwargs)
+        else:
+            raise ValueError("task `%s` is not available in this build" % task)
+        for metric, value in sorted(result.items()):
+            logger.warning("%s: %g" % (metric, value))
+        return result
+
+    def _tokenize(self, line):
+        fmt = getattr(self, "_format", dict(delimiters=" \t\r\n", comment="#"))
+        comment = fmt["comment"]
+        if comment and comment in line:
+            line = line[:line.index(comment)]
+        for delimiter in fmt["delimiters"]:
+            line = line.replace(delimiter, " ")
+        return line.split()
+
+    def _read_triplets(self, file_name):
+        H, R, T = [], [], []
+        with open(file_name, "r") as fin:
+            for i, line in enumerate(fin):
+                tokens = self._tokenize(line)
+                if not tokens:
+                    continue
+                if not 3 <= len(tokens) <= 4:
+                    raise ValueError("Invalid line format at line %d in %s" % (i + 1, file_name))
+                H.append(tokens[0])
+                R.append(tokens[1])
+                T.append(tokens[2])
+        return H, R, T
+
+    def _map_names(self, H, R, T):
+        """name_map (application.py:204-219): keep the triplets whose three names are known"""
+        entity2id, relation2id = self.graph.entity2id, self.graph.relation2id
+        rows = [(entity2id[h], relation2id[r], entity2id[t]) for h, r, t in zip(H, R, T)
+                if h in entity2id and r in relation2id and t in entity2id]
+        array = np.asarray(rows, dtype=np.uint32).reshape(-1, 3)
+        return array[:, 0], array[:, 1], array[:, 2]
+
+    def _batch_size(self, sample_size):
+        """get_batch_size (application.py:948-961) without the psutil bound: triplets per predict() call"""
+        size = int(self.SAMPLE_PER_DIMENSION * self.dim * self.graph.num_vertex / max(1, sample_size))
+        return max(1, min(size, max(1, (1 << 26) // max(1, sample_size))))
+
+    def _scores(self, H, R, T, target):
+        """one-vs-rest scores [len(H) * (2 if both else 1)][num_entity] (generate_one_vs_rest, :963-977)"""
+        num_entity = self.graph.num_vertex
+        every = np.arange(num_entity, dtype=np.uint32)
+        rows = []
+        for h, r, t in zip(H, R, T):
+            if target in ("head", "both"):
+                rows.append(np.stack([every, np.full(num_entity, t, np.uint32), np.full(num_entity, r, np.uint32)], 1))
+            if target in ("tail", "both"):
+                rows.append(np.stack([np.full(num_entity, h, np.uint32), every, np.full(num_entity, r, np.uint32)], 1))
+        return self.solver.predict(np.concatenate(rows)).reshape(-1, num_entity)
+
+    def link_prediction(self, H=None, R=None, T=None, filter_H=None, filter_R=None, filter_T=None, file_name=None,
+                        filter_files=None, target="both", fast_mode=None, backend="graphvite"):
+        """MR, MRR, HITS@1 / 3 / 10 of filtered ranking (application.py:787-946)."""
+        if target not in ("head", "tail", "both"):
+            raise ValueError("Unknown target `%s`" % target)
+        if file_name:
+            if not (H is None and R is None and T is None):
+                raise ValueError("Evaluation data and file should not be provided at the same time")
+            H, R, T = self._read_triplets(file_name)
+        if H is None or R is None or T is None:
+            raise ValueError("Either evaluation data or file should be provided")
+        if filter_files:
+            if not (filter_H is None and filter_R is None and filter_T is None):
+                raise ValueError("Filter data and file should not be provided at the same time")
+            filter_H, filter_R, filter_T = [], [], []
+            for filter_file in filter_files:
+                h, r, t = self._read_triplets(filter_file)
+                filter_H += h
+                filter_R += r
+                filter_T += t
+        elif filter_H is None:
+            filter_H, filter_R, filter_T = [], [], []
+        total = len(H)
+        H, R, T = self._map_names(H, R, T)
+        logger.info("effective triplets: %d / %d" % (len(H), total))
+        filter_H, filter_R, filter_T = self._map_names(filter_H, filter_R, filter_T)
+        exclude_H, exclude_T = {}, {}
+        for h, r, t in zip(filter_H.tolist(), filter_R.tolist(), filter_T.tolist()):
+            exclude_H.setdefault((t, r), set()).add(h)
+            exclude_T.setdefault((h, r), set()).add(t)
+        num_sample = len(H)
+        if num_sample == 0:
+            raise ValueError("no evaluation triplet is known to the graph")
+        fast_mode = fast_mode or num_sample
+        indexes = np.random.permutation(num_sample)[:fast_mode]
+        H, R, T = H[indexes], R[indexes], T[indexes]
+        num_entity = self.graph.num_vertex
+        batch_size = self._batch_size(num_entity * (2 if target == "both" else 1))
+        rankings = []
+        for i in range(0, len(H), batch_size):
+            h, r, t = H[i:i + batch_size], R[i:i + batch_size], T[i:i + batch_size]
+            scores = self._scores(h, r, t, target)
+            row = 0
+            for hh, rr, tt in zip(h.tolist(), r.tolist(), t.tolist()):
+                if target in ("head", "both"):
+                    mask = np.ones(num_entity, dtype=bool)
+                    mask[list(exclude_H.get((tt, rr), ()))] = False
+                    mask[hh] = True
+                    rankings.append(int(np.sum((scores[row] >= scores[row, hh]) & mask)))
+                    row += 1
+                if target in ("tail", "both"):
+                    mask = np.ones(num_entity, dtype=bool)
+                    mask[list(exclude_T.get((hh, rr), ()))] = False
+                    mask[tt] = True
+                    rankings.append(int(np.sum((scores[row] >= scores[row, tt]) & mask)))
+                    row += 1
+        rankings = np.asarray(rankings, dtype=np.float64)
+        return {"MR": float(np.mean(rankings)), "MRR": float(np.mean(1 / rankings)),
+                "HITS@1": float(np.mean(rankings <= 1)), "HITS@3": float(np.mean(rankings <= 3)),
+                "HITS@10": float(np.mean(rankings <= 10))}
+
+    def entity_prediction(self, H=None, R=None, T=None, file_name=None, save_file=None, target="tail", k=10,
+                          backend="graphvite"):
+        """Top-k entities for the missing head / tail of every triplet (application.py:646-785): a list, per
+        triplet, of (entity name, score) pairs; optionally pickled / written as text to `save_file`."""
+        if target not in ("head", "tail"):
+            raise ValueError("Unknown target `%s`" % target)
+        if file_name:
+            if not (H is None and R is None and T is None):
+                raise ValueError("Evaluation data and file should not be provided at the same time")
+            H, R, T = [], [], []
+            with open(file_name, "r") as fin:
+                for i, line in enumerate(fin):
+                    tokens = self._tokenize(line)
+                    if not tokens:
+                        continue
+                    if len(tokens) == 3:
+                        h, r, t = tokens
+                    elif len(tokens) == 2:  # the missing side is absent from the file
+                        h, r, t = (tokens[0], tokens[1], tokens[0]) if target == "tail" else (tokens[1], tokens[0], tokens[1])
+                    else:
+                        raise ValueError("Invalid line format at line %d in %s" % (i + 1, file_name))
+                    H.append(h)
+                    R.append(r)
+                    T.append(t)
+        if target == "tail":
+            if H is None or R is None:
+                raise ValueError("Either evaluation data or file should be provided")
+            T = H if T is None else T
+        else:
+            if T is None or R is None:
+                raise ValueError("Either evaluation data or file should be provided")
+            H = T if H is None else H
+        H, R, T = self._map_names(H, R, T)
+        id2entity = self.graph.id2entity
+        k = min(k, self.graph.num_vertex)
+        batch_size = self._batch_size(self.graph.num_vertex)
+        recalls = []
+        for i in range(0, len(H), batch_size):
+            scores = self._scores(H[i:i + batch_size], R[i:i + batch_size], T[i:i + batch_size], target)
+            top = np.argsort(-scores, axis=1, kind="stable")[:, :k]
+            for row, index in enumerate(top):
+                recalls.append([(id2entity[e], float(scores[row, e])) for e in index])
+        if save_file:
+            if save_file.endswith(".pkl"):
+                with open(save_file, "wb") as fout:
+                    pickle.dump(recalls, fout, protocol=pickle.HIGHEST_PROTOCOL)
+            else:
+                with open(save_file, "w") as fout:
+                    for recall in recalls:
+                        fout.write("\t".join("%s\t%g" % pair for pair in recall) + "\n")
+        return recalls
+
+    def save_model(self, file_name, save_hyperparameter=False):
+        objects = {"graph": {"entity2id": dict(self.graph.entity2id.items()), "id2entity": list(self.graph.id2entity),
+                             "relation2id": dict(self.graph.relation2id.items()),
+                             "id2relation": list(self.graph.id2relation)},
+                   "solver": {"entity_embeddings": np.array(self.solver.entity_embeddings),
+                              "relation_embeddings": np.array(self.solver.relation_embeddings)}}
+        with open(file_name, "wb") as fout:
+            pickle.dump(objects, fout, protocol=pickle.HIGHEST_PROTOCOL)
+
+    def load_model(self, file_name):
+        """set_parameters (application.py:640-644): rows are matched by entity / relation NAME"""
+        with open(file_name, "rb") as fin:
+            objects = pickle.load(fin)
+        for mapping, current, key in (("entity2id", self.graph.entity2id, "entity_embeddings"),
+                                      ("relation2id", self.graph.relation2id, "relation_embeddings")):
+            view, stored = getattr(self.solver, key), objects["solver"][key]
+            for name, old in objects["graph"][mapping].items():
+                if name in current:
+                    view[current[name]] = stored[old]
+        return self
+
+
+__all__ = ["Application", "GraphApplication", "KnowledgeGraphApplication", "link_prediction_auc"]

@@ -137,7 +137,8 @@ def test_hogwild_training_matches_the_reference_statistically(tmp_path):
         pytest.skip("the reference itself needs a real GPU")
     if not os.path.exists(os.path.join(root, "oracle", "_ref", "libgraphvite.so")):
         pytest.skip("oracle/_ref/libgraphvite.so is not built")
-    sys.path.insert(0, root)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import bench
     u, v = datasets.power_law_edges(20000, 200000, seed=5)
     path = str(tmp_path / "mid.txt")

@@ -19,7 +19,8 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 NUM_VERTEX, NUM_EDGE, BATCH = 1138499, 4945382, 100000
 

@@ -192,3 +192,45 @@ def test_error_paths():
         solver.train("LINE", num_epoch=1)
     with pytest.raises(_lib.GVError, match="shape"):
         solver.predict(np.zeros((4, 2), dtype=np.uint32))
+
+
+def test_config_driven_knowledge_graph_run(tmp_path):
+    """The reference's config/knowledge_graph/*.yaml layout through the `run` entry: train on the toy graph,
+    filtered link prediction (MR / MRR / HITS@k), entity prediction, save_model / load_model by name."""
+    import yaml
+    from graphvite_b200 import application, cmd
+    lines = [l for l in open(TOY_KG) if l.strip() and not l.startswith("#")]
+    test_file, model_file = tmp_path / "test.txt", tmp_path / "model.pkl"
+    test_file.write_text("".join(lines[:40]))
+    config = {
+        "application": "knowledge graph",
+        "resource": {"gpus": [0], "cpu_per_gpu": "auto", "dim": 32},
+        "graph": {"file_name": TOY_KG},
+        "build": {"optimizer": {"type": "Adam", "lr": 5e-3, "weight_decay": 0}, "num_partition": "auto",
+                  "num_negative": 8, "batch_size": 256, "episode_size": 2},
+        "train": {"model": "RotatE", "num_epoch": 40, "margin": 6, "sample_batch_size": 100,
+                  "adversarial_temperature": 2, "log_frequency": 100},
+        "evaluate": {"task": "link prediction", "file_name": str(test_file), "filter_files": [TOY_KG]},
+        "save": {"file_name": str(model_file)},
+    }
+    config_file = tmp_path / "rotate_toy.yaml"
+    config_file.write_text(yaml.safe_dump(config))
+    app, results = cmd.run_main(cmd.get_parser().parse_args(["run", str(config_file)]))
+    metrics = results[0]
+    assert set(metrics) == {"MR", "MRR", "HITS@1", "HITS@3", "HITS@10"}
+    num_entity = app.graph.num_vertex
+    assert 1 <= metrics["MR"] < num_entity / 4 and metrics["MRR"] > 4.0 / num_entity  # far better than chance
+    assert metrics["HITS@1"] <= metrics["HITS@3"] <= metrics["HITS@10"] <= 1
+
+    tokens = lines[0].split()
+    recalls = app.entity_prediction(H=[tokens[0]], R=[tokens[1]], target="tail", k=5)
+    assert len(recalls) == 1 and len(recalls[0]) == 5
+    assert all(name in app.graph.entity2id for name, _ in recalls[0])
+    assert recalls[0][0][1] >= recalls[0][-1][1]
+
+    other = application.Application("knowledge graph", 32, gpus=[0])
+    other.load(file_name=TOY_KG)
+    other.build(num_negative=8, batch_size=256, episode_size=2)
+    other.load_model(str(model_file))
+    np.testing.assert_array_equal(other.solver.entity_embeddings, app.solver.entity_embeddings)
+    np.testing.assert_array_equal(other.solver.relation_embeddings, app.solver.relation_embeddings)
