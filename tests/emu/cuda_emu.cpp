@@ -13,9 +13,14 @@
 #include "cuda_emu.h"
 
 #include <execinfo.h>
+#include <fcntl.h>
+#include <sched.h>
 #include <signal.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
+
+#include <map>
 
 #include <chrono>
 #include <mutex>
@@ -317,7 +322,9 @@ unsigned __activemask() {
     return 0xFFFFFFFFu;
 }
 
-void __nanosleep(unsigned) {}
+void __nanosleep(unsigned) {
+    sched_yield();  // a spinning "kernel" waits for another PROCESS (an emulated peer device): let it run
+}
 
 unsigned long long gv_global_timer_ns() {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -406,11 +413,51 @@ cudaError_t cudaDeviceSynchronize(void) {
     return cudaSuccess;
 }
 
+// GV_EMU_IPC=1: device allocations live in POSIX shared memory so that cudaIpcGetMemHandle /
+// cudaIpcOpenMemHandle work between the processes of an emulated multi-GPU run (peer stores over "NVLink"
+// are then plain stores into the other process's pool, and the peer-exchange kernels really wait for each other)
+struct SharedAllocation {
+    std::string name;
+    size_t bytes;
+};
+static std::mutex g_allocation_mutex;
+static std::map<void *, SharedAllocation> g_shared_allocations, g_opened_allocations;
+static bool ipc_enabled() {
+    static const bool on = getenv("GV_EMU_IPC") != nullptr && atoi(getenv("GV_EMU_IPC")) != 0;
+    return on;
+}
+static void unlink_all_shared() {
+    for (auto &entry : g_shared_allocations)
+        shm_unlink(entry.second.name.c_str());
+}
+
 cudaError_t cudaMalloc(void **pointer, size_t bytes) {
     const size_t rounded = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
-    void *memory = aligned_alloc(256, rounded);
-    if (!memory)
-        return remember(cudaErrorMemoryAllocation);
+    void *memory = nullptr;
+    if (ipc_enabled()) {
+        static unsigned long long counter = 0;
+        std::lock_guard<std::mutex> lock(g_allocation_mutex);
+        if (counter == 0)
+            atexit(unlink_all_shared);
+        const std::string name = "/gv_emu_" + std::to_string(getpid()) + "_" + std::to_string(counter++);
+        const int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, off_t(rounded)) != 0) {
+            if (fd >= 0)
+                close(fd);
+            return remember(cudaErrorMemoryAllocation);
+        }
+        memory = mmap(nullptr, rounded, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (memory == MAP_FAILED) {
+            shm_unlink(name.c_str());
+            return remember(cudaErrorMemoryAllocation);
+        }
+        g_shared_allocations[memory] = {name, rounded};
+    } else {
+        memory = aligned_alloc(256, rounded);
+        if (!memory)
+            return remember(cudaErrorMemoryAllocation);
+    }
     if (rounded <= (size_t(64) << 20))
         memset(memory, 0xA5, rounded);  // cudaMalloc does not zero: make reads of unwritten memory visible
     *pointer = memory;
@@ -418,6 +465,18 @@ cudaError_t cudaMalloc(void **pointer, size_t bytes) {
 }
 
 cudaError_t cudaFree(void *pointer) {
+    if (!pointer)
+        return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(g_allocation_mutex);
+        auto found = g_shared_allocations.find(pointer);
+        if (found != g_shared_allocations.end()) {
+            munmap(pointer, found->second.bytes);
+            shm_unlink(found->second.name.c_str());
+            g_shared_allocations.erase(found);
+            return cudaSuccess;
+        }
+    }
     free(pointer);
     return cudaSuccess;
 }
@@ -541,16 +600,46 @@ cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int *blocks, 
     return cudaSuccess;
 }
 
-// no peer mapping in the emulation: the solver falls back to replicated sampling
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) {
-    return remember(cudaErrorNotSupported);
+// CUDA IPC between emulated devices (= processes): see GV_EMU_IPC above; without it there is no peer
+// mapping and the solver falls back to replicated sampling
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *handle, void *pointer) {
+    std::lock_guard<std::mutex> lock(g_allocation_mutex);
+    auto found = g_shared_allocations.find(pointer);
+    if (found == g_shared_allocations.end())
+        return remember(cudaErrorNotSupported);
+    memset(handle, 0, sizeof(*handle));
+    unsigned long long bytes = found->second.bytes;
+    memcpy(handle->reserved, &bytes, sizeof(bytes));
+    strncpy(handle->reserved + sizeof(bytes), found->second.name.c_str(), sizeof(handle->reserved) - sizeof(bytes) - 1);
+    return cudaSuccess;
 }
 
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned int) {
-    return remember(cudaErrorNotSupported);
+cudaError_t cudaIpcOpenMemHandle(void **pointer, cudaIpcMemHandle_t handle, unsigned int) {
+    unsigned long long bytes = 0;
+    memcpy(&bytes, handle.reserved, sizeof(bytes));
+    const char *name = handle.reserved + sizeof(bytes);
+    if (bytes == 0 || name[0] != '/')
+        return remember(cudaErrorNotSupported);
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0)
+        return remember(cudaErrorInvalidValue);
+    void *memory = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (memory == MAP_FAILED)
+        return remember(cudaErrorMemoryAllocation);
+    std::lock_guard<std::mutex> lock(g_allocation_mutex);
+    g_opened_allocations[memory] = {name, size_t(bytes)};
+    *pointer = memory;
+    return cudaSuccess;
 }
 
-cudaError_t cudaIpcCloseMemHandle(void *) {
+cudaError_t cudaIpcCloseMemHandle(void *pointer) {
+    std::lock_guard<std::mutex> lock(g_allocation_mutex);
+    auto found = g_opened_allocations.find(pointer);
+    if (found == g_opened_allocations.end())
+        return remember(cudaErrorInvalidValue);
+    munmap(pointer, found->second.bytes);
+    g_opened_allocations.erase(found);
     return cudaSuccess;
 }
 

@@ -126,7 +126,9 @@ inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) {
 }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
-inline void __threadfence_system() {}
+inline void __threadfence_system() {
+    __sync_synchronize();  // peers are other processes sharing memory
+}
 void __nanosleep(unsigned ns);
 
 // ---- warp collectives -------------------------------------------------------------------------------
