@@ -7,11 +7,18 @@
 // sampling over head + tail partition, self-adversarial weighting) with the models TransE,
 // DistMult, ComplEx, SimplE and RotatE and all five optimizers.  QuatE is not restated.
 //
-// PARITY STATUS: the graph loader is pinned (tests/test_reference_surface.py compares the product
-// and this file with the live reference object on CPU).  The solver and kernels are **parity
-// unpinned**: their golden vectors come from oracle/ref_harness_kg.cu, which needs a GPU
-// (oracle/make_golden.py kg_* cases); until those fixtures are committed, agreement with the
-// reference rests on this file's line-by-line citations only.
+// PARITY STATUS: pinned against the UNMODIFIED reference.  The graph loader is compared with the live reference
+// object on CPU (tests/test_reference_surface.py).  Kernels and solver are compared with golden vectors
+// (tests/golden/kg_kernel_*, kg_predict_*, kg_solver_*.npz) that oracle/make_golden_kg.py --emulated recorded by
+// running the reference's own headers through oracle/ref_harness_kg.cu under the CUDA emulation of tests/emu
+// (two-pass build like nvcc's, see oracle/Makefile target ref_emu and oracle/emulate_reference.py): train kernels
+// of the 5 models x 5 optimizers and predict to rtol 5e-4; six solver runs with partition, both sample pools, last
+// negatives, schedule and batch accounting bit-exact, and -- for one partition -- embeddings, loss and predict of
+// the whole training run to rtol 1e-4 (same sample order; host libm / no-FMA rounding on both sides).  What this
+// does NOT cover: the device's own rounding (libdevice, FMA contraction) -- rerun make_golden_kg.py on a GPU for
+// that -- and, with several partitions, the reference's partition cache, which can train a stale second copy of
+// an entity partition (see tests/test_oracle_kg_golden.py::test_solver_runs); there only integer state and
+// magnitudes are compared.
 //
 // Paths are relative to /root/reference/include.  Workers are emulated one after another with
 // sequentially consistent entity matrices (the reference races its write-backs against the other

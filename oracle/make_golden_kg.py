@@ -1,8 +1,12 @@
 """Generate the knowledge-graph golden vectors (tests/golden/kg_*.npz) by running the UNMODIFIED reference.
 
-TEST INFRASTRUCTURE.  Needs a GPU box (the reference's solver needs a CUDA device):
+TEST INFRASTRUCTURE.  The reference's solver needs a CUDA device:
     gpurun -- 'python oracle/make_golden_kg.py gpurun_out/golden_kg'
-then copy gpurun_out/golden_kg/*.npz into tests/golden/ and commit them.  The reference is driven through
+then copy gpurun_out/golden_kg/*.npz into tests/golden/ and commit them.  Without a GPU,
+    make -C oracle ref_emu && python oracle/make_golden_kg.py --emulated <out_dir>
+runs the very same unmodified reference code under the CUDA emulation of tests/emu (see
+oracle/emulate_reference.py): integer outputs (pools, negatives, partitions) are what a GPU produces; float
+outputs carry the host's libm / no-FMA rounding instead of the device's (differences of a few ulp).  The reference is driven through
 oracle/_ref/libref_harness_kg.so (oracle/ref_harness_kg.cu, built by `make -C oracle ref` in the authoring
 container; /root/reference does not exist on the GPU box).  The toy knowledge graph the cases run on is
 generated here deterministically and committed as tests/golden/toy_kg.txt.
@@ -45,8 +49,17 @@ SOLVER_CASES = {
 }
 
 
+EMULATED = "--emulated" in sys.argv  # the reference executed by tests/emu's CUDA emulation (`make -C oracle ref_emu`)
+
+
 def load_harness():
-    lib = c.CDLL(os.path.join(HERE, "_ref", "libref_harness_kg.so"))
+    if EMULATED:
+        # two-pass build (oracle/Makefile, ref_emu): launches swap the host-pass kernel for its device-pass twin
+        os.environ["GV_EMU_DEVICE_LIBRARY"] = os.path.join(HERE, "_ref", "libref_harness_kg_emu_device.so")
+        os.environ["GV_EMU_DEVICE_NAMESPACE"] = "graphvite=graphvite_device"
+        lib = c.CDLL(os.path.join(HERE, "_ref", "libref_harness_kg_emu.so"), mode=c.RTLD_GLOBAL)
+    else:
+        lib = c.CDLL(os.path.join(HERE, "_ref", "libref_harness_kg.so"))
     V, I, F, U64, S = c.c_void_p, c.c_int, c.c_float, c.c_uint64, c.c_char_p
     lib.rk_graph_load.restype = V
     lib.rk_graph_load.argtypes = [S, I]
@@ -159,7 +172,8 @@ def write_solver_cases(lib, out_dir, toy, only):
                              rng.randint(0, num_relation, 400)], axis=1).astype(np.uint32)
         logits = np.zeros(400, dtype=np.float32)
         lib.rk_solver_predict(solver, ptr(triplets), 400, ptr(logits))
-        np.savez_compressed(os.path.join(out_dir, "kg_solver_%s.npz" % name), info=info, part_of=part_of,
+        np.savez_compressed(os.path.join(out_dir, "kg_solver_%s.npz" % name), emulated=np.array(int(EMULATED)),
+                            info=info, part_of=part_of,
                             local_of=local_of, pools=pools, negatives=negatives, loss=loss, negative_prob=prob,
                             negative_alias=alias, schedule=schedule[:steps * 2].reshape(steps, 1, 2), triplets=triplets,
                             logits=logits, **matrices, **{"cfg_" + k: np.array(v) for k, v in cfg.items()})
@@ -202,6 +216,8 @@ def write_kernel_cases(lib, out_dir):
                 rng = np.random.RandomState(1000 + 7 * dim + 13 * otype + len(model))
                 n, k = 24, 3
                 num_head, num_tail, num_relation = 130, 140, 40
+                if dim == 512:  # keeps the fixture small
+                    n, num_head, num_tail, num_relation = 12, 60, 70, 30
                 scale = 0.3 if dim == 512 else 1.0
                 head = ((rng.rand(num_head, dim) - 0.5) * scale).astype(np.float32)
                 tail = ((rng.rand(num_tail, dim) - 0.5) * scale).astype(np.float32)
@@ -256,4 +272,5 @@ def main(out_dir, only=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_kg"), set(sys.argv[2:]) or None)
+    arguments = [a for a in sys.argv[1:] if a != "--emulated"]
+    main(arguments[0] if arguments else os.path.join(ROOT, "gpurun_out", "golden_kg"), set(arguments[1:]) or None)

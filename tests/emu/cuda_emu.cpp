@@ -12,6 +12,7 @@
 // =============================================================================
 #include "cuda_emu.h"
 
+#include <dlfcn.h>
 #include <execinfo.h>
 #include <fcntl.h>
 #include <sched.h>
@@ -227,6 +228,40 @@ void run(dim3 grid, dim3 block, size_t shared_bytes, const std::function<void()>
             }
     g_body = nullptr;
     g_in_kernel = false;
+}
+
+void *resolve_kernel(void *kernel) {
+    static void *library = nullptr;
+    static std::string from, to;
+    static bool ready = false;
+    if (!ready) {
+        ready = true;
+        const char *path = getenv("GV_EMU_DEVICE_LIBRARY"), *rename = getenv("GV_EMU_DEVICE_NAMESPACE");
+        if (path && *path) {
+            library = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+            if (!library)
+                die(std::string("cannot load the device-pass library: ") + dlerror());
+            const std::string spec = rename ? rename : "";
+            const size_t equal = spec.find('=');
+            if (equal == std::string::npos)
+                die("GV_EMU_DEVICE_NAMESPACE must be from=to");
+            // Itanium mangling spells a namespace as <length><name>
+            from = std::to_string(equal) + spec.substr(0, equal);
+            to = std::to_string(spec.size() - equal - 1) + spec.substr(equal + 1);
+        }
+    }
+    if (!library)
+        return kernel;
+    Dl_info info;
+    if (!dladdr(kernel, &info) || !info.dli_sname)
+        die("cannot name the kernel of a launch (is it exported from its shared object?)");
+    std::string name = info.dli_sname;
+    for (size_t at = name.find(from); at != std::string::npos; at = name.find(from, at + to.size()))
+        name.replace(at, from.size(), to);
+    void *twin = dlsym(library, name.c_str());
+    if (!twin)
+        die("the device-pass library has no kernel " + name);
+    return twin;
 }
 
 void *dynamic_shared() {

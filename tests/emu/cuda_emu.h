@@ -43,6 +43,11 @@ namespace gv_emu {
 
 // ---- scheduler interface (cuda_emu.cpp) ------------------------------------------------------
 void run(dim3 grid, dim3 block, size_t shared_bytes, const std::function<void()> &thread_body);
+// Two-pass sources (code that switches on __CUDA_ARCH__, i.e. the reference): the kernel a launch names is the
+// HOST-pass instantiation; its device-pass twin lives in the library GV_EMU_DEVICE_LIBRARY, compiled from the same
+// source with __CUDA_ARCH__ defined and its namespace renamed (GV_EMU_DEVICE_NAMESPACE="from=to").  Returns the
+// twin's address (looked up by mangled name), or `kernel` itself when no device library is configured.
+void *resolve_kernel(void *kernel);
 void *dynamic_shared();
 // all lanes in `mask` deposit a 64-bit value; returns the 32 deposited values once everyone arrived
 const uint64_t *warp_gather(unsigned mask, uint64_t value);
@@ -70,7 +75,7 @@ struct Launcher {
     void (*kernel)(P...);
     template<class... A>
     void operator()(A &&...args) const {
-        void (*k)(P...) = kernel;
+        void (*k)(P...) = reinterpret_cast<void (*)(P...)>(resolve_kernel(reinterpret_cast<void *>(kernel)));
         // parameters are converted once, by value, like a kernel launch does
         auto bound = [k](P... converted) {
             return std::function<void()>([=]() { k(converted...); });
@@ -83,6 +88,19 @@ template<class... P>
 inline Launcher<P...> launcher(dim3 grid, dim3 block, size_t shared, cudaStream_t, void (*kernel)(P...)) {
     return Launcher<P...>{grid, block, shared, kernel};
 }
+
+// kernel<<<grid, block[, shared[, stream]]>>>(args) of sources that cannot use GV_LAUNCH (the reference, see
+// oracle/emulate_reference.py) is rewritten to gv_emu::LaunchConfig(grid, block[, shared[, stream]])(kernel)(args)
+struct LaunchConfig {
+    dim3 grid, block;
+    size_t shared;
+    LaunchConfig(dim3 _grid, dim3 _block, size_t _shared = 0, cudaStream_t = nullptr)
+        : grid(_grid), block(_block), shared(_shared) {}
+    template<class... P>
+    Launcher<P...> operator()(void (*kernel)(P...)) const {
+        return Launcher<P...>{grid, block, shared, kernel};
+    }
+};
 
 }  // namespace gv_emu
 

@@ -238,3 +238,56 @@ def test_arguments_are_checked():
     status = _lib.lib.gv_cuda_kg_train_block(ctypes.byref(m), 4, 1, 1, 0, None, None, 0, None, ctypes.byref(optimizer), 1,
                                              1, 1.0, 1.0, 0.0, None, None, 0, None)
     assert status == -1 and "moment" in _lib.last_error()
+
+
+# ---- the product against the REFERENCE's own kernels (tests/golden/kg_kernel_*.npz, recorded by
+# oracle/make_golden_kg.py from the unmodified reference) -----------------------------------------------------
+import glob
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KERNEL_FILES = sorted(glob.glob(os.path.join(GOLDEN, "kg_kernel_*.npz")))
+PREDICT_FILES = sorted(glob.glob(os.path.join(GOLDEN, "kg_predict_*.npz")))
+
+
+@pytest.mark.skipif(not KERNEL_FILES, reason="no kg_kernel_*.npz fixtures")
+@pytest.mark.parametrize("path", KERNEL_FILES, ids=[os.path.basename(p)[10:-4] for p in KERNEL_FILES])
+@pytest.mark.parametrize("num_group", [1, 0], ids=["one-group", "full-grid"])
+def test_train_kernel_matches_the_reference_kernels(path, num_group):
+    """race-free batches (no row is named twice), so the full Hogwild grid must give the same result as one group"""
+    g = np.load(path)
+    model, dim = os.path.basename(path).split("_")[2], int(os.path.basename(path).split("_")[3][1:])
+    otype, lr, wd, a, b, eps, rlm, margin_or_l3, temperature = (float(x) for x in g["hyper"])
+    num_moment = 0 if otype == 0 else (2 if otype == 4 else 1)
+    moments = {name: (g["before_" + name] if num_moment >= int(name[2]) else None)
+               for name in ("hm1", "tm1", "rm1", "hm2", "tm2", "rm2")}
+    got = run_kg_train(model, dim, g["before_head"], g["before_tail"], g["before_relation"], moments, g["batch"],
+                       g["negatives"], (int(otype), lr, wd, a, b, eps), g["before_head"].shape[0], rlm, margin_or_l3,
+                       temperature, num_group)
+    tolerance = dict(rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(got["loss"], g["loss"], **tolerance)
+    for ours, theirs in (("head", "after_head"), ("tail", "after_tail"), ("relation", "after_relation")):
+        np.testing.assert_allclose(got[ours], g[theirs], err_msg=ours, **tolerance)
+    for name in ("hm1", "tm1", "rm1", "hm2", "tm2", "rm2"):
+        if num_moment >= int(name[2]):
+            np.testing.assert_allclose(got[name], g["after_" + name], err_msg=name, **tolerance)
+
+
+@pytest.mark.skipif(not PREDICT_FILES, reason="no kg_predict_*.npz fixtures")
+@pytest.mark.parametrize("path", PREDICT_FILES, ids=[os.path.basename(p)[11:-4] for p in PREDICT_FILES])
+def test_predict_kernel_matches_the_reference_kernel(path):
+    import torch
+    import gpu_util
+    from graphvite_b200 import _lib
+    from gpu_util import dev, stream_pointer
+    g = np.load(path)
+    model, dim = os.path.basename(path).split("_")[2], g["entity"].shape[1]
+    d_entity, d_relation, d_batch = dev(g["entity"]), dev(g["relation"]), dev(g["batch"], np.uint32)
+    n = len(g["batch"])
+    logits = torch.zeros(n, dtype=torch.float32, device=gpu_util.DEVICE)
+    m = _lib.KgMatrices(dim, g["entity"].shape[0], d_entity.data_ptr(), d_entity.data_ptr(), d_relation.data_ptr(),
+                        None, None, None, None, None, None)
+    _lib.check(_lib.lib.gv_cuda_kg_predict(ctypes.byref(m), MODEL_IDS[model], d_batch.data_ptr(), n, float(g["margin"]),
+                                           logits.data_ptr(), stream_pointer()))
+    gpu_util.synchronize()
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=1e-3, atol=1e-4)

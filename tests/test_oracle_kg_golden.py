@@ -1,9 +1,10 @@
 """The knowledge-graph oracle (and the product's loader) against golden vectors recorded from the
 UNMODIFIED reference by oracle/make_golden_kg.py.
 
-kg_graph_n*.npz were produced in the authoring container (the reference's graph loader is host code);
-the kernel and solver fixtures need a GPU box and are compared as soon as they are committed -- until
-then those tests skip and the solver half of the oracle stays "parity unpinned"."""
+kg_graph_n*.npz were produced in the authoring container (the reference's graph loader is host code); the
+kernel / predict / solver fixtures were recorded there too, from the reference's own kernels and solver executed
+by the CUDA emulation of tests/emu (`make -C oracle ref_emu && python oracle/make_golden_kg.py --emulated DIR`,
+no GPU needed; see the header of oracle/gv_oracle_kg.cpp for what that does and does not cover)."""
 import glob
 import os
 
@@ -129,6 +130,21 @@ def test_solver_runs(path):
     np.testing.assert_array_equal(solver.last_negatives(), g["negatives"])
     np.testing.assert_array_equal(solver.schedule(1), g["schedule"])
     assert (g["negative_prob"] == 1).all() and (g["negative_alias"] == np.arange(len(g["negative_alias"]))).all()
+    emulated = "emulated" in g.files and int(g["emulated"]) == 1
+    if emulated and P == 1:
+        # Recorded from the reference under the CUDA emulation, where the samples of a batch are processed in
+        # order (one warp per sample, warps and CTAs one after another): exactly the oracle's order, so the floats
+        # must agree too -- the whole training run, not only its integer state.
+        tolerance = dict(rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(solver.entity_embeddings, g["entity_0"], **tolerance)
+        np.testing.assert_allclose(solver.relation_embeddings, g["relation_0"], **tolerance)
+        np.testing.assert_allclose(solver.last_loss(), g["loss"], **tolerance)
+        np.testing.assert_allclose(solver.predict(g["triplets"]), g["logits"], rtol=1e-4, atol=1e-5)
+        return
+    # Hogwild on a GPU, or several partitions: with P > 1 the reference's partition cache can keep a second, stale
+    # copy of an entity partition (a "tail hit" leaves the trained tail copy on the device while the head copy of
+    # the same partition is reloaded from host memory, core/solver.h:1436-1476) and the later write-back wins,
+    # which the oracle's single in-place matrix does not imitate: only magnitudes are compared.
     for ours, name in ((solver.entity_embeddings, "entity_0"), (solver.relation_embeddings, "relation_0")):
         assert np.linalg.norm(ours) == pytest.approx(np.linalg.norm(g[name]), rel=0.05), name
     assert float(solver.last_loss().mean()) == pytest.approx(float(g["loss"].mean()), rel=0.2, abs=0.02)
