@@ -117,6 +117,7 @@ SIGNATURES = {
     "gv_graph_create": (c_void_p, []),
     "gv_graph_destroy": (None, [c_void_p]),
     "gv_graph_load_file": (c_int, [c_void_p, c_char_p, c_int, c_int, c_char_p, c_char_p]),
+    "gv_graph_load_corpus": (c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_char_p, c_char_p]),
     "gv_graph_load_edges": (c_int, [c_void_p, P(c_char_p), P(c_char_p), P(c_float), c_uint64, c_int, c_int]),
     "gv_graph_save": (c_int, [c_void_p, c_char_p, c_int, c_int]),
     "gv_graph_num_vertex": (c_uint64, [c_void_p]),

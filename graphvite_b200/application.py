@@ -33,9 +33,11 @@ def Application(type, *args, **kwargs):
     application ("graph") is in scope."""
     if type == "graph":
         return GraphApplication(*args, **kwargs)
+    if type in ("word graph", "word_graph"):
+        return WordGraphApplication(*args, **kwargs)
     if type in ("knowledge graph", "knowledge_graph"):
         return KnowledgeGraphApplication(*args, **kwargs)
-    raise ValueError("Unknown application `%s` (this build ships `graph` and `knowledge graph`)" % type)
+    raise ValueError("Unknown application `%s` (this build ships `graph`, `word graph` and `knowledge graph`)" % type)
 
 
 class GraphApplication(object):
@@ -222,6 +224,16 @@ class GraphApplication(object):
                 if name in name2id:
                     view[name2id[name]] = stored[old]
         return self
+
+
+class WordGraphApplication(GraphApplication):
+    """WordGraphApplication(dim, gpus=[], ...) (application.py:536-573): node embeddings of a word co-occurrence
+    graph; `load(file_name=corpus, window=5, min_count=5, ...)` builds the graph from a corpus."""
+
+    def __init__(self, dim, gpus=(), cpu_per_gpu=auto, gpu_memory_limit=auto, float_type=None, index_type=None,
+                 **kwargs):
+        GraphApplication.__init__(self, dim, gpus, cpu_per_gpu, gpu_memory_limit, float_type, index_type, **kwargs)
+        self.graph = _graph.WordGraph(index_type)
 
 
 class KnowledgeGraphApplication(object):
@@ -459,4 +471,5 @@ class KnowledgeGraphApplication(object):
         return self
 
 
-__all__ = ["Application", "GraphApplication", "KnowledgeGraphApplication", "link_prediction_auc"]
+__all__ = ["Application", "GraphApplication", "WordGraphApplication", "KnowledgeGraphApplication",
+           "link_prediction_auc"]

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <deque>
 #include <sstream>
 
@@ -192,6 +193,96 @@ void Graph::load_file(const char *file_name, bool undirected, bool normalized, c
         normalize();
 }
 
+// WordGraph::load_file_compact, instance/word_graph.cuh:75-166: a word co-occurrence graph from a corpus.
+// Pass 1 counts the words (ids in order of first appearance) and drops those rarer than min_count; pass 2 counts
+// every pair of kept words at distance <= window inside a line, in both directions.  The out-edges of a vertex
+// are emitted in the iteration order of the reference's std::unordered_map<Index, float> -- the very same
+// container is filled with the very same insertion sequence here, so the order (libstdc++'s) is reproduced.
+void Graph::load_corpus(const char *file_name, int window, int min_count, bool normalized, const char *delimiters,
+                        const char *comment) {
+    clear();
+    as_undirected = true;
+    normalization = normalized;
+    FILE *fin = fopen(file_name, "r");
+    if (!fin)
+        throw std::runtime_error(std::string("File `") + file_name + "` doesn't exist");
+    const size_t kMaxLineLength = size_t(1) << 22;  // util/common.h:30
+    std::vector<char> line(kMaxLineLength);
+    auto for_each_word = [&](const std::function<void(const std::string &)> &visit) {
+        char *cut = strstr(line.data(), comment);  // an empty prefix cuts the whole line, as in the reference
+        if (cut)
+            *cut = 0;
+        std::string word;
+        for (char *cursor = line.data(); *cursor;) {
+            cursor += strspn(cursor, delimiters);
+            if (!*cursor)
+                break;
+            const size_t length = strcspn(cursor, delimiters);
+            word.assign(cursor, length);
+            visit(word);
+            cursor += length;
+        }
+    };
+    std::vector<uint32_t> frequency;
+    std::vector<std::string> words;
+    std::unordered_map<std::string, uint32_t> word2id;
+    while (fgets(line.data(), int(kMaxLineLength), fin))
+        for_each_word([&](const std::string &word) {
+            auto found = word2id.find(word);
+            if (found != word2id.end())
+                frequency[found->second]++;
+            else {
+                word2id.emplace(word, uint32_t(words.size()));
+                words.push_back(word);
+                frequency.push_back(1);
+            }
+        });
+    for (size_t i = 0; i < words.size(); i++)
+        if (int64_t(frequency[i]) >= int64_t(min_count))
+            intern(words[i]);
+    const uint32_t n = num_vertex();
+    fseek(fin, 0, SEEK_SET);
+    std::vector<std::unordered_map<uint32_t, float>> edge_map(n);
+    std::vector<uint32_t> sentence;
+    while (fgets(line.data(), int(kMaxLineLength), fin)) {
+        sentence.clear();
+        for_each_word([&](const std::string &word) {
+            auto found = name2id.find(word);
+            if (found != name2id.end())
+                sentence.push_back(found->second);
+        });
+        for (size_t i = 0; i < sentence.size(); i++)
+            for (int j = 1; j <= window && i + j < sentence.size(); j++) {
+                const uint32_t u = sentence[i], v = sentence[i + j];
+                auto edge = edge_map[u].find(v);
+                if (edge == edge_map[u].end())
+                    edge_map[u][v] = 1;
+                else
+                    edge->second++;
+                edge = edge_map[v].find(u);
+                if (edge == edge_map[v].end())
+                    edge_map[v][u] = 1;
+                else
+                    edge->second++;
+                vertex_weights[u]++;
+                vertex_weights[v]++;
+            }
+    }
+    fclose(fin);
+    for (uint32_t u = 0; u < n; u++) {
+        for (const auto &edge : edge_map[u]) {
+            log_u.push_back(u);
+            log_v.push_back(edge.first);
+            log_w.push_back(edge.second);
+        }
+        degrees[u] = uint32_t(edge_map[u].size());
+        num_edge += edge_map[u].size();
+    }
+    flatten();
+    if (normalization)
+        normalize();
+}
+
 // Graph::load_edge_list / load_weighted_edge_list, instance/graph.cuh:209-252
 void Graph::load_edges(const char *const *u_names, const char *const *v_names, const float *weights,
                        uint64_t count, bool undirected, bool normalized) {
@@ -275,6 +366,15 @@ int gv_graph_load_file(gv_graph_t *graph, const char *file_name, int as_undirect
     GV_TRY
     graph->graph.load_file(file_name, as_undirected != 0, normalization != 0, delimiters ? delimiters : " \t\r\n",
                            comment ? comment : "#");
+    return 0;
+    GV_CATCH(-1)
+}
+
+int gv_graph_load_corpus(gv_graph_t *graph, const char *file_name, int window, int min_count, int normalization,
+                         const char *delimiters, const char *comment) {
+    GV_TRY
+    graph->graph.load_corpus(file_name, window, min_count, normalization != 0, delimiters ? delimiters : " \t\r\n",
+                             comment ? comment : "#");
     return 0;
     GV_CATCH(-1)
 }

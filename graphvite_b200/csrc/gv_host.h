@@ -41,6 +41,8 @@ struct Graph {
     void normalize();
     void load_file(const char *file_name, bool undirected, bool normalized, const char *delimiters,
                    const char *comment);
+    void load_corpus(const char *file_name, int window, int min_count, bool normalized, const char *delimiters,
+                     const char *comment);  // WordGraph, instance/word_graph.cuh:75-166
     void load_edges(const char *const *u_names, const char *const *v_names, const float *weights, uint64_t count,
                     bool undirected, bool normalized);
     void save(const char *file_name, bool weighted, bool anonymous);

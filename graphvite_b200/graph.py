@@ -134,6 +134,21 @@ class Graph(object):
         return buffer.value.decode()
 
 
+class WordGraph(Graph):
+    """WordGraph(index_type=dtype.uint32): normal graphs of word co-occurrences (bind.h:190-234 over
+    include/instance/word_graph.cuh:42-166).  A Graph in every other respect: solvers take it like any Graph."""
+
+    def load(self, file_name, window=5, min_count=5, normalization=False, delimiters=" \t\r\n", comment="#"):
+        """load(file_name, window=5, min_count=5, normalization=False, delimiters=' \\t\\r\\n', comment='#')"""
+        self._id2name = None
+        path = file_name if isinstance(file_name, bytes) else str(file_name).encode()
+        _lib.check(lib.gv_graph_load_corpus(self._handle, path, int(window), int(min_count), int(bool(normalization)),
+                                            delimiters.encode(), comment.encode()))
+
+    def __repr__(self):
+        return Graph.__repr__(self).replace("Graph<", "WordGraph<", 1)
+
+
 class KnowledgeGraph(object):
     """KnowledgeGraph(index_type=dtype.uint32): knowledge graphs (triplets `head relation tail [weight]`)."""
 
@@ -235,4 +250,4 @@ class KnowledgeGraph(object):
         return buffer.value.decode()
 
 
-__all__ = ["Graph", "KnowledgeGraph"]
+__all__ = ["Graph", "WordGraph", "KnowledgeGraph"]

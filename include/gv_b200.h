@@ -298,6 +298,10 @@ void gv_graph_destroy(gv_graph_t *graph);
 /* Graph::load_file (instance/graph.cuh:163-201) */
 int gv_graph_load_file(gv_graph_t *graph, const char *file_name, int as_undirected, int normalization,
                        const char *delimiters, const char *comment);
+/* WordGraph::load_file_compact (instance/word_graph.cuh:75-166, bind.h:216-230): word co-occurrence graph of a
+ * corpus; words rarer than min_count are dropped, pairs at distance <= window inside a line count as edges */
+int gv_graph_load_corpus(gv_graph_t *graph, const char *file_name, int window, int min_count, int normalization,
+                         const char *delimiters, const char *comment);
 /* Graph::load_edge_list / load_weighted_edge_list (instance/graph.cuh:209-252); weights may be NULL */
 int gv_graph_load_edges(gv_graph_t *graph, const char *const *u_names, const char *const *v_names,
                         const float *weights, uint64_t num_edge, int as_undirected, int normalization);

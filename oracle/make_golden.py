@@ -19,8 +19,17 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 c = ctypes
 
 
+EMULATED = "--emulated" in sys.argv  # the reference executed by tests/emu's CUDA emulation (`make -C oracle ref_emu`)
+
+
 def load_harness():
-    lib = c.CDLL(os.path.join(HERE, "_ref", "libref_harness.so"))
+    if EMULATED:
+        # two-pass build (oracle/Makefile, ref_emu): launches swap the host-pass kernel for its device-pass twin
+        os.environ["GV_EMU_DEVICE_LIBRARY"] = os.path.join(HERE, "_ref", "libref_harness_emu_device.so")
+        os.environ["GV_EMU_DEVICE_NAMESPACE"] = "graphvite=graphvite_device"
+        lib = c.CDLL(os.path.join(HERE, "_ref", "libref_harness_emu.so"), mode=c.RTLD_GLOBAL)
+    else:
+        lib = c.CDLL(os.path.join(HERE, "_ref", "libref_harness.so"))
     lib.ref_graph_load.restype = c.c_void_p
     lib.ref_graph_load.argtypes = [c.c_char_p, c.c_int, c.c_int]
     for name in ("ref_graph_num_vertex", "ref_graph_num_edge", "ref_graph_num_directed_edge"):
@@ -219,8 +228,14 @@ def write_solver_cases(lib, out_dir, toy, only):
         lib.ref_solver_free(solver)
         print("solver case", name, "info", info.tolist(), flush=True)
 
+    if not only:
+        write_kernel_cases(lib, out_dir)
+    print("golden vectors written to", out_dir)
+
+
+def write_kernel_cases(lib, out_dir):
     # ---- the reference kernels on race-free batches ---------------------------------------------
-    for dim in (() if only else (32, 128)):
+    for dim in (32, 128):
         for oname, (otype, lr, wd, a, b, eps) in OPTIMIZERS.items():
             rng = np.random.RandomState(100 + dim + otype)
             n, k = 64, 2
@@ -244,9 +259,8 @@ def write_solver_cases(lib, out_dir, toy, only):
                                 after_vm1=moments[0], after_cm1=moments[1], after_vm2=moments[2],
                                 after_cm2=moments[3], hyper=np.array([otype, lr, wd, a, b, eps, 5.0]),
                                 **{"before_" + key: value for key, value in before.items()})
-    print("golden vectors written to", out_dir)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"),
-         set(sys.argv[2:]) or None)
+    arguments = [a for a in sys.argv[1:] if a != "--emulated"]
+    main(arguments[0] if arguments else os.path.join(ROOT, "gpurun_out", "golden"), set(arguments[1:]) or None)

@@ -335,3 +335,41 @@ def test_knowledge_graph_rejects_malformed_lines(gv, tmp_path):
         out.write("a r b 1 extra\n")
     with pytest.raises(_lib.GVError, match="Invalid format at line 1"):
         gv.graph.KnowledgeGraph().load(source)
+
+
+# ---- WordGraph (bind.h:190-234, instance/word_graph.cuh) ------------------------------------------------------------
+def write_corpus(path, rng, vocabulary, lines):
+    words = ["w%d" % i for i in range(vocabulary)]
+    weights = np.arange(1, vocabulary + 1) ** -1.0
+    weights /= weights.sum()
+    with open(path, "w") as out:
+        out.write("# a corpus\n\n")
+        for i in range(lines):
+            sentence = rng.choice(words, size=int(rng.integers(1, 25)), p=weights)
+            text = " ".join(sentence)
+            if i % 13 == 0:
+                text = text.replace(" ", "\t", 2) + "   # trailing comment with words w1 w2"
+            out.write(text + "\n")
+
+
+@pytest.mark.parametrize("window,min_count,normalization", [(5, 5, False), (2, 1, False), (7, 3, True)])
+def test_word_graph_loader_matches_the_reference_object(ref, gv, tmp_path, window, min_count, normalization):
+    """Vocabulary (ids by first appearance, min_count filter), co-occurrence counts and -- because the out-edges of
+    a vertex are emitted in the iteration order of an unordered_map -- the edge ORDER: save() must be byte-identical."""
+    rng = np.random.default_rng(11 + window)
+    corpus = str(tmp_path / "corpus.txt")
+    write_corpus(corpus, rng, 150, 400)
+    theirs, ours = ref.graph.WordGraph_j(), gv.graph.WordGraph()
+    theirs.load(corpus, window, min_count, normalization)
+    ours.load(corpus, window, min_count, normalization)
+    assert [n for n, _ in doc_signature(theirs.load)] == [n for n, _ in our_signature(gv.graph.WordGraph.load)]
+    assert (theirs.num_vertex, theirs.num_edge) == (ours.num_vertex, ours.num_edge)
+    assert ours.num_vertex > 20 and ours.num_edge > 100
+    assert (theirs.as_undirected, theirs.normalization) == (ours.as_undirected, ours.normalization) == (True, normalization)
+    assert list(theirs.id2name) == list(ours.id2name)
+    for mode, (weighted, anonymous) in enumerate(((True, False), (False, True))):
+        a, b = str(tmp_path / ("ref%d.txt" % mode)), str(tmp_path / ("ours%d.txt" % mode))
+        theirs.save(a, weighted, anonymous)
+        ours.save(b, weighted, anonymous)
+        assert filecmp.cmp(a, b, shallow=False), (weighted, anonymous)
+    assert repr(ours).splitlines()[0] == repr(theirs).splitlines()[0] == "WordGraph<uint32>"
