@@ -239,7 +239,7 @@ class WordGraphApplication(GraphApplication):
 class KnowledgeGraphApplication(object):
     """KnowledgeGraphApplication(dim, gpus=[], cpu_per_gpu=auto, gpu_memory_limit=auto, float_type, index_type)
     (application.py:576-1067): load / build / train / link_prediction / entity_prediction / save_model /
-    load_model for TransE, DistMult, ComplEx, SimplE and RotatE.  Triplets are scored with the solver's own
+    load_model for TransE, DistMult, ComplEx, SimplE, RotatE and QuatE.  Triplets are scored with the solver's own
     predict kernel (the reference's "graphvite" backend, application.py:828-853)."""
 
     SAMPLE_PER_DIMENSION = 7  # application.py:626

@@ -2,8 +2,8 @@
 // gv_kg.cu -- knowledge-graph embedding kernels, hand-written for sm_100a.
 //
 // Replaces gpu::knowledge_graph::train / train_1_moment / train_2_moment / predict (reference
-// include/instance/gpu/knowledge_graph.cuh:38-366) for the models TransE, DistMult, ComplEx, SimplE
-// and RotatE (include/instance/model/knowledge_graph.h:34-575) with the update rules of
+// include/instance/gpu/knowledge_graph.cuh:38-366) for the models TransE, DistMult, ComplEx, SimplE,
+// RotatE and QuatE (include/instance/model/knowledge_graph.h:34-860) with the update rules of
 // include/core/optimizer.h:161-210 and the uniform negative draw of gpu::Sample
 // (include/base/alias_table.cuh:148-152,175-183 over the all-ones table of
 // instance/knowledge_graph.cuh:316-319).
@@ -218,6 +218,19 @@ __device__ __forceinline__ float partial_logit(const float (&h)[E], const float 
             const float product_im = h[i * 2] * r[i * 2 + 1] + h[i * 2 + 1] * r[i * 2];
             output += product_re * t[i * 2] + product_im * t[i * 2 + 1];
         }
+    } else if constexpr (MODEL == GV_KG_QUATE) {  // model/knowledge_graph.h:594-618
+#pragma unroll
+        for (int i = 0; i < E / 4; i++) {
+            const float h_r = h[i * 4], h_i = h[i * 4 + 1], h_j = h[i * 4 + 2], h_k = h[i * 4 + 3];
+            const float r_r = r[i * 4], r_i = r[i * 4 + 1], r_j = r[i * 4 + 2], r_k = r[i * 4 + 3];
+            const float t_r = t[i * 4], t_i = t[i * 4 + 1], t_j = t[i * 4 + 2], t_k = t[i * 4 + 3];
+            const float r_norm = sqrtf(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
+            const float product_r = h_r * r_r - h_i * r_i - h_j * r_j - h_k * r_k;
+            const float product_i = h_r * r_i + h_i * r_r + h_j * r_k - h_k * r_j;
+            const float product_j = h_r * r_j - h_i * r_k + h_j * r_r + h_k * r_i;
+            const float product_k = h_r * r_k + h_i * r_j - h_j * r_i + h_k * r_r;
+            output += (product_r * t_r + product_i * t_i + product_j * t_j + product_k * t_k) / (r_norm + kEps);
+        }
     } else {  // RotatE
 #pragma unroll
         for (int i = 0; i < E / 2; i++) {
@@ -288,6 +301,46 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
                                                          R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
             R.v[im] -= relation_lr_multiplier * step<NM>(o, r_im, r_im_grad + l3 * fabsf(r_im) * r_im,
                                                          R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+        }
+    } else if constexpr (MODEL == GV_KG_QUATE) {  // model/knowledge_graph.h:620-674 (and the moment overloads)
+        const float l3 = margin_or_l3 * 3;
+#pragma unroll
+        for (int i = 0; i < E / 4; i++) {
+            const int q = i * 4;
+            const float h_r = H.v[q], h_i = H.v[q + 1], h_j = H.v[q + 2], h_k = H.v[q + 3];
+            const float r_r = R.v[q], r_i = R.v[q + 1], r_j = R.v[q + 2], r_k = R.v[q + 3];
+            const float t_r = T.v[q], t_i = T.v[q + 1], t_j = T.v[q + 2], t_k = T.v[q + 3];
+            const float r_norm = sqrtf(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
+            const float grad = gradient / (r_norm + kEps);
+            const float head_grad[4] = {grad * (r_r * t_r + r_i * t_i + r_j * t_j + r_k * t_k),
+                                        grad * (-r_i * t_r + r_r * t_i - r_k * t_j + r_j * t_k),
+                                        grad * (-r_j * t_r + r_k * t_i + r_r * t_j - r_i * t_k),
+                                        grad * (-r_k * t_r - r_j * t_i + r_i * t_j + r_r * t_k)};
+            const float head_old[4] = {h_r, h_i, h_j, h_k};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                H.v[q + c] -= step<NM>(o, head_old[c], head_grad[c] + l3 * fabsf(head_old[c]) * head_old[c],
+                                       H.m1[NM >= 1 ? q + c : 0], H.m2[NM >= 2 ? q + c : 0], weight);
+            const float tail_grad[4] = {grad * (h_r * r_r - h_i * r_i - h_j * r_j - h_k * r_k),
+                                        grad * (h_r * r_i + h_i * r_r + h_j * r_k - h_k * r_j),
+                                        grad * (h_r * r_j - h_i * r_k + h_j * r_r + h_k * r_i),
+                                        grad * (h_r * r_k + h_i * r_j - h_j * r_i + h_k * r_r)};
+            const float tail_old[4] = {t_r, t_i, t_j, t_k};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                T.v[q + c] -= step<NM>(o, tail_old[c], tail_grad[c] + l3 * fabsf(tail_old[c]) * tail_old[c],
+                                       T.m1[NM >= 1 ? q + c : 0], T.m2[NM >= 2 ? q + c : 0], weight);
+            const float relation_grad[4] = {grad * (h_r * t_r + h_i * t_i + h_j * t_j + h_k * t_k),
+                                            grad * (-h_i * t_r + h_r * t_i + h_k * t_j - h_j * t_k),
+                                            grad * (-h_j * t_r - h_k * t_i + h_r * t_j + h_i * t_k),
+                                            grad * (-h_k * t_r + h_j * t_i - h_i * t_j + h_r * t_k)};
+            const float relation_old[4] = {r_r, r_i, r_j, r_k};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                R.v[q + c] -= relation_lr_multiplier *
+                              step<NM>(o, relation_old[c],
+                                       relation_grad[c] + l3 * fabsf(relation_old[c]) * relation_old[c],
+                                       R.m1[NM >= 1 ? q + c : 0], R.m2[NM >= 2 ? q + c : 0], weight);
         }
     } else {  // RotatE
 #pragma unroll
@@ -617,10 +670,10 @@ __global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *he
     }
 }
 
-int floats_per_thread(int dim) {
+int floats_per_thread(int dim, int model) {
     if (dim % 8 == 0 && dim >= 256)
         return 8;
-    if (dim % 4 == 0 && dim >= 64)
+    if (dim % 4 == 0 && (dim >= 64 || model == GV_KG_QUATE))  // a quaternion never straddles two threads
         return 4;
     return 2;
 }
@@ -644,6 +697,10 @@ cudaError_t launch_train(const KgParams &p, int model, int num_moment, dim3 grid
         case GV_KG_DISTMULT: return launch_train_nm<E, GV_KG_DISTMULT>(p, num_moment, grid, block, shared, s);
         case GV_KG_COMPLEX: return launch_train_nm<E, GV_KG_COMPLEX>(p, num_moment, grid, block, shared, s);
         case GV_KG_SIMPLE: return launch_train_nm<E, GV_KG_SIMPLE>(p, num_moment, grid, block, shared, s);
+        case GV_KG_QUATE:
+            if constexpr (E % 4 == 0)
+                return launch_train_nm<E, GV_KG_QUATE>(p, num_moment, grid, block, shared, s);
+            return cudaErrorInvalidValue;
         default: return launch_train_nm<E, GV_KG_ROTATE>(p, num_moment, grid, block, shared, s);
     }
 }
@@ -658,6 +715,12 @@ cudaError_t launch_predict(int model, const float *head, const float *tail, cons
         case GV_KG_DISTMULT: GV_PREDICT(GV_KG_DISTMULT); break;
         case GV_KG_COMPLEX: GV_PREDICT(GV_KG_COMPLEX); break;
         case GV_KG_SIMPLE: GV_PREDICT(GV_KG_SIMPLE); break;
+        case GV_KG_QUATE:
+            if constexpr (E % 4 == 0)
+                GV_PREDICT(GV_KG_QUATE);
+            else
+                return cudaErrorInvalidValue;
+            break;
         default: GV_PREDICT(GV_KG_ROTATE);
     }
 #undef GV_PREDICT
@@ -665,11 +728,13 @@ cudaError_t launch_predict(int model, const float *head, const float *tail, cons
 }
 
 int check_geometry(const char *who, int dim, int model, int &E, int &group_threads) {
-    if (model < GV_KG_TRANSE || model > GV_KG_ROTATE)
+    if (model < GV_KG_TRANSE || model > GV_KG_QUATE)
         return fail(std::string(who) + ": unknown model");
     if (dim < 2 || dim % 2 != 0 || dim > 2048)
         return fail(std::string(who) + ": dim must be even and at most 2048");
-    E = floats_per_thread(dim);
+    if (model == GV_KG_QUATE && dim % 4 != 0)
+        return fail(std::string(who) + ": QuatE needs a dimension divisible by 4");
+    E = floats_per_thread(dim, model);
     if (dim % E != 0)
         return fail(std::string(who) + ": dim must be a multiple of " + std::to_string(E));
     group_threads = (dim / E + 31) / 32 * 32;

@@ -27,10 +27,10 @@
 namespace gv {
 
 static const int kSamplePerVertexWithGlobal = 50;  // core/solver.h:55
-static const char *kModelNames[] = {"TransE", "DistMult", "ComplEx", "SimplE", "RotatE"};
+static const char *kModelNames[] = {"TransE", "DistMult", "ComplEx", "SimplE", "RotatE", "QuatE"};
 
 static int kg_model_id(const std::string &name) {
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < 6; i++)
         if (name == kModelNames[i])
             return i;
     return -1;
@@ -609,7 +609,7 @@ struct KgSolver {
         GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
     }
 
-    // KnowledgeGraphSolver::init_embeddings, knowledge_graph.cuh:567-597 (QuatE is not offered)
+    // KnowledgeGraphSolver::init_embeddings, knowledge_graph.cuh:567-627
     void init_embeddings() {
         static const float kPi = atan(1) * 4;
         const size_t d = dim;
@@ -626,6 +626,29 @@ struct KgSolver {
                 x = init(g_engine);
             for (auto &x : relation_host)
                 x = init(g_engine);
+        }
+        if (model == "QuatE") {
+            std::uniform_real_distribution<float> init_modulus(-1 / sqrt(d / 2), 1 / sqrt(d / 2));  // he init
+            std::uniform_real_distribution<float> init_phase(-kPi, kPi);
+            std::uniform_real_distribution<float> init(0, 1);
+            for (auto *matrix : {&entity_host, &relation_host})
+                for (size_t row = 0; row < matrix->size() / d; row++)
+                    for (size_t i = 0; i < d / 4; i++) {
+                        const float modulus = init_modulus(g_engine);
+                        const float phase = init_phase(g_engine);
+                        float v_i = init(g_engine);
+                        float v_j = init(g_engine);
+                        float v_k = init(g_engine);
+                        const float norm = sqrtf(v_i * v_i + v_j * v_j + v_k * v_k);
+                        v_i /= norm + 1e-15f;
+                        v_j /= norm + 1e-15f;
+                        v_k /= norm + 1e-15f;
+                        float *e = matrix->data() + row * d + i * 4;
+                        e[0] = modulus * cosf(phase);
+                        e[1] = modulus * v_i * sinf(phase);
+                        e[2] = modulus * v_j * sinf(phase);
+                        e[3] = modulus * v_k * sinf(phase);
+                    }
         }
         if (model == "RotatE") {
             std::uniform_real_distribution<float> init(-margin * 2 / d, margin * 2 / d);
@@ -649,9 +672,8 @@ struct KgSolver {
         margin = _margin;
         l3_regularization = _l3_regularization;
         adversarial_temperature = _adversarial_temperature;
-        if (_model == "QuatE")
-            throw std::runtime_error("Model `QuatE` is not implemented by graphvite_b200");
         require(kg_model_id(_model) >= 0, "Invalid model `" + _model + "`");
+        require(_model != "QuatE" || dim % 4 == 0, "Model `QuatE` needs a dimension divisible by 4");
         model = _model;
         model_id = kg_model_id(model);
         num_epoch = _num_epoch;
@@ -939,7 +961,7 @@ struct KgSolver {
         ss << "resume: " << yes_no(resume) << ", relation lr multiplier: " << relation_lr_multiplier << std::endl;
         if (model == "TransE" || model == "RotatE")
             ss << "margin: " << margin << ", positive reuse: " << positive_reuse << std::endl;
-        if (model == "DistMult" || model == "ComplEx" || model == "SimplE")
+        if (model == "DistMult" || model == "ComplEx" || model == "SimplE" || model == "QuatE")
             ss << "l3 regularization: " << l3_regularization << ", positive reuse: " << positive_reuse << std::endl;
         ss << "adversarial temperature: " << adversarial_temperature;
         return ss.str();

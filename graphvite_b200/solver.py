@@ -171,7 +171,7 @@ class KnowledgeGraphSolver(object):
     num_sampler_per_worker=auto, gpu_memory_limit=auto)
 
     Knowledge graph embedding solver (reference include/bind.h:516-639 over
-    include/instance/knowledge_graph.cuh:531-677).  Models: TransE, DistMult, ComplEx, SimplE, RotatE.
+    include/instance/knowledge_graph.cuh:531-677).  Models: TransE, DistMult, ComplEx, SimplE, RotatE, QuatE.
     Extra keyword arguments (not in the reference): rank, world_size for one-process-per-GPU runs.
     """
 

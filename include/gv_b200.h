@@ -38,7 +38,7 @@ enum { GV_SCHEDULE_CONSTANT = 0, GV_SCHEDULE_LINEAR = 1, GV_SCHEDULE_CUSTOM = 2 
 /* instance/graph.cuh:620-622 available models */
 enum { GV_MODEL_DEEPWALK = 0, GV_MODEL_LINE = 1, GV_MODEL_NODE2VEC = 2 };
 /* instance/knowledge_graph.cuh:575-577 available models (QuatE is not implemented) */
-enum { GV_KG_TRANSE = 0, GV_KG_DISTMULT = 1, GV_KG_COMPLEX = 2, GV_KG_SIMPLE = 3, GV_KG_ROTATE = 4 };
+enum { GV_KG_TRANSE = 0, GV_KG_DISTMULT = 1, GV_KG_COMPLEX = 2, GV_KG_SIMPLE = 3, GV_KG_ROTATE = 4, GV_KG_QUATE = 5 };
 
 /* Device-side view of core/optimizer.h Optimizer (the reference passes the whole C++
  * object, std::string included, by value into its kernels; appendix A.14 of SURVEY.md). */

@@ -5,7 +5,7 @@
 // DeepGraphLearning/graphvite v0.2.2: KnowledgeGraph,
 // KnowledgeGraphSolver (tied head / tail entity matrix, global relation matrix, uniform negative
 // sampling over head + tail partition, self-adversarial weighting) with the models TransE,
-// DistMult, ComplEx, SimplE and RotatE and all five optimizers.  QuatE is not restated.
+// DistMult, ComplEx, SimplE, RotatE and QuatE and all five optimizers.
 //
 // PARITY STATUS: pinned against the UNMODIFIED reference.  The graph loader is compared with the live reference
 // object on CPU (tests/test_reference_surface.py).  Kernels and solver are compared with golden vectors
@@ -160,11 +160,11 @@ static float warp_sum(float *lane) {
     return lane[0];
 }
 
-enum ModelType { kTransE = 0, kDistMult, kComplEx, kSimplE, kRotatE };
+enum ModelType { kTransE = 0, kDistMult, kComplEx, kSimplE, kRotatE, kQuatE };
 
 static int model_id(const std::string &name) {
-    static const char *names[] = {"TransE", "DistMult", "ComplEx", "SimplE", "RotatE"};
-    for (int i = 0; i < 5; i++)
+    static const char *names[] = {"TransE", "DistMult", "ComplEx", "SimplE", "RotatE", "QuatE"};
+    for (int i = 0; i < 6; i++)
         if (name == names[i])
             return i;
     return -1;
@@ -202,6 +202,20 @@ static float kg_forward(int model, int dim, const float *head, const float *tail
             case kSimplE:
                 for (int i = l; i < dim; i += 32)
                     output += head[i] * relation[i] * tail[i ^ 1];
+                break;
+            case kQuatE:  // :594-618
+                for (int i = l; i < dim / 4; i += 32) {
+                    float h_r = head[i * 4], h_i = head[i * 4 + 1], h_j = head[i * 4 + 2], h_k = head[i * 4 + 3];
+                    float r_r = relation[i * 4], r_i = relation[i * 4 + 1], r_j = relation[i * 4 + 2],
+                          r_k = relation[i * 4 + 3];
+                    float t_r = tail[i * 4], t_i = tail[i * 4 + 1], t_j = tail[i * 4 + 2], t_k = tail[i * 4 + 3];
+                    float r_norm = sqrtf(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
+                    float product_r = h_r * r_r - h_i * r_i - h_j * r_j - h_k * r_k;
+                    float product_i = h_r * r_i + h_i * r_r + h_j * r_k - h_k * r_j;
+                    float product_j = h_r * r_j - h_i * r_k + h_j * r_r + h_k * r_i;
+                    float product_k = h_r * r_k + h_i * r_j - h_j * r_i + h_k * r_r;
+                    output += (product_r * t_r + product_i * t_i + product_j * t_j + product_k * t_k) / (r_norm + kEpsilon);
+                }
                 break;
             default:  // RotatE
                 for (int i = l; i < dim / 2; i += 32) {
@@ -279,6 +293,40 @@ static void kg_backward(int model, int dim, const KGRows &x, const Optimizer &op
                                                              m1(x.relation_m1, i), m1(x.relation_m2, i));
             x.relation[i * 2 + 1] -= relation_lr_multiplier * up(r_im, r_im_grad + l3 * fabsf(r_im) * r_im,
                                                                  m1(x.relation_m1, i), m1(x.relation_m2, i));
+        }
+    } else if (model == kQuatE) {  // :620-860, per-element moments for all three rows
+        float l3 = margin_or_l3 * 3;
+        for (int i = 0; i < dim / 4; i++) {
+            int q = i * 4;
+            float h_r = x.head[q], h_i = x.head[q + 1], h_j = x.head[q + 2], h_k = x.head[q + 3];
+            float r_r = x.relation[q], r_i = x.relation[q + 1], r_j = x.relation[q + 2], r_k = x.relation[q + 3];
+            float t_r = x.tail[q], t_i = x.tail[q + 1], t_j = x.tail[q + 2], t_k = x.tail[q + 3];
+            float r_norm = sqrtf(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
+            float grad = gradient / (r_norm + kEpsilon);
+            float h_grad[4] = {grad * (r_r * t_r + r_i * t_i + r_j * t_j + r_k * t_k),
+                               grad * (-r_i * t_r + r_r * t_i - r_k * t_j + r_j * t_k),
+                               grad * (-r_j * t_r + r_k * t_i + r_r * t_j - r_i * t_k),
+                               grad * (-r_k * t_r - r_j * t_i + r_i * t_j + r_r * t_k)};
+            float h_old[4] = {h_r, h_i, h_j, h_k};
+            for (int c = 0; c < 4; c++)
+                x.head[q + c] -= up(h_old[c], h_grad[c] + l3 * fabsf(h_old[c]) * h_old[c], m1(x.head_m1, q + c),
+                                    m1(x.head_m2, q + c));
+            float t_grad[4] = {grad * (h_r * r_r - h_i * r_i - h_j * r_j - h_k * r_k),
+                               grad * (h_r * r_i + h_i * r_r + h_j * r_k - h_k * r_j),
+                               grad * (h_r * r_j - h_i * r_k + h_j * r_r + h_k * r_i),
+                               grad * (h_r * r_k + h_i * r_j - h_j * r_i + h_k * r_r)};
+            float t_old[4] = {t_r, t_i, t_j, t_k};
+            for (int c = 0; c < 4; c++)
+                x.tail[q + c] -= up(t_old[c], t_grad[c] + l3 * fabsf(t_old[c]) * t_old[c], m1(x.tail_m1, q + c),
+                                    m1(x.tail_m2, q + c));
+            float r_grad[4] = {grad * (h_r * t_r + h_i * t_i + h_j * t_j + h_k * t_k),
+                               grad * (-h_i * t_r + h_r * t_i + h_k * t_j - h_j * t_k),
+                               grad * (-h_j * t_r - h_k * t_i + h_r * t_j + h_i * t_k),
+                               grad * (-h_k * t_r + h_j * t_i - h_i * t_j + h_r * t_k)};
+            float r_old[4] = {r_r, r_i, r_j, r_k};
+            for (int c = 0; c < 4; c++)
+                x.relation[q + c] -= relation_lr_multiplier * up(r_old[c], r_grad[c] + l3 * fabsf(r_old[c]) * r_old[c],
+                                                                 m1(x.relation_m1, q + c), m1(x.relation_m2, q + c));
         }
     } else {  // RotatE
         for (int i = 0; i < dim / 2; i++) {
@@ -564,7 +612,7 @@ struct KGSolver {
             sample_edges(i, work_load * i, std::min(work_load * (i + 1), num_sample));
     }
 
-    // instance/knowledge_graph.cuh:588-641 (QuatE not restated)
+    // instance/knowledge_graph.cuh:567-627
     void init_embeddings() {
         static const float kPi = atan(1) * 4;
         const size_t d = dim;
@@ -582,6 +630,29 @@ struct KGSolver {
                 x = init(global_engine());
             for (auto &x : relation_embeddings)
                 x = init(global_engine());
+        }
+        if (id == kQuatE) {  // :604-626
+            std::uniform_real_distribution<float> init_modulus(-1 / sqrt(d / 2), 1 / sqrt(d / 2));
+            std::uniform_real_distribution<float> init_phase(-kPi, kPi);
+            std::uniform_real_distribution<float> init(0, 1);
+            for (auto *matrix : {&entity_embeddings, &relation_embeddings})
+                for (size_t row = 0; row < matrix->size() / d; row++)
+                    for (size_t i = 0; i < d / 4; i++) {
+                        float modulus = init_modulus(global_engine());
+                        float phase = init_phase(global_engine());
+                        float v_i = init(global_engine());
+                        float v_j = init(global_engine());
+                        float v_k = init(global_engine());
+                        float norm = sqrtf(v_i * v_i + v_j * v_j + v_k * v_k);
+                        v_i /= norm + kEpsilon;
+                        v_j /= norm + kEpsilon;
+                        v_k /= norm + kEpsilon;
+                        float *e = matrix->data() + row * d + i * 4;
+                        e[0] = modulus * cosf(phase);
+                        e[1] = modulus * v_i * sinf(phase);
+                        e[2] = modulus * v_j * sinf(phase);
+                        e[3] = modulus * v_k * sinf(phase);
+                    }
         }
         if (id == kRotatE) {
             std::uniform_real_distribution<float> init(-margin * 2 / d, margin * 2 / d);
@@ -610,6 +681,8 @@ struct KGSolver {
             fail("Invalid model `" + model + "`");
         if ((model == "ComplEx" || model == "SimplE" || model == "RotatE") && dim % 2)
             fail("Model `" + model + "` needs an even dimension");
+        if (model == "QuatE" && dim % 4)
+            fail("Model `QuatE` needs a dimension divisible by 4");
         num_epoch = _num_epoch;
         resume = _resume;
         sample_batch_size = _sample_batch_size;

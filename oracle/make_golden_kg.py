@@ -30,7 +30,7 @@ OPTIMIZERS = {
     "RMSprop": (3, 0.001, 0.001, 0.99, 0.0, 1e-8),
     "Adam": (4, 0.001, 0.001, 0.9, 0.999, 1e-8),
 }
-MODELS = ("TransE", "DistMult", "ComplEx", "SimplE", "RotatE")
+MODELS = ("TransE", "DistMult", "ComplEx", "SimplE", "RotatE", "QuatE")
 
 # solver cases, one GPU; each runs on tests/golden/toy_kg.txt
 SOLVER_CASES = {
@@ -44,6 +44,8 @@ SOLVER_CASES = {
                             margin=12.0, l3=1e-3, temperature=2.0, sbs=30, rlm=1.0, reuse=1),
     "simple_p1_momentum": dict(dim=32, P=1, k=3, B=150, E=2, S=3, model="SimplE", epochs=2, optimizer="Momentum",
                                margin=12.0, l3=2e-3, temperature=0.5, sbs=50, rlm=1.0, reuse=2),
+    "quate_p1_adam": dict(dim=32, P=1, k=3, B=150, E=2, S=1, model="QuatE", epochs=3, optimizer="Adam", margin=12.0,
+                          l3=2e-3, temperature=2.0, sbs=45, rlm=1.0, reuse=1),
     "rotate_p4_rmsprop": dict(dim=32, P=4, k=2, B=60, E=2, S=1, model="RotatE", epochs=6, optimizer="RMSprop",
                               margin=9.0, l3=2e-3, temperature=2.0, sbs=25, rlm=0.5, reuse=1),
 }

@@ -274,6 +274,8 @@ int dispatch_kernel(const std::string &model, int opt_type, const graphvite::Opt
         RUN(SimplE);
     else if (model == "RotatE")
         RUN(RotatE);
+    else if (model == "QuatE")
+        RUN(QuatE);
     else
         return -1;
 #undef RUN
@@ -294,6 +296,8 @@ int dispatch_predict(const std::string &model, size_t num_entity, size_t num_rel
         run_predict<dim, SimplE>(num_entity, num_relation, entity, relation, batch, n, margin, logits);
     else if (model == "RotatE")
         run_predict<dim, RotatE>(num_entity, num_relation, entity, relation, batch, n, margin, logits);
+    else if (model == "QuatE")
+        run_predict<dim, QuatE>(num_entity, num_relation, entity, relation, batch, n, margin, logits);
     else
         return -1;
     return 0;

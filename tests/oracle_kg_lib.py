@@ -55,7 +55,7 @@ def lib():
     return L
 
 
-MODELS = ("TransE", "DistMult", "ComplEx", "SimplE", "RotatE")
+MODELS = ("TransE", "DistMult", "ComplEx", "SimplE", "RotatE", "QuatE")
 
 
 class OracleKnowledgeGraph(object):

@@ -15,7 +15,7 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 
-MODEL_IDS = {"TransE": 0, "DistMult": 1, "ComplEx": 2, "SimplE": 3, "RotatE": 4}
+MODEL_IDS = {"TransE": 0, "DistMult": 1, "ComplEx": 2, "SimplE": 3, "RotatE": 4, "QuatE": 5}
 TOLERANCE = dict(rtol=1e-3, atol=1e-5)
 
 

@@ -30,6 +30,8 @@ CASES = {
                            train=dict(l3_regularization=2e-3, relation_lr_multiplier=0.5)),
     "simple_momentum_p2": dict(dim=32, P=2, k=3, B=90, E=1, S=2, model="SimplE", epochs=2, optimizer="Momentum",
                                sb=77, train=dict(adversarial_temperature=0.5, positive_reuse=2)),
+    "quate_adam_p2": dict(dim=64, P=2, k=3, B=75, E=2, S=1, model="QuatE", epochs=2, optimizer="Adam", sb=33,
+                          train=dict(l3_regularization=1e-3, adversarial_temperature=1.5)),
     "rotate_rmsprop_p2": dict(dim=96, P=2, k=2, B=70, E=2, S=1, model="RotatE", epochs=2, optimizer="RMSprop",
                               sb=25, train=dict(margin=9.0, log_frequency=3)),
 }
