@@ -110,6 +110,10 @@ def test_backward_is_the_gradient_of_forward(model):
     width = dim // 2 if model == "RotatE" else dim  # RotatE relations are dim/2 phases
     for which, (after, before, count) in enumerate([(entity[0], before_e[0], dim), (entity[2], before_e[2], dim),
                                                     (relation[1], before_r[1], width)]):
+        if model == "QuatE" and which == 2:
+            # the reference differentiates the Hamilton product only and treats the relation's norm as a constant
+            # (model/knowledge_graph.h:661-664): its relation update is not the gradient of its own forward
+            continue
         expected = -lr * (prob - 1) * numeric_gradient(model, before_e[0], before_e[2], before_r[1], margin_or_l3, which)
         np.testing.assert_allclose((after - before)[:count], expected[:count], rtol=2e-2, atol=2e-5)
     # rows not named by the sample are untouched
