@@ -80,3 +80,32 @@ def link_prediction_split(u, v, portions=(100, 1, 1), seed=1024):
         y = np.concatenate([np.ones(count, dtype=np.int64), np.zeros(count, dtype=np.int64)])
         tests.append((h, t, y))
     return which == 0, tests
+
+
+# entities, relations, training triplets (doc/source/benchmark.rst:112)
+KG_SHAPES = {"fb15k-237": (14541, 237, 272115), "toy": (120, 7, 1400)}
+
+
+def power_law_triplets(num_entity, num_relation, num_triplet, seed=20260922):
+    """Synthetic knowledge graph shaped like the benchmark's: heads and tails drawn from power-law weights,
+    relations from a skewed distribution; every entity and relation occurs at least once.  Returns int64 arrays
+    (head, relation, tail)."""
+    rng = np.random.default_rng(seed)
+    weights = np.arange(1, num_entity + 1, dtype=np.float64) ** -0.8
+    cdf = np.cumsum(weights) / weights.sum()
+    head = np.minimum(np.searchsorted(cdf, rng.random(num_triplet), side="right"), num_entity - 1)
+    tail = np.minimum(np.searchsorted(cdf, rng.random(num_triplet), side="right"), num_entity - 1)
+    relation_weights = np.arange(1, num_relation + 1, dtype=np.float64) ** -1.0
+    relation = rng.choice(num_relation, size=num_triplet, p=relation_weights / relation_weights.sum())
+    cover = min(num_entity, num_triplet)
+    head[:cover] = rng.permutation(num_entity)[:cover]
+    relation[:min(num_relation, num_triplet)] = np.arange(min(num_relation, num_triplet))
+    return head.astype(np.int64), relation.astype(np.int64), tail.astype(np.int64)
+
+
+def synthetic_knowledge_graph_file(name, path, seed=20260922):
+    num_entity, num_relation, num_triplet = KG_SHAPES[name]
+    head, relation, tail = power_law_triplets(num_entity, num_relation, num_triplet, seed)
+    with open(path, "w") as fout:
+        np.savetxt(fout, np.stack([head, relation, tail], axis=1), fmt="/m/%d\t/r/%d\t/m/%d")
+    return num_entity, num_relation, num_triplet
