@@ -16,9 +16,10 @@
 // negatives, schedule and batch accounting bit-exact, and -- for one partition -- embeddings, loss and predict of
 // the whole training run to rtol 1e-4 (same sample order; host libm / no-FMA rounding on both sides).  What this
 // does NOT cover: the device's own rounding (libdevice, FMA contraction) -- rerun make_golden_kg.py on a GPU for
-// that -- and, with several partitions, the reference's partition cache, which can train a stale second copy of
-// an entity partition (see tests/test_oracle_kg_golden.py::test_solver_runs); there only integer state and
-// magnitudes are compared.
+// that.  With several partitions the reference's partition cache can train a stale second copy of an entity
+// partition (KGSolver::reference_cache below): the default restatement trains in place, as the protocol intends,
+// and is compared on integer state and magnitudes there; with reference_cache switched on it reproduces those
+// runs float for float as well (tests/test_oracle_kg_golden.py::test_solver_runs).
 //
 // Paths are relative to /root/reference/include.  Workers are emulated one after another with
 // sequentially consistent entity matrices (the reference races its write-backs against the other
@@ -480,10 +481,22 @@ struct KGSolver {
     // per worker: the relation copy of the block being trained, its values at load time, and the
     // worker-resident relation moments (loaded once after build(), never written back:
     // core/solver.h:1378-1385,1422-1427)
+    // reference_cache: a worker's device copies of its head / tail entity partitions with the hit / miss protocol
+    // of WorkerMixin::load_partition (core/solver.h:1436-1500).  The default (off) trains in place on the global
+    // matrix, which is what the protocol intends; with the cache ON the restatement also reproduces its one
+    // incoherent case -- after a block (q, p) a block (p, p) is a "tail hit": the trained tail copy of p stays, the
+    // head copy of the SAME partition p is loaded from host memory that has not seen the tail's updates, both
+    // copies are trained and the later write-back overwrites the earlier.
+    struct Block {
+        std::vector<float> v, m1, m2;
+    };
     struct Worker {
         std::vector<float> relation, relation_loaded, relation_m1, relation_m2;
         bool has_block = false, moments_loaded = false;
+        int head_id = -1, tail_id = -1;
+        std::shared_ptr<Block> entity[2];  // [0] head, [1] tail; the same object when shared
     };
+    bool reference_cache = false;
     std::vector<Worker> workers;
 
     std::vector<float> last_loss, logged_loss;
@@ -747,6 +760,70 @@ struct KGSolver {
     }
 
     // WorkerMixin::train for one block (core/solver.h:1511-1557) around the KG kernels
+    // write_embedding / load_embedding for the entity partitions (in place protocol: scatter / gather by the
+    // partition's global ids), core/solver.h:1349-1428
+    void write_entity(Worker &w, int i) {
+        if (i > 0 && w.entity[i] == w.entity[i - 1])
+            return;
+        const std::vector<Index> &ids = partitions[i == 0 ? w.head_id : w.tail_id];
+        Block &b = *w.entity[i];
+        const size_t d = dim;
+        for (size_t r = 0; r < ids.size(); r++) {
+            std::copy(b.v.begin() + r * d, b.v.begin() + (r + 1) * d, entity_embeddings.begin() + size_t(ids[r]) * d);
+            if (!b.m1.empty())
+                std::copy(b.m1.begin() + r * d, b.m1.begin() + (r + 1) * d, entity_m1.begin() + size_t(ids[r]) * d);
+            if (!b.m2.empty())
+                std::copy(b.m2.begin() + r * d, b.m2.begin() + (r + 1) * d, entity_m2.begin() + size_t(ids[r]) * d);
+        }
+    }
+    void load_entity(Worker &w, int i) {
+        if (i == 1 && w.head_id == w.tail_id) {
+            w.entity[1] = w.entity[0];
+            return;
+        }
+        if (!w.entity[i] || (i > 0 && w.entity[i] == w.entity[i - 1]))
+            w.entity[i] = std::make_shared<Block>();
+        const std::vector<Index> &ids = partitions[i == 0 ? w.head_id : w.tail_id];
+        Block &b = *w.entity[i];
+        const size_t d = dim;
+        const int nm = optimizer.num_moment();
+        b.v.resize(ids.size() * d);
+        b.m1.resize(nm >= 1 ? ids.size() * d : 0);
+        b.m2.resize(nm >= 2 ? ids.size() * d : 0);
+        for (size_t r = 0; r < ids.size(); r++) {
+            std::copy(entity_embeddings.begin() + size_t(ids[r]) * d, entity_embeddings.begin() + size_t(ids[r] + 1) * d,
+                      b.v.begin() + r * d);
+            if (nm >= 1)
+                std::copy(entity_m1.begin() + size_t(ids[r]) * d, entity_m1.begin() + size_t(ids[r] + 1) * d,
+                          b.m1.begin() + r * d);
+            if (nm >= 2)
+                std::copy(entity_m2.begin() + size_t(ids[r]) * d, entity_m2.begin() + size_t(ids[r] + 1) * d,
+                          b.m2.begin() + r * d);
+        }
+    }
+    // the entity part of WorkerMixin::load_partition, core/solver.h:1436-1500
+    void load_entity_partitions(Worker &w, int head_partition, int tail_partition) {
+        const bool cold = w.head_id == -1 || w.tail_id == -1;
+        bool hit[2] = {false, false};
+        if (!cold) {
+            hit[0] = w.head_id == head_partition;
+            if (!hit[0] && w.head_id == tail_partition && w.tail_id == head_partition) {  // swap hit
+                std::swap(w.entity[0], w.entity[1]);
+                hit[0] = hit[1] = true;
+            }
+            if (!(w.entity[1] == w.entity[0] && !hit[0]))
+                hit[1] = hit[1] || w.tail_id == tail_partition;
+            for (int i = 0; i < 2; i++)
+                if (!hit[i])
+                    write_entity(w, i);
+        }
+        w.head_id = head_partition;
+        w.tail_id = tail_partition;
+        for (int i = 0; i < 2; i++)
+            if (!hit[i])
+                load_entity(w, i);
+    }
+
     void train_block(int worker_id, int head_partition, int tail_partition, int first_batch_id, int batch_stride) {
         Worker &w = workers[worker_id];
         // load_partition, core/solver.h:1436-1500: write the previous block's relation delta back, load
@@ -781,6 +858,17 @@ struct KGSolver {
         if (nm >= 2) {
             m.head_m2 = m.tail_m2 = entity_m2.data();
             m.relation_m2 = w.relation_m2.data();
+        }
+        if (reference_cache) {  // train the worker's copies instead of the global matrix
+            load_entity_partitions(w, head_partition, tail_partition);
+            Block &h = *w.entity[0], &t = *w.entity[1];
+            m.head_rows = m.tail_rows = nullptr;
+            m.head = h.v.data();
+            m.tail = t.v.data();
+            m.head_m1 = nm >= 1 ? h.m1.data() : nullptr;
+            m.tail_m1 = nm >= 1 ? t.m1.data() : nullptr;
+            m.head_m2 = nm >= 2 ? h.m2.data() : nullptr;
+            m.tail_m2 = nm >= 2 ? t.m2.data() : nullptr;
         }
         int id = model_id(model);
         float margin_or_l3 = (id == kTransE || id == kRotatE) ? margin : l3_regularization;
@@ -836,8 +924,12 @@ struct KGSolver {
         }
         fill_pool();
         if (batch_id >= num_batch)  // Worker::write_back of every worker, core/solver.h:650-653
-            for (auto &w : workers)
+            for (auto &w : workers) {
+                if (reference_cache && w.head_id != -1 && w.tail_id != -1)
+                    for (int i = 0; i < 2; i++)
+                        write_entity(w, i);
                 write_relation(w);
+            }
         return true;
     }
 
@@ -1003,6 +1095,11 @@ int og_kg_solver_build(void *s, void *graph, int opt_type, int schedule, float l
 void og_kg_solver_set_emulation(void *s, int shuffle_override, int synchronous_relation) {
     ((KGSolver *)s)->shuffle_override = shuffle_override;
     ((KGSolver *)s)->synchronous_relation = synchronous_relation != 0;
+}
+
+// see KGSolver::reference_cache; call before build()
+void og_kg_solver_set_reference_cache(void *s, int on) {
+    ((KGSolver *)s)->reference_cache = on != 0;
 }
 
 int og_kg_solver_train_begin(void *s, const char *model, int num_epoch, int resume, float relation_lr_multiplier,

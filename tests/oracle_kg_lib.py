@@ -37,6 +37,7 @@ def lib():
     L.og_kg_solver_free.argtypes = [V]
     L.og_kg_solver_build.argtypes = [V, V, I, I, F, F, F, F, F, I, I, I, I]
     L.og_kg_solver_set_emulation.argtypes = [V, I, I]
+    L.og_kg_solver_set_reference_cache.argtypes = [V, I]
     L.og_kg_solver_train_begin.argtypes = [V, S, I, I, F, F, F, I, I, F, I]
     L.og_kg_solver_train_episode.argtypes = [V]
     L.og_kg_solver_info.argtypes = [V, V]
@@ -136,6 +137,10 @@ class OracleKGSolver(object):
     def set_emulation(self, shuffle_override=-1, synchronous_relation=False):
         """multi-worker emulation switches (see KGSolver in gv_oracle_kg.cpp); call before build()"""
         lib().og_kg_solver_set_emulation(self.handle, shuffle_override, int(synchronous_relation))
+
+    def set_reference_cache(self, on=True):
+        """restate the reference's per-worker partition cache, its incoherent "tail hit" included (call before build())"""
+        lib().og_kg_solver_set_reference_cache(self.handle, int(on))
 
     def build(self, optimizer="Adam", num_partition=0, num_negative=64, batch_size=100000, episode_size=0, schedule=1):
         otype, lr, wd, a, b, eps = OPTIMIZERS[optimizer] if isinstance(optimizer, str) else optimizer
