@@ -72,3 +72,24 @@ def test_train_kernels_match_the_b200_to_rounding(regenerated, dim, optimizer):
 def test_solver_runs_reproduce_the_b200s_integer_state(regenerated, case):
     # vertex / context / loss / logits: Hogwild on the B200, in order here; edge_prob is float but host-built
     compare(regenerated, "solver_%s.npz" % case, skip=("vertex", "context", "loss", "logits"))
+
+
+@pytest.mark.parametrize("case", SOLVER_CASES)
+def test_oracle_training_arithmetic_equals_the_references_in_order(regenerated, case):
+    """On the B200 the reference's solver runs are Hogwild, so tests/test_oracle_golden.py can pin the oracle's
+    integer state only.  The emulation processes a batch in order (one warp per sample, warps one after another) --
+    the oracle's order -- so here the oracle's whole training run is compared with the reference's float for float:
+    vertex / context embeddings, the last batch's losses and predict."""
+    import oracle_lib as O
+    g = np.load(os.path.join(regenerated, "solver_%s.npz" % case))
+    cfg = {key[4:]: g[key].item() for key in g.files if key.startswith("cfg_")}
+    graph = O.OracleGraph(os.path.join(GOLDEN, "toy_graph.txt"))
+    solver = O.OracleSolver(graph, cfg["dim"], 1, cfg["S"])
+    solver.build(cfg["optimizer"], cfg["P"], cfg["k"], cfg["B"], cfg["E"])
+    solver.train(model=cfg["model"], num_epoch=cfg["epochs"], augmentation_step=cfg["aug"],
+                 random_walk_length=cfg["L"], random_walk_batch_size=cfg["wb"], p=cfg.get("p", 1.0),
+                 q=cfg.get("q", 1.0))
+    tolerance = dict(rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(solver.embeddings(0), g["vertex"], **tolerance)
+    np.testing.assert_allclose(solver.embeddings(1), g["context"], **tolerance)
+    np.testing.assert_allclose(solver.predict(g["pairs"]), g["logits"], rtol=1e-4, atol=1e-6)
