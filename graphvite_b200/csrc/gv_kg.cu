@@ -8,7 +8,9 @@
 // (include/base/alias_table.cuh:148-152,175-183 over the all-ones table of
 // instance/knowledge_graph.cuh:316-319).
 //
-// STATUS: compiles for sm_100a; NOT yet run on a GPU (written after the round's GPU budget was spent).
+// STATUS: compiles for sm_100a (224-234 registers for 8 floats per thread with Adam, no spills); NOT yet run on a
+// GPU (written after the round's GPU budget was spent) -- executed under the CUDA emulation of tests/emu against
+// the oracle and against golden vectors recorded from the reference's own kernels.
 //
 // Design.  One positive sample = 1 + k targets that share the relation row and, each, either the
 // positive head or the positive tail.  The reference walks the targets with one warp and
@@ -23,6 +25,10 @@
 // against each other Hogwild-style exactly like the reference's warps.
 // The logit is a group-wide sum: butterfly shuffles inside a warp, one shared-memory hop (double
 // buffered, a single named barrier) across the warps of a group.
+// Latency hiding: the logits of the normaliser pass are independent, so kPass1Batch targets are loaded together and
+// reduced with one barrier; in the update pass the targets depend on each other through the cached rows, but the
+// next target's negative row (+ moments) is requested while the current one is reduced and updated (never a row
+// the current target writes).
 // =============================================================================
 #include <cuda_runtime.h>
 
@@ -399,7 +405,34 @@ struct Group {
         parity ^= 1;  // the next sum uses the other buffer: one barrier per sum is enough
         return total;
     }
+    // N independent sums with ONE barrier (scratch holds [2][N][warps]); every value is reduced exactly like sum()
+    template<int N>
+    __device__ __forceinline__ void sum_many(float (&value)[N]) {
+#pragma unroll
+        for (int n = 0; n < N; n++)
+#pragma unroll
+            for (int delta = 16; delta > 0; delta >>= 1)
+                value[n] += __shfl_xor_sync(kFull, value[n], delta);
+        if (warps == 1)
+            return;
+        float *slot = scratch + parity * N * warps;
+        if (lane == 0)
+#pragma unroll
+            for (int n = 0; n < N; n++)
+                slot[n * warps + warp] = value[n];
+        sync();
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            float total = 0.f;
+            for (int w = 0; w < warps; w++)
+                total += slot[n * warps + w];
+            value[n] = total;
+        }
+        parity ^= 1;
+    }
 };
+
+constexpr int kPass1Batch = 4;  // targets per barrier in the normaliser pass
 
 template<int MODEL>
 __device__ __forceinline__ float finish_logit(float sum, float margin_or_l3) {
@@ -415,7 +448,7 @@ __device__ __forceinline__ uint32_t uniform_negative(uint32_t count, double rand
 
 // -----------------------------------------------------------------------------
 // The train kernel.  E floats per thread, NM moments per row.
-// Dynamic shared memory per group: 2 * warps floats (sums) + num_negative ids.
+// Dynamic shared memory per group: 2 * kPass1Batch * warps floats (sums) + num_negative ids.
 // -----------------------------------------------------------------------------
 template<int E, int MODEL, int NM>
 __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p) {
@@ -432,10 +465,11 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
     g.lane = c & 31;
     g.warp = c >> 5;
     g.parity = 0;
-    const size_t per_group = size_t(2) * g.warps * sizeof(float) + size_t(p.num_negative) * sizeof(uint32_t);
+    const size_t scratch_bytes = size_t(2) * kPass1Batch * g.warps * sizeof(float);
+    const size_t per_group = scratch_bytes + size_t(p.num_negative) * sizeof(uint32_t);
     unsigned char *mine = shared_bytes + per_group * g.id_in_cta;
     g.scratch = reinterpret_cast<float *>(mine);
-    uint32_t *negative_ids = reinterpret_cast<uint32_t *>(mine + size_t(2) * g.warps * sizeof(float));
+    uint32_t *negative_ids = reinterpret_cast<uint32_t *>(mine + scratch_bytes);
     const bool active = c < chunks;
     const size_t slice = size_t(c) * E;                 // offset of this thread inside an entity row
     const size_t relation_value = size_t(c) * G::RV, relation_moment = size_t(c) * G::RM;
@@ -509,37 +543,53 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
             }
         };
 
-        // pass 1: normaliser of the self-adversarial weights (gpu/knowledge_graph.cuh:59-77)
+        // pass 1: normaliser of the self-adversarial weights (gpu/knowledge_graph.cuh:59-77).  The k logits are
+        // independent of each other: kPass1Batch targets are loaded together (that many rows in flight per
+        // thread) and reduced with one barrier; the normaliser is still accumulated in target order.
         float bias = 0.f, normalizer = 0.f;
         if (adversarial)
-            for (int s = 0; s < k; s++) {
-                uint32_t head_id, tail_id;
-                target(s, head_id, tail_id);
-                float partial = 0.f;
-                if (active) {
-                    float h[E], t[E];
-                    if (cached && head_id == positive_head) {
+            for (int s0 = 0; s0 < k; s0 += kPass1Batch) {
+                float partial[kPass1Batch];
 #pragma unroll
-                        for (int i = 0; i < E; i++)
-                            h[i] = PH.v[i];
-                    } else
-                        load_vec<E>(h, p.head + size_t(head_id) * dim + slice);
-                    if (cached && tail_id == positive_tail) {
+                for (int b = 0; b < kPass1Batch; b++) {
+                    partial[b] = 0.f;
+                    if (s0 + b < k && active) {
+                        uint32_t head_id, tail_id;
+                        target(s0 + b, head_id, tail_id);
+                        float h[E], t[E];
+                        if (cached && head_id == positive_head) {
 #pragma unroll
-                        for (int i = 0; i < E; i++)
-                            t[i] = PT.v[i];
-                    } else
-                        load_vec<E>(t, p.tail + size_t(tail_id) * dim + slice);
-                    partial = partial_logit<E, MODEL>(h, t, R.v);
+                            for (int i = 0; i < E; i++)
+                                h[i] = PH.v[i];
+                        } else
+                            load_vec<E>(h, p.head + size_t(head_id) * dim + slice);
+                        if (cached && tail_id == positive_tail) {
+#pragma unroll
+                            for (int i = 0; i < E; i++)
+                                t[i] = PT.v[i];
+                        } else
+                            load_vec<E>(t, p.tail + size_t(tail_id) * dim + slice);
+                        partial[b] = partial_logit<E, MODEL>(h, t, R.v);
+                    }
                 }
-                const float logit = finish_logit<MODEL>(g.sum(partial), p.margin_or_l3);
-                if (s == 0)
-                    bias = logit;
-                normalizer += safe_exp((logit - bias) / p.temperature);
+                g.sum_many<kPass1Batch>(partial);
+#pragma unroll
+                for (int b = 0; b < kPass1Batch; b++)
+                    if (s0 + b < k) {
+                        const float logit = finish_logit<MODEL>(partial[b], p.margin_or_l3);
+                        if (s0 + b == 0)
+                            bias = logit;
+                        normalizer += safe_exp((logit - bias) / p.temperature);
+                    }
             }
 
         // pass 2: negatives first, the positive triple last (gpu/knowledge_graph.cuh:79-118)
+        // The targets of a sample are sequentially dependent through the cached rows, but the NEXT target's
+        // negative row (with its moments) can already be in flight while this one is reduced and updated: it is
+        // requested right after this target's own rows, unless it is a row this target is about to write.
         float sample_loss = 0.f;
+        Slice<E, NM> NX;
+        bool next_valid = false, next_is_head = false;
         for (int s = 0; s <= k; s++) {
             uint32_t head_id, tail_id;
             target(s, head_id, tail_id);
@@ -556,13 +606,41 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                 WH = PH;
             else if (head_source == 2)
                 WH = PT;
+            else if (next_valid && next_is_head)
+                WH = NX;
             else
                 load_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, active);
             if (!alias) {
                 if (tail_cached)
                     WT = PT;
+                else if (next_valid && !next_is_head)
+                    WT = NX;
                 else
                     load_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, active);
+            }
+            next_valid = false;
+            if (s + 1 < k && cached) {  // target s + 1 is a negative: exactly one of its rows may be uncached
+                uint32_t next_head, next_tail;
+                target(s + 1, next_head, next_tail);
+                const bool next_head_cached = next_head == positive_head, next_tail_cached = next_tail == positive_tail;
+                const bool next_alias = p.shared && next_head == next_tail;
+                if (!next_alias && next_head_cached != next_tail_cached) {
+                    next_is_head = !next_head_cached;
+                    const uint32_t next_id = next_is_head ? next_head : next_tail;
+                    bool written_now = false;  // is it a row this target stores below?
+                    if (head_source == 0)
+                        written_now |= (p.shared || next_is_head) && next_id == head_id;
+                    if (!alias && !tail_cached)
+                        written_now |= (p.shared || !next_is_head) && next_id == tail_id;
+                    if (!written_now) {
+                        const size_t offset = size_t(next_id) * dim + slice;
+                        if (next_is_head)
+                            load_slice<E, NM>(NX, p.head, p.head_m1, p.head_m2, offset, active);
+                        else
+                            load_slice<E, NM>(NX, p.tail, p.tail_m1, p.tail_m2, offset, active);
+                        next_valid = true;
+                    }
+                }
             }
 
             float partial = 0.f;
@@ -805,7 +883,8 @@ int gv_cuda_kg_train_block(const gv_kg_matrices_t *m, int model, const uint32_t 
     // num_group == 1: one group, samples in order (the parity tests); 0: fill the device
     const int groups_per_cta = num_group == 1 ? 1 : kCtaThreads / group_threads;
     const dim3 block(groups_per_cta * group_threads);
-    const size_t per_group = size_t(2) * (group_threads / 32) * sizeof(float) + size_t(num_negative) * sizeof(uint32_t);
+    const size_t per_group =
+        size_t(2) * kPass1Batch * (group_threads / 32) * sizeof(float) + size_t(num_negative) * sizeof(uint32_t);
     const size_t shared = per_group * groups_per_cta;
     if (shared > 48 * 1024)
         return fail("gv_cuda_kg_train_block: too many negatives per sample for the shared-memory id buffer");

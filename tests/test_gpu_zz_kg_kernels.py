@@ -291,3 +291,35 @@ def test_predict_kernel_matches_the_reference_kernel(path):
                                            logits.data_ptr(), stream_pointer()))
     gpu_util.synchronize()
     np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("shared", [True, False], ids=["one-matrix", "two-matrices"])
+@pytest.mark.parametrize("model,opt", [("RotatE", "Adam"), ("TransE", "SGD"), ("QuatE", "Momentum"), ("ComplEx", "SGD")])
+def test_next_target_prefetch_never_uses_a_row_the_current_target_writes(model, opt, shared):
+    """4 entity rows and 12 negatives per sample: consecutive targets keep naming the same row -- on the same side,
+    and (one shared matrix) as head then tail of the same memory -- so the row requested ahead for target s + 1 is
+    very often the one target s is about to update.  Sequential semantics must survive (one group vs the oracle)."""
+    if not shared and opt != "SGD":
+        pytest.skip("the oracle binding takes separate tail matrices without moments only")
+    optimizer = O.OPTIMIZERS[opt]
+    nm = num_moment_of(optimizer)
+    dim, n, k, rows = 64, 30, 12, 4
+    entity, relation, ms, batch, negatives = make_problem(dim, n, k, rows, 3, 77, nm)
+    negatives[0, :6] = [1, 1, rows + 1, 1, rows + 1, rows + 1]  # same row: head, head, tail, head, tail, tail
+    margin_or_l3 = 6.0 if model in ("TransE", "RotatE") else 2e-3
+    if shared:
+        e, r, m, loss = oracle_shared(model, dim, entity, relation, ms, batch, negatives, optimizer, 1.0, margin_or_l3, 2.0)
+        got = run_kg_train(model, dim, entity, None, relation, ms, batch, negatives, optimizer, rows, 1.0,
+                           margin_or_l3, 2.0, num_group=1)
+        np.testing.assert_allclose(got["head"], e, **TOLERANCE)
+    else:
+        tail = ((np.random.RandomState(5).rand(rows, dim) - 0.5)).astype(np.float32)
+        e, t, r = entity.copy(), tail.copy(), relation.copy()
+        loss = K.train_batch(model, dim, e, r, None, batch, negatives, optimizer, 1.0, margin_or_l3, 2.0, tail=t,
+                             num_head=rows)
+        got = run_kg_train(model, dim, entity, tail, relation, None, batch, negatives, optimizer, rows, 1.0,
+                           margin_or_l3, 2.0, num_group=1)
+        np.testing.assert_allclose(got["head"], e, **TOLERANCE)
+        np.testing.assert_allclose(got["tail"], t, **TOLERANCE)
+    np.testing.assert_allclose(got["relation"], r, **TOLERANCE)
+    np.testing.assert_allclose(got["loss"], loss, **TOLERANCE)
