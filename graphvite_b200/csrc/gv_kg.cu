@@ -250,6 +250,21 @@ __device__ __forceinline__ float partial_logit(const float (&h)[E], const float 
     return output;
 }
 
+// RotatE with the relation's rotation (cos, sin of its phases) already evaluated: the relation row does not change
+// during the normaliser pass, so its sincosf are hoisted out of the k targets (same values, same order of operations)
+template<int E>
+__device__ __forceinline__ float partial_logit_rotated(const float (&h)[E], const float (&t)[E],
+                                                       const float (&r_re)[E / 2], const float (&r_im)[E / 2]) {
+    float output = 0.f;
+#pragma unroll
+    for (int i = 0; i < E / 2; i++) {
+        const float distance_re = h[i * 2] * r_re[i] - h[i * 2 + 1] * r_im[i] - t[i * 2];
+        const float distance_im = h[i * 2] * r_im[i] + h[i * 2 + 1] * r_re[i] - t[i * 2 + 1];
+        output += sqrtf(distance_re * distance_re + distance_im * distance_im);
+    }
+    return output;
+}
+
 // Model::backward on a thread's slices, statement order of the reference kept
 // (model/knowledge_graph.h:51-108,125-190,225-340,368-433,470-575).  ALIAS: head and tail are the SAME
 // row of the same matrix; every tail access then goes to the head slice (and its moments), which
@@ -547,6 +562,13 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
         // independent of each other: kPass1Batch targets are loaded together (that many rows in flight per
         // thread) and reduced with one barrier; the normaliser is still accumulated in target order.
         float bias = 0.f, normalizer = 0.f;
+        float rotation_re[E / 2], rotation_im[E / 2];
+        if constexpr (MODEL == GV_KG_ROTATE)
+            if (adversarial) {
+#pragma unroll
+                for (int i = 0; i < E / 2; i++)
+                    sincosf(R.v[i], &rotation_im[i], &rotation_re[i]);
+            }
         if (adversarial)
             for (int s0 = 0; s0 < k; s0 += kPass1Batch) {
                 float partial[kPass1Batch];
@@ -569,7 +591,10 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                                 t[i] = PT.v[i];
                         } else
                             load_vec<E>(t, p.tail + size_t(tail_id) * dim + slice);
-                        partial[b] = partial_logit<E, MODEL>(h, t, R.v);
+                        if constexpr (MODEL == GV_KG_ROTATE)
+                            partial[b] = partial_logit_rotated<E>(h, t, rotation_re, rotation_im);
+                        else
+                            partial[b] = partial_logit<E, MODEL>(h, t, R.v);
                     }
                 }
                 g.sum_many<kPass1Batch>(partial);
