@@ -3,14 +3,16 @@ kernels and solvers can be executed on a machine without a GPU (golden vectors f
 could not be pinned on a GPU box yet).
 
 g++ cannot parse CUDA's launch syntax, so the reference's headers (read where they lie, /root/reference/include)
-and the harness sources of this directory are mirrored into oracle/_ref/emu/ with two textual changes:
+and the harness sources of this directory are mirrored into a scratch directory OUTSIDE the repository (default
+/tmp/gv_b200_ref_emu, see oracle/Makefile) with two textual changes:
 
     kernel<<<grid, block[, shared[, stream]]>>>(args)   ->   gv_emu::LaunchConfig(grid, block, ...)(kernel)(args)
     model.backward<optimizer_type>(...)                 ->   model.template backward<optimizer_type>(...)
 
 (the second is the `template` disambiguator ISO C++ requires for a dependent member template; nvcc's front end
-accepts its absence, g++ does not).  Nothing else is touched; the mirror is a build intermediate under oracle/_ref/ (git-ignored) like an nvcc
---keep directory, never committed.  oracle/Makefile (target ref_emu) compiles it with tests/emu/cuda_emu.h
+accepts its absence, g++ does not).  Nothing else is touched; the mirror is a build intermediate like an nvcc --keep
+directory: it never enters the repository (not even as an ignored file), only the shared objects built from it
+land in oracle/_ref/.  oracle/Makefile (target ref_emu) compiles it with tests/emu/cuda_emu.h
 force-included and cuRAND's device generator redirected to its host generator (same XORWOW stream; in the
 emulation "device" memory is host memory).
 """
@@ -46,8 +48,7 @@ def mirror(source, destination):
     return count
 
 
-def main(reference):
-    out = os.path.join(HERE, "_ref", "emu")
+def main(reference, out):
     launches = mirror(os.path.join(reference, "include"), os.path.join(out, "include"))
     os.makedirs(os.path.join(out, "src"), exist_ok=True)
     for name in ("ref_harness.cu", "ref_harness_kg.cu"):
@@ -60,4 +61,5 @@ def main(reference):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference",
+         sys.argv[2] if len(sys.argv) > 2 else "/tmp/gv_b200_ref_emu")
