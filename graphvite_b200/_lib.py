@@ -190,6 +190,7 @@ SIGNATURES = {
     # test hooks
     "gv_schedule_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int]),
     "gv_reset_global_engine": (None, [c_uint32]),
+    "gv_engine_self_check": (c_int, [c_uint32, c_uint64]),
     "gv_solver_locations": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gv_solver_pool": (c_int64, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "gv_solver_train_begin": (c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,

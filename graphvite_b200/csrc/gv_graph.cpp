@@ -33,11 +33,22 @@ void build_alias(const float *weights, size_t count, float *prob, I *alias) {
     for (size_t i = 0; i < count; i++)
         norm += weights[i];
     norm = norm / count;
+    size_t num_little = 0;
+    for (size_t i = 0; i < count; i++) {
+        prob[i] = float(double(weights[i]) / norm);
+        num_little += prob[i] < 1;
+    }
+    // One of the queues starts empty (always the case for uniform weights, i.e. every table of an unweighted
+    // graph): the pairing loop never runs and every entry is a leftover that aliases to itself.
+    if (num_little == 0 || num_little == count) {
+        for (size_t i = 0; i < count; i++)
+            alias[i] = I(i);
+        return;
+    }
     std::vector<I> little, large;
     little.reserve(count);
     large.reserve(count);
     for (size_t i = 0; i < count; i++) {
-        prob[i] = float(double(weights[i]) / norm);
         if (prob[i] < 1)
             little.push_back(I(i));
         else

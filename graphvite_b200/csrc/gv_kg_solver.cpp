@@ -613,19 +613,15 @@ struct KgSolver {
     void init_embeddings() {
         static const float kPi = atan(1) * 4;
         const size_t d = dim;
-        if (model == "TransE") {
+        if (model == "TransE") {  // every element in order: drawn in bulk (gv_engine.h), same values
             std::uniform_real_distribution<float> init(-margin / d, margin / d);
-            for (auto &x : entity_host)
-                x = init(g_engine);
-            for (auto &x : relation_host)
-                x = init(g_engine);
+            g_engine.fill_uniform(entity_host.data(), entity_host.size(), init.a(), init.b());
+            g_engine.fill_uniform(relation_host.data(), relation_host.size(), init.a(), init.b());
         }
         if (model == "DistMult" || model == "ComplEx" || model == "SimplE") {
             std::uniform_real_distribution<float> init(-0.5, 0.5);
-            for (auto &x : entity_host)
-                x = init(g_engine);
-            for (auto &x : relation_host)
-                x = init(g_engine);
+            g_engine.fill_uniform(entity_host.data(), entity_host.size(), init.a(), init.b());
+            g_engine.fill_uniform(relation_host.data(), relation_host.size(), init.a(), init.b());
         }
         if (model == "QuatE") {
             std::uniform_real_distribution<float> init_modulus(-1 / sqrt(d / 2), 1 / sqrt(d / 2));  // he init
@@ -653,8 +649,7 @@ struct KgSolver {
         if (model == "RotatE") {
             std::uniform_real_distribution<float> init(-margin * 2 / d, margin * 2 / d);
             std::uniform_real_distribution<float> init_phase(-kPi, kPi);
-            for (auto &x : entity_host)
-                x = init(g_engine);
+            g_engine.fill_uniform(entity_host.data(), entity_host.size(), init.a(), init.b());
             for (uint32_t r = 0; r < graph->num_relation(); r++)
                 for (size_t i = 0; i < d / 2; i++)
                     relation_host[r * d + i] = init_phase(g_engine);

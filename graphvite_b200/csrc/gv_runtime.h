@@ -15,12 +15,13 @@
 #include <string>
 #include <vector>
 
+#include "gv_engine.h"
 #include "gv_host.h"
 
 namespace gv {
 
 // core/solver.h:50-57 and instance/graph.cuh:56
-extern std::mt19937 g_engine;  // defined in gv_solver.cpp; shared by every solver of the process
+extern Mt19937 g_engine;  // defined in gv_solver.cpp; shared by every solver of the process (std::mt19937's sequence)
 static const int kMaxPartition = 16;
 static const int kRandBatchSize = 5000000;
 static const int kMinBatchSize = 10000;

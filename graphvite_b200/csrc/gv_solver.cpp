@@ -34,7 +34,7 @@
 
 namespace gv {
 
-std::mt19937 g_engine;  // core/solver.h:50: one engine per process, never re-seedable from Python
+Mt19937 g_engine;  // core/solver.h:50: one engine per process (default seed 5489), never re-seedable from Python
 
 struct Assignment {
     int head, tail;
@@ -504,6 +504,7 @@ struct Solver {
             return;
         }
         sampling_ready = false;
+        PhaseTimer phase;  // GV_LOG=2
         // edge_table.build(graph->edge_weights), core/solver.h:255-256
         std::vector<float> edge_prob(m);
         std::vector<uint64_t> edge_alias(m);
@@ -527,6 +528,7 @@ struct Solver {
         d_offsets.upload(graph->offsets, sample_stream);
         d_edge_u.upload(graph->edge_u, sample_stream);
         d_edge_v.upload(graph->edge_v, sample_stream);
+        phase.mark("  CSR upload");
         device_graph.num_vertex = graph->num_vertex();
         device_graph.num_edge = m;
         device_graph.offsets = d_offsets.as<uint64_t>();
@@ -568,10 +570,12 @@ struct Solver {
             for (auto &thread : threads)
                 thread.join();
             require(!failed, "Invalid sampling distribution");
+            phase.mark("  per-vertex alias tables");
             d_vertex_tables.upload(tables, sample_stream);
             device_graph.vertex_tables = d_vertex_tables.as<gv_alias_entry_t>();
         }
         edge_builder.join();
+        phase.mark("  edge alias table (rest)");
         if (edge_error)
             std::rethrow_exception(edge_error);
         d_edge_prob.upload(edge_prob, sample_stream);
@@ -953,9 +957,9 @@ struct Solver {
 
     // GraphSolver::init_embeddings, instance/graph.cuh:724-731
     void init_embeddings() {
+        // x = init(seed) for every element, in row-major order -- drawn in bulk (gv_engine.h), same values
         std::uniform_real_distribution<float> init(-0.5 / dim, 0.5 / dim);
-        for (auto &x : vertex_host)
-            x = init(g_engine);
+        g_engine.fill_uniform(vertex_host.data(), vertex_host.size(), init.a(), init.b());
         std::fill(context_host.begin(), context_host.end(), 0.f);
     }
 
@@ -1441,7 +1445,34 @@ int gv_schedule_plan(int num_partition, int num_worker, int num_episode, int *ou
 }
 
 void gv_reset_global_engine(uint32_t seed) {
-    gv::g_engine = std::mt19937(seed);
+    gv::g_engine = gv::Mt19937(seed);
+}
+
+// test hook: gv::Mt19937 against libstdc++'s std::mt19937 -- raw draws, the seeds' distribution, and
+// fill_uniform() against std::uniform_real_distribution<float> for awkward sizes; 0 = identical
+int gv_engine_self_check(uint32_t seed, uint64_t bulk) {
+    std::mt19937 reference(seed);
+    gv::Mt19937 ours(seed);
+    for (int i = 0; i < 2000; i++)
+        if (reference() != ours())
+            return 1;
+    std::uniform_int_distribution<unsigned long long> seeds(0, ULLONG_MAX);
+    for (int i = 0; i < 16; i++)
+        if (seeds(reference) != seeds(ours))
+            return 2;
+    const uint64_t sizes[] = {1, 3, 623, 624, 625, bulk, 5};
+    for (uint64_t n : sizes) {
+        std::uniform_real_distribution<float> distribution(-0.5 / 96, 0.5 / 96);
+        std::vector<float> expected(n), got(n);
+        for (auto &x : expected)
+            x = distribution(reference);
+        ours.fill_uniform(got.data(), n, distribution.a(), distribution.b());
+        if (memcmp(expected.data(), got.data(), n * sizeof(float)) != 0)
+            return 3;
+        if (reference() != ours())
+            return 4;
+    }
+    return 0;
 }
 
 gv_solver_t *gv_solver_create(int dim, const int *device_ids, int num_device, int num_sampler_per_worker,

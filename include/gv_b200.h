@@ -465,6 +465,8 @@ int gv_kg_schedule(int num_partition, int num_worker, int *out, int capacity);
 int gv_schedule_plan(int num_partition, int num_worker, int num_episode, int *out, int capacity);
 /* the process-wide engine core/solver.h:50: re-seed (5489 = default-constructed) */
 void gv_reset_global_engine(uint32_t seed);
+/* the bulk generator behind init_embeddings against libstdc++'s std::mt19937 + distributions (0 = identical) */
+int gv_engine_self_check(uint32_t seed, uint64_t bulk);
 /* head_locations (core/solver.h:399-410) */
 int gv_solver_locations(const gv_solver_t *solver, uint32_t *part_of, uint32_t *local_of);
 /* copy one sample-pool block (pairs {tail, head}) to host; returns #pairs */

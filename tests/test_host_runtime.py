@@ -227,3 +227,12 @@ def test_node_classification_on_separable_embeddings():
     Y = ["c%d" % c for c in FakeSolver.cls] + ["c0"]
     result = app.node_classification(X=X, Y=Y, portions=(0.2,), times=2, patience=20)
     assert result["macro-F1@20%"] > 0.95 and result["micro-F1@20%"] > 0.95
+
+
+@pytest.mark.parametrize("seed,bulk", [(5489, 1000003), (1, 4097), (20260922, 624 * 5)])
+def test_bulk_engine_is_std_mt19937(seed, bulk):
+    """init_embeddings draws |V| * dim floats: gv::Mt19937 (SSE2 twist + conversion, csrc/gv_engine.h) must be
+    std::mt19937 + std::uniform_real_distribution<float> bit for bit, and interchangeable with it for the seeds'
+    uniform_int_distribution -- compared inside the library against libstdc++ itself."""
+    from graphvite_b200 import _lib
+    assert _lib.lib.gv_engine_self_check(seed, bulk) == 0
