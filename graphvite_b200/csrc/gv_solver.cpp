@@ -845,7 +845,9 @@ struct Solver {
     HostState context_state() { return {{&context_host, &context_m1_host, &context_m2_host}}; }
 
     // load every resident block from the host matrices (load_partition/load_embedding, solver.h:1349-1495)
-    void load_blocks() {
+    // fresh: train(resume=False) has just initialised the host matrices, so the context matrix and every moment
+    // matrix are known to be all zeros -- those blocks are cleared on the device instead of uploaded and gathered
+    void load_blocks(bool fresh) {
         const size_t total = size_t(graph->num_vertex()) * dim * sizeof(float);
         DeviceArray staging;
         staging.allocate(total);
@@ -859,22 +861,36 @@ struct Solver {
         for (int s = next_slot; s < int(vertex_slots.size()); s++)
             free_slots.push_back(s);
         HostState vertex = vertex_state(), context = context_state();
+        const size_t block_bytes = block_floats * sizeof(float);
         for (int s = 0; s < num_state; s++) {
-            GV_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, vertex.matrix[s]->data(), total, cudaMemcpyHostToDevice,
-                                          work_stream));
-            for (int h = 0; h < num_partition; h++)
-                if (slot_of_head[h] >= 0)
-                    GV_CHECK_ABI(gv_cuda_move_rows(vertex_slots[slot_of_head[h]].as<float>() + s * block_floats,
-                                                   staging.as<float>(), partition_ids[h].as<uint32_t>(),
-                                                   partitions[h].size(), dim, 1, work_stream));
-            GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
-            GV_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, context.matrix[s]->data(), total, cudaMemcpyHostToDevice,
-                                          work_stream));
-            for (int g = 0; g < num_group; g++) {
-                const int t = g * num_worker + rank;
-                GV_CHECK_ABI(gv_cuda_move_rows(context_blocks[g].as<float>() + s * block_floats, staging.as<float>(),
-                                               partition_ids[t].as<uint32_t>(), partitions[t].size(), dim, 1,
-                                               work_stream));
+            if (fresh && s > 0) {
+                for (int h = 0; h < num_partition; h++)
+                    if (slot_of_head[h] >= 0)
+                        GV_CHECK_CUDA(cudaMemsetAsync(vertex_slots[slot_of_head[h]].as<float>() + s * block_floats, 0,
+                                                      block_bytes, work_stream));
+            } else {
+                GV_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, vertex.matrix[s]->data(), total, cudaMemcpyHostToDevice,
+                                              work_stream));
+                for (int h = 0; h < num_partition; h++)
+                    if (slot_of_head[h] >= 0)
+                        GV_CHECK_ABI(gv_cuda_move_rows(vertex_slots[slot_of_head[h]].as<float>() + s * block_floats,
+                                                       staging.as<float>(), partition_ids[h].as<uint32_t>(),
+                                                       partitions[h].size(), dim, 1, work_stream));
+                GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+            }
+            if (fresh) {
+                for (int g = 0; g < num_group; g++)
+                    GV_CHECK_CUDA(cudaMemsetAsync(context_blocks[g].as<float>() + s * block_floats, 0, block_bytes,
+                                                  work_stream));
+            } else {
+                GV_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, context.matrix[s]->data(), total, cudaMemcpyHostToDevice,
+                                              work_stream));
+                for (int g = 0; g < num_group; g++) {
+                    const int t = g * num_worker + rank;
+                    GV_CHECK_ABI(gv_cuda_move_rows(context_blocks[g].as<float>() + s * block_floats, staging.as<float>(),
+                                                   partition_ids[t].as<uint32_t>(), partitions[t].size(), dim, 1,
+                                                   work_stream));
+                }
             }
             GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
         }
@@ -1031,7 +1047,7 @@ struct Solver {
         if (initializer.joinable())
             initializer.join();
         phase.mark("init embeddings (rest)");
-        load_blocks();
+        load_blocks(!resume);
         phase.mark("embedding upload");
         if (capture_negatives)
             d_negatives_out.allocate(uint64_t(chunk_batches) * batch_size * std::max(1, num_negative) * 4);
