@@ -466,6 +466,17 @@ static void unlink_all_shared() {
         shm_unlink(entry.second.name.c_str());
 }
 
+// GV_EMU_GUARD=0 switches the guard pages off (they cost a mapping per allocation)
+struct GuardedAllocation {
+    void *base;
+    size_t bytes;
+};
+static std::map<void *, GuardedAllocation> g_guarded_allocations;
+static bool guard_enabled() {
+    static const bool on = !(getenv("GV_EMU_GUARD") != nullptr && atoi(getenv("GV_EMU_GUARD")) == 0);
+    return on;
+}
+
 cudaError_t cudaMalloc(void **pointer, size_t bytes) {
     const size_t rounded = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
     void *memory = nullptr;
@@ -488,6 +499,18 @@ cudaError_t cudaMalloc(void **pointer, size_t bytes) {
             return remember(cudaErrorMemoryAllocation);
         }
         g_shared_allocations[memory] = {name, rounded};
+    } else if (guard_enabled()) {
+        // the allocation ends at an inaccessible page: a kernel (or copy) that runs past it faults immediately,
+        // with a backtrace under GV_EMU_BACKTRACE=1 -- the emulation's stand-in for compute-sanitizer memcheck
+        const size_t page = 4096, usable = (rounded + page - 1) / page * page;
+        char *base = static_cast<char *>(mmap(nullptr, usable + page, PROT_READ | PROT_WRITE,
+                                              MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
+        if (base == MAP_FAILED)
+            return remember(cudaErrorMemoryAllocation);
+        mprotect(base + usable, page, PROT_NONE);
+        memory = base + usable - rounded;  // 256-byte aligned: rounded is a multiple of 256
+        std::lock_guard<std::mutex> lock(g_allocation_mutex);
+        g_guarded_allocations[memory] = {base, usable + page};
     } else {
         memory = aligned_alloc(256, rounded);
         if (!memory)
@@ -511,6 +534,12 @@ cudaError_t cudaFree(void *pointer) {
             g_shared_allocations.erase(found);
             return cudaSuccess;
         }
+        auto guarded = g_guarded_allocations.find(pointer);
+        if (guarded != g_guarded_allocations.end()) {
+            munmap(guarded->second.base, guarded->second.bytes);
+            g_guarded_allocations.erase(guarded);
+            return cudaSuccess;
+        }
     }
     free(pointer);
     return cudaSuccess;
@@ -521,8 +550,7 @@ cudaError_t cudaMallocHost(void **pointer, size_t bytes) {
 }
 
 cudaError_t cudaFreeHost(void *pointer) {
-    free(pointer);
-    return cudaSuccess;
+    return cudaFree(pointer);
 }
 
 cudaError_t cudaHostRegister(void *, size_t, unsigned int) {
