@@ -25,7 +25,11 @@ const char *gv_last_error(void) {
 }
 
 const char *gv_version(void) {
+#ifdef GV_EMULATE_BUILD  // tests/emu/Makefile: the host build on top of the CUDA emulation, never shipped
+    return GV_VERSION " (CUDA emulation -- test build, not a product)";
+#else
     return GV_VERSION;
+#endif
 }
 
 }  // extern "C"

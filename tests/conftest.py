@@ -18,6 +18,12 @@ if EMULATED:
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu", "_pkg"))
 
 
+def pytest_report_header(config):
+    if EMULATED:
+        from graphvite_b200 import _lib
+        return "graphvite_b200 under test: %s -- %s" % (_lib.LIB_PATH, _lib.lib.gv_version().decode())
+
+
 def _ensure_built():
     """The shared objects are git-ignored build products: compile them once if a fresh checkout has
     none (same recipe as __graft_entry__.build(); building is not a fallback -- the product still
