@@ -1,0 +1,28 @@
+#!/bin/bash
+# Tunable sweep at N GPUs for the multi-GPU efficiency question left open in round 1 (inside one
+# block of the 2-D partition the hub rows are P x hotter, and the samplers' kernels compete with a persistent train
+# grid).  Run on an N-GPU box:   gpurun --gpus 2 --timeout 1500 -- 'bash tools/round2_sweep.sh 2'
+# Every line of gpurun_out/sweep_n<N>.jsonl is one bench.py result (value = edges/s over all ranks) tagged with the
+# environment it ran under.
+set -u
+N=${1:-2}
+OUT=gpurun_out/sweep_n${N}.jsonl
+mkdir -p gpurun_out
+: > $OUT
+run() {
+    local tag="$1"; shift
+    local port=$((29500 + RANDOM % 400))
+    local line
+    line=$(env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+        --master-port $port bench.py --gpus $N --steps 8 --warmup 3 --no-e2e 2>/dev/null | tail -1)
+    echo "{\"tag\": \"$tag\", \"result\": ${line:-null}}" | tee -a $OUT
+}
+run "default" GV_LOG=0
+for hot in 256 512 1024 4096; do
+    run "hot_rows=$hot" GV_HOT_ROWS=$hot
+done
+run "blocks_per_sm=3" GV_TRAIN_BLOCKS_PER_SM=3
+run "blocks_per_sm=3,hot_rows=512" GV_TRAIN_BLOCKS_PER_SM=3 GV_HOT_ROWS=512
+run "chunk_batches=8" GV_CHUNK_BATCHES=8
+run "chunk_batches=32" GV_CHUNK_BATCHES=32
+run "replicated_sampling" GV_REPLICATED_SAMPLING=1
