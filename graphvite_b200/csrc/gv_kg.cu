@@ -16,7 +16,8 @@
 // positive head or the positive tail.  The reference walks the targets with one warp and
 // read-modify-writes head, tail and relation rows (plus moments) in global memory for every target:
 // ~7.8 MB per positive at d = 2048, k = 64 with Adam.  Here a *group* of dim / E threads (E = 2, 4 or 8
-// contiguous floats per thread; 256 threads at d = 2048) owns the sample and keeps the relation row,
+// floats per thread as 64- / 128-bit units interleaved over the threads, so that a warp's access is one
+// contiguous 512-B run; 256 threads at d = 2048) owns the sample and keeps the relation row,
 // the positive head row and the positive tail row -- with their moments -- in registers across all
 // targets; only the negative rows travel: read once for the self-adversarial normaliser, then one
 // read-modify-write with their moments.  That is ~3.6 MB per positive, with identical sequential
@@ -68,49 +69,48 @@ struct KgParams {
     float *loss_per_sample, *loss_per_batch;
 };
 
-// ---- N contiguous floats per thread, moved with the widest aligned vector type ----------------
-template<int N>
-__device__ __forceinline__ void load_vec(float (&dst)[N], const float *src) {
-    if constexpr (N % 4 == 0) {
+// ---- a thread's N floats of a row: N / U vector units of U floats (128-, 64- or 32-bit accesses) ------------
+// Unit i of thread c lives at unit index c + i * (threads of the group): consecutive lanes touch consecutive
+// units, so every warp-wide access is one contiguous run (32 x 16 B = 512 B for float4) -- with 8 floats per
+// thread a thread therefore owns two float4 units half a row apart, not 8 contiguous floats.  `stride` is the
+// distance between a thread's units in floats.
+template<int N, int U>
+__device__ __forceinline__ void load_vec(float (&dst)[N], const float *src, size_t stride) {
+    static_assert(N % U == 0 && (U == 4 || U == 2 || U == 1), "unit width");
 #pragma unroll
-        for (int i = 0; i < N / 4; i++) {
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src) + i);
+    for (int i = 0; i < N / U; i++) {
+        const float *unit = src + i * stride;
+        if constexpr (U == 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(unit));
             dst[i * 4] = v.x, dst[i * 4 + 1] = v.y, dst[i * 4 + 2] = v.z, dst[i * 4 + 3] = v.w;
-        }
-    } else if constexpr (N % 2 == 0) {
-#pragma unroll
-        for (int i = 0; i < N / 2; i++) {
-            const float2 v = __ldcg(reinterpret_cast<const float2 *>(src) + i);
+        } else if constexpr (U == 2) {
+            const float2 v = __ldcg(reinterpret_cast<const float2 *>(unit));
             dst[i * 2] = v.x, dst[i * 2 + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; i++)
-            dst[i] = __ldcg(src + i);
+        } else
+            dst[i] = __ldcg(unit);
     }
 }
 
-template<int N>
-__device__ __forceinline__ void store_vec(float *dst, const float (&src)[N]) {
-    if constexpr (N % 4 == 0) {
+template<int N, int U>
+__device__ __forceinline__ void store_vec(float *dst, const float (&src)[N], size_t stride) {
+    static_assert(N % U == 0 && (U == 4 || U == 2 || U == 1), "unit width");
 #pragma unroll
-        for (int i = 0; i < N / 4; i++)
-            __stcg(reinterpret_cast<float4 *>(dst) + i,
+    for (int i = 0; i < N / U; i++) {
+        float *unit = dst + i * stride;
+        if constexpr (U == 4)
+            __stcg(reinterpret_cast<float4 *>(unit),
                    make_float4(src[i * 4], src[i * 4 + 1], src[i * 4 + 2], src[i * 4 + 3]));
-    } else if constexpr (N % 2 == 0) {
-#pragma unroll
-        for (int i = 0; i < N / 2; i++)
-            __stcg(reinterpret_cast<float2 *>(dst) + i, make_float2(src[i * 2], src[i * 2 + 1]));
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; i++)
-            __stcg(dst + i, src[i]);
+        else if constexpr (U == 2)
+            __stcg(reinterpret_cast<float2 *>(unit), make_float2(src[i * 2], src[i * 2 + 1]));
+        else
+            __stcg(unit, src[i]);
     }
 }
 
-// a thread's slice of one row and of its NM moment rows
+// a thread's slice of one (entity) row and of its NM moment rows
 template<int N, int NM>
 struct Slice {
+    static constexpr int U = N >= 4 ? 4 : N;  // floats per vector unit
     float v[N];
     float m1[NM >= 1 ? N : 1];
     float m2[NM >= 2 ? N : 1];
@@ -118,13 +118,13 @@ struct Slice {
 
 template<int N, int NM>
 __device__ __forceinline__ void load_slice(Slice<N, NM> &s, const float *v, const float *m1, const float *m2,
-                                           size_t offset, bool active) {
+                                           size_t offset, size_t stride, bool active) {
     if (active) {
-        load_vec<N>(s.v, v + offset);
+        load_vec<N, Slice<N, NM>::U>(s.v, v + offset, stride);
         if constexpr (NM >= 1)
-            load_vec<N>(s.m1, m1 + offset);
+            load_vec<N, Slice<N, NM>::U>(s.m1, m1 + offset, stride);
         if constexpr (NM >= 2)
-            load_vec<N>(s.m2, m2 + offset);
+            load_vec<N, Slice<N, NM>::U>(s.m2, m2 + offset, stride);
     } else {
 #pragma unroll
         for (int i = 0; i < N; i++)
@@ -134,14 +134,14 @@ __device__ __forceinline__ void load_slice(Slice<N, NM> &s, const float *v, cons
 
 template<int N, int NM>
 __device__ __forceinline__ void store_slice(const Slice<N, NM> &s, float *v, float *m1, float *m2, size_t offset,
-                                            bool active) {
+                                            size_t stride, bool active) {
     if (!active)
         return;
-    store_vec<N>(v + offset, s.v);
+    store_vec<N, Slice<N, NM>::U>(v + offset, s.v, stride);
     if constexpr (NM >= 1)
-        store_vec<N>(m1 + offset, s.m1);
+        store_vec<N, Slice<N, NM>::U>(m1 + offset, s.m1, stride);
     if constexpr (NM >= 2)
-        store_vec<N>(m2 + offset, s.m2);
+        store_vec<N, Slice<N, NM>::U>(m2 + offset, s.m2, stride);
 }
 
 // ---- optimizers, core/optimizer.h:161-210: the step to subtract from `parameter` --------------
@@ -190,6 +190,12 @@ template<int E, int MODEL>
 struct Geometry {
     static constexpr int RV = MODEL == GV_KG_ROTATE ? E / 2 : E;
     static constexpr int RM = (MODEL == GV_KG_ROTATE || MODEL == GV_KG_COMPLEX) ? E / 2 : E;
+    // floats per vector unit: entity rows, relation values, relation moments.  An entity unit of UE floats holds
+    // UE / 2 complex pairs, whose phases (RotatE) / shared moments (RotatE, ComplEx) form a unit of UE / 2 floats at
+    // the same unit index, so the local order of pairs is the same in all three.
+    static constexpr int UE = E >= 4 ? 4 : E;
+    static constexpr int URV = MODEL == GV_KG_ROTATE ? UE / 2 : UE;
+    static constexpr int URM = (MODEL == GV_KG_ROTATE || MODEL == GV_KG_COMPLEX) ? UE / 2 : UE;
 };
 
 template<int E, int MODEL, int NM>
@@ -486,8 +492,11 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
     g.scratch = reinterpret_cast<float *>(mine);
     uint32_t *negative_ids = reinterpret_cast<uint32_t *>(mine + scratch_bytes);
     const bool active = c < chunks;
-    const size_t slice = size_t(c) * E;                 // offset of this thread inside an entity row
-    const size_t relation_value = size_t(c) * G::RV, relation_moment = size_t(c) * G::RM;
+    // this thread's first vector unit inside an entity row / relation row / relation moment row, and the distance
+    // between its units (see load_vec)
+    const size_t slice = size_t(c) * G::UE, slice_stride = size_t(chunks) * G::UE;
+    const size_t relation_value = size_t(c) * G::URV, value_stride = size_t(chunks) * G::URV;
+    const size_t relation_moment = size_t(c) * G::URM, moment_stride = size_t(chunks) * G::URM;
     const size_t dim = p.dim;
     const int k = p.num_negative;
     const bool adversarial = p.temperature > kEps;
@@ -526,11 +535,11 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
         {
             const size_t base = size_t(relation_id) * dim;
             if (active) {
-                load_vec<G::RV>(R.v, p.relation + base + relation_value);
+                load_vec<G::RV, G::URV>(R.v, p.relation + base + relation_value, value_stride);
                 if constexpr (NM >= 1)
-                    load_vec<G::RM>(R.m1, p.relation_m1 + base + relation_moment);
+                    load_vec<G::RM, G::URM>(R.m1, p.relation_m1 + base + relation_moment, moment_stride);
                 if constexpr (NM >= 2)
-                    load_vec<G::RM>(R.m2, p.relation_m2 + base + relation_moment);
+                    load_vec<G::RM, G::URM>(R.m2, p.relation_m2 + base + relation_moment, moment_stride);
             } else {
 #pragma unroll
                 for (int i = 0; i < G::RV; i++)
@@ -541,8 +550,8 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
         const bool cached = !(p.shared && positive_head == positive_tail);
         Slice<E, NM> PH, PT;
         if (cached) {
-            load_slice<E, NM>(PH, p.head, p.head_m1, p.head_m2, size_t(positive_head) * dim + slice, active);
-            load_slice<E, NM>(PT, p.tail, p.tail_m1, p.tail_m2, size_t(positive_tail) * dim + slice, active);
+            load_slice<E, NM>(PH, p.head, p.head_m1, p.head_m2, size_t(positive_head) * dim + slice, slice_stride, active);
+            load_slice<E, NM>(PT, p.tail, p.tail_m1, p.tail_m2, size_t(positive_tail) * dim + slice, slice_stride, active);
         }
 
         // ids of target s (s == k: the positive triple)
@@ -584,13 +593,13 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                             for (int i = 0; i < E; i++)
                                 h[i] = PH.v[i];
                         } else
-                            load_vec<E>(h, p.head + size_t(head_id) * dim + slice);
+                            load_vec<E, G::UE>(h, p.head + size_t(head_id) * dim + slice, slice_stride);
                         if (cached && tail_id == positive_tail) {
 #pragma unroll
                             for (int i = 0; i < E; i++)
                                 t[i] = PT.v[i];
                         } else
-                            load_vec<E>(t, p.tail + size_t(tail_id) * dim + slice);
+                            load_vec<E, G::UE>(t, p.tail + size_t(tail_id) * dim + slice, slice_stride);
                         if constexpr (MODEL == GV_KG_ROTATE)
                             partial[b] = partial_logit_rotated<E>(h, t, rotation_re, rotation_im);
                         else
@@ -634,14 +643,14 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
             else if (next_valid && next_is_head)
                 WH = NX;
             else
-                load_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, active);
+                load_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, slice_stride, active);
             if (!alias) {
                 if (tail_cached)
                     WT = PT;
                 else if (next_valid && !next_is_head)
                     WT = NX;
                 else
-                    load_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, active);
+                    load_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, slice_stride, active);
             }
             next_valid = false;
             if (s + 1 < k && cached) {  // target s + 1 is a negative: exactly one of its rows may be uncached
@@ -660,9 +669,9 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                     if (!written_now) {
                         const size_t offset = size_t(next_id) * dim + slice;
                         if (next_is_head)
-                            load_slice<E, NM>(NX, p.head, p.head_m1, p.head_m2, offset, active);
+                            load_slice<E, NM>(NX, p.head, p.head_m1, p.head_m2, offset, slice_stride, active);
                         else
-                            load_slice<E, NM>(NX, p.tail, p.tail_m1, p.tail_m2, offset, active);
+                            load_slice<E, NM>(NX, p.tail, p.tail_m1, p.tail_m2, offset, slice_stride, active);
                         next_valid = true;
                     }
                 }
@@ -699,27 +708,27 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
             else if (head_source == 2)
                 PT = WH;
             else
-                store_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, active);
+                store_slice<E, NM>(WH, p.head, p.head_m1, p.head_m2, head_offset, slice_stride, active);
             if (!alias) {
                 if (tail_cached)
                     PT = WT;
                 else
-                    store_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, active);
+                    store_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, slice_stride, active);
             }
         }
 
         // write the cached rows back
         if (cached) {
-            store_slice<E, NM>(PH, p.head, p.head_m1, p.head_m2, size_t(positive_head) * dim + slice, active);
-            store_slice<E, NM>(PT, p.tail, p.tail_m1, p.tail_m2, size_t(positive_tail) * dim + slice, active);
+            store_slice<E, NM>(PH, p.head, p.head_m1, p.head_m2, size_t(positive_head) * dim + slice, slice_stride, active);
+            store_slice<E, NM>(PT, p.tail, p.tail_m1, p.tail_m2, size_t(positive_tail) * dim + slice, slice_stride, active);
         }
         if (active) {
             const size_t base = size_t(relation_id) * dim;
-            store_vec<G::RV>(p.relation + base + relation_value, R.v);
+            store_vec<G::RV, G::URV>(p.relation + base + relation_value, R.v, value_stride);
             if constexpr (NM >= 1)
-                store_vec<G::RM>(p.relation_m1 + base + relation_moment, R.m1);
+                store_vec<G::RM, G::URM>(p.relation_m1 + base + relation_moment, R.m1, moment_stride);
             if constexpr (NM >= 2)
-                store_vec<G::RM>(p.relation_m2 + base + relation_moment, R.m2);
+                store_vec<G::RM, G::URM>(p.relation_m2 + base + relation_moment, R.m2, moment_stride);
         }
         if (c == 0) {
             const float loss = sample_loss / 2;
@@ -762,9 +771,10 @@ __global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *he
         float partial = 0.f;
         if (active) {
             float h[E], t[E], r[G::RV];
-            load_vec<E>(h, head + size_t(head_id) * dim + size_t(c) * E);
-            load_vec<E>(t, tail + size_t(tail_id) * dim + size_t(c) * E);
-            load_vec<G::RV>(r, relation + size_t(relation_id) * dim + size_t(c) * G::RV);
+            load_vec<E, G::UE>(h, head + size_t(head_id) * dim + size_t(c) * G::UE, size_t(chunks) * G::UE);
+            load_vec<E, G::UE>(t, tail + size_t(tail_id) * dim + size_t(c) * G::UE, size_t(chunks) * G::UE);
+            load_vec<G::RV, G::URV>(r, relation + size_t(relation_id) * dim + size_t(c) * G::URV,
+                                    size_t(chunks) * G::URV);
             partial = partial_logit<E, MODEL>(h, t, r);
         }
         const float logit = finish_logit<MODEL>(g.sum(partial), margin);
