@@ -47,6 +47,7 @@ namespace {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr float kEps = 1e-15f;  // util/common.h:28
 constexpr int kCtaThreads = 256;
+constexpr int kPass1Batch = 4;  // targets per barrier in the normaliser pass
 
 struct KgParams {
     int dim;
@@ -416,7 +417,9 @@ struct Group {
             value += __shfl_xor_sync(kFull, value, delta);
         if (warps == 1)
             return value;
-        float *slot = scratch + parity * warps;
+        // (both kinds of sum alternate between the SAME two regions: a fast warp may already write the next sum's
+        // partials while a slow one still reads this one's, so consecutive sums must never share memory)
+        float *slot = scratch + parity * kPass1Batch * warps;
         if (lane == 0)
             slot[warp] = value;
         sync();
@@ -453,7 +456,7 @@ struct Group {
     }
 };
 
-constexpr int kPass1Batch = 4;  // targets per barrier in the normaliser pass
+
 
 template<int MODEL>
 __device__ __forceinline__ float finish_logit(float sum, float margin_or_l3) {
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *he
     g.lane = c & 31;
     g.warp = c >> 5;
     g.parity = 0;
-    g.scratch = reinterpret_cast<float *>(shared_bytes) + size_t(2) * g.warps * g.id_in_cta;
+    g.scratch = reinterpret_cast<float *>(shared_bytes) + size_t(2) * kPass1Batch * g.warps * g.id_in_cta;
     const bool active = c < chunks;
     const size_t dim = dim_;
     for (unsigned long long sample = (unsigned long long)blockIdx.x * groups_per_cta + g.id_in_cta; sample < num_sample;
@@ -957,7 +960,7 @@ int gv_cuda_kg_predict(const gv_kg_matrices_t *m, int model, const uint32_t *bat
     GV_CUDA_OK(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, device));
     const int groups_per_cta = kCtaThreads / group_threads;
     const dim3 block(groups_per_cta * group_threads);
-    const size_t shared = size_t(2) * (group_threads / 32) * sizeof(float) * groups_per_cta;
+    const size_t shared = size_t(2) * kPass1Batch * (group_threads / 32) * sizeof(float) * groups_per_cta;
     const unsigned long long ctas =
         std::min<unsigned long long>((num_sample + groups_per_cta - 1) / groups_per_cta, (unsigned long long)num_sm * 8);
     const dim3 grid((unsigned)ctas);
