@@ -169,9 +169,18 @@ void run_block() {
         barrier = Barrier();
     for (int t = 0; t < g_num_thread; t++)
         prepare(g_fibers[t]);
+    // GV_EMU_WARP_ORDER=reverse|rotate: visit the warps of a CTA in another order (the order decides which warp runs
+    // ahead of a barrier first, i.e. which write-after-read hazards between warps become visible)
+    static const int order_mode = []() {
+        const char *mode = getenv("GV_EMU_WARP_ORDER");
+        return !mode ? 0 : (std::string(mode) == "reverse" ? 1 : (std::string(mode) == "rotate" ? 2 : 0));
+    }();
+    int sweep = 0;
     while (g_exited < g_num_thread) {
         bool progress = false;
-        for (int w = 0; w < num_warp; w++) {
+        sweep++;
+        for (int visit = 0; visit < num_warp; visit++) {
+            const int w = order_mode == 1 ? num_warp - 1 - visit : (order_mode == 2 ? (visit + sweep) % num_warp : visit);
             // run this warp until all of its lanes wait for the CTA or have exited
             for (bool warp_progress = true; warp_progress;) {
                 warp_progress = false;

@@ -27,10 +27,19 @@ GROUPS = [
 ]
 
 
-@pytest.mark.parametrize("files,what", GROUPS, ids=[g[0][0].split("test_gpu_")[1][:-3] for g in GROUPS])
+# kernel-level files once more with the warps of a CTA visited in reverse order: which warp runs ahead of a barrier
+# decides which write-after-read hazards between warps can show up
+GROUPS.append((["tests/test_gpu_kernels.py", "tests/test_gpu_y_fill.py", "tests/test_gpu_zz_kg_kernels.py"],
+               "kernels, warps scheduled in reverse"))
+
+
+@pytest.mark.parametrize("files,what", GROUPS,
+                         ids=[g[0][0].split("test_gpu_")[1][:-3] + ("-reverse" if "reverse" in g[1] else "") for g in GROUPS])
 def test_gpu_suite_under_cuda_emulation(files, what):
     files = [f for f in files if os.path.exists(os.path.join(ROOT, f))]
     env = dict(os.environ, GV_EMULATE="1", GV_EMU_BACKTRACE="1")
+    if "reverse" in what:
+        env["GV_EMU_WARP_ORDER"] = "reverse"
     result = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + files,
                             cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                             timeout=1500)

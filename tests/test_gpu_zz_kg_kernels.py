@@ -323,3 +323,21 @@ def test_next_target_prefetch_never_uses_a_row_the_current_target_writes(model, 
         np.testing.assert_allclose(got["tail"], t, **TOLERANCE)
     np.testing.assert_allclose(got["relation"], r, **TOLERANCE)
     np.testing.assert_allclose(got["loss"], loss, **TOLERANCE)
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 7, 9])
+@pytest.mark.parametrize("dim", [512, 2048])
+def test_multi_warp_groups_with_every_batching_remainder(dim, k):
+    """Groups of several warps (dim >= 512) reduce through shared memory; the normaliser pass handles 4 targets per
+    barrier, so k = 1, 3, 4, 7, 9 covers a lone partial batch, full batches and both parities of the double-buffered
+    scratch at the hand-over from the normaliser pass to the update pass."""
+    optimizer = O.OPTIMIZERS["Adam"]
+    n, rows = 12, 20
+    entity, relation, ms, batch, negatives = make_problem(dim, n, k, rows, 3, 300 + k, 2, scale=0.2)
+    e, r, m, loss = oracle_shared("RotatE", dim, entity, relation, ms, batch, negatives, optimizer, 1.0, 6.0, 1.5)
+    got = run_kg_train("RotatE", dim, entity, None, relation, ms, batch, negatives, optimizer, rows, 1.0, 6.0, 1.5,
+                       num_group=1)
+    np.testing.assert_allclose(got["loss"], loss, **TOLERANCE)
+    np.testing.assert_allclose(got["head"], e, **TOLERANCE)
+    np.testing.assert_allclose(got["relation"], r, **TOLERANCE)
+    np.testing.assert_allclose(got["hm2"], m[2], **TOLERANCE)
