@@ -29,8 +29,7 @@ GROUPS = [
 
 # kernel-level files once more with the warps of a CTA visited in reverse order: which warp runs ahead of a barrier
 # decides which write-after-read hazards between warps can show up
-GROUPS.append((["tests/test_gpu_kernels.py", "tests/test_gpu_y_fill.py", "tests/test_gpu_zz_kg_kernels.py"],
-               "kernels, warps scheduled in reverse"))
+GROUPS.append((["tests/test_gpu_zz_kg_kernels.py", "tests/test_gpu_y_fill.py"], "kernels, warps scheduled in reverse"))
 
 
 @pytest.mark.parametrize("files,what", GROUPS,
