@@ -592,6 +592,9 @@ static int g_kernel_flags = getenv("GV_KERNEL_FLAGS") ? atoi(getenv("GV_KERNEL_F
 // resident train CTAs per SM (0 = as many as fit).  One less than the maximum leaves registers and
 // thread slots for the samplers' kernels, which otherwise only run between train launches.
 static int g_blocks_per_sm = getenv("GV_TRAIN_BLOCKS_PER_SM") ? atoi(getenv("GV_TRAIN_BLOCKS_PER_SM")) : 0;
+// experiment: size the persistent grid for this many SMs fewer than the device has, so that some SMs keep room for
+// the samplers' kernels while a train launch is resident (0 = use every SM)
+static int g_reserve_sms = getenv("GV_TRAIN_RESERVE_SMS") ? atoi(getenv("GV_TRAIN_RESERVE_SMS")) : 0;
 
 // -----------------------------------------------------------------------------
 // launch helpers
@@ -625,7 +628,8 @@ static int launch_train(void (*kernel)(const TrainParams), const TrainParams &p,
             per_sm = g_blocks_per_sm;
         if (per_sm < 1)
             per_sm = 1;
-        blocks = device_sm_count() * per_sm;  // persistent: exactly one resident wave
+        const int sms = device_sm_count();
+        blocks = (g_reserve_sms > 0 && g_reserve_sms < sms ? sms - g_reserve_sms : sms) * per_sm;  // one resident wave
         const unsigned long long needed = ((p.num_sample + 31) / 32 + threads / 32 - 1) / (threads / 32);
         if ((unsigned long long)blocks > needed)
             blocks = int(needed);
@@ -739,6 +743,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_kernel_flags = int(value);
     else if (key == "train_blocks_per_sm")
         g_blocks_per_sm = int(value);
+    else if (key == "train_reserve_sms")
+        g_reserve_sms = int(value);
     else
         return fail("unknown tunable `" + key + "`");
     return 0;

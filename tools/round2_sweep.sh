@@ -23,6 +23,8 @@ for hot in 256 512 1024 4096; do
 done
 run "blocks_per_sm=3" GV_TRAIN_BLOCKS_PER_SM=3
 run "blocks_per_sm=3,hot_rows=512" GV_TRAIN_BLOCKS_PER_SM=3 GV_HOT_ROWS=512
+run "reserve_sms=8" GV_TRAIN_RESERVE_SMS=8
+run "reserve_sms=16" GV_TRAIN_RESERVE_SMS=16
 run "chunk_batches=8" GV_CHUNK_BATCHES=8
 run "chunk_batches=32" GV_CHUNK_BATCHES=32
 run "replicated_sampling" GV_REPLICATED_SAMPLING=1
