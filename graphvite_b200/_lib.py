@@ -65,6 +65,11 @@ class DeviceKGraph(ctypes.Structure):
                 ("edge_prob", c_void_p), ("edge_alias", c_void_p), ("locations", c_void_p)]
 
 
+class TableShards(ctypes.Structure):
+    """gv_table_shards_t"""
+    _fields_ = [("num_shard", c_int), ("shard", c_void_p * 16), ("first_entry", ctypes.c_ulonglong * 17)]
+
+
 class FillParams(ctypes.Structure):
     """gv_fill_params_t"""
     _fields_ = [("num_partition", c_int), ("walk_length", c_int), ("augmentation_step", c_int),
@@ -96,6 +101,8 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_biased_walk": (c_int, [P(DeviceGraph), c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_uint64, c_uint32,
                                     c_uint64, c_void_p, c_void_p]),
+    "gv_cuda_biased_walk_sharded": (c_int, [P(DeviceGraph), P(TableShards), c_void_p, c_void_p, c_uint32, c_int, c_uint64,
+                                            c_uint32, c_uint64, c_void_p, c_void_p]),
     "gv_cuda_fill_scratch_bytes": (c_size_t, [c_uint32, c_int]),
     "gv_cuda_fill_pool": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),

@@ -111,8 +111,19 @@ __device__ __forceinline__ Count alias_slot(double rand1, Count count) {
     return index < count ? index : count - 1;
 }
 
+// The flat table array split over the ranks of a multi-GPU run: shard r holds the entries
+// [first_entry[r], first_entry[r + 1]) (whole tables) and may live in a peer GPU's memory (CUDA IPC over NVLink).
+// One shard covering everything is the single-GPU case.
+__device__ __forceinline__ uint2 load_table_entry(const gv_table_shards_t &shards, unsigned long long entry) {
+    int r = 0;
+    while (r + 1 < shards.num_shard && entry >= shards.first_entry[r + 1])
+        r++;
+    const uint2 *shard = reinterpret_cast<const uint2 *>(shards.shard[r]);
+    return shard[entry - shards.first_entry[r]];  // a plain load: the shard may be peer memory
+}
+
 // walk part of sample_biased_random_walk, graph.cuh:321-349
-__global__ void __launch_bounds__(256) biased_walk_kernel(const gv_device_graph_t g, const gv_alias_entry_t *tables,
+__global__ void __launch_bounds__(256) biased_walk_kernel(const gv_device_graph_t g, const gv_table_shards_t tables,
                                                           const unsigned long long *table_offsets,
                                                           const double *random, uint32_t num_walk, int walk_length,
                                                           uint64_t first_walk, uint32_t walks_per_buffer,
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(256) biased_walk_kernel(const gv_device_graph_
         }
         draw = __ldcs(r + j - 1);
         const uint32_t slot = alias_slot<uint32_t>(draw.y, degree);
-        const uint2 entry = __ldg(reinterpret_cast<const uint2 *>(tables) + __ldg(table_offsets + edge) + slot);
+        const uint2 entry = load_table_entry(tables, __ldg(table_offsets + edge) + slot);
         const uint32_t neighbor = float(draw.x) < __uint_as_float(entry.x) ? slot : entry.y;
         edge = begin + neighbor;  // edge_id = flat_offsets[current] + neighbor_id, graph.cuh:341
         current = __ldg(g.edge_v + edge);
@@ -173,20 +184,39 @@ int gv_cuda_node2vec_build(const gv_device_graph_t *graph, const float *edge_wei
     return 0;
 }
 
+int gv_cuda_biased_walk_sharded(const gv_device_graph_t *graph, const gv_table_shards_t *tables,
+                                const unsigned long long *table_offsets, const double *random, uint32_t num_walk,
+                                int walk_length, uint64_t first_walk, uint32_t walks_per_buffer,
+                                uint64_t buffer_doubles, gv_location_t *chains, void *stream) {
+    if (num_walk == 0)
+        return 0;
+    if (!graph || !tables || !table_offsets || !random || !chains || walk_length < 1 || walks_per_buffer == 0 ||
+        buffer_doubles < uint64_t(walks_per_buffer) * 2 * walk_length || buffer_doubles % 2 != 0 ||
+        tables->num_shard < 1 || tables->num_shard > GV_MAX_TABLE_SHARDS)
+        return fail("gv_cuda_biased_walk: invalid argument");
+    for (int r = 0; r < tables->num_shard; r++)
+        if (!tables->shard[r] && tables->first_entry[r + 1] > tables->first_entry[r])
+            return fail("gv_cuda_biased_walk: a non-empty table shard has no memory");
+    GV_LAUNCH((num_walk + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), biased_walk_kernel)(
+        *graph, *tables, table_offsets, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles,
+        chains);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int gv_cuda_biased_walk(const gv_device_graph_t *graph, const gv_alias_entry_t *tables,
                         const unsigned long long *table_offsets, const double *random, uint32_t num_walk,
                         int walk_length, uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,
                         gv_location_t *chains, void *stream) {
-    if (num_walk == 0)
-        return 0;
-    if (!graph || !tables || !table_offsets || !random || !chains || walk_length < 1 || walks_per_buffer == 0 ||
-        buffer_doubles < uint64_t(walks_per_buffer) * 2 * walk_length || buffer_doubles % 2 != 0)
+    if (!tables)
         return fail("gv_cuda_biased_walk: invalid argument");
-    GV_LAUNCH((num_walk + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), biased_walk_kernel)(
-        *graph, tables, table_offsets, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles,
-        chains);
-    GV_CUDA_OK(cudaGetLastError());
-    return 0;
+    gv_table_shards_t one;
+    one.num_shard = 1;
+    one.shard[0] = tables;
+    one.first_entry[0] = 0;
+    one.first_entry[1] = ~0ull;
+    return gv_cuda_biased_walk_sharded(graph, &one, table_offsets, random, num_walk, walk_length, first_walk,
+                                       walks_per_buffer, buffer_doubles, chains, stream);
 }
 
 }  // extern "C"

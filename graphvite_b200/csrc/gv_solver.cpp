@@ -152,6 +152,11 @@ struct Solver {
     // device graph
     DeviceArray d_offsets, d_edge_u, d_edge_v, d_edge_prob, d_edge_alias, d_vertex_tables, d_locations;
     DeviceArray d_edge_tables, d_table_offsets;  // node2vec: one alias table per directed edge
+    // With partitioned sampling the tables are split over the ranks by entry count (d_edge_tables is then this rank's
+    // shard) and every rank maps the others' shards with CUDA IPC: Sigma deg^2 x 8 B does not fit one GPU beyond
+    // small graphs (209 GB on the Youtube-shaped graph), but 1 / W of it does.
+    gv_table_shards_t table_shards;
+    std::vector<void *> peer_tables;  // [W] mapped shards of the other ranks (own entry = nullptr)
     gv_device_graph_t device_graph;
     bool sampling_ready = false;
     int sample_mode = 0, tables_mode = -1;
@@ -280,7 +285,31 @@ struct Solver {
     uint32_t *pool_block(int side, int head, int group) const {
         return reinterpret_cast<uint32_t *>(static_cast<char *>(pool_arena.ptr) + pool_block_offset(side, head, group));
     }
+    void close_peer_tables() {
+        for (void *mapped : peer_tables)
+            if (mapped)
+                cudaIpcCloseMemHandle(mapped);
+        if (!peer_tables.empty()) {
+            peer_tables.clear();
+            sampling_ready = false;  // the shard table referenced the peers: rebuild before sampling again
+        }
+    }
+
+    // Free this rank's table shard.  If the peers map it, every importer has to close it first (CUDA IPC rule):
+    // all ranks get here together (prepare_sampling is collective), close their imports and meet at a host barrier.
+    void release_table_shard() {
+        if (!peer_tables.empty()) {
+            close_peer_tables();
+            int token = 0, all[256] = {0};
+            require(host_allgather_fn && host_allgather_fn(&token, all, sizeof(int), host_allgather_ctx) == 0,
+                    "host barrier before freeing the node2vec table shard failed");
+        }
+        d_edge_tables.release();
+        d_table_offsets.release();
+    }
+
     void close_peers() {
+        close_peer_tables();
         for (int r = 0; r < int(peer_arenas.size()); r++)
             if (r != rank && peer_arenas[r])
                 cudaIpcCloseMemHandle(peer_arenas[r]);
@@ -584,10 +613,8 @@ struct Solver {
         device_graph.edge_alias = d_edge_alias.as<uint64_t>();
         if (sample_mode == 2)
             build_node2vec_tables();
-        else {
-            d_edge_tables.release();
-            d_table_offsets.release();
-        }
+        else
+            release_table_shard();
         tables_mode = sample_mode;
         tables_p = p;
         tables_q = q;
@@ -617,14 +644,30 @@ struct Solver {
             table_offsets[e + 1] = table_offsets[e] + (graph->offsets[v + 1] - graph->offsets[v]);
         }
         const unsigned long long total = table_offsets[m];
+        // shards: rank r owns the tables of the edges [first_edge[r], first_edge[r + 1]), cut where the entry count
+        // passes r / W of the total (one shard = everything unless the sampling is partitioned)
+        release_table_shard();
+        const int num_shard = partitioned_sampling ? num_worker : 1;
+        require(num_shard <= GV_MAX_TABLE_SHARDS, "too many workers for sharded node2vec tables");
+        std::vector<size_t> first_edge(num_shard + 1, m);
+        first_edge[0] = 0;
+        for (int r = 1; r < num_shard; r++)
+            first_edge[r] = std::lower_bound(table_offsets.begin(), table_offsets.end(), total / num_shard * r) -
+                            table_offsets.begin();
+        memset(&table_shards, 0, sizeof(table_shards));
+        table_shards.num_shard = num_shard;
+        for (int r = 0; r <= num_shard; r++)
+            table_shards.first_entry[r] = table_offsets[first_edge[r]];
+        const int mine = partitioned_sampling ? rank : 0;
+        const unsigned long long own = table_shards.first_entry[mine + 1] - table_shards.first_entry[mine];
         size_t free_bytes = 0, total_bytes = 0;
         GV_CHECK_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
-        const unsigned long long budget = std::min<unsigned long long>(total, 1ull << 27);  // entries per build batch
-        const unsigned long long needed = total * sizeof(gv_alias_entry_t) + budget * 8 + m * 8 + (m + 1) * 8;
+        const unsigned long long budget = std::min<unsigned long long>(std::max<unsigned long long>(own, 1), 1ull << 27);
+        const unsigned long long needed = own * sizeof(gv_alias_entry_t) + budget * 8 + m * 8 + (m + 1) * 8;
         require(needed + (1ull << 30) < free_bytes,
                 "node2vec needs " + std::to_string(needed >> 20) + " MiB of device memory for its per-edge alias tables "
-                "(sum of squared degrees = " + std::to_string(total) + " entries), only " +
-                std::to_string(free_bytes >> 20) + " MiB are free");
+                "(sum of squared degrees = " + std::to_string(total) + " entries over " + std::to_string(num_shard) +
+                " GPU(s)), only " + std::to_string(free_bytes >> 20) + " MiB are free");
         // neighbour lists sorted inside every vertex's CSR range, for the membership test
         std::vector<uint32_t> sorted(graph->edge_v);
         for (uint32_t v = 0; v < graph->num_vertex(); v++)
@@ -633,22 +676,44 @@ struct Solver {
         d_sorted.upload(sorted, sample_stream);
         d_weights.upload(graph->edge_w, sample_stream);
         d_table_offsets.upload(table_offsets, sample_stream);
-        d_edge_tables.allocate(total * sizeof(gv_alias_entry_t));
+        d_edge_tables.allocate(std::max<unsigned long long>(own, 1) * sizeof(gv_alias_entry_t));
         d_little.allocate(budget * sizeof(uint32_t));
         d_large.allocate(budget * sizeof(uint32_t));
-        for (size_t first = 0; first < m;) {
+        // the build kernel addresses tables[table_offsets[e]]: hand it the shard's virtual origin
+        gv_alias_entry_t *origin = d_edge_tables.as<gv_alias_entry_t>() - table_shards.first_entry[mine];
+        for (size_t first = first_edge[mine]; first < first_edge[mine + 1];) {
             size_t last = first;
-            while (last < m && table_offsets[last + 1] - table_offsets[first] <= budget)
+            while (last < first_edge[mine + 1] && table_offsets[last + 1] - table_offsets[first] <= budget)
                 last++;
             require(last > first, "internal error: node2vec table larger than the build batch");
             GV_CHECK_ABI(gv_cuda_node2vec_build(&device_graph, d_weights.as<float>(), d_sorted.as<uint32_t>(),
                                                 d_table_offsets.as<unsigned long long>(), first,
-                                                uint32_t(last - first), p, q, d_edge_tables.as<gv_alias_entry_t>(),
-                                                d_little.as<uint32_t>(), d_large.as<uint32_t>(), sample_stream));
+                                                uint32_t(last - first), p, q, origin, d_little.as<uint32_t>(),
+                                                d_large.as<uint32_t>(), sample_stream));
             stat_launches++;
             first = last;
         }
         GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+        table_shards.shard[mine] = d_edge_tables.as<gv_alias_entry_t>();
+        if (num_shard > 1) {
+            // trade the shards' IPC handles; every rank must have finished building before anybody walks
+            cudaIpcMemHandle_t handle;
+            std::vector<cudaIpcMemHandle_t> all(num_worker);
+            require(cudaIpcGetMemHandle(&handle, d_edge_tables.ptr) == cudaSuccess,
+                    "cannot export the node2vec table shard (CUDA IPC)");
+            require(host_allgather_fn(&handle, all.data(), sizeof(handle), host_allgather_ctx) == 0,
+                    "host all-gather of the table handles failed");
+            peer_tables.assign(num_worker, nullptr);
+            for (int r = 0; r < num_worker; r++)
+                if (r != rank) {
+                    require(cudaIpcOpenMemHandle(&peer_tables[r], all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess,
+                            "cannot map a peer's node2vec table shard (CUDA IPC)");
+                    table_shards.shard[r] = static_cast<const gv_alias_entry_t *>(peer_tables[r]);
+                }
+            if (rank == 0 && getenv("GV_LOG"))
+                fprintf(stderr, "node2vec tables: %llu entries sharded over %d ranks (%llu on rank 0)\n", total,
+                        num_shard, own);
+        }
     }
 
     // ---- one sampler's share of a pool (SamplerMixin::sample / GraphSampler::sample_random_walk) ----
@@ -721,11 +786,12 @@ struct Solver {
                 const uint32_t lo = uint32_t(uint64_t(count) * (partitioned_sampling ? rank : 0) / share);
                 const uint32_t hi = uint32_t(uint64_t(count) * (partitioned_sampling ? rank + 1 : 1) / share);
                 if (sample_mode == 2)
-                    GV_CHECK_ABI(gv_cuda_biased_walk(&device_graph, d_edge_tables.as<gv_alias_entry_t>(),
-                                                     d_table_offsets.as<unsigned long long>(),
-                                                     d_sampler_random.as<double>(), hi - lo, L, done_in_span + lo,
-                                                     uint32_t(walks_per_buffer), kRandBatchSize,
-                                                     d_chains.as<gv_location_t>(), sample_stream));
+                    GV_CHECK_ABI(gv_cuda_biased_walk_sharded(&device_graph, &table_shards,
+                                                             d_table_offsets.as<unsigned long long>(),
+                                                             d_sampler_random.as<double>(), hi - lo, L,
+                                                             done_in_span + lo, uint32_t(walks_per_buffer),
+                                                             kRandBatchSize, d_chains.as<gv_location_t>(),
+                                                             sample_stream));
                 else
                     GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, d_sampler_random.as<double>(), hi - lo, L,
                                                      done_in_span + lo, uint32_t(walks_per_buffer), kRandBatchSize,

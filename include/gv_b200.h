@@ -175,8 +175,21 @@ int gv_cuda_node2vec_build(const gv_device_graph_t *graph, const float *edge_wei
                            const unsigned long long *table_offsets, uint64_t first_edge, uint32_t num_table, float p,
                            float q, gv_alias_entry_t *tables, uint32_t *scratch_little, uint32_t *scratch_large,
                            void *stream);
+/* The flat array of per-edge tables split over the ranks of a multi-GPU run (Sigma deg^2 entries do not fit one GPU
+ * beyond small graphs): shard r holds the entries [first_entry[r], first_entry[r + 1]) -- whole tables -- and may be
+ * peer memory mapped with CUDA IPC. */
+#define GV_MAX_TABLE_SHARDS 16
+typedef struct {
+    int num_shard;
+    const gv_alias_entry_t *shard[GV_MAX_TABLE_SHARDS];
+    unsigned long long first_entry[GV_MAX_TABLE_SHARDS + 1];
+} gv_table_shards_t;
 /* Walk part of GraphSampler::sample_biased_random_walk (instance/graph.cuh:321-349); arguments as
  * gv_cuda_random_walk, steps drawn from the table of the edge the walk arrived by. */
+int gv_cuda_biased_walk_sharded(const gv_device_graph_t *graph, const gv_table_shards_t *tables,
+                                const unsigned long long *table_offsets, const double *random, uint32_t num_walk,
+                                int walk_length, uint64_t first_walk, uint32_t walks_per_buffer,
+                                uint64_t buffer_doubles, gv_location_t *chains, void *stream);
 int gv_cuda_biased_walk(const gv_device_graph_t *graph, const gv_alias_entry_t *tables,
                         const unsigned long long *table_offsets, const double *random, uint32_t num_walk,
                         int walk_length, uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,

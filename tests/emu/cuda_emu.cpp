@@ -175,6 +175,13 @@ void run_block() {
         const char *mode = getenv("GV_EMU_WARP_ORDER");
         return !mode ? 0 : (std::string(mode) == "reverse" ? 1 : (std::string(mode) == "rotate" ? 2 : 0));
     }();
+    // GV_EMU_LANE_ORDER=reverse: visit the lanes of a warp from 31 down to 0.  Lanes run one after another up to their
+    // next collective, so the visiting order decides whether a lane sees a shared-memory write of another lane that no
+    // __syncwarp() orders: in ascending order lane 5 sees what lane 0 wrote "by luck", in descending order it does not
+    static const bool reverse_lanes = []() {
+        const char *mode = getenv("GV_EMU_LANE_ORDER");
+        return mode && std::string(mode) == "reverse";
+    }();
     int sweep = 0;
     while (g_exited < g_num_thread) {
         bool progress = false;
@@ -184,7 +191,9 @@ void run_block() {
             // run this warp until all of its lanes wait for the CTA or have exited
             for (bool warp_progress = true; warp_progress;) {
                 warp_progress = false;
-                for (int t = w * 32; t < std::min(g_num_thread, w * 32 + 32); t++) {
+                const int lane_end = std::min(g_num_thread, w * 32 + 32);
+                for (int lane = w * 32; lane < lane_end; lane++) {
+                    const int t = reverse_lanes ? w * 32 + (lane_end - 1 - lane) : lane;
                     Fiber &fiber = g_fibers[t];
                     if (!runnable(fiber))
                         continue;

@@ -4,6 +4,7 @@ emulation of tests/emu with GV_EMULATE=1: "device" memory is host memory, so the
 relation all-reduce run over gloo on a machine without GPUs).
 
     GV_TEST_SOLVER      graph | kg
+    GV_TEST_MODEL       graph only: LINE | DeepWalk | node2vec
     GV_TEST_PARTITIONS  number of partitions
     GV_TEST_OPTIMIZER   kg only: SGD | Adam ...
 """
@@ -43,9 +44,11 @@ def run_graph(rank, world, local, num_partition):
     ograph = O.OracleGraph(toy)
     osolver = O.OracleSolver(ograph, cfg["dim"], world, cfg["S"])
     osolver.build("SGD", num_partition, cfg["k"], cfg["B"], cfg["E"])
-    args = (b"LINE", cfg["epochs"], 0, cfg["aug"], cfg["L"], cfg["wb"], 0, 1.0, 1.0, 1, 0.75, 5.0, 1000)
+    model = os.environ.get("GV_TEST_MODEL", "LINE")  # node2vec: per-edge tables sharded over the ranks (needs IPC)
+    p, q = (0.5, 2.0) if model == "node2vec" else (1.0, 1.0)
+    args = (model.encode(), cfg["epochs"], 0, cfg["aug"], cfg["L"], cfg["wb"], 0, p, q, 1, 0.75, 5.0, 1000)
     _lib.check(_lib.lib.gv_solver_train_begin(solver._handle, *args))
-    osolver.train_begin("LINE", cfg["epochs"], False, cfg["aug"], cfg["L"], cfg["wb"])
+    osolver.train_begin(model, cfg["epochs"], False, cfg["aug"], cfg["L"], cfg["wb"], 0, p, q)
     size = cfg["B"] * cfg["E"]
 
     def check_pools(side):

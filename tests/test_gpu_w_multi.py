@@ -45,6 +45,17 @@ def test_multi_gpu_matches_oracle(world, partitions, replicated):
     launch(world, env)
 
 
+@pytest.mark.parametrize("world,partitions", [(2, 2), (4, 4)])
+def test_multi_gpu_node2vec_tables_sharded_over_the_ranks(world, partitions):
+    """node2vec's per-edge alias tables: every rank builds 1/W of them, the walk kernel reads the peers' shards
+    through CUDA IPC; pools bit-exact with the oracle."""
+    if gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ, GV_TEST_SOLVER="graph", GV_TEST_PARTITIONS=str(partitions), GV_TEST_MODEL="node2vec")
+    env.pop("GV_EMULATE", None)
+    launch(world, env)
+
+
 @pytest.mark.parametrize("world,partitions,optimizer", [(2, 4, "SGD"), (2, 4, "Adam"), (4, 8, "Adam")])
 def test_multi_gpu_knowledge_graph_matches_oracle(world, partitions, optimizer):
     if gpu_count() < world:
