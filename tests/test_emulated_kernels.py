@@ -27,8 +27,9 @@ GROUPS = [
 ]
 
 
-# kernel-level files once more with the warps of a CTA visited in reverse order: which warp runs ahead of a barrier
-# decides which write-after-read hazards between warps can show up
+# kernel-level files once more with the warps of a CTA and the lanes of a warp visited in reverse order: which warp
+# runs ahead of a barrier decides which write-after-read hazards between warps can show up, which lane runs first
+# decides whether a shared-memory exchange inside a warp that lacks its __syncwarp() goes unnoticed
 GROUPS.append((["tests/test_gpu_zz_kg_kernels.py", "tests/test_gpu_y_fill.py"], "kernels, warps scheduled in reverse"))
 
 
@@ -39,6 +40,7 @@ def test_gpu_suite_under_cuda_emulation(files, what):
     env = dict(os.environ, GV_EMULATE="1", GV_EMU_BACKTRACE="1")
     if "reverse" in what:
         env["GV_EMU_WARP_ORDER"] = "reverse"
+        env["GV_EMU_LANE_ORDER"] = "reverse"
     result = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + files,
                             cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                             timeout=1500)
