@@ -97,6 +97,7 @@ SIGNATURES = {
     "gv_cuda_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
     "gv_cuda_random_walk": (c_int, [P(DeviceGraph), c_void_p, c_uint32, c_int, c_uint64, c_uint32, c_uint64,
                                     c_void_p, c_void_p]),
+    "gv_cuda_vertex_tables_build": (c_int, [P(DeviceGraph), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_node2vec_build": (c_int, [P(DeviceGraph), c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_float, c_float,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_biased_walk": (c_int, [P(DeviceGraph), c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_uint64, c_uint32,

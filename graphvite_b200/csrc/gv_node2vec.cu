@@ -8,6 +8,7 @@
 //
 // Layout: the table of edge e = (u -> v) has deg(v) entries {prob, alias} and starts at
 // table_offsets[e] (prefix sum of deg(v_e) in flatten() order) inside one flat device array.
+// The per-vertex tables of the first-order walk (build_vertex_edge, graph.cuh:645-653) are built by the same code.
 // Build: one thread per table runs Vose's method with the reference's FIFO pairing order
 // (include/base/alias_table.cuh:84-128), so the tables -- and therefore the walks -- are
 // bit-identical; the two FIFO queues live in a scratch ring of deg(v) entries each.
@@ -39,6 +40,44 @@ __device__ __forceinline__ bool contains(const uint32_t *sorted, unsigned long l
     return false;
 }
 
+// AliasTable::build, include/base/alias_table.cuh:84-128, for one table whose entries hold the raw weights in
+// .prob: normalise, then Vose's method with the reference's two FIFO queues (rings of capacity `count`: an index is
+// in at most one queue).  `norm` = sum of the weights, accumulated in double in entry order (alias_table.cuh:92).
+__device__ __forceinline__ void finish_alias_table(gv_alias_entry_t *table, uint32_t count, double norm,
+                                                   uint32_t *little_ring, uint32_t *large_ring) {
+    norm = norm / count;
+    uint32_t num_little = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        const float prob = float(double(table[i].prob) / norm);
+        table[i].prob = prob;
+        table[i].alias = i;
+        num_little += prob < 1;
+    }
+    // one queue starts empty (every table of an unweighted graph): the pairing loop never runs and all entries are
+    // leftovers that alias to themselves -- the rings are not touched
+    if (num_little == 0 || num_little == count)
+        return;
+    uint32_t little_head = 0, little_tail = 0, large_head = 0, large_tail = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        if (table[i].prob < 1)
+            little_ring[little_tail++ % count] = i;
+        else
+            large_ring[large_tail++ % count] = i;
+    }
+    while (little_head != little_tail && large_head != large_tail) {
+        const uint32_t i = little_ring[little_head++ % count], j = large_ring[large_head++ % count];
+        table[i].alias = j;
+        const float sum = table[i].prob + table[j].prob;
+        const float rest = sum - 1;
+        table[j].prob = rest;
+        if (rest < 1)
+            little_ring[little_tail++ % count] = j;
+        else
+            large_ring[large_tail++ % count] = j;
+    }
+    // leftovers keep the self alias written above ("suppress some truncation error", alias_table.cuh:117-127)
+}
+
 __global__ void __launch_bounds__(128) node2vec_build_kernel(const gv_device_graph_t g, const float *edge_w,
                                                              const uint32_t *sorted_v,
                                                              const unsigned long long *table_offsets,
@@ -56,10 +95,9 @@ __global__ void __launch_bounds__(128) node2vec_build_kernel(const gv_device_gra
         return;
     gv_alias_entry_t *table = tables + table_offsets[e];
     const unsigned long long ring = table_offsets[e] - table_offsets[first_edge];
-    uint32_t *little_ring = little + ring, *large_ring = large + ring;
 
     // build_edge_edge, graph.cuh:660-670: w / p back to u, w / q to non-neighbours of u, w otherwise
-    double norm = 0;  // alias_table.cuh:92: accumulated in double
+    double norm = 0;
     for (uint32_t i = 0; i < count; i++) {
         const uint32_t x = __ldg(g.edge_v + v_begin + i);
         const float w = __ldg(edge_w + v_begin + i);
@@ -73,36 +111,29 @@ __global__ void __launch_bounds__(128) node2vec_build_kernel(const gv_device_gra
         table[i].prob = weight;
         norm += weight;
     }
-    norm = norm / count;
-    // Vose with two FIFO queues (rings of capacity `count`: an index is in at most one queue)
-    uint32_t little_head = 0, little_tail = 0, large_head = 0, large_tail = 0;
+    finish_alias_table(table, count, norm, little + ring, large + ring);
+}
+
+// GraphSolver::build_vertex_edge, instance/graph.cuh:645-653: one alias table per vertex over its out-edges, laid
+// out at the vertex's CSR range (and so are its two rings).  Thread per vertex.
+__global__ void __launch_bounds__(128) vertex_tables_kernel(const gv_device_graph_t g, const float *edge_w,
+                                                            gv_alias_entry_t *tables, uint32_t *little,
+                                                            uint32_t *large) {
+    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.num_vertex)
+        return;
+    const unsigned long long begin = __ldg(g.offsets + v);
+    const uint32_t count = uint32_t(__ldg(g.offsets + v + 1) - begin);
+    if (count == 0)
+        return;
+    gv_alias_entry_t *table = tables + begin;
+    double norm = 0;
     for (uint32_t i = 0; i < count; i++) {
-        const float prob = float(double(table[i].prob) / norm);
-        table[i].prob = prob;
-        if (prob < 1)
-            little_ring[little_tail++ % count] = i;
-        else
-            large_ring[large_tail++ % count] = i;
+        const float w = __ldg(edge_w + begin + i);
+        table[i].prob = w;
+        norm += w;
     }
-    while (little_head != little_tail && large_head != large_tail) {
-        const uint32_t i = little_ring[little_head++ % count], j = large_ring[large_head++ % count];
-        table[i].alias = j;
-        const float sum = table[i].prob + table[j].prob;
-        const float rest = sum - 1;
-        table[j].prob = rest;
-        if (rest < 1)
-            little_ring[little_tail++ % count] = j;
-        else
-            large_ring[large_tail++ % count] = j;
-    }
-    for (; little_head != little_tail; little_head++) {
-        const uint32_t i = little_ring[little_head % count];
-        table[i].alias = i;
-    }
-    for (; large_head != large_tail; large_head++) {
-        const uint32_t i = large_ring[large_head % count];
-        table[i].alias = i;
-    }
+    finish_alias_table(table, count, norm, little + begin, large + begin);
 }
 
 template<class Count>
@@ -180,6 +211,18 @@ int gv_cuda_node2vec_build(const gv_device_graph_t *graph, const float *edge_wei
     GV_LAUNCH((num_table + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), node2vec_build_kernel)(
         *graph, edge_weights, sorted_neighbors, table_offsets, first_edge, num_table, p, q, tables, scratch_little,
         scratch_large);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gv_cuda_vertex_tables_build(const gv_device_graph_t *graph, const float *edge_weights, gv_alias_entry_t *tables,
+                                uint32_t *scratch_little, uint32_t *scratch_large, void *stream) {
+    if (!graph || !edge_weights || !tables || !scratch_little || !scratch_large)
+        return fail("gv_cuda_vertex_tables_build: null argument");
+    if (graph->num_vertex == 0)
+        return 0;
+    GV_LAUNCH(unsigned((uint64_t(graph->num_vertex) + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream),
+              vertex_tables_kernel)(*graph, edge_weights, tables, scratch_little, scratch_large);
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -568,39 +568,19 @@ struct Solver {
         device_graph.locations = d_locations.as<gv_location_t>();
         device_graph.vertex_tables = nullptr;
         if (sample_mode == 1) {
-            // build_vertex_edge, graph.cuh:645-653: one alias table per vertex over its out-edges,
-            // laid out at the vertex's CSR range; built by a few host threads.
-            std::vector<gv_alias_entry_t> tables(m);
-            const uint32_t n = graph->num_vertex();
-            const int num_thread = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-            std::vector<std::thread> threads;
-            std::atomic<bool> failed(false);
-            for (int t = 0; t < num_thread; t++)
-                threads.emplace_back([&, t]() {
-                    std::vector<float> prob;
-                    std::vector<uint32_t> alias;
-                    const uint32_t work = (n + num_thread - 1) / num_thread;
-                    for (uint32_t v = work * t; v < std::min(n, work * (t + 1)); v++) {
-                        const uint64_t begin = graph->offsets[v], degree = graph->offsets[v + 1] - begin;
-                        if (!degree)
-                            continue;
-                        prob.resize(degree);
-                        alias.resize(degree);
-                        try {
-                            build_alias<uint32_t>(&graph->edge_w[begin], degree, prob.data(), alias.data());
-                        } catch (...) {
-                            failed = true;
-                            return;
-                        }
-                        for (uint64_t i = 0; i < degree; i++)
-                            tables[begin + i] = {prob[i], alias[i]};
-                    }
-                });
-            for (auto &thread : threads)
-                thread.join();
-            require(!failed, "Invalid sampling distribution");
+            // build_vertex_edge, graph.cuh:645-653: one alias table per vertex over its out-edges, laid out at the
+            // vertex's CSR range; built on the device (thread per vertex, the reference's pairing order)
+            DeviceArray d_weights, d_little, d_large;
+            d_weights.upload(graph->edge_w, sample_stream);
+            d_vertex_tables.allocate(std::max<size_t>(m, 1) * sizeof(gv_alias_entry_t));
+            d_little.allocate(std::max<size_t>(m, 1) * sizeof(uint32_t));
+            d_large.allocate(std::max<size_t>(m, 1) * sizeof(uint32_t));
+            GV_CHECK_ABI(gv_cuda_vertex_tables_build(&device_graph, d_weights.as<float>(),
+                                                     d_vertex_tables.as<gv_alias_entry_t>(), d_little.as<uint32_t>(),
+                                                     d_large.as<uint32_t>(), sample_stream));
+            stat_launches++;
+            GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));  // the scratch arrays go out of scope
             phase.mark("  per-vertex alias tables");
-            d_vertex_tables.upload(tables, sample_stream);
             device_graph.vertex_tables = d_vertex_tables.as<gv_alias_entry_t>();
         }
         edge_builder.join();

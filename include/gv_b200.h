@@ -164,6 +164,13 @@ int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, ui
                         uint64_t first_walk, uint32_t walks_per_buffer, uint64_t buffer_doubles,
                         gv_location_t *chains, void *stream);
 
+/* GraphSolver::build_vertex_edge (instance/graph.cuh:645-653) on the device: the alias table of vertex v over its
+ * out-edges, built from edge_weights[offsets[v] ..] into tables[offsets[v] ..] with the reference's FIFO pairing
+ * order (include/base/alias_table.cuh:84-128; bit-identical tables).  scratch_little / scratch_large hold num_edge
+ * entries each; they are only touched by tables whose weights are not uniform. */
+int gv_cuda_vertex_tables_build(const gv_device_graph_t *graph, const float *edge_weights, gv_alias_entry_t *tables,
+                                uint32_t *scratch_little, uint32_t *scratch_large, void *stream);
+
 /* node2vec.  GraphSolver::build_edge_edge (instance/graph.cuh:656-677): the alias table of directed
  * edge e = (u -> v) covers the out-edges (v -> x) with weight w/p if x == u, w/q if u is not a
  * neighbour of x, w otherwise; it has deg(v) entries and lives at tables[table_offsets[e]].  One

@@ -32,7 +32,7 @@ def full(shape, value, dtype):
 
 def synchronize():
     if not EMULATED:
-        synchronize()
+        torch.cuda.synchronize()
 
 
 def dev(array, dtype=None):

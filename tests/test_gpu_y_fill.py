@@ -118,3 +118,41 @@ def test_partitioned_fill_equals_single_rank():
     gpu_util.synchronize()
     for b in range(num_block):
         np.testing.assert_array_equal(d_pools[b].cpu().numpy().view(np.uint32), expected[b], err_msg="block %d" % b)
+
+
+def test_vertex_alias_tables_built_on_the_device_are_bit_identical():
+    """gv_cuda_vertex_tables_build (build_vertex_edge, instance/graph.cuh:645-653) against the oracle's AliasTable
+    restatement: weighted vertices (Vose pairing through the rings), uniform vertices (no pairing), isolated
+    vertices, one hub."""
+    import torch
+    import gpu_util
+    import oracle_lib as O
+    from graphvite_b200 import _lib
+    from gpu_util import dev, stream_pointer
+    rng = np.random.RandomState(11)
+    degrees = rng.randint(0, 40, 300)
+    degrees[7] = 3000  # hub
+    degrees[[0, 50, 299]] = 0
+    offsets = np.concatenate([[0], np.cumsum(degrees)]).astype(np.uint64)
+    m = int(offsets[-1])
+    weights = (rng.rand(m) * 4 + 0.01).astype(np.float32)
+    for v in range(0, 300, 3):  # every third vertex is unweighted
+        weights[int(offsets[v]):int(offsets[v + 1])] = 1.5
+    weights[int(offsets[8]):int(offsets[9])] = rng.choice([0.5, 2.0], degrees[8]).astype(np.float32)
+    d_offsets, d_weights = dev(offsets), dev(weights)
+    d_tables = torch.zeros(m, dtype=torch.int64, device=gpu_util.DEVICE)
+    d_little = torch.zeros(m, dtype=torch.int32, device=gpu_util.DEVICE)
+    d_large = torch.zeros(m, dtype=torch.int32, device=gpu_util.DEVICE)
+    graph = _lib.DeviceGraph()
+    graph.num_vertex, graph.num_edge, graph.offsets = 300, m, d_offsets.data_ptr()
+    _lib.check(_lib.lib.gv_cuda_vertex_tables_build(ctypes.byref(graph), d_weights.data_ptr(), d_tables.data_ptr(),
+                                                    d_little.data_ptr(), d_large.data_ptr(), stream_pointer()))
+    gpu_util.synchronize()
+    tables = d_tables.cpu().numpy().view([("prob", np.float32), ("alias", np.uint32)])
+    for v in range(300):
+        lo, hi = int(offsets[v]), int(offsets[v + 1])
+        if lo == hi:
+            continue
+        prob, alias = O.alias_build(weights[lo:hi])
+        np.testing.assert_array_equal(tables["prob"][lo:hi].view(np.uint32), prob.view(np.uint32), err_msg="vertex %d" % v)
+        np.testing.assert_array_equal(tables["alias"][lo:hi], alias.astype(np.uint32), err_msg="vertex %d" % v)
