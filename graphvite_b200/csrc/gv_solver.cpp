@@ -1068,8 +1068,9 @@ struct Solver {
         if (log_enabled())
             fprintf(stderr, "%s\n", info().c_str());
         PhaseTimer phase;
-        // init_embeddings draws |V| * dim floats from the process-wide mt19937 (inherently sequential,
-        // 0.4 s at Youtube size): it runs on its own thread while the sampler tables are built and uploaded
+        // init_embeddings draws |V| * dim floats from the process-wide mt19937 (inherently sequential, 0.1-0.2 s at
+        // Youtube size): it runs on its own thread while the sampler tables are built and uploaded and the first
+        // pool is sampled -- none of which touches the engine or the embeddings
         std::thread initializer;
         if (!resume) {
             initializer = std::thread([this]() {
@@ -1085,6 +1086,10 @@ struct Solver {
             phase.mark("sampler tables + graph upload");
             build_negative_tables();
             phase.mark("negative tables");
+            stat_positive = stat_kernel_seconds = stat_train_seconds = stat_sample_seconds = 0;
+            stat_launches = 0;
+            fill_pool(pool_id ^ 1);
+            phase.mark("first pool fill");
         } catch (...) {
             if (initializer.joinable())
                 initializer.join();
@@ -1097,13 +1102,9 @@ struct Solver {
         phase.mark("embedding upload");
         if (capture_negatives)
             d_negatives_out.allocate(uint64_t(chunk_batches) * batch_size * std::max(1, num_negative) * 4);
-        stat_positive = stat_kernel_seconds = stat_train_seconds = stat_sample_seconds = 0;
-        stat_launches = 0;
         previous_batch_loss = 0;
         training = true;
         step_in_episode = 0;
-        fill_pool(pool_id ^ 1);
-        phase.mark("first pool fill");
     }
 
     // WorkerMixin::train for one block, core/solver.h:1511-1557: positive_reuse * episode_size batches
