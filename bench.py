@@ -135,20 +135,31 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    origin = time.time()
+
+    def progress(what):  # stderr only: if a multi-GPU run stalls, the log says in which phase
+        if rank == 0 or world > 1 and os.environ.get("GV_BENCH_VERBOSE"):
+            sys.stderr.write("[bench %7.2f s] rank %d: %s\n" % (time.time() - origin, rank, what))
+            sys.stderr.flush()
+
     if rank == 0:
         path = graph_file(cfg["graph"])
     barrier()
     path = graph_file(cfg["graph"])
+    progress("graph file ready, building the solver")
     gv, graph, solver = make_solver(cfg, path, rank, world, local_rank, args.partitions)
+    progress("solver built (%d partitions)" % solver.num_partition)
     lib, handle = _lib.lib, solver._handle
     edges_per_step = cfg["episode_size"] * cfg["batch_size"]  # per GPU
     kw = train_kwargs(cfg, 4000)  # config/graph/line_youtube.yaml; far more epochs than we will run
     _lib.check(lib.gv_solver_train_begin(handle, kw["model"].encode(), kw["num_epoch"], 0, kw["augmentation_step"],
                                          kw["random_walk_length"], kw["random_walk_batch_size"], 0, 1.0, 1.0, 1,
                                          0.75, float(kw["negative_weight"]), 1000))
+    progress("train_begin done (tables, first pool, embeddings resident)")
     for _ in range(args.warmup):
         assert lib.gv_solver_train_step(handle) == 1, _lib.last_error()
     barrier()
+    progress("%d warm-up steps done" % args.warmup)
     before = solver.stats
     sampler = ClockSampler(local_rank) if rank == 0 else None
     lib.gv_solver_device_timer(handle, 0)
@@ -156,6 +167,7 @@ def run_ours(args, cfg):
         assert lib.gv_solver_train_step(handle) == 1, _lib.last_error()
     seconds = lib.gv_solver_device_timer(handle, 1)
     barrier()
+    progress("%d timed steps done" % args.steps)
     clocks = sampler.stop() if sampler else None
     after = solver.stats
     if world > 1:
@@ -195,6 +207,7 @@ def run_ours(args, cfg):
     # end to end through the public API: host graph + host embeddings in, host embeddings out
     solver.close()  # collective teardown (IPC importers close before exporters free)
     del solver
+    progress("steady-state solver closed, building the end-to-end solver")
     gv2, graph2, solver2 = make_solver(cfg, path, rank, world, local_rank)
     per_episode = edges_per_step * world * (solver2.num_partition // world) ** 2 * world  # edges per episode
     episodes = max(1, int(round(args.steps * edges_per_step * world / per_episode)))
@@ -204,6 +217,7 @@ def run_ours(args, cfg):
     solver2.train(**train_kwargs(cfg, num_epoch))
     barrier()
     e2e_seconds = time.time() - start
+    progress("end-to-end train() done")
     if world > 1:
         t = torch.tensor([e2e_seconds], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
