@@ -15,6 +15,8 @@
 // =============================================================================
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdint>
 #include <string>
 
@@ -254,9 +256,21 @@ __global__ void __launch_bounds__(512) peer_gather_kernel(int rank, int W, int n
 }
 
 // every walk re-emits its pairs in order and writes the ones that still fit
+// Staging (multi-GPU): 8-byte stores of 32 lanes to 32 unrelated places of a PEER's pool are 32 NVLink write
+// requests.  Pairs of blocks flagged in stage.remote are therefore written to a local staging array, in append
+// order behind the rank's first pair of the block (stage.offsets[b] + in_slice - bases[b]), and fill_forward_kernel
+// moves them to their shuffled positions with consecutive lanes on consecutive addresses.
+struct StageParams {
+    uint2 *staging;                       // nullptr: write everything in place
+    const unsigned char *remote;          // [num_block] 1 = stage and forward
+    const unsigned long long *offsets;    // [num_block] first staging entry of the block
+    const unsigned long long *bases;      // [num_block] slice offset of this rank's first pair
+};
+
 __global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk,
                                     unsigned long long first_walk, const uint32_t *cta_bases,
-                                    uint32_t *const *pool_blocks, unsigned long long *last_walk) {
+                                    uint32_t *const *pool_blocks, unsigned long long *last_walk,
+                                    const StageParams stage) {
     GV_DYNAMIC_SHARED(uint32_t, counters);
     const int T = blockDim.x, num_block = p.num_partition * p.num_partition;
     const uint32_t w = blockIdx.x * T + threadIdx.x;
@@ -301,7 +315,9 @@ __global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uin
                 // pseudo shuffle, instance/graph.cuh:440-441
                 const unsigned long long shuffled = offset % p.shuffle_base * shuffle_stride + offset / p.shuffle_base;
                 uint32_t *block = pool_blocks[b];
-                if (block)
+                if (stage.staging && stage.remote[b])
+                    stage.staging[stage.offsets[b] + (in_slice - stage.bases[b])] = make_uint2(tail.y, head.y);
+                else if (block)
                     write_entry(p, block, shuffled, w, tail.y, head.y);
                 completed |= in_slice + 1 == slice;
             }
@@ -309,6 +325,46 @@ __global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uin
     }
     if (completed)
         atomicMax(last_walk, first_walk + w);
+}
+
+// staging offsets: exclusive prefix sum of the rank's totals over the staged blocks (one small CTA)
+__global__ void fill_stage_offsets_kernel(int num_block, const unsigned char *remote, const unsigned long long *totals,
+                                          unsigned long long *offsets) {
+    if (threadIdx.x == 0) {
+        unsigned long long running = 0;
+        for (int b = 0; b < num_block; b++) {
+            offsets[b] = running;
+            if (remote[b])
+                running += totals[b];
+        }
+    }
+}
+
+// Move the staged pairs of block blockIdx.y to their pool: entry i of the rank's run has slice offset
+// g = start + base + i and lives at (g % shuffle_base) * stride + g / shuffle_base (instance/graph.cuh:440-441), so
+// the entries i = c, c + shuffle_base, c + 2 shuffle_base ... are neighbours in the pool: consecutive threads take
+// consecutive members of one such class -> a warp writes 256 contiguous bytes (to a peer: full NVLink packets).
+__global__ void __launch_bounds__(256) fill_forward_kernel(const FillParams p, const StageParams stage,
+                                                           const unsigned long long *totals,
+                                                           uint32_t *const *pool_blocks) {
+    const int b = blockIdx.y;
+    uint2 *block = reinterpret_cast<uint2 *>(pool_blocks[b]);
+    if (!stage.remote[b] || !block)
+        return;
+    const unsigned long long slice = p.slice;
+    const unsigned long long begin = min(stage.bases[b], slice), end = min(stage.bases[b] + totals[b], slice);
+    const unsigned long long n = end - begin;
+    const uint2 *source = stage.staging + stage.offsets[b];
+    const unsigned long long g0 = p.start + begin, base = p.shuffle_base, stride = p.pool_size / base;
+    const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long c = 0; c < base && c < n; c++) {
+        const unsigned long long members = (n - c + base - 1) / base;
+        for (unsigned long long q = first; q < members; q += threads) {
+            const unsigned long long i = c + q * base, g = g0 + i;
+            block[g % base * stride + g / base] = source[i];
+        }
+    }
 }
 
 // single-block fast path (num_partition == 1): the slice offset of a pair is its stream index
@@ -444,7 +500,8 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
     GV_CUDA_OK(cudaGetLastError());
     GV_LAUNCH(num_block, 1024, 0, s, fill_scan_kernel)(p, num_cta, cta_counts, fill, fill, nullptr);
     GV_CUDA_OK(cudaGetLastError());
-    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk);
+    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk,
+                                                   StageParams{nullptr, nullptr, nullptr, nullptr});
     GV_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -518,6 +575,19 @@ __global__ void fill_rebase_kernel(unsigned long long slice, uint32_t num_cta, u
 int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
                          uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
                          unsigned long long *last_walk, void *scratch, void *stream) {
+    return gv_cuda_fill_scatter_staged(params, chains, num_walk, first_walk, pool_blocks, bases, last_walk, scratch,
+                                       nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+size_t gv_cuda_fill_staging_bytes(uint32_t num_walk, int walk_length, int augmentation_step) {
+    return size_t(num_walk) * pairs_per_walk(walk_length, augmentation_step) * sizeof(uint2) + 16;
+}
+
+int gv_cuda_fill_scatter_staged(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
+                                uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
+                                unsigned long long *last_walk, void *scratch, const unsigned char *remote_blocks,
+                                const unsigned long long *totals, void *staging, unsigned long long *stage_offsets,
+                                void *stream) {
     FillParams p;
     if (make_fill_params(params, p))
         return -1;
@@ -525,6 +595,11 @@ int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *ch
         return 0;
     if (!chains || !scratch || !bases || !pool_blocks || !last_walk)
         return fail("gv_cuda_fill_scatter: null argument");
+    const bool staged = remote_blocks != nullptr;
+    if (staged && (!totals || !staging || !stage_offsets))
+        return fail("gv_cuda_fill_scatter_staged: totals, staging and stage_offsets are required with remote_blocks");
+    if (staged && p.attributes)
+        return fail("gv_cuda_fill_scatter_staged: staging moves 8-byte pairs only (no attributes)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
     const int num_block = p.num_partition * p.num_partition;
@@ -533,9 +608,22 @@ int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *ch
     const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
     GV_LAUNCH(dim3((num_cta + 255) / 256, num_block), 256, 0, s, fill_rebase_kernel)(p.slice, num_cta, cta_counts, bases);
     GV_CUDA_OK(cudaGetLastError());
+    StageParams stage{nullptr, nullptr, nullptr, nullptr};
+    if (staged) {
+        stage = StageParams{static_cast<uint2 *>(staging), remote_blocks, stage_offsets, bases};
+        GV_LAUNCH(1, 32, 0, s, fill_stage_offsets_kernel)(num_block, remote_blocks, totals, stage_offsets);
+        GV_CUDA_OK(cudaGetLastError());
+    }
     GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, reinterpret_cast<const uint2 *>(chains), num_walk, first_walk,
-                                                   cta_counts, pool_blocks, last_walk);
+                                                   cta_counts, pool_blocks, last_walk, stage);
     GV_CUDA_OK(cudaGetLastError());
+    if (staged) {
+        // enough CTAs per block to keep the copy engines of the NVLink path busy, few enough to stay cheap
+        const uint64_t per_block = uint64_t(num_walk) * pairs_per_walk(p.walk_length, p.augmentation_step) / num_block;
+        const unsigned ctas = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(64, per_block / 2048)));
+        GV_LAUNCH(dim3(ctas, num_block), 256, 0, s, fill_forward_kernel)(p, stage, totals, pool_blocks);
+        GV_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 

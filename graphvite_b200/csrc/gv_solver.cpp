@@ -155,6 +155,8 @@ struct Solver {
     // With partitioned sampling the tables are split over the ranks by entry count (d_edge_tables is then this rank's
     // shard) and every rank maps the others' shards with CUDA IPC: Sigma deg^2 x 8 B does not fit one GPU beyond
     // small graphs (209 GB on the Youtube-shaped graph), but 1 / W of it does.
+    bool staged_scatter = false;  // partitioned sampling: stage + forward the pairs of peer-owned blocks
+    DeviceArray d_stage, d_stage_offsets, d_remote_blocks;
     gv_table_shards_t table_shards;
     std::vector<void *> peer_tables;  // [W] mapped shards of the other ranks (own entry = nullptr)
     gv_device_graph_t device_graph;
@@ -488,6 +490,15 @@ struct Solver {
             d_totals.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
             d_bases.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
             peer_round = 0;
+            // pairs of blocks owned by other ranks are staged locally and forwarded with coalesced peer stores
+            // (gv_cuda_fill_scatter_staged); GV_DIRECT_PEER_SCATTER=1 keeps the direct 8-byte peer stores
+            staged_scatter = !getenv("GV_DIRECT_PEER_SCATTER");
+            std::vector<unsigned char> remote(size_t(num_partition) * num_partition, 0);
+            for (int h = 0; h < num_partition; h++)
+                for (int t = 0; t < num_partition; t++)
+                    remote[size_t(h) * num_partition + t] = t % num_worker != rank;
+            d_remote_blocks.upload(remote, work_stream);
+            d_stage_offsets.allocate(remote.size() * sizeof(unsigned long long));
         }
         negative_tables = std::vector<DeviceArray>(num_group);
         negative_counts.assign(num_group, 0);
@@ -611,6 +622,8 @@ struct Solver {
         walk_chunk = std::max<uint64_t>(walk_chunk, 1024);
         d_chains.allocate(walk_chunk * (L + 1) * sizeof(gv_location_t));
         d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(walk_chunk), num_partition));
+        if (partitioned_sampling && staged_scatter)
+            d_stage.allocate(gv_cuda_fill_staging_bytes(uint32_t(walk_chunk), L, sample_mode == 0 ? 1 : augmentation_step));
         d_sampler_random.allocate(size_t(kSpanBuffers) * kRandBatchSize * sizeof(double));
     }
 
@@ -790,12 +803,13 @@ struct Solver {
                                                     d_fill_scratch.ptr, d_totals.as<unsigned long long>(),
                                                     sample_stream));
                     peer_barrier(d_totals.as<unsigned long long>());
-                    GV_CHECK_ABI(gv_cuda_fill_scatter(&params, d_chains.as<gv_location_t>(), hi - lo, walks_done + lo,
-                                                      pool_pointers[side].as<uint32_t *>(),
-                                                      d_bases.as<unsigned long long>(),
-                                                      d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
-                                                      sample_stream));
-                    stat_launches += 7;
+                    GV_CHECK_ABI(gv_cuda_fill_scatter_staged(
+                        &params, d_chains.as<gv_location_t>(), hi - lo, walks_done + lo,
+                        pool_pointers[side].as<uint32_t *>(), d_bases.as<unsigned long long>(),
+                        d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
+                        staged_scatter ? d_remote_blocks.as<unsigned char>() : nullptr, d_totals.as<unsigned long long>(),
+                        d_stage.ptr, d_stage_offsets.as<unsigned long long>(), sample_stream));
+                    stat_launches += staged_scatter ? 9 : 7;
                 }
                 GV_CHECK_CUDA(cudaMemcpyAsync(fill.data(), d_fill.ptr, num_block * sizeof(unsigned long long),
                                               cudaMemcpyDeviceToHost, sample_stream));
@@ -1369,7 +1383,8 @@ struct Solver {
             pool_pointers[side].release();
         for (auto *a : {&d_offsets, &d_edge_u, &d_edge_v, &d_edge_prob, &d_edge_alias, &d_vertex_tables, &d_locations,
                         &d_sampler_random, &d_chains, &d_fill, &d_last_walk, &d_fill_scratch, &d_random[0],
-                        &d_random[1], &d_random[2], &d_random[3], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_edge_tables,
+                        &d_random[1], &d_random[2], &d_random[3], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_stage,
+                        &d_stage_offsets, &d_remote_blocks, &d_edge_tables,
                         &d_table_offsets})
             a->release();
         for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})

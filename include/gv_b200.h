@@ -242,6 +242,17 @@ int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chai
 int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
                          uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
                          unsigned long long *last_walk, void *scratch, void *stream);
+/* gv_cuda_fill_scatter for pools that live on peer GPUs: pairs of the blocks flagged in remote_blocks [P*P] (device)
+ * are first written to `staging` (gv_cuda_fill_staging_bytes; local memory) in append order and then moved to their
+ * shuffled positions with coalesced stores -- scattered 8-byte stores over NVLink are one request each.  `totals` =
+ * this rank's output of gv_cuda_fill_count, stage_offsets = scratch of P*P entries.  remote_blocks == NULL is
+ * gv_cuda_fill_scatter.  Pairs only (no attributes). */
+size_t gv_cuda_fill_staging_bytes(uint32_t num_walk, int walk_length, int augmentation_step);
+int gv_cuda_fill_scatter_staged(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
+                                uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
+                                unsigned long long *last_walk, void *scratch, const unsigned char *remote_blocks,
+                                const unsigned long long *totals, void *staging, unsigned long long *stage_offsets,
+                                void *stream);
 /* All-gather of the per-block totals through NVLink peer memory, fused with the prefix over ranks:
  * publishes `totals` (NULL = zeros) and *last_walk into every rank's control region (`controls` [W]
  * device pointers, peers mapped with CUDA IPC), waits until all W ranks published round `round_id`

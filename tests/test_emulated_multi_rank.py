@@ -17,7 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # memory in POSIX shared memory, the peer-exchange kernels of different processes really wait for each other),
 # "replicated" = every rank samples all blocks itself (the fallback when IPC is unavailable)
 # "node2vec" = "ipc" with the biased walk: the per-edge alias tables are sharded over the ranks and read through IPC
+# "direct" = "ipc" with GV_DIRECT_PEER_SCATTER=1 (8-byte peer stores instead of staging + coalesced forwarding)
 CASES = [("graph", 2, 2, "ipc"), ("graph", 2, 4, "ipc"), ("graph", 2, 2, "replicated"), ("graph", 4, 4, "node2vec"),
+         ("graph", 2, 4, "direct"),
          ("kg", 2, 4, "SGD"), ("kg", 2, 4, "Adam"), ("kg", 4, 8, "Adam")]
 
 
@@ -30,8 +32,10 @@ def test_multi_rank_under_emulation(solver, world, partitions, optimizer):
         port = s.getsockname()[1]
     env = dict(os.environ, GV_EMULATE="1", GV_EMU_BACKTRACE="1", GV_TEST_SOLVER=solver,
                GV_TEST_PARTITIONS=str(partitions), GV_TEST_OPTIMIZER=optimizer, OMP_NUM_THREADS="1",
-               GV_EMU_IPC="1" if optimizer in ("ipc", "node2vec") else "0", GV_LOG="1",
+               GV_EMU_IPC="1" if optimizer in ("ipc", "node2vec", "direct") else "0", GV_LOG="1",
                GV_TEST_MODEL="node2vec" if optimizer == "node2vec" else "LINE")
+    if optimizer == "direct":
+        env["GV_DIRECT_PEER_SCATTER"] = "1"
     command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                "--master-addr", "127.0.0.1", "--master-port", str(port),
                os.path.join(ROOT, "tests", "multi_rank_worker.py")]

@@ -73,16 +73,20 @@ def test_fill_pool_matches_sequential_append(P, L, aug, shuffle_base):
     assert int(d_last.item()) == last_expected
 
 
-def test_partitioned_fill_equals_single_rank():
-    """count / exchange-by-hand / scatter over 3 'ranks' gives the pools of one sequential pass"""
+@pytest.mark.parametrize("staged,shuffle_base,pool_size", [(False, 3, 900), (True, 3, 900), (True, 1, 900),
+                                                          (True, 7, 910), (True, 455, 910)])
+def test_partitioned_fill_equals_single_rank(staged, shuffle_base, pool_size):
+    """count / exchange-by-hand / scatter over 3 'ranks' gives the pools of one sequential pass.  staged: the blocks a
+    rank does not own (tail partition != rank) go through the local staging array and the coalescing forward kernel
+    (gv_cuda_fill_scatter_staged), as they do when the pool lives on a peer GPU."""
     import torch
     import gpu_util
     from graphvite_b200 import _lib
     from gpu_util import stream_pointer
     lib = _lib.lib
     rng = np.random.RandomState(5)
-    P, L, aug, shuffle_base = 3, 6, 3, 3
-    num_block, pool_size = P * P, 900
+    P, L, aug = 3, 6, 3
+    num_block = P * P
     start, end = 30, 630
     num_walk = 700
     chains = np.zeros((L + 1, num_walk, 2), dtype=np.uint32)
@@ -113,8 +117,21 @@ def test_partitioned_fill_equals_single_rank():
     for r in range(3):
         d_chains, scratch, lo, hi = state[r]
         bases = gpu_util.to_device(torch.from_numpy(sum(totals[:r], np.zeros(num_block, dtype=np.int64))))
-        _lib.check(lib.gv_cuda_fill_scatter(ctypes.byref(params), d_chains.data_ptr(), hi - lo, lo, pointers.data_ptr(),
-                                            bases.data_ptr(), d_last.data_ptr(), scratch.data_ptr(), stream_pointer()))
+        if not staged:
+            _lib.check(lib.gv_cuda_fill_scatter(ctypes.byref(params), d_chains.data_ptr(), hi - lo, lo,
+                                                pointers.data_ptr(), bases.data_ptr(), d_last.data_ptr(),
+                                                scratch.data_ptr(), stream_pointer()))
+            continue
+        remote = gpu_util.to_device(torch.tensor([int(b % P != r) for b in range(num_block)], dtype=torch.uint8))
+        staging = torch.full((lib.gv_cuda_fill_staging_bytes(hi - lo, L, aug),), 0xEE, dtype=torch.uint8,
+                             device=gpu_util.DEVICE)
+        offsets = torch.zeros(num_block, dtype=torch.int64, device=gpu_util.DEVICE)
+        d_totals = gpu_util.to_device(torch.from_numpy(totals[r]))
+        _lib.check(lib.gv_cuda_fill_scatter_staged(ctypes.byref(params), d_chains.data_ptr(), hi - lo, lo,
+                                                   pointers.data_ptr(), bases.data_ptr(), d_last.data_ptr(),
+                                                   scratch.data_ptr(), remote.data_ptr(), d_totals.data_ptr(),
+                                                   staging.data_ptr(), offsets.data_ptr(), stream_pointer()))
+        gpu_util.synchronize()
     gpu_util.synchronize()
     for b in range(num_block):
         np.testing.assert_array_equal(d_pools[b].cpu().numpy().view(np.uint32), expected[b], err_msg="block %d" % b)

@@ -28,3 +28,4 @@ run "reserve_sms=16" GV_TRAIN_RESERVE_SMS=16
 run "chunk_batches=8" GV_CHUNK_BATCHES=8
 run "chunk_batches=32" GV_CHUNK_BATCHES=32
 run "replicated_sampling" GV_REPLICATED_SAMPLING=1
+run "direct_peer_scatter" GV_DIRECT_PEER_SCATTER=1
