@@ -360,9 +360,12 @@ __global__ void __launch_bounds__(256) fill_forward_kernel(const FillParams p, c
     const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned long long c = 0; c < base && c < n; c++) {
         const unsigned long long members = (n - c + base - 1) / base;
+        // g % base is constant inside a class; 4 independent loads in flight per thread
+        const unsigned long long row = (g0 + c) % base * stride;
+#pragma unroll 4
         for (unsigned long long q = first; q < members; q += threads) {
-            const unsigned long long i = c + q * base, g = g0 + i;
-            block[g % base * stride + g / base] = source[i];
+            const unsigned long long i = c + q * base;
+            block[row + (g0 + i) / base] = source[i];
         }
     }
 }
@@ -620,7 +623,7 @@ int gv_cuda_fill_scatter_staged(const gv_fill_params_t *params, const gv_locatio
     if (staged) {
         // enough CTAs per block to keep the copy engines of the NVLink path busy, few enough to stay cheap
         const uint64_t per_block = uint64_t(num_walk) * pairs_per_walk(p.walk_length, p.augmentation_step) / num_block;
-        const unsigned ctas = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(64, per_block / 2048)));
+        const unsigned ctas = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(128, per_block / 2048)));
         GV_LAUNCH(dim3(ctas, num_block), 256, 0, s, fill_forward_kernel)(p, stage, totals, pool_blocks);
         GV_CUDA_OK(cudaGetLastError());
     }
