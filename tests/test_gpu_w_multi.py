@@ -34,14 +34,19 @@ def launch(world, env):
         assert "rank %d ok" % rank in result.stdout
 
 
-@pytest.mark.parametrize("world,partitions,replicated", [(2, 2, 0), (2, 4, 0), (2, 2, 1), (4, 4, 0), (8, 8, 0)])
-def test_multi_gpu_matches_oracle(world, partitions, replicated):
+@pytest.mark.parametrize("world,partitions,mode", [(2, 2, "staged"), (2, 4, "staged"), (2, 2, "replicated"),
+                                                   (2, 4, "direct"), (4, 4, "staged"), (8, 8, "staged")])
+def test_multi_gpu_matches_oracle(world, partitions, mode):
+    """staged: partitioned sampling, pairs of peer-owned blocks staged locally and forwarded with coalesced NVLink
+    stores (the default); direct: 8-byte peer stores; replicated: every rank samples all blocks itself (no CUDA IPC)."""
     if gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
     env = dict(os.environ, GV_TEST_SOLVER="graph", GV_TEST_PARTITIONS=str(partitions))
     env.pop("GV_EMULATE", None)
-    if replicated:  # every rank samples all blocks itself (no CUDA IPC): the fallback path
+    if mode == "replicated":
         env["GV_REPLICATED_SAMPLING"] = "1"
+    if mode == "direct":
+        env["GV_DIRECT_PEER_SCATTER"] = "1"
     launch(world, env)
 
 
