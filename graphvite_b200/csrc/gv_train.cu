@@ -27,7 +27,10 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 
 #include "gv_common.h"
 #include "gv_device.cuh"
@@ -54,9 +57,37 @@ struct TrainParams {
     uint32_t batch_size;
     float negative_weight;
     float *loss_per_sample, *loss_per_batch;
-    int flags;  // experiment switches: 1 = L1-cached (.ca) loads for ALL rows, 4 = never use train_sgd_kernel
+    int flags;  // experiment switches: 1 = L1-cached (.ca) loads for ALL rows, 4 = never use train_sgd_kernel,
+                // 8 = warps claim their 32-sample chunks from a counter instead of a fixed stride
+    unsigned int *work_counter;  // flags & 8: {next ticket, warps done}; both zero between launches
     uint32_t hot_rows;  // rows with a local id below this are loaded through L1 (.ca), the rest L2-only (.cg)
 };
+
+// Which 32-sample chunk a warp takes after `chunk`.  Static: the grid-stride successor.  Dynamic (work_counter):
+// the first num_warp chunks go by warp index, every further one by ticket -- a CTA that starts late (its SM was
+// busy with a sampler kernel when the launch began) or sits on hot rows takes fewer chunks instead of becoming the
+// straggler of the launch.  One warp alone still visits the chunks in order (the parity tests' mode).
+__device__ __forceinline__ unsigned long long next_chunk(const TrainParams &p, unsigned long long chunk,
+                                                         unsigned long long num_warp, int lane) {
+    if (!p.work_counter)
+        return chunk + num_warp;
+    unsigned int ticket = 0;
+    if (lane == 0)
+        ticket = atomicAdd(p.work_counter, 1u);
+    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+    return num_warp + ticket;
+}
+
+// the last warp to leave a launch re-arms the counter for the next one (launches of a stream are serial)
+__device__ __forceinline__ void release_work_counter(const TrainParams &p, unsigned long long num_warp, int lane) {
+    if (p.work_counter && lane == 0) {
+        const unsigned int done = atomicAdd(p.work_counter + 1, 1u);
+        if (done + 1 == num_warp) {
+            p.work_counter[0] = 0;
+            p.work_counter[1] = 0;
+        }
+    }
+}
 
 // -----------------------------------------------------------------------------
 // A d-dim fp32 row spread over a warp: pass p, lane l holds elements
@@ -237,7 +268,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
     const bool l1 = p.flags & 1;
 
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-         chunk < num_chunk; chunk += num_warp) {
+         chunk < num_chunk; chunk = next_chunk(p, chunk, num_warp, lane)) {
         const unsigned long long base = chunk * 32;
         const unsigned long long i = base + lane;
         const bool valid = i < p.num_sample;
@@ -390,6 +421,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
         }
         __syncwarp();  // ids[] is rewritten by the next chunk
     }
+    release_work_counter(p, num_warp, lane);
 }
 
 // -----------------------------------------------------------------------------
@@ -480,7 +512,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainPar
     const bool l1 = p.flags & 1;
 
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-         chunk < num_chunk; chunk += num_warp) {
+         chunk < num_chunk; chunk = next_chunk(p, chunk, num_warp, lane)) {
         const unsigned long long base = chunk * 32;
         const unsigned long long i = base + lane;
         const bool valid = i < p.num_sample;
@@ -547,6 +579,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainPar
         }
         __syncwarp();  // ids[] is rewritten by the next chunk
     }
+    release_work_counter(p, num_warp, lane);
 }
 
 // gpu::Sample, base/alias_table.cuh:175-183
@@ -599,6 +632,27 @@ static int g_reserve_sms = getenv("GV_TRAIN_RESERVE_SMS") ? atoi(getenv("GV_TRAI
 // -----------------------------------------------------------------------------
 // launch helpers
 // -----------------------------------------------------------------------------
+// kernel_flags & 8: the ticket counter of the launches of one stream (two zeroed words; the kernel re-arms them)
+static unsigned int *work_counter_for(cudaStream_t stream) {
+    static std::mutex mutex;
+    static std::map<std::pair<int, cudaStream_t>, unsigned int *> counters;
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess)
+        return nullptr;
+    std::lock_guard<std::mutex> lock(mutex);
+    auto found = counters.find({device, stream});
+    if (found != counters.end())
+        return found->second;
+    unsigned int *counter = nullptr;
+    if (cudaMalloc(&counter, 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(counter, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;  // fall back to the fixed stride
+    }
+    counters[{device, stream}] = counter;
+    return counter;
+}
+
 static int device_sm_count() {
     int device = 0, sms = 0;
     if (cudaGetDevice(&device) != cudaSuccess)
@@ -724,6 +778,7 @@ int gv_cuda_train_block(const gv_matrices_t *m, const uint32_t *pool, uint64_t n
     p.flags = g_kernel_flags;
     p.hot_rows = g_hot_rows;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    p.work_counter = (g_kernel_flags & 8) ? work_counter_for(s) : nullptr;
     switch (m->dim) {  // src/graphvite.cu:52-59 instantiates exactly these dimensions
         case 32: return dispatch_optimizer<32>(p, num_warps, s);
         case 64: return dispatch_optimizer<64>(p, num_warps, s);

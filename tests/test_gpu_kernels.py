@@ -89,6 +89,33 @@ def test_train_full_grid_race_free(dim, opt, k):
     compare(got, v, c, m, loss)
 
 
+@pytest.mark.parametrize("opt,k,num_warps", [("SGD", 1, 0), ("SGD", 1, 3), ("Adam", 2, 0), ("SGD", 1, 1)])
+def test_dynamic_chunk_scheduling_covers_every_sample_once(opt, k, num_warps):
+    """kernel_flags & 8: warps take their 32-sample chunks by ticket.  Distinct rows make the order irrelevant, so
+    the result must equal the oracle's (every sample trained exactly once); three launches in a row check that the
+    counter is re-armed by the last warp of a launch; one warp alone keeps the sequential order (colliding rows)."""
+    from graphvite_b200 import _lib
+    from gpu_util import run_train_block
+    optimizer = O.OPTIMIZERS[opt]
+    moments = 0 if opt == "SGD" else 2
+    dim, n = 128, 40000 if num_warps != 1 else 700
+    unique = num_warps != 1
+    rows = n if unique else 50
+    vertex, context, ms, batch, negatives = make_problem(dim, n, k, rows, rows * (k + 1) if unique else 80, seed=9,
+                                                         unique=unique, moments=moments)
+    lr = np.full(4, optimizer[1], dtype=np.float32)
+    batch_size = (n + 3) // 4
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives.reshape(n, k), optimizer, 5.0, lr, batch_size)
+    assert _lib.lib.gv_cuda_set_tunable(b"kernel_flags", 8) == 0
+    try:
+        for _ in range(3):
+            got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr,
+                                  batch_size=batch_size, num_warps=num_warps)
+            compare(got, v, c, m, loss)
+    finally:
+        assert _lib.lib.gv_cuda_set_tunable(b"kernel_flags", 0) == 0
+
+
 def test_train_large_k_shared_memory_opt_in():
     """k = 200 needs > 48 KB of dynamic shared memory for the id staging"""
     from gpu_util import run_train_block

@@ -29,3 +29,6 @@ run "chunk_batches=8" GV_CHUNK_BATCHES=8
 run "chunk_batches=32" GV_CHUNK_BATCHES=32
 run "replicated_sampling" GV_REPLICATED_SAMPLING=1
 run "direct_peer_scatter" GV_DIRECT_PEER_SCATTER=1
+run "dynamic_chunks" GV_KERNEL_FLAGS=8
+run "dynamic_chunks,reserve_sms=8" GV_KERNEL_FLAGS=8 GV_TRAIN_RESERVE_SMS=8
+run "dynamic_chunks,blocks_per_sm=3" GV_KERNEL_FLAGS=8 GV_TRAIN_BLOCKS_PER_SM=3
