@@ -15,6 +15,8 @@
 // =============================================================================
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdint>
 #include <string>
 
@@ -159,9 +161,7 @@ __global__ void __launch_bounds__(256) biased_walk_kernel(const gv_device_graph_
                                                           const double *random, uint32_t num_walk, int walk_length,
                                                           uint64_t first_walk, uint32_t walks_per_buffer,
                                                           uint64_t buffer_doubles, gv_location_t *chains) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= num_walk)
-        return;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < num_walk; w += gridDim.x * blockDim.x) {  // see gv_sampler.cu
     const uint64_t walk = first_walk + w;
     const double2 *r = reinterpret_cast<const double2 *>(random + (walk / walks_per_buffer) * buffer_doubles) +
                        (walk % walks_per_buffer) * walk_length;
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(256) biased_walk_kernel(const gv_device_graph_
         edge = begin + neighbor;  // edge_id = flat_offsets[current] + neighbor_id, graph.cuh:341
         current = __ldg(g.edge_v + edge);
         out[size_t(j) * num_walk] = __ldg(locations + current);
+    }
     }
 }
 
@@ -240,7 +241,10 @@ int gv_cuda_biased_walk_sharded(const gv_device_graph_t *graph, const gv_table_s
     for (int r = 0; r < tables->num_shard; r++)
         if (!tables->shard[r] && tables->first_entry[r + 1] > tables->first_entry[r])
             return fail("gv_cuda_biased_walk: a non-empty table shard has no memory");
-    GV_LAUNCH((num_walk + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), biased_walk_kernel)(
+    uint32_t blocks = (num_walk + 255) / 256;
+    if (gv::sampler_max_ctas() > 0)
+        blocks = std::min<uint32_t>(blocks, uint32_t(gv::sampler_max_ctas()));
+    GV_LAUNCH(blocks, 256, 0, static_cast<cudaStream_t>(stream), biased_walk_kernel)(
         *graph, *tables, table_offsets, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles,
         chains);
     GV_CUDA_OK(cudaGetLastError());

@@ -39,9 +39,9 @@ __global__ void __launch_bounds__(256) random_walk_kernel(const gv_device_graph_
                                                           uint32_t num_walk, int walk_length, uint64_t first_walk,
                                                           uint32_t walks_per_buffer, uint64_t buffer_doubles,
                                                           gv_location_t *chains) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= num_walk)
-        return;
+    // one walk per thread and round: the grid may be capped (sampler_max_ctas) so that the walker, which is latency
+    // bound, shares the device with a resident train launch instead of displacing it
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < num_walk; w += gridDim.x * blockDim.x) {
     // walk (first_walk + w) of the span: buffer (index / walks_per_buffer), slot (index % walks_per_buffer);
     // the unused tail of a refill buffer (when 5e6 is not a multiple of 2L) is skipped like the reference does
     const uint64_t walk = first_walk + w;
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) random_walk_kernel(const gv_device_graph_
         const uint32_t neighbor = float(draw.x) < __uint_as_float(entry.x) ? slot : entry.y;
         current = __ldg(g.edge_v + begin + neighbor);
         out[size_t(j) * num_walk] = __ldg(locations + current);
+    }
     }
 }
 
@@ -431,7 +432,9 @@ int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, ui
     if (walk_length > 1 && !graph->vertex_tables)
         return fail("gv_cuda_random_walk: per-vertex alias tables are required for walk_length > 1");
     const int threads = 256;
-    const uint32_t blocks = (num_walk + threads - 1) / threads;
+    uint32_t blocks = (num_walk + threads - 1) / threads;
+    if (gv::sampler_max_ctas() > 0)
+        blocks = std::min<uint32_t>(blocks, uint32_t(gv::sampler_max_ctas()));
     GV_LAUNCH(blocks, threads, 0, static_cast<cudaStream_t>(stream), random_walk_kernel)(
         *graph, random, num_walk, walk_length, first_walk, walks_per_buffer, buffer_doubles, chains);
     GV_CUDA_OK(cudaGetLastError());

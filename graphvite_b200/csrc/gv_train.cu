@@ -628,6 +628,9 @@ static int g_blocks_per_sm = getenv("GV_TRAIN_BLOCKS_PER_SM") ? atoi(getenv("GV_
 // experiment: size the persistent grid for this many SMs fewer than the device has, so that some SMs keep room for
 // the samplers' kernels while a train launch is resident (0 = use every SM)
 static int g_reserve_sms = getenv("GV_TRAIN_RESERVE_SMS") ? atoi(getenv("GV_TRAIN_RESERVE_SMS")) : 0;
+// experiment: cap the grid of the walk kernels (grid-stride loops), so that they take a slice of the device next to a
+// resident train launch instead of all of it between two launches (0 = one thread per walk)
+static int g_sampler_max_ctas = getenv("GV_SAMPLER_MAX_CTAS") ? atoi(getenv("GV_SAMPLER_MAX_CTAS")) : 0;
 
 // -----------------------------------------------------------------------------
 // launch helpers
@@ -730,6 +733,11 @@ static int dispatch_optimizer(const TrainParams &p, int num_warps, cudaStream_t 
 }
 
 }  // namespace device
+
+int sampler_max_ctas() {
+    return device::g_sampler_max_ctas;
+}
+
 }  // namespace gv
 
 using namespace gv;
@@ -798,6 +806,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_kernel_flags = int(value);
     else if (key == "train_blocks_per_sm")
         g_blocks_per_sm = int(value);
+    else if (key == "sampler_max_ctas")
+        g_sampler_max_ctas = int(value);
     else if (key == "train_reserve_sms")
         g_reserve_sms = int(value);
     else

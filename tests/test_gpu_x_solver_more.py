@@ -46,3 +46,19 @@ def test_custom_schedule_callback(toy_graph_file):
         results.append(np.array(solver.vertex_embeddings))
     np.testing.assert_allclose(results[0], results[1], rtol=1e-5, atol=1e-7)
     assert np.abs(results[0]).max() > 0
+
+
+@pytest.mark.parametrize("case", ["deepwalk_p1", "node2vec_p2"])
+def test_scheduling_experiments_do_not_change_results(case, toy_graph_file):
+    """The co-scheduling knobs of DESIGN.md section 8 -- walk kernels on a capped grid (grid-stride over the walks),
+    train warps that take their chunks by ticket -- only change who computes what: pools, negatives and (single
+    warp) embeddings must still equal the oracle's."""
+    import test_gpu_solver as base
+    from graphvite_b200 import _lib
+    assert _lib.lib.gv_cuda_set_tunable(b"sampler_max_ctas", 1) == 0   # 256 threads walk all walks of a launch
+    assert _lib.lib.gv_cuda_set_tunable(b"kernel_flags", 8) == 0
+    try:
+        base.test_solver_matches_oracle_step_by_step(case, toy_graph_file)
+    finally:
+        assert _lib.lib.gv_cuda_set_tunable(b"sampler_max_ctas", 0) == 0
+        assert _lib.lib.gv_cuda_set_tunable(b"kernel_flags", 0) == 0
