@@ -126,7 +126,7 @@ def test_hogwild_training_matches_the_reference_statistically(tmp_path):
     On a graph this small (10 MB of embeddings, all cache resident) the norms depend on how many
     updates each implementation's race pattern loses (measured: ours 192 / 206, reference 224 / 167),
     so only their magnitude is asserted (within 30 %); the link-prediction AUC must agree within 0.015
-    (run-to-run spread ~0.003).  The at-scale comparison is tools/validate_parity.py."""
+    (run-to-run spread ~0.003).  The at-scale comparison is tests/validate_parity.py."""
     import os
     import sys
     import graphvite_b200 as gv

@@ -2,7 +2,7 @@
 """Float parity at scale: train the same configuration with the reference (oracle/_ref/libgraphvite.so,
 unmodified, through its pybind API) and with graphvite_b200, then compare embedding L2 norms,
 link-prediction AUC on a held-out split (semantics of Dataset.link_prediction_split) and the
-logged loss.  Runs on a GPU box:  python tools/validate_parity.py --workload blogcatalog --epochs 400
+logged loss.  Runs on a GPU box:  python tests/validate_parity.py --workload blogcatalog --epochs 400
 TEST / MEASUREMENT TOOLING (it executes oracle/_ref); not part of the product.
 """
 import argparse
