@@ -401,6 +401,70 @@ __global__ void __launch_bounds__(256) fill_direct_kernel(const FillParams p, co
         atomicMax(last_walk, first_walk + w);
 }
 
+// The same fill with coalesced traffic (walk_length > 1, pairs only).  fill_direct_kernel gives a walk to a thread:
+// the 32 stores of a warp instruction land 8 bytes each in 32 places of the pool (pairs_per_walk entries apart).
+// Here a CTA owns kTileWalks consecutive walks, whose pairs are ONE contiguous range of slice offsets:
+//   1. the tile's chains go to shared memory with coalesced loads (rows of kTileWalks locations);
+//   2. the range is written class by class: offset g lives at (g % shuffle_base) * stride + g / shuffle_base
+//      (instance/graph.cuh:440-441), so the offsets of one residue class are neighbours in the pool and consecutive
+//      threads take consecutive members -- every warp store is 256 contiguous bytes;
+//   3. the pair behind offset g is recovered from g alone: walk = g / pairs_per_walk, position -> (j, k).
+constexpr int kTileWalks = 32;
+
+__global__ void __launch_bounds__(256) fill_direct_tiled_kernel(const FillParams p, const uint2 *chains,
+                                                                uint32_t num_walk, unsigned long long first_walk,
+                                                                uint32_t pairs_per_walk,
+                                                                const unsigned long long *fill,
+                                                                uint32_t *const *pool_blocks,
+                                                                unsigned long long *last_walk) {
+    GV_DYNAMIC_SHARED(uint2, tile);  // [walk_length + 1][kTileWalks]
+    const uint32_t w0 = blockIdx.x * kTileWalks;
+    const uint32_t walks = min(uint32_t(kTileWalks), num_walk - w0);
+    const unsigned long long first = fill[0] + (unsigned long long)w0 * pairs_per_walk;  // slice offset of the tile
+    if (first >= p.slice)
+        return;
+    for (uint32_t e = threadIdx.x; e < uint32_t(p.walk_length + 1) * kTileWalks; e += blockDim.x) {
+        const uint32_t j = e / kTileWalks, w = e % kTileWalks;
+        if (w < walks)
+            tile[e] = chains[size_t(j) * num_walk + w0 + w];
+    }
+    __syncthreads();
+    uint2 *block = reinterpret_cast<uint2 *>(pool_blocks[0]);
+    const unsigned long long count = min((unsigned long long)walks * pairs_per_walk, p.slice - first);
+    const unsigned long long g0 = p.start + first, base = p.shuffle_base, stride = p.pool_size / base;
+    // pairs (j, k) of a walk in emission order: j-major, k = 1 .. min(augmentation_step, walk_length - j); the first
+    // `full` values of j have all augmentation_step pairs
+    const uint32_t aug = uint32_t(p.augmentation_step), L = uint32_t(p.walk_length);
+    const uint32_t full = L >= aug ? L - aug + 1 : 0;
+    for (unsigned long long c = 0; c < base && c < count; c++) {
+        const unsigned long long members = (count - c + base - 1) / base;
+        // (g0 + c + q * base) / base = (g0 + c) / base + q: one 64-bit division per class, none per pair
+        const unsigned long long cell = (g0 + c) % base * stride + (g0 + c) / base;
+        for (uint32_t q = threadIdx.x; q < members; q += blockDim.x) {
+            const uint32_t i = uint32_t(c) + q * uint32_t(base);  // position inside the tile's range (< 2^32)
+            const uint32_t w = i / pairs_per_walk;
+            uint32_t position = i % pairs_per_walk, j, k;
+            if (position < full * aug) {
+                j = position / aug;
+                k = position % aug + 1;
+            } else {  // the last walk positions emit walk_length - j < augmentation_step pairs each
+                position -= full * aug;
+                j = full;
+                while (position >= L - j) {
+                    position -= L - j;
+                    j++;
+                }
+                k = position + 1;
+            }
+            const uint2 head = tile[j * kTileWalks + w], tail = tile[(j + k) * kTileWalks + w];
+            if (block)
+                block[cell + q] = make_uint2(tail.y, head.y);
+            if (first + i + 1 == p.slice)
+                atomicMax(last_walk, first_walk + w0 + w);
+        }
+    }
+}
+
 __global__ void fill_advance_kernel(unsigned long long *fill, unsigned long long amount) {
     fill[0] += amount;
 }
@@ -488,8 +552,13 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
         // every walk is full length, so pair (w, j, k) sits at stream index w * pairs_per_walk + f(j, k);
         // fill[0] is read on the device and advanced by a 1-thread kernel behind the fill (same stream)
         const uint32_t per_walk = pairs_per_walk(p.walk_length, p.augmentation_step);
-        GV_LAUNCH(blocks, threads, 0, s, fill_direct_kernel)(p, c, num_walk, first_walk, per_walk, fill, pool_blocks,
-                                                      last_walk);
+        const size_t tile_bytes = size_t(p.walk_length + 1) * kTileWalks * sizeof(uint2);
+        if (p.walk_length > 1 && !p.attributes && tile_bytes <= 48 * 1024 && !gv::direct_fill_per_walk())
+            GV_LAUNCH((num_walk + kTileWalks - 1) / kTileWalks, 256, tile_bytes, s, fill_direct_tiled_kernel)(
+                p, c, num_walk, first_walk, per_walk, fill, pool_blocks, last_walk);
+        else
+            GV_LAUNCH(blocks, threads, 0, s, fill_direct_kernel)(p, c, num_walk, first_walk, per_walk, fill, pool_blocks,
+                                                          last_walk);
         GV_CUDA_OK(cudaGetLastError());
         GV_LAUNCH(1, 1, 0, s, fill_advance_kernel)(fill, (unsigned long long)num_walk * per_walk);
         GV_CUDA_OK(cudaGetLastError());

@@ -630,6 +630,9 @@ static int g_blocks_per_sm = getenv("GV_TRAIN_BLOCKS_PER_SM") ? atoi(getenv("GV_
 static int g_reserve_sms = getenv("GV_TRAIN_RESERVE_SMS") ? atoi(getenv("GV_TRAIN_RESERVE_SMS")) : 0;
 // experiment: cap the grid of the walk kernels (grid-stride loops), so that they take a slice of the device next to a
 // resident train launch instead of all of it between two launches (0 = one thread per walk)
+// comparison switch: 1 = fill the single-block pool with one thread per walk (scattered 8-byte stores) instead of the
+// tiled, coalesced fill
+static int g_fill_per_walk = getenv("GV_FILL_PER_WALK") ? atoi(getenv("GV_FILL_PER_WALK")) : 0;
 static int g_sampler_max_ctas = getenv("GV_SAMPLER_MAX_CTAS") ? atoi(getenv("GV_SAMPLER_MAX_CTAS")) : 0;
 
 // -----------------------------------------------------------------------------
@@ -738,6 +741,10 @@ int sampler_max_ctas() {
     return device::g_sampler_max_ctas;
 }
 
+bool direct_fill_per_walk() {
+    return device::g_fill_per_walk != 0;
+}
+
 }  // namespace gv
 
 using namespace gv;
@@ -806,6 +813,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_kernel_flags = int(value);
     else if (key == "train_blocks_per_sm")
         g_blocks_per_sm = int(value);
+    else if (key == "fill_per_walk")
+        g_fill_per_walk = int(value);
     else if (key == "sampler_max_ctas")
         g_sampler_max_ctas = int(value);
     else if (key == "train_reserve_sms")

@@ -173,3 +173,51 @@ def test_vertex_alias_tables_built_on_the_device_are_bit_identical():
         prob, alias = O.alias_build(weights[lo:hi])
         np.testing.assert_array_equal(tables["prob"][lo:hi].view(np.uint32), prob.view(np.uint32), err_msg="vertex %d" % v)
         np.testing.assert_array_equal(tables["alias"][lo:hi], alias.astype(np.uint32), err_msg="vertex %d" % v)
+
+
+@pytest.mark.parametrize("L,aug,shuffle_base", [(40, 5, 5), (7, 3, 1), (6, 6, 4), (4, 9, 3), (5, 2, 2), (2, 1, 7)])
+@pytest.mark.parametrize("per_walk_kernel", [0, 1])
+def test_single_block_fill_over_long_slices(L, aug, shuffle_base, per_walk_kernel):
+    """P = 1: the tiled, coalesced fill (a CTA owns 32 walks = one contiguous range of slice offsets, written class by
+    class of the pseudo shuffle) and the thread-per-walk fill (`fill_per_walk` = 1) against the sequential append, over
+    several launches that continue each other and a slice that ends inside the last one."""
+    import torch
+    import gpu_util
+    from graphvite_b200 import _lib
+    from gpu_util import stream_pointer
+    lib = _lib.lib
+    rng = np.random.RandomState(L * 10 + aug)
+    per_walk = sum(min(aug, L - j) for j in range(L))
+    walks = [70, 1, 333, 64, 5]
+    total = sum(walks) * per_walk
+    slice_length = total - per_walk * 3 - 1           # ends inside the last launch, not on a walk boundary
+    pool_size = (slice_length + 100 + shuffle_base) // shuffle_base * shuffle_base
+    start = 37 if 37 + slice_length <= pool_size else 0
+    end = start + slice_length
+    expected = [np.full((pool_size, 2), 0xFFFFFFFF, dtype=np.uint32)]
+    fill = np.zeros(1, dtype=np.int64)
+    d_pool = torch.full((pool_size, 2), -1, dtype=torch.int32, device=gpu_util.DEVICE)
+    pointers = torch.tensor([d_pool.data_ptr()], dtype=torch.int64, device=gpu_util.DEVICE)
+    d_fill = torch.zeros(1, dtype=torch.int64, device=gpu_util.DEVICE)
+    d_last = torch.zeros(1, dtype=torch.int64, device=gpu_util.DEVICE)
+    params = _lib.FillParams(1, L, aug, shuffle_base, pool_size, start, end)
+    assert lib.gv_cuda_set_tunable(b"fill_per_walk", per_walk_kernel) == 0
+    try:
+        first_walk, last_expected = 0, 0
+        for num_walk in walks:
+            chains = np.zeros((L + 1, num_walk, 2), dtype=np.uint32)
+            chains[:, :, 1] = rng.randint(0, 100000, (L + 1, num_walk))
+            last = sequential_fill(chains, 1, L, aug, shuffle_base, pool_size, start, end, fill, expected)
+            if last >= 0:
+                last_expected = max(last_expected, first_walk + last)
+            d_chains = gpu_util.to_device(torch.from_numpy(chains.view(np.int32)))
+            _lib.check(lib.gv_cuda_fill_pool(ctypes.byref(params), d_chains.data_ptr(), num_walk, first_walk,
+                                             pointers.data_ptr(), d_fill.data_ptr(), d_last.data_ptr(), None,
+                                             stream_pointer()))
+            gpu_util.synchronize()
+            first_walk += num_walk
+            np.testing.assert_array_equal(d_fill.cpu().numpy(), fill)
+    finally:
+        assert lib.gv_cuda_set_tunable(b"fill_per_walk", 0) == 0
+    np.testing.assert_array_equal(d_pool.cpu().numpy().view(np.uint32), expected[0])
+    assert int(d_last.cpu().numpy()[0]) == last_expected
