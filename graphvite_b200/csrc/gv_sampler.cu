@@ -328,6 +328,106 @@ __global__ void fill_scatter_kernel(const FillParams p, const uint2 *chains, uin
         atomicMax(last_walk, first_walk + w);
 }
 
+// fill_scatter_kernel with coalesced traffic.  The pairs a CTA emits for block b are a contiguous range of b's slice
+// offsets, starting at cta_bases[b][cta]: every thread parks its pairs in shared memory at (start of b inside the
+// CTA) + (offset - CTA base) and the CTA then writes block after block -- a staged block as one contiguous run of the
+// staging array, a pool block class by class of the pseudo shuffle (offsets = c mod shuffle_base are neighbours in
+// the pool), consecutive threads on consecutive addresses.  Shared memory: counters [num_block][T], block starts
+// [num_block + 1], kept counts [num_block], pairs [T * pairs_per_walk].
+__global__ void fill_scatter_tiled_kernel(const FillParams p, const uint2 *chains, uint32_t num_walk,
+                                          unsigned long long first_walk, const uint32_t *cta_bases,
+                                          uint32_t *const *pool_blocks, unsigned long long *last_walk,
+                                          const StageParams stage, uint32_t pairs_per_walk) {
+    GV_DYNAMIC_SHARED(uint32_t, counters);
+    const int T = blockDim.x, num_block = p.num_partition * p.num_partition;
+    uint32_t *block_start = counters + size_t(num_block) * T;  // [num_block + 1] first pair of block b in `pairs`
+    uint32_t *block_kept = block_start + num_block + 1;        // [num_block] pairs of b below the slice end
+    uint2 *pairs = reinterpret_cast<uint2 *>(block_kept + num_block + ((num_block * 2 + 1) & 1));  // 8-byte aligned
+    const uint32_t w = blockIdx.x * T + threadIdx.x;
+    for (int b = 0; b < num_block; b++)
+        counters[b * T + threadIdx.x] = 0;
+    if (w < num_walk)
+        count_walk_pairs(p, chains, num_walk, w, counters, T);
+    __syncthreads();
+    // per block: exclusive scan over the threads (slice offsets, saturating) and the CTA's total
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, num_warp = T >> 5;
+    const uint32_t slice = uint32_t(p.slice);
+    for (int b = warp; b < num_block; b += num_warp) {
+        const uint32_t cta_base = cta_bases[size_t(b) * gridDim.x + blockIdx.x];
+        uint32_t running = cta_base, total = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const uint32_t count = counters[b * T + t0 + lane];
+            uint32_t inclusive = count;
+            for (int delta = 1; delta < 32; delta <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inclusive, delta);
+                if (lane >= delta)
+                    inclusive += up;
+            }
+            const unsigned long long start = (unsigned long long)running + inclusive - count;
+            counters[b * T + t0 + lane] = uint32_t(min(start, (unsigned long long)slice));
+            const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+            const unsigned long long next = (unsigned long long)running + chunk_total;
+            running = uint32_t(min(next, (unsigned long long)slice));
+            total += chunk_total;
+        }
+        if (lane == 0) {
+            block_start[b + 1] = total;  // turned into a prefix sum below
+            block_kept[b] = min(total, slice - min(cta_base, slice));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        block_start[0] = 0;
+        for (int b = 0; b < num_block; b++)
+            block_start[b + 1] += block_start[b];
+    }
+    __syncthreads();
+    if (w < num_walk) {
+        bool completed = false;
+        for (int j = 0; j < p.walk_length; j++) {
+            const uint2 head = chains[size_t(j) * num_walk + w];
+            for (int k = 1; k <= p.augmentation_step && j + k <= p.walk_length; k++) {
+                const uint2 tail = chains[size_t(j + k) * num_walk + w];
+                const int b = head.x * p.num_partition + tail.x;
+                const uint32_t in_slice = counters[b * T + threadIdx.x];
+                if (in_slice < slice) {
+                    counters[b * T + threadIdx.x] = in_slice + 1;
+                    const uint32_t cta_base = cta_bases[size_t(b) * gridDim.x + blockIdx.x];
+                    pairs[block_start[b] + (in_slice - cta_base)] = make_uint2(tail.y, head.y);
+                    completed |= in_slice + 1 == slice;
+                }
+            }
+        }
+        if (completed)
+            atomicMax(last_walk, first_walk + w);
+    }
+    __syncthreads();
+    const unsigned long long base = p.shuffle_base, stride = p.pool_size / base;
+    for (int b = 0; b < num_block; b++) {
+        const uint32_t kept = block_kept[b];
+        if (kept == 0)
+            continue;
+        const uint32_t cta_base = cta_bases[size_t(b) * gridDim.x + blockIdx.x];
+        const uint2 *source = pairs + block_start[b];
+        if (stage.staging && stage.remote[b]) {
+            uint2 *run = stage.staging + stage.offsets[b] + (cta_base - stage.bases[b]);
+            for (uint32_t i = threadIdx.x; i < kept; i += T)
+                run[i] = source[i];
+            continue;
+        }
+        uint2 *block = reinterpret_cast<uint2 *>(pool_blocks[b]);
+        if (!block)
+            continue;
+        const unsigned long long g0 = p.start + cta_base;
+        for (unsigned long long c = 0; c < base && c < kept; c++) {
+            const uint32_t members = uint32_t((kept - c + base - 1) / base);
+            const unsigned long long cell = (g0 + c) % base * stride + (g0 + c) / base;
+            for (uint32_t q = threadIdx.x; q < members; q += T)
+                block[cell + q] = source[uint32_t(c) + q * uint32_t(base)];
+        }
+    }
+}
+
 // staging offsets: exclusive prefix sum of the rank's totals over the staged blocks (one small CTA)
 __global__ void fill_stage_offsets_kernel(int num_block, const unsigned char *remote, const unsigned long long *totals,
                                           unsigned long long *offsets) {
@@ -506,18 +606,67 @@ int gv_cuda_random_walk(const gv_device_graph_t *graph, const double *random, ui
 }
 
 // CTA size of the histogram kernels: as many walks per CTA as 48 KB of counters allow
-static int fill_threads(int num_partition) {
+static int fill_threads_untiled(int num_partition) {
     const int num_block = num_partition * num_partition;
     int threads = int((48 * 1024) / (size_t(num_block) * sizeof(uint32_t))) / 32 * 32;
     return threads > 128 ? 128 : (threads < 32 ? 32 : threads);
 }
 
+// shared memory of fill_scatter_tiled_kernel for T walks per CTA
+static size_t tiled_shared_bytes(int num_partition, uint32_t per_walk, int T) {
+    const size_t num_block = size_t(num_partition) * num_partition;
+    const size_t words = num_block * T + (num_block + 1) + num_block + ((num_block * 2 + 1) & 1);
+    return words * sizeof(uint32_t) + size_t(T) * per_walk * sizeof(uint2);
+}
+
+// The tiled scatter parks all pairs of a CTA in shared memory, which bounds the walks per CTA; count, scan and scatter
+// must agree on that number.  Returns the CTA size and whether the tiled kernel is used (pairs only, and at least
+// one warp of walks must fit into 160 KB).
+static int fill_threads(const FillParams &p, bool &tiled) {
+    int threads = fill_threads_untiled(p.num_partition);
+    tiled = false;
+    if (p.attributes || gv::direct_fill_per_walk())
+        return threads;
+    const uint32_t per_walk = pairs_per_walk(p.walk_length, p.augmentation_step);
+    while (threads > 32 && tiled_shared_bytes(p.num_partition, per_walk, threads) > 160 * 1024)
+        threads -= 32;
+    if (tiled_shared_bytes(p.num_partition, per_walk, threads) > 160 * 1024)
+        return fill_threads_untiled(p.num_partition);
+    tiled = true;
+    return threads;
+}
+
 size_t gv_cuda_fill_scratch_bytes(uint32_t num_walk, int num_partition) {
     if (num_partition <= 1)
         return 16;
-    const int threads = fill_threads(num_partition);
+    const int threads = 32;  // the smallest CTA any configuration uses: an upper bound of the CTA count
     const size_t num_cta = (size_t(num_walk) + threads - 1) / threads;
     return num_cta * num_partition * num_partition * sizeof(uint32_t) + 256;
+}
+
+// launches fill_scatter_kernel or its tiled variant (same arguments)
+static int launch_scatter(const FillParams &p, const uint2 *chains, uint32_t num_walk, unsigned long long first_walk,
+                          const uint32_t *cta_counts, uint32_t *const *pool_blocks, unsigned long long *last_walk,
+                          const StageParams &stage, cudaStream_t s) {
+    bool tiled;
+    const int T = fill_threads(p, tiled);
+    const int num_block = p.num_partition * p.num_partition;
+    const uint32_t num_cta = (num_walk + T - 1) / T;
+    if (!tiled) {
+        GV_LAUNCH(num_cta, T, size_t(num_block) * T * sizeof(uint32_t), s, fill_scatter_kernel)(
+            p, chains, num_walk, first_walk, cta_counts, pool_blocks, last_walk, stage);
+        GV_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    const uint32_t per_walk = pairs_per_walk(p.walk_length, p.augmentation_step);
+    const size_t shared = tiled_shared_bytes(p.num_partition, per_walk, T);
+    if (shared > 48 * 1024)
+        GV_CUDA_OK(cudaFuncSetAttribute(fill_scatter_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(shared)));
+    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_tiled_kernel)(p, chains, num_walk, first_walk, cta_counts,
+                                                                pool_blocks, last_walk, stage, per_walk);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
@@ -568,17 +717,16 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
         return fail("gv_cuda_fill_pool: scratch required for num_partition > 1");
     uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
     const int num_block = p.num_partition * p.num_partition;
-    const int T = fill_threads(p.num_partition);
+    bool tiled;
+    const int T = fill_threads(p, tiled);
     const uint32_t num_cta = (num_walk + T - 1) / T;
     const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
     GV_LAUNCH(num_cta, T, shared, s, fill_count_kernel)(p, c, num_walk, cta_counts);
     GV_CUDA_OK(cudaGetLastError());
     GV_LAUNCH(num_block, 1024, 0, s, fill_scan_kernel)(p, num_cta, cta_counts, fill, fill, nullptr);
     GV_CUDA_OK(cudaGetLastError());
-    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk,
-                                                   StageParams{nullptr, nullptr, nullptr, nullptr});
-    GV_CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_scatter(p, c, num_walk, first_walk, cta_counts, pool_blocks, last_walk,
+                          StageParams{nullptr, nullptr, nullptr, nullptr}, s);
 }
 
 }  // extern "C"
@@ -624,7 +772,8 @@ int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chai
         return 0;
     }
     uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
-    const int T = fill_threads(p.num_partition);
+    bool tiled;
+    const int T = fill_threads(p, tiled);
     const uint32_t num_cta = (num_walk + T - 1) / T;
     const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
     GV_LAUNCH(num_cta, T, shared, s, fill_count_kernel)(p, reinterpret_cast<const uint2 *>(chains), num_walk, cta_counts);
@@ -678,9 +827,9 @@ int gv_cuda_fill_scatter_staged(const gv_fill_params_t *params, const gv_locatio
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint32_t *cta_counts = static_cast<uint32_t *>(scratch);
     const int num_block = p.num_partition * p.num_partition;
-    const int T = fill_threads(p.num_partition);
+    bool tiled;
+    const int T = fill_threads(p, tiled);
     const uint32_t num_cta = (num_walk + T - 1) / T;
-    const size_t shared = size_t(num_block) * T * sizeof(uint32_t);
     GV_LAUNCH(dim3((num_cta + 255) / 256, num_block), 256, 0, s, fill_rebase_kernel)(p.slice, num_cta, cta_counts, bases);
     GV_CUDA_OK(cudaGetLastError());
     StageParams stage{nullptr, nullptr, nullptr, nullptr};
@@ -689,9 +838,9 @@ int gv_cuda_fill_scatter_staged(const gv_fill_params_t *params, const gv_locatio
         GV_LAUNCH(1, 32, 0, s, fill_stage_offsets_kernel)(num_block, remote_blocks, totals, stage_offsets);
         GV_CUDA_OK(cudaGetLastError());
     }
-    GV_LAUNCH(num_cta, T, shared, s, fill_scatter_kernel)(p, reinterpret_cast<const uint2 *>(chains), num_walk, first_walk,
-                                                   cta_counts, pool_blocks, last_walk, stage);
-    GV_CUDA_OK(cudaGetLastError());
+    if (launch_scatter(p, reinterpret_cast<const uint2 *>(chains), num_walk, first_walk, cta_counts, pool_blocks,
+                       last_walk, stage, s))
+        return -1;
     if (staged) {
         // enough CTAs per block to keep the copy engines of the NVLink path busy, few enough to stay cheap
         const uint64_t per_block = uint64_t(num_walk) * pairs_per_walk(p.walk_length, p.augmentation_step) / num_block;
