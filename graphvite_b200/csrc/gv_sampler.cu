@@ -621,16 +621,17 @@ static size_t tiled_shared_bytes(int num_partition, uint32_t per_walk, int T) {
 
 // The tiled scatter parks all pairs of a CTA in shared memory, which bounds the walks per CTA; count, scan and scatter
 // must agree on that number.  Returns the CTA size and whether the tiled kernel is used (pairs only, and at least
-// one warp of walks must fit into 160 KB).
+// one warp of walks must fit into 200 KB).
 static int fill_threads(const FillParams &p, bool &tiled) {
     int threads = fill_threads_untiled(p.num_partition);
     tiled = false;
     if (p.attributes || gv::direct_fill_per_walk())
         return threads;
     const uint32_t per_walk = pairs_per_walk(p.walk_length, p.augmentation_step);
-    while (threads > 32 && tiled_shared_bytes(p.num_partition, per_walk, threads) > 160 * 1024)
+    // <= 110 KB keeps two CTAs on an SM (228 KB); a single warp of walks may take up to 200 KB
+    while (threads > 32 && tiled_shared_bytes(p.num_partition, per_walk, threads) > 110 * 1024)
         threads -= 32;
-    if (tiled_shared_bytes(p.num_partition, per_walk, threads) > 160 * 1024)
+    if (tiled_shared_bytes(p.num_partition, per_walk, threads) > 200 * 1024)
         return fill_threads_untiled(p.num_partition);
     tiled = true;
     return threads;
