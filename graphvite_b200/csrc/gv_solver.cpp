@@ -170,6 +170,7 @@ struct Solver {
     // (tiny) generator kernel slips into SM slots freed between train launches instead of delaying one
     static const int kRandomBuffers = 4;
     DeviceArray d_random[kRandomBuffers], d_lr, d_loss, d_negatives_out;
+    DeviceArray d_random_step;  // the worker's randoms of a whole sub-episode, when they fit (see train_block)
     cudaEvent_t random_ready[kRandomBuffers] = {}, random_free[kRandomBuffers] = {};
     int chunk_batches = 1;
     bool capture_negatives = false;
@@ -1141,16 +1142,34 @@ struct Solver {
         std::vector<float> lr(episode_size), loss(episode_size);
         std::vector<cudaEvent_t> timers;
         int buffer = 0;
+        // The stream is positional (one call for n batches == n calls for one batch), and a call is 4096 sequential
+        // XORWOW streams however short it is: the randoms of the whole sub-episode are generated by ONE call when they
+        // fit 2 GB (long calls are split by skip-ahead, gv_rng.cu) instead of one 4096-thread launch per chunk that the
+        // next train launch has to wait for.  GV_RNG_PER_CHUNK=1 keeps the per-chunk calls.
+        const uint64_t step_random = uint64_t(episode_size) * per_batch_random;
+        const bool whole_step = num_negative > 0 && step_random * sizeof(double) <= (uint64_t(2) << 30) &&
+                                !getenv("GV_RNG_PER_CHUNK");
+        if (whole_step)
+            d_random_step.allocate(step_random * sizeof(double));
         for (int reuse = 0; reuse < positive_reuse; reuse++) {
             for (int j = 0; j < episode_size; j++)
                 lr[j] = optimizer.lr_at(first_batch + (reuse * episode_size + j) * batch_stride, num_batch);
             GV_CHECK_CUDA(cudaMemcpyAsync(d_lr.ptr, lr.data(), episode_size * sizeof(float), cudaMemcpyHostToDevice,
                                           work_stream));
             GV_CHECK_CUDA(cudaMemsetAsync(d_loss.ptr, 0, episode_size * sizeof(float), work_stream));
+            if (whole_step) {  // random_free[0] / random_ready[0] guard the step buffer
+                GV_CHECK_CUDA(cudaStreamWaitEvent(random_stream, random_free[0], 0));
+                GV_CHECK_ABI(gv_rng_generate(worker_generator, d_random_step.as<double>(), step_random, random_stream));
+                stat_launches++;
+                GV_CHECK_CUDA(cudaEventRecord(random_ready[0], random_stream));
+                GV_CHECK_CUDA(cudaStreamWaitEvent(work_stream, random_ready[0], 0));
+            }
             for (int j0 = 0; j0 < episode_size; j0 += chunk_batches, buffer = (buffer + 1) % kRandomBuffers) {
                 const int count = std::min(chunk_batches, episode_size - j0);
+                const double *chunk_random = whole_step ? d_random_step.as<double>() + uint64_t(j0) * per_batch_random
+                                                        : d_random[buffer].as<double>();
                 // negatives: one curandGenerateUniformDouble(2 * B * k) per batch, like train_batch (solver.h:1536)
-                if (num_negative > 0) {
+                if (num_negative > 0 && !whole_step) {
                     GV_CHECK_CUDA(cudaStreamWaitEvent(random_stream, random_free[buffer], 0));
                     // (the stream is positional: one call for the chunk == one call per batch)
                     GV_CHECK_ABI(gv_rng_generate(worker_generator, d_random[buffer].as<double>(),
@@ -1175,7 +1194,7 @@ struct Solver {
                         j1++;
                     GV_CHECK_ABI(gv_cuda_train_block(
                         &matrices, pool + uint64_t(j) * batch_size * 2, uint64_t(j1 - j) * batch_size, num_negative,
-                        nullptr, d_random[buffer].as<double>() + uint64_t(j - j0) * per_batch_random,
+                        nullptr, chunk_random + uint64_t(j - j0) * per_batch_random,
                         negative_tables[g].as<gv_alias_entry_t>(), negative_counts[g],
                         capture_negatives ? d_negatives_out.as<uint32_t>() + uint64_t(j - j0) * batch_size * num_negative
                                           : nullptr,
@@ -1185,7 +1204,8 @@ struct Solver {
                     j = j1;
                 }
                 GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
-                GV_CHECK_CUDA(cudaEventRecord(random_free[buffer], work_stream));
+                if (!whole_step)
+                    GV_CHECK_CUDA(cudaEventRecord(random_free[buffer], work_stream));
                 timers.push_back(begin);
                 timers.push_back(end);
                 if (capture_negatives && reuse == positive_reuse - 1 && j0 + count == episode_size) {
@@ -1196,6 +1216,8 @@ struct Solver {
                                                   last_negatives.size() * 4, cudaMemcpyDeviceToHost, work_stream));
                 }
             }
+            if (whole_step)
+                GV_CHECK_CUDA(cudaEventRecord(random_free[0], work_stream));
             GV_CHECK_CUDA(cudaMemcpyAsync(loss.data(), d_loss.ptr, episode_size * sizeof(float),
                                           cudaMemcpyDeviceToHost, work_stream));
             GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
@@ -1383,7 +1405,7 @@ struct Solver {
             pool_pointers[side].release();
         for (auto *a : {&d_offsets, &d_edge_u, &d_edge_v, &d_edge_prob, &d_edge_alias, &d_vertex_tables, &d_locations,
                         &d_sampler_random, &d_chains, &d_fill, &d_last_walk, &d_fill_scratch, &d_random[0],
-                        &d_random[1], &d_random[2], &d_random[3], &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_stage,
+                        &d_random[1], &d_random[2], &d_random[3], &d_random_step, &d_lr, &d_loss, &d_negatives_out, &d_peer_controls, &d_totals, &d_bases, &d_stage,
                         &d_stage_offsets, &d_remote_blocks, &d_edge_tables,
                         &d_table_offsets})
             a->release();

@@ -201,6 +201,44 @@ def test_move_rows_round_trip():
     np.testing.assert_array_equal(d_back.cpu().numpy(), expected)
 
 
+def test_rng_long_calls_split_by_skip_ahead_equal_the_sequential_stream():
+    """A call of >= 2 * 1024 doubles per subsequence is generated by several threads per subsequence (XORWOW skip-ahead
+    to each piece).  Same stream as the one-thread-per-subsequence kernel (which the cuRAND goldens pin), same state
+    afterwards, for a start position and a length that are not multiples of 4096."""
+    import torch
+    import gpu_util
+    from graphvite_b200 import _lib
+    from gpu_util import stream_pointer
+    lib = _lib.lib
+
+    def generate(rng, n):
+        out = torch.zeros(n, dtype=torch.float64, device=gpu_util.DEVICE)
+        _lib.check(lib.gv_rng_generate(rng, out.data_ptr(), n, stream_pointer()))
+        gpu_util.synchronize()
+        return out.cpu().numpy()
+
+    long_call = 3 * 1024 * 4096 + 1234  # 3 pieces per subsequence
+    a, b = lib.gv_rng_create(777, stream_pointer()), lib.gv_rng_create(777, stream_pointer())
+    assert a and b
+    head_a, head_b = generate(a, 1001), generate(b, 1001)
+    np.testing.assert_array_equal(head_a, head_b)
+    whole = generate(a, long_call)                                           # segmented
+    pieces = []
+    remaining = long_call
+    while remaining:                                                         # sequential kernel: short calls
+        n = min(remaining, 4096 * 1000 + 77)
+        pieces.append(generate(b, n))
+        remaining -= n
+    np.testing.assert_array_equal(whole, np.concatenate(pieces))
+    assert lib.gv_rng_position(a) == lib.gv_rng_position(b) == 1001 + long_call
+    np.testing.assert_array_equal(generate(a, 50000), generate(b, 50000))   # the states agree afterwards
+    whole = generate(a, long_call)                                           # and a second long call continues
+    tail = np.concatenate([generate(b, long_call - 4096 * 1500), generate(b, 4096 * 1500)])
+    np.testing.assert_array_equal(whole, tail)
+    lib.gv_rng_destroy(a)
+    lib.gv_rng_destroy(b)
+
+
 def test_rng_reproduces_curand_stream(golden_dir):
     """gv_rng (our XORWOW kernel) == cuRAND's device generator (golden from the reference harness) ==
     cuRAND's host generator (oracle), for any call split; snapshots rewind it exactly."""

@@ -22,6 +22,7 @@ run() {
 run "default" GV_LOG=0
 run "direct_peer_scatter" GV_DIRECT_PEER_SCATTER=1
 run "fill_per_walk (round-1 fill kernels)" GV_FILL_PER_WALK=1
+run "rng_per_chunk (round-1 generator calls)" GV_RNG_PER_CHUNK=1 GV_RNG_SEQUENTIAL=1
 run "dynamic_chunks" GV_KERNEL_FLAGS=8
 run "dynamic_chunks,sampler_max_ctas=64" GV_KERNEL_FLAGS=8 GV_SAMPLER_MAX_CTAS=64
 run "dynamic_chunks,reserve_sms=8" GV_KERNEL_FLAGS=8 GV_TRAIN_RESERVE_SMS=8
