@@ -237,12 +237,19 @@ void run(dim3 grid, dim3 block, size_t shared_bytes, const std::function<void()>
     g_block = block;
     g_num_thread = int(threads);
     gv_emu_set_dimensions(grid, block);
-    g_shared.assign(shared_bytes + 16, 0xA5);
+    // dynamic shared memory + a canary behind it: a CTA that writes past the bytes it asked for aborts the run
+    constexpr size_t kCanary = 256;
+    g_shared.assign(shared_bytes + 16 + kCanary, 0xA5);
+    const unsigned char *canary = static_cast<const unsigned char *>(dynamic_shared()) + shared_bytes;
     for (unsigned z = 0; z < grid.z; z++)
         for (unsigned y = 0; y < grid.y; y++)
             for (unsigned x = 0; x < grid.x; x++) {
                 gv_emu_set_block_index(x, y, z);
                 run_block();
+                for (size_t i = 0; i < kCanary; i++)
+                    if (canary[i] != 0xA5)
+                        die("a CTA wrote " + std::to_string(i + 1) + "+ bytes past its " + std::to_string(shared_bytes) +
+                            " bytes of dynamic shared memory");
             }
     g_body = nullptr;
     g_in_kernel = false;
