@@ -382,8 +382,17 @@ def main():
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)
-    else:
+        return
+    try:
         run_ours(args, cfg)
+    except BaseException:
+        # leave at once: a rank that unwinds normally would first wait for its sampler thread, which may be waiting
+        # for the peers -- torchrun only stops the other ranks once this process is gone
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":
