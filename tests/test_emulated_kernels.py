@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # (files, what they cover)
 GROUPS = [
-    (["tests/test_gpu_kernels.py"], "train / sample / predict / rng / move_rows kernels"),
+    (["tests/test_gpu_kernels.py", "tests/test_gpu_yy_later_kernels.py"],
+     "train / sample / predict / rng / move_rows kernels"),
     (["tests/test_gpu_y_fill.py"], "pool-fill kernels (count / scan / scatter, direct)"),
     (["tests/test_gpu_solver.py", "tests/test_gpu_x_solver_more.py"], "GraphSolver end to end vs the oracle"),
     (["tests/test_gpu_zz_kg_kernels.py", "tests/test_gpu_zz_kg_solver.py", "tests/test_gpu_zzzz_kg_full_size.py"],

@@ -89,33 +89,6 @@ def test_train_full_grid_race_free(dim, opt, k):
     compare(got, v, c, m, loss)
 
 
-@pytest.mark.parametrize("opt,k,num_warps", [("SGD", 1, 0), ("SGD", 1, 3), ("Adam", 2, 0), ("SGD", 1, 1)])
-def test_dynamic_chunk_scheduling_covers_every_sample_once(opt, k, num_warps):
-    """kernel_flags & 8: warps take their 32-sample chunks by ticket.  Distinct rows make the order irrelevant, so
-    the result must equal the oracle's (every sample trained exactly once); three launches in a row check that the
-    counter is re-armed by the last warp of a launch; one warp alone keeps the sequential order (colliding rows)."""
-    from graphvite_b200 import _lib
-    from gpu_util import run_train_block
-    optimizer = O.OPTIMIZERS[opt]
-    moments = 0 if opt == "SGD" else 2
-    dim, n = 128, 40000 if num_warps != 1 else 700
-    unique = num_warps != 1
-    rows = n if unique else 50
-    vertex, context, ms, batch, negatives = make_problem(dim, n, k, rows, rows * (k + 1) if unique else 80, seed=9,
-                                                         unique=unique, moments=moments)
-    lr = np.full(4, optimizer[1], dtype=np.float32)
-    batch_size = (n + 3) // 4
-    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives.reshape(n, k), optimizer, 5.0, lr, batch_size)
-    assert _lib.lib.gv_cuda_set_tunable(b"kernel_flags", 8) == 0
-    try:
-        for _ in range(3):
-            got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr,
-                                  batch_size=batch_size, num_warps=num_warps)
-            compare(got, v, c, m, loss)
-    finally:
-        assert _lib.lib.gv_cuda_set_tunable(b"kernel_flags", 0) == 0
-
-
 def test_train_large_k_shared_memory_opt_in():
     """k = 200 needs > 48 KB of dynamic shared memory for the id staging"""
     from gpu_util import run_train_block
@@ -199,44 +172,6 @@ def test_move_rows_round_trip():
     expected = np.zeros_like(matrix)
     expected[ids] = matrix[ids]
     np.testing.assert_array_equal(d_back.cpu().numpy(), expected)
-
-
-def test_rng_long_calls_split_by_skip_ahead_equal_the_sequential_stream():
-    """A call of >= 2 * 1024 doubles per subsequence is generated by several threads per subsequence (XORWOW skip-ahead
-    to each piece).  Same stream as the one-thread-per-subsequence kernel (which the cuRAND goldens pin), same state
-    afterwards, for a start position and a length that are not multiples of 4096."""
-    import torch
-    import gpu_util
-    from graphvite_b200 import _lib
-    from gpu_util import stream_pointer
-    lib = _lib.lib
-
-    def generate(rng, n):
-        out = torch.zeros(n, dtype=torch.float64, device=gpu_util.DEVICE)
-        _lib.check(lib.gv_rng_generate(rng, out.data_ptr(), n, stream_pointer()))
-        gpu_util.synchronize()
-        return out.cpu().numpy()
-
-    long_call = 3 * 1024 * 4096 + 1234  # 3 pieces per subsequence
-    a, b = lib.gv_rng_create(777, stream_pointer()), lib.gv_rng_create(777, stream_pointer())
-    assert a and b
-    head_a, head_b = generate(a, 1001), generate(b, 1001)
-    np.testing.assert_array_equal(head_a, head_b)
-    whole = generate(a, long_call)                                           # segmented
-    pieces = []
-    remaining = long_call
-    while remaining:                                                         # sequential kernel: short calls
-        n = min(remaining, 4096 * 1000 + 77)
-        pieces.append(generate(b, n))
-        remaining -= n
-    np.testing.assert_array_equal(whole, np.concatenate(pieces))
-    assert lib.gv_rng_position(a) == lib.gv_rng_position(b) == 1001 + long_call
-    np.testing.assert_array_equal(generate(a, 50000), generate(b, 50000))   # the states agree afterwards
-    whole = generate(a, long_call)                                           # and a second long call continues
-    tail = np.concatenate([generate(b, long_call - 4096 * 1500), generate(b, 4096 * 1500)])
-    np.testing.assert_array_equal(whole, tail)
-    lib.gv_rng_destroy(a)
-    lib.gv_rng_destroy(b)
 
 
 def test_rng_reproduces_curand_stream(golden_dir):
