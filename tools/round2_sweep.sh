@@ -39,3 +39,14 @@ for hot in 256 512 1024 4096; do
     run "hot_rows=$hot" GV_HOT_ROWS=$hot
 done
 run "blocks_per_sm=3,hot_rows=512" GV_TRAIN_BLOCKS_PER_SM=3 GV_HOT_ROWS=512
+python - "$OUT" <<'PY'
+import json, sys
+print("%-52s %12s %10s %8s" % ("tag", "edges/s", "ms/step", "frac"))
+for line in open(sys.argv[1]):
+    row = json.loads(line)
+    r = row["result"]
+    if r:
+        print("%-52s %12.4g %10.2f %8.3f" % (row["tag"], r["value"], r["ms_per_step"], r["frac"]))
+    else:
+        print("%-52s failed" % row["tag"])
+PY
