@@ -12,6 +12,14 @@
 // (head part, tail part) block until that block's slice is full -- is a stable
 // partition, done as count / scan / scatter so that the pools are bit-identical to the
 // reference's (stream order preserved inside every block, pseudo-shuffle included).
+//
+// Memory traffic: a walk emits pairs_per_walk pairs (190 at L = 40, a = 5), so "one thread writes its walk's pairs"
+// means 32 lanes storing 8 bytes each to places ~1.5 KB apart.  The default fill kernels therefore stage a CTA's walks
+// in shared memory and write runs: fill_direct_tiled_kernel (one block: the offsets are analytic),
+// fill_scatter_tiled_kernel (P x P blocks: per-thread scan, pairs parked per block), fill_forward_kernel (pairs of
+// blocks owned by a peer GPU: staged locally, forwarded as 256-byte warp stores over NVLink).  The thread-per-walk
+// kernels remain for edge sampling (one pair per walk: already coalesced), for entries with attributes (knowledge
+// graphs) and as the comparison switch `fill_per_walk`.
 // =============================================================================
 #include <cuda_runtime.h>
 
