@@ -27,6 +27,25 @@ def test_abi_exports_every_declared_symbol():
     assert len(declared) >= 40
 
 
+def test_ctypes_signatures_have_the_arity_of_the_header():
+    """every prototype of include/gv_b200.h against graphvite_b200/_lib.py: the same number of parameters (a wrong
+    count is a silent stack bug with ctypes)"""
+    header = open(os.path.join(ROOT, "include", "gv_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    header = re.sub(r"typedef[^;{]*\(\s*\*\s*\w+\s*\)\s*\([^;]*\);", "", header)  # function-pointer typedefs
+    from graphvite_b200 import _lib
+    checked = 0
+    for name, parameters in re.findall(r"\b(gv_[a-z0-9_]+)\s*\(([^()]*(?:\([^()]*\)[^()]*)*)\)\s*;", header):
+        if name not in _lib.SIGNATURES:
+            continue
+        parameters = parameters.strip()
+        count = 0 if parameters in ("", "void") else parameters.count(",") + 1
+        assert len(_lib.SIGNATURES[name][1]) == count, "%s: %d parameters in the header, %d in _lib.py" % (
+            name, count, len(_lib.SIGNATURES[name][1]))
+        checked += 1
+    assert checked >= 100
+
+
 def test_missing_extension_fails_loudly(tmp_path, monkeypatch):
     """the product never falls back to CPU / PyTorch code when the .so is absent"""
     import importlib.util
