@@ -46,6 +46,31 @@ def test_ctypes_signatures_have_the_arity_of_the_header():
     assert checked >= 100
 
 
+def test_ctypes_structures_have_the_layout_of_the_header(tmp_path):
+    """sizeof and the offset of every member, as gcc lays out include/gv_b200.h, against the ctypes mirrors"""
+    import subprocess
+    from graphvite_b200 import _lib
+    pairs = {"gv_optimizer_t": _lib.OptimizerDesc, "gv_device_optimizer_t": _lib.DeviceOptimizer,
+             "gv_matrices_t": _lib.Matrices, "gv_device_graph_t": _lib.DeviceGraph, "gv_kg_matrices_t": _lib.KgMatrices,
+             "gv_device_kgraph_t": _lib.DeviceKGraph, "gv_table_shards_t": _lib.TableShards,
+             "gv_fill_params_t": _lib.FillParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gv_b200.h"', 'int main(void) {']
+    for c_name, mirror in pairs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (c_name, c_name))
+        for field in mirror._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (c_name, field[0], c_name, field[0]))
+    lines += ['return 0;', '}']
+    source = tmp_path / "layout.c"
+    source.write_text("\n".join(lines))
+    binary = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(source), "-o", binary])
+    for line in subprocess.check_output([binary], text=True).splitlines():
+        c_name, member, value = line.split()
+        mirror = pairs[c_name]
+        expected = ctypes.sizeof(mirror) if member == "sizeof" else getattr(mirror, member).offset
+        assert int(value) == expected, "%s.%s: %s in C, %d in ctypes" % (c_name, member, value, expected)
+
+
 def test_missing_extension_fails_loudly(tmp_path, monkeypatch):
     """the product never falls back to CPU / PyTorch code when the .so is absent"""
     import importlib.util
