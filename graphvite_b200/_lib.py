@@ -93,6 +93,7 @@ SIGNATURES = {
     "gv_rng_save": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gv_rng_restore": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gv_cuda_set_tunable": (c_int, [c_char_p, ctypes.c_long]),
+    "gv_cuda_get_tunable": (ctypes.c_long, [c_char_p]),
     "gv_cuda_sample_negatives": (c_int, [c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_void_p]),
     "gv_cuda_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
     "gv_cuda_random_walk": (c_int, [P(DeviceGraph), c_void_p, c_uint32, c_int, c_uint64, c_uint32, c_uint64,

@@ -524,6 +524,16 @@ struct Solver {
         logged_loss.clear();
     }
 
+    // batches per train launch (1 = the reference's launch granularity); the per-chunk random buffers follow
+    void set_chunk_batches(int value) {
+        require(built && !training, "chunk_batches can be set between build() and train()");
+        GV_CHECK_CUDA(cudaSetDevice(device));
+        chunk_batches = std::max(1, std::min(episode_size, value));
+        const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2 * sizeof(double);
+        for (int i = 0; i < kRandomBuffers; i++)
+            d_random[i].allocate(std::max<uint64_t>(16, per_batch_random * chunk_batches));
+    }
+
     // ---- device graph + sampler tables (GraphSolver::get_sample_function, graph.cuh:680-721) ----
     void prepare_sampling() {
         require(!graph->has_dead_end() || augmentation_step == 1,
@@ -1622,6 +1632,8 @@ int gv_solver_set_option(gv_solver_t *solver, const char *name, int value) {
         solver->solver->capture_negatives = value != 0;
     else if (std::string(name) == "train_num_warps")
         solver->solver->train_num_warps = value;
+    else if (std::string(name) == "chunk_batches")
+        solver->solver->set_chunk_batches(value);
     else
         throw std::runtime_error(std::string("unknown option `") + name + "`");
     return 0;

@@ -13,13 +13,17 @@
 //    exactly one 512-B warp-wide transaction), the vertex row lives in registers
 //    for the whole sample, dot products are butterfly warp-shuffle reductions and
 //    the Hogwild update is written back in place;
-//  * rows are loaded/stored with the .cg (L2-only) policy: a persistent kernel never
-//    flushes L1, and stale L1 copies of hub rows would otherwise hide other SMs'
-//    updates for the whole episode;
-//  * a warp takes 32 consecutive samples at a time: lane i loads sample i's
-//    {tail, head} pair (coalesced 256 B), draws its k negatives from the alias table
-//    (fused gpu::Sample) and parks the ids in shared memory, so index latency is paid
-//    once per 32 samples and every row address is known up front;
+//  * cache policy (TrainParams::flags / hot_rows): rows are read either L2-only
+//    (ld.global.cg) or through L1 (ld.global.ca, what the reference's plain loads compile to);
+//    the L1 path is incoherent across SMs exactly like the reference's, and how much of it is
+//    used decides how the Hogwild races fall -- the shipped setting is the one that passed the
+//    statistical parity test against the unmodified reference (tests/test_gpu_zzzzz_parity.py);
+//  * a warp stages 32 samples at a time: lane i loads sample i's {tail, head} pair, draws its k
+//    negatives from the alias table (fused gpu::Sample) and parks the ids in shared memory, so
+//    index latency is paid once per 32 samples and every row address is known up front.  The 32
+//    samples are either consecutive pool entries or (flags & 16) entries one grid-width apart,
+//    which is the reference's concurrency structure: neighbouring pool entries are trained by
+//    different warps at the same time, a warp's own samples lie far apart in the pool;
 //  * persistent grid: one launch consumes a whole pool block (any number of reference
 //    batches); the per-batch learning rate comes from a small array.
 // =============================================================================
@@ -57,8 +61,13 @@ struct TrainParams {
     uint32_t batch_size;
     float negative_weight;
     float *loss_per_sample, *loss_per_batch;
-    int flags;  // experiment switches: 1 = L1-cached (.ca) loads for ALL rows, 4 = never use train_sgd_kernel,
-                // 8 = warps claim their 32-sample chunks from a counter instead of a fixed stride
+    int flags;  // 1 = L1-cached (.ca) loads for ALL rows, 4 = never use train_sgd_kernel,
+                // 8 = warps claim their 32-sample chunks from a counter instead of a fixed stride,
+                // 16 = interleaved mapping: warp w trains samples w, w + G, w + 2G ... (G = warps of the grid), so
+                //      that neighbouring pool entries run concurrently on different warps like the reference's
+                //      one-warp-per-sample grid (instance/gpu/graph.cuh:54-60); ignored with 8,
+                // 32 = rows are stored with the default write-back policy (st.global, what the reference's stores
+                //      compile to: the writing SM's L1 copy stays current) instead of st.global.cg
     unsigned int *work_counter;  // flags & 8: {next ticket, warps done}; both zero between launches
     uint32_t hot_rows;  // rows with a local id below this are loaded through L1 (.ca), the rest L2-only (.cg)
 };
@@ -117,11 +126,29 @@ __device__ __forceinline__ void load_row(Row<DIM> &row, const float *base, int l
 }
 
 template<int DIM>
-__device__ __forceinline__ void store_row(const Row<DIM> &row, float *base, int lane) {
+__device__ __forceinline__ void store_row(const Row<DIM> &row, float *base, int lane, bool write_back = false) {
 #pragma unroll
     for (int p = 0; p < Row<DIM>::kPass; p++)
-        if (lane_active<DIM>(p, lane))
-            __stcg(reinterpret_cast<float4 *>(base) + p * 32 + lane, row.x[p]);
+        if (lane_active<DIM>(p, lane)) {
+            if (write_back)
+                reinterpret_cast<float4 *>(base)[p * 32 + lane] = row.x[p];
+            else
+                __stcg(reinterpret_cast<float4 *>(base) + p * 32 + lane, row.x[p]);
+        }
+}
+
+// Which samples a warp stages in its m-th visit.  Consecutive: chunk c covers pool entries [32c, 32c + 32).
+// Interleaved (flags & 16): the grid's G warps sweep the pool together -- in visit m warp w takes the entries
+// (32m + l) * G + w for l = 0..31, so at any moment the samples in flight form a window of about G consecutive
+// pool entries, one per warp.  One warp alone (G = 1, the parity tests' mode) visits the pool in order either way.
+struct ChunkMap {
+    unsigned long long first, step;
+    __device__ __forceinline__ unsigned long long sample(int lane) const { return first + step * lane; }
+};
+__device__ __forceinline__ ChunkMap map_chunk(bool interleaved, unsigned long long chunk, unsigned long long num_warp) {
+    if (!interleaved)
+        return {chunk * 32, 1};
+    return {(chunk / num_warp * 32) * num_warp + chunk % num_warp, num_warp};
 }
 
 __device__ __forceinline__ float warp_sum(float value) {
@@ -265,17 +292,23 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
     const unsigned long long num_chunk = (p.num_sample + 31) / 32;
     const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const gv_device_optimizer_t o = p.optimizer;
-    const bool l1 = p.flags & 1;
+    const bool l1 = p.flags & 1, wb = p.flags & 32;
+    const bool interleaved = (p.flags & 16) && !p.work_counter;
 
+    // interleaved: every warp owns pool entries however few there are; its loop ends at the `break` below
+    const unsigned long long chunk_limit = interleaved ? ~0ull : num_chunk;
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-         chunk < num_chunk; chunk = next_chunk(p, chunk, num_warp, lane)) {
-        const unsigned long long base = chunk * 32;
-        const unsigned long long i = base + lane;
+         chunk < chunk_limit; chunk = next_chunk(p, chunk, num_warp, lane)) {
+        const ChunkMap map = map_chunk(interleaved, chunk, num_warp);
+        if (map.first >= p.num_sample)
+            break;  // interleaved: this warp's share of the pool is exhausted (later visits start even further)
+        const unsigned long long i = map.sample(lane);
         const bool valid = i < p.num_sample;
         float lr_lane = 0.f;
         uint32_t batch_lane = 0;
         if (valid) {
-            const uint2 pair = __ldcs(p.pool + i);  // {tail, head}, streamed once
+            // {tail, head}; consecutive: streamed once, interleaved: the CTA's warps share the 32-byte sectors
+            const uint2 pair = interleaved ? __ldg(p.pool + i) : __ldcs(p.pool + i);
             ids[lane * stride] = pair.y;
             ids[lane * stride + 1 + k] = pair.x;
             for (int s = 0; s < k; s++) {
@@ -296,7 +329,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
         }
         __syncwarp();
 
-        const int count = int(min(32ull, p.num_sample - base));
+        const int count = __popc(__ballot_sync(kFullMask, valid));  // valid lanes are a prefix
         float loss_lane = 0.f;
         Row<DIM> v, vm1, vm2, c, cm1, cm2, c_next, cm1_next, cm2_next, v_ahead, c_ahead;
         uint32_t head = ids[0], tail = ids[1];
@@ -368,11 +401,11 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                         sample_loss += weight * -logf(1 - prob + kEpsilon);
                 }
                 backward<DIM, OPT>(o, lr, gradient, weight, v, c, vm1, cm1, vm2, cm2);
-                store_row<DIM>(c, p.context + size_t(tail) * DIM, lane);
+                store_row<DIM>(c, p.context + size_t(tail) * DIM, lane, wb);
                 if (NM >= 1)
-                    store_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane);
+                    store_row<DIM>(cm1, p.context_m1 + size_t(tail) * DIM, lane, wb);
                 if (NM >= 2)
-                    store_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane);
+                    store_row<DIM>(cm2, p.context_m2 + size_t(tail) * DIM, lane, wb);
                 stale_ahead |= tail == tail_ahead;
                 if (s < k && tail_next != tail) {
                     c = c_next;
@@ -383,11 +416,11 @@ __global__ void __launch_bounds__(kBlockThreads) train_kernel(const TrainParams 
                 }  // else: the same row again -- keep the just-updated registers
                 tail = tail_next;
             }
-            store_row<DIM>(v, p.vertex + head_offset, lane);
+            store_row<DIM>(v, p.vertex + head_offset, lane, wb);
             if (NM >= 1)
-                store_row<DIM>(vm1, p.vertex_m1 + head_offset, lane);
+                store_row<DIM>(vm1, p.vertex_m1 + head_offset, lane, wb);
             if (NM >= 2)
-                store_row<DIM>(vm2, p.vertex_m2 + head_offset, lane);
+                store_row<DIM>(vm2, p.vertex_m2 + head_offset, lane, wb);
             if (LOSS) {
                 sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
                 if (lane == t)
@@ -480,13 +513,13 @@ __device__ __forceinline__ float process_sample(SampleRows<DIM, K> &cur, SampleR
                 sample_loss += weight * -logf(1 - prob + kEpsilon);
         }
         backward<DIM, GV_OPT_SGD>(p.optimizer, lr, gradient, weight, cur.v, cur.c[s], unused, unused, unused, unused);
-        store_row<DIM>(cur.c[s], p.context + size_t(cur.tail[s]) * DIM, lane);
+        store_row<DIM>(cur.c[s], p.context + size_t(cur.tail[s]) * DIM, lane, p.flags & 32);
     }
     // consecutive samples of one walk often share the head (DeepWalk / node2vec: k = 1..augmentation_step
     // with shuffle_base 1): the row is carried in registers and written once at the end of the run
     const bool same_head = has_next && next.head == cur.head;
     if (!same_head)
-        store_row<DIM>(cur.v, p.vertex + size_t(cur.head) * DIM, lane);
+        store_row<DIM>(cur.v, p.vertex + size_t(cur.head) * DIM, lane, p.flags & 32);
     if (has_next) {  // forward what the next sample requested before these stores were issued
         if (same_head)
             next.v = cur.v;
@@ -510,16 +543,21 @@ __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainPar
     const unsigned long long num_chunk = (p.num_sample + 31) / 32;
     const unsigned long long num_warp = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const bool l1 = p.flags & 1;
+    const bool interleaved = (p.flags & 16) && !p.work_counter;
 
+    // interleaved: every warp owns pool entries however few there are; its loop ends at the `break` below
+    const unsigned long long chunk_limit = interleaved ? ~0ull : num_chunk;
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-         chunk < num_chunk; chunk = next_chunk(p, chunk, num_warp, lane)) {
-        const unsigned long long base = chunk * 32;
-        const unsigned long long i = base + lane;
+         chunk < chunk_limit; chunk = next_chunk(p, chunk, num_warp, lane)) {
+        const ChunkMap map = map_chunk(interleaved, chunk, num_warp);
+        if (map.first >= p.num_sample)
+            break;
+        const unsigned long long i = map.sample(lane);
         const bool valid = i < p.num_sample;
         float lr_lane = 0.f;
         uint32_t batch_lane = 0;
         if (valid) {
-            const uint2 pair = __ldcs(p.pool + i);  // {tail, head}, streamed once
+            const uint2 pair = interleaved ? __ldg(p.pool + i) : __ldcs(p.pool + i);  // {tail, head}
             ids[lane * stride] = pair.y;
             ids[lane * stride + 1 + K] = pair.x;
 #pragma unroll
@@ -541,7 +579,7 @@ __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainPar
         }
         __syncwarp();
 
-        const int count = int(min(32ull, p.num_sample - base));
+        const int count = __popc(__ballot_sync(kFullMask, valid));
         float loss_lane = 0.f;
         SampleRows<DIM, K> a, b;
         request_sample<DIM, K>(a, ids, p, lane, l1);
@@ -822,6 +860,24 @@ int gv_cuda_set_tunable(const char *name, long value) {
     else
         return fail("unknown tunable `" + key + "`");
     return 0;
+}
+
+long gv_cuda_get_tunable(const char *name) {
+    const std::string key = name ? name : "";
+    if (key == "hot_rows")
+        return long(g_hot_rows);
+    if (key == "kernel_flags")
+        return g_kernel_flags;
+    if (key == "train_blocks_per_sm")
+        return g_blocks_per_sm;
+    if (key == "fill_per_walk")
+        return g_fill_per_walk;
+    if (key == "sampler_max_ctas")
+        return g_sampler_max_ctas;
+    if (key == "train_reserve_sms")
+        return g_reserve_sms;
+    fail("unknown tunable `" + key + "`");
+    return -1;
 }
 
 int gv_cuda_sample_negatives(const gv_alias_entry_t *table, uint32_t count, const double *random, uint64_t num,

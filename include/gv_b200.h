@@ -122,6 +122,8 @@ int gv_rng_restore(gv_rng_t *rng, const void *snapshot, void *stream);
 /* Device-layer tunables: "hot_rows" = rows with a local id below this value are read through L1
  * (default 128; rows are in degree order, so these are the hubs), "kernel_flags" = experiment bits. */
 int gv_cuda_set_tunable(const char *name, long value);
+/* current value of a tunable, or -1 (and gv_last_error) for an unknown name */
+long gv_cuda_get_tunable(const char *name);
 
 /* gpu::Sample (base/alias_table.cuh:175-183): out[t] = table.sample(float(random[2t]), float(random[2t+1])). */
 int gv_cuda_sample_negatives(const gv_alias_entry_t *table, uint32_t count, const double *random, uint64_t num,

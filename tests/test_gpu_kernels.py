@@ -89,6 +89,55 @@ def test_train_full_grid_race_free(dim, opt, k):
     compare(got, v, c, m, loss)
 
 
+@pytest.fixture
+def kernel_flags():
+    """sets gv_cuda_set_tunable("kernel_flags") for one test and restores the library default afterwards"""
+    from graphvite_b200 import _lib
+
+    def set_flags(value):
+        _lib.check(_lib.lib.gv_cuda_set_tunable(b"kernel_flags", int(value)))
+    before = _lib.lib.gv_cuda_get_tunable(b"kernel_flags")
+    yield set_flags
+    set_flags(before)
+
+
+@pytest.mark.parametrize("flags", [16, 1 | 16 | 32, 1 | 32])
+@pytest.mark.parametrize("opt,k,dim,num_warps", [("SGD", 1, 128, 0), ("SGD", 1, 128, 5), ("SGD", 3, 64, 7),
+                                                 ("Adam", 2, 128, 3), ("Momentum", 5, 32, 0)])
+def test_train_interleaved_mapping_race_free(kernel_flags, flags, opt, k, dim, num_warps):
+    """flags & 16: warp w trains the pool entries w, w + G, w + 2G ... (the reference's concurrency structure);
+    flags & 32: write-back stores; flags & 1: every row through L1.  On a batch whose rows are all distinct the
+    mapping and the cache policy cannot change the result; 2 999 samples leave a ragged last visit."""
+    from gpu_util import run_train_block
+    kernel_flags(flags)
+    optimizer = O.OPTIMIZERS[opt]
+    moments = 0 if opt == "SGD" else (2 if opt == "Adam" else 1)
+    n = 2999
+    vertex, context, ms, batch, negatives = make_problem(dim, n, k, n, n * (k + 1), seed=k + dim + flags, unique=True,
+                                                         moments=moments)
+    lr = np.array([optimizer[1], optimizer[1] * 0.5, optimizer[1] * 0.25], dtype=np.float32)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives.reshape(n, k), optimizer, 5.0, lr, 1000)
+    got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr, batch_size=1000,
+                          num_warps=num_warps)
+    compare(got, v, c, m, loss)
+    expected_batch = np.array([loss[i:i + 1000].sum() for i in range(0, n, 1000)])
+    np.testing.assert_allclose(got["batch_loss"], expected_batch, rtol=1e-4)
+
+
+@pytest.mark.parametrize("flags", [16, 1 | 16 | 32])
+def test_train_interleaved_single_warp_is_sequential(kernel_flags, flags):
+    """one warp alone visits the pool in order in either mapping: collisions resolve as in the reference's loop"""
+    from gpu_util import run_train_block
+    kernel_flags(flags)
+    optimizer = O.OPTIMIZERS["SGD"]
+    dim, n, k = 128, 257, 1
+    vertex, context, ms, batch, negatives = make_problem(dim, n, k, 40, 50, seed=11)
+    lr = np.array([optimizer[1], optimizer[1] * 0.5, optimizer[1] * 0.25], dtype=np.float32)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr, 100)
+    got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr, batch_size=100, num_warps=1)
+    compare(got, v, c, m, loss)
+
+
 def test_train_large_k_shared_memory_opt_in():
     """k = 200 needs > 48 KB of dynamic shared memory for the id staging"""
     from gpu_util import run_train_block

@@ -1,0 +1,166 @@
+#!/usr/bin/env python
+"""Shipped-mode float parity against the UNMODIFIED reference, and what each kernel policy costs.
+
+For one workload (BlogCatalog-shaped quick start, Youtube-shaped LINE) this trains the same split
+ * with the reference (oracle/_ref/libgraphvite.so through its own pybind API) `--repeat` times, and
+ * with graphvite_b200 under every kernel policy of SETTINGS `--repeat` times,
+and records embedding L2 norms, held-out link-prediction AUC (Dataset.link_prediction_split semantics), the
+wall time of train() and the train kernel's edges/s.  One JSON object per run, then one summary per setting
+with the distance to the reference's mean and the reference's own run-to-run spread.
+
+    python tools/parity_sweep.py --workload blogcatalog --epochs 2000 --out gpurun_out/parity_blogcatalog.jsonl
+
+MEASUREMENT TOOLING (it executes oracle/_ref); not part of the product.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+from validate_parity import auc_of, make_split  # noqa: E402
+
+# name -> tunables (gv_cuda_set_tunable) + chunk_batches (solver option) + num_partition
+SETTINGS = {
+    # round-1 shipped policy: hub rows through L1, everything else L2-only, 16 batches per launch
+    "r1_shipped": dict(hot_rows=128, kernel_flags=0, chunk_batches=16),
+    "l2_only": dict(hot_rows=0, kernel_flags=0, chunk_batches=16),
+    "hot128_chunk1": dict(hot_rows=128, kernel_flags=0, chunk_batches=1),
+    # the reference's memory policy: every row through L1, write-back stores; 1 or 16 batches per launch
+    "all_l1_chunk16": dict(hot_rows=0, kernel_flags=1, chunk_batches=16),
+    "all_l1_chunk1": dict(hot_rows=0, kernel_flags=1, chunk_batches=1),
+    "all_l1_wb_chunk16": dict(hot_rows=0, kernel_flags=1 | 32, chunk_batches=16),
+    "all_l1_wb_chunk1": dict(hot_rows=0, kernel_flags=1 | 32, chunk_batches=1),
+    # + the reference's concurrency structure: neighbouring pool entries on different warps
+    "interleaved_l2": dict(hot_rows=0, kernel_flags=16, chunk_batches=16),
+    "interleaved_hot128": dict(hot_rows=128, kernel_flags=16, chunk_batches=16),
+    "interleaved_all_l1_chunk16": dict(hot_rows=0, kernel_flags=1 | 16, chunk_batches=16),
+    "interleaved_all_l1_wb_chunk16": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=16),
+    "interleaved_all_l1_wb_chunk4": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=4),
+    "interleaved_all_l1_wb_chunk1": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=1),
+    "hot1024": dict(hot_rows=1024, kernel_flags=0, chunk_batches=16),
+    "hot8192": dict(hot_rows=8192, kernel_flags=0, chunk_batches=16),
+    "interleaved_hot1024": dict(hot_rows=1024, kernel_flags=16, chunk_batches=16),
+    "interleaved_all_l1_wb_chunk1_3cta": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=1,
+                                              train_blocks_per_sm=3),
+}
+
+
+def apply(gv, setting):
+    for name in ("hot_rows", "kernel_flags", "train_blocks_per_sm"):
+        gv._clib.gv_cuda_set_tunable(name.encode(), int(setting.get(name, 0)))
+
+
+def run_ours(gv, cfg, graph, test, epochs, setting, num_partition):
+    from graphvite_b200 import _lib
+    gv._clib.gv_reset_global_engine(5489)
+    apply(gv, setting)
+    solver = gv.solver.GraphSolver(cfg["dim"], device_ids=[0])
+    solver.build(graph, gv.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), num_partition=num_partition,
+                 num_negative=cfg["num_negative"], batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
+    _lib.check(_lib.lib.gv_solver_set_option(solver._handle, b"chunk_batches", int(setting["chunk_batches"])))
+    start = time.time()
+    solver.train(**bench.train_kwargs(cfg, epochs))
+    seconds = time.time() - start
+    vertex, context = solver.vertex_embeddings, solver.context_embeddings
+    scores = lambda pairs: np.einsum("ij,ij->i", vertex[pairs[:, 0]], context[pairs[:, 1]])
+    stats = solver.stats
+    row = {"vertex_norm": float(np.linalg.norm(vertex)), "context_norm": float(np.linalg.norm(context)),
+           "auc": auc_of(scores, graph.name2id, test), "seconds": seconds, "edges": solver.batch_id * cfg["batch_size"],
+           "kernel_edges_per_s": stats["positives"] / max(stats["kernel_seconds"], 1e-9),
+           "train_loop_edges_per_s": stats["positives"] / max(stats["train_seconds"], 1e-9),
+           "num_partition": solver.num_partition}
+    solver.close()
+    return row
+
+
+def run_reference(ref, cfg, path, test, epochs):
+    graph = ref.graph.Graph_j()
+    graph.load(path, True, False)
+    solver = getattr(ref.solver, "GraphSolver_%d_f_j" % cfg["dim"])([0], 0, 0)
+    solver.build(graph, ref.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), 0, cfg["num_negative"],
+                 cfg["batch_size"], cfg["episode_size"])
+    start = time.time()
+    solver.train(model=cfg["model"], num_epoch=epochs, augmentation_step=cfg["augmentation_step"],
+                 random_walk_length=cfg["random_walk_length"], random_walk_batch_size=cfg["random_walk_batch_size"],
+                 negative_weight=cfg["negative_weight"], log_frequency=1 << 30)
+    seconds = time.time() - start
+    vertex, context = np.array(solver.vertex_embeddings), np.array(solver.context_embeddings)
+    scores = lambda pairs: np.einsum("ij,ij->i", vertex[pairs[:, 0]], context[pairs[:, 1]])
+    return {"vertex_norm": float(np.linalg.norm(vertex)), "context_norm": float(np.linalg.norm(context)),
+            "auc": auc_of(scores, graph.name2id, test), "seconds": seconds}
+
+
+def summarise(name, runs, reference):
+    out = {"summary": name, "runs": len(runs)}
+    for key in ("vertex_norm", "context_norm", "auc"):
+        mine = np.array([r[key] for r in runs])
+        out[key] = float(mine.mean())
+        out[key + "_spread"] = float(np.ptp(mine))
+        if reference:
+            theirs = np.array([r[key] for r in reference])
+            out[key + "_reference"] = float(theirs.mean())
+            out[key + "_reference_spread"] = float(np.ptp(theirs))
+            out[key + ("_diff" if key == "auc" else "_rel")] = float(
+                mine.mean() - theirs.mean() if key == "auc" else (mine.mean() - theirs.mean()) / theirs.mean())
+    if runs and "kernel_edges_per_s" in runs[0]:
+        out["kernel_edges_per_s"] = float(np.mean([r["kernel_edges_per_s"] for r in runs]))
+        out["train_loop_edges_per_s"] = float(np.mean([r["train_loop_edges_per_s"] for r in runs]))
+    if reference:
+        out["within_north_star"] = bool(abs(out["vertex_norm_rel"]) <= 1e-3 and abs(out["context_norm_rel"]) <= 1e-3
+                                        and abs(out["auc_diff"]) <= 3e-3)
+    return out
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--workload", default="blogcatalog")
+    parser.add_argument("--epochs", type=int, default=2000)
+    parser.add_argument("--repeat", type=int, default=3)
+    parser.add_argument("--reference-repeat", type=int, default=3)
+    parser.add_argument("--settings", default="", help="comma-separated subset of SETTINGS (default: all)")
+    parser.add_argument("--partitions", type=int, default=0)
+    parser.add_argument("--out", default="")
+    args = parser.parse_args()
+    cfg = bench.WORKLOADS[args.workload]
+    path, test = make_split(cfg["graph"])
+    sink = open(args.out, "a") if args.out else None
+
+    def emit(row):
+        line = json.dumps(row)
+        print(line, flush=True)
+        if sink:
+            sink.write(line + "\n")
+            sink.flush()
+
+    emit({"workload": args.workload, "epochs": args.epochs, "partitions": args.partitions, "time": time.time()})
+    reference = []
+    if args.reference_repeat > 0:
+        ref = bench.load_reference()
+        for run in range(args.reference_repeat):
+            row = run_reference(ref, cfg, path, test, args.epochs)
+            reference.append(row)
+            emit(dict(row, impl="reference", run=run))
+        emit(summarise("reference", reference, None))
+
+    import graphvite_b200 as gv
+    graph = gv.graph.Graph()
+    graph.load(path)
+    names = [n for n in args.settings.split(",") if n] or list(SETTINGS)
+    for name in names:
+        runs = []
+        for run in range(args.repeat):
+            row = run_ours(gv, cfg, graph, test, args.epochs, SETTINGS[name], args.partitions)
+            runs.append(row)
+            emit(dict(row, impl="graphvite_b200", setting=name, run=run, **SETTINGS[name]))
+        emit(summarise(name, runs, reference))
+
+
+if __name__ == "__main__":
+    main()
