@@ -119,6 +119,7 @@ SIGNATURES = {
     "gv_cuda_fill_count": (c_int, [P(FillParams), c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_fill_scatter": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
+    "gv_cuda_fill_advance": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_fill_staging_bytes": (c_size_t, [c_uint32, c_int, c_int]),
     "gv_cuda_fill_scatter_staged": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -8,9 +8,10 @@
 // (include/base/alias_table.cuh:148-152,175-183 over the all-ones table of
 // instance/knowledge_graph.cuh:316-319).
 //
-// STATUS: compiles for sm_100a (224-234 registers for 8 floats per thread with Adam, no spills); NOT yet run on a
-// GPU (written after the round's GPU budget was spent) -- executed under the CUDA emulation of tests/emu against
-// the oracle and against golden vectors recorded from the reference's own kernels.
+// STATUS: sm_100a, 224-234 registers for 8 floats per thread with Adam, no spills.  Parity: tests/test_gpu_zz_kg_*.py
+// and tests/test_gpu_zzzz_kg_full_size.py (green on a B200 in the round-1 driver run, GPUTEST_r01.json) against the
+// oracle and against golden vectors recorded from the reference's own kernels; the same files also run under the
+// CUDA emulation of tests/emu.
 //
 // Design.  One positive sample = 1 + k targets that share the relation row and, each, either the
 // positive head or the positive tail.  The reference walks the targets with one warp and

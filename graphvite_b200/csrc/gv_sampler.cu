@@ -812,6 +812,25 @@ int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *ch
                                        nullptr, nullptr, nullptr, nullptr, stream);
 }
 
+// bases = fill, fill += totals: where this round's pairs start in every block's slice (one sampler, one rank)
+__global__ void fill_advance_bases_kernel(int num_block, const unsigned long long *totals, unsigned long long *fill,
+                                          unsigned long long *bases) {
+    for (int b = threadIdx.x; b < num_block; b += blockDim.x) {
+        const unsigned long long before = fill[b];
+        bases[b] = before;
+        fill[b] = before + totals[b];
+    }
+}
+
+int gv_cuda_fill_advance(int num_block, const unsigned long long *totals, unsigned long long *fill,
+                         unsigned long long *bases, void *stream) {
+    if (num_block < 1 || !totals || !fill || !bases)
+        return fail("gv_cuda_fill_advance: invalid argument");
+    GV_LAUNCH(1, 256, 0, static_cast<cudaStream_t>(stream), fill_advance_bases_kernel)(num_block, totals, fill, bases);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 size_t gv_cuda_fill_staging_bytes(uint32_t num_walk, int walk_length, int augmentation_step) {
     return size_t(num_walk) * pairs_per_walk(walk_length, augmentation_step) * sizeof(uint2) + 16;
 }

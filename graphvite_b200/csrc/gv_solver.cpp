@@ -145,9 +145,9 @@ struct Solver {
     // With partitioned sampling the arenas of all ranks are mapped into every rank (CUDA IPC).
     DeviceArray pool_arena;
     DeviceArray pool_pointers[2];                  // [P*P] block pointers (NULL: not reachable from here)
-    bool partitioned_sampling = false;
+    bool peer_pools = false;
     std::vector<void *> peer_arenas;               // [W] mapped arenas (own entry = pool_arena.ptr)
-    DeviceArray d_peer_controls, d_totals, d_bases;
+    DeviceArray d_peer_controls, d_totals, d_bases, d_barrier_scratch, d_barrier_marker;
     uint64_t peer_round = 0;
     // device graph
     DeviceArray d_offsets, d_edge_u, d_edge_v, d_edge_prob, d_edge_alias, d_vertex_tables, d_locations;
@@ -171,6 +171,8 @@ struct Solver {
     static const int kRandomBuffers = 4;
     DeviceArray d_random[kRandomBuffers], d_lr, d_loss, d_negatives_out;
     DeviceArray d_random_step;  // the worker's randoms of a whole sub-episode, when they fit (see train_block)
+    DeviceArray d_negatives_step;  // ... and the negatives drawn from them
+    cudaEvent_t step_timer[2] = {nullptr, nullptr};
     cudaEvent_t random_ready[kRandomBuffers] = {}, random_free[kRandomBuffers] = {};
     int chunk_batches = 1;
     bool capture_negatives = false;
@@ -254,6 +256,9 @@ struct Solver {
         for (auto g : sampler_generators)
             gv_rng_destroy(g);
         gv_rng_destroy(worker_generator);
+        for (cudaEvent_t event : step_timer)
+            if (event)
+                cudaEventDestroy(event);
         for (int i = 0; i < kRandomBuffers; i++) {
             if (random_ready[i])
                 cudaEventDestroy(random_ready[i]);
@@ -317,9 +322,9 @@ struct Solver {
             if (r != rank && peer_arenas[r])
                 cudaIpcCloseMemHandle(peer_arenas[r]);
         peer_arenas.clear();
-        if (partitioned_sampling)
+        if (peer_pools)
             built = false;  // the pool pointer tables referenced the peers: build() again before training
-        partitioned_sampling = false;
+        peer_pools = false;
     }
 
     // bytes this rank keeps resident for a given partition count (our memory model; the
@@ -460,7 +465,7 @@ struct Solver {
                 ok = ok && all_ok[r];
             cudaGetLastError();
             if (ok)
-                partitioned_sampling = true;
+                peer_pools = true;
             else {
                 for (int r = 0; r < num_worker; r++)
                     if (r != rank && peer_arenas[r]) {
@@ -482,7 +487,7 @@ struct Solver {
                 }
             pool_pointers[side].upload(pointers, work_stream);
         }
-        if (partitioned_sampling) {
+        if (peer_pools) {
             std::vector<unsigned long long *> controls(num_worker);
             for (int r = 0; r < num_worker; r++)
                 controls[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(peer_arenas[r]) +
@@ -490,6 +495,10 @@ struct Solver {
             d_peer_controls.upload(controls, work_stream);
             d_totals.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
             d_bases.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
+            d_barrier_scratch.allocate(size_t(2) * num_partition * num_partition * sizeof(unsigned long long));
+            d_barrier_marker.allocate(sizeof(unsigned long long));
+            GV_CHECK_CUDA(cudaMemsetAsync(d_barrier_scratch.ptr, 0, d_barrier_scratch.bytes, work_stream));
+            GV_CHECK_CUDA(cudaMemsetAsync(d_barrier_marker.ptr, 0, d_barrier_marker.bytes, work_stream));
             peer_round = 0;
             // pairs of blocks owned by other ranks are staged locally and forwarded with coalesced peer stores
             // (gv_cuda_fill_scatter_staged); GV_DIRECT_PEER_SCATTER=1 keeps the direct 8-byte peer stores
@@ -509,6 +518,11 @@ struct Solver {
         // (16 batches = 1.6e6 edges ~ 1 ms), short enough that the samplers' kernels get SMs in between
         chunk_batches = int(std::max<uint64_t>(1, std::min<uint64_t>(std::min(episode_size, 16), (uint64_t(192) << 20) /
                                                                                     std::max<uint64_t>(1, per_batch_random))));
+        // SGD trains with the reference's geometry -- one warp per sample, ONE LAUNCH PER BATCH (the launch boundary
+        // bounds the staleness of L1 copies exactly as in the reference, instance/graph.cuh:487); the persistent
+        // kernels (other optimizers, or kernel_flags & 64) amortise their launch over a chunk of batches
+        if (optimizer.desc.type == GV_OPT_SGD && !(gv_cuda_get_tunable("kernel_flags") & 64))
+            chunk_batches = 1;
         if (getenv("GV_CHUNK_BATCHES"))  // experiment: launch granularity in batches
             chunk_batches = std::max(1, std::min(episode_size, atoi(getenv("GV_CHUNK_BATCHES"))));
         for (int i = 0; i < kRandomBuffers; i++)
@@ -633,7 +647,7 @@ struct Solver {
         walk_chunk = std::max<uint64_t>(walk_chunk, 1024);
         d_chains.allocate(walk_chunk * (L + 1) * sizeof(gv_location_t));
         d_fill_scratch.allocate(gv_cuda_fill_scratch_bytes(uint32_t(walk_chunk), num_partition));
-        if (partitioned_sampling && staged_scatter)
+        if (peer_pools && staged_scatter)
             d_stage.allocate(gv_cuda_fill_staging_bytes(uint32_t(walk_chunk), L, sample_mode == 0 ? 1 : augmentation_step));
         d_sampler_random.allocate(size_t(kSpanBuffers) * kRandBatchSize * sizeof(double));
     }
@@ -651,7 +665,7 @@ struct Solver {
         // shards: rank r owns the tables of the edges [first_edge[r], first_edge[r + 1]), cut where the entry count
         // passes r / W of the total (one shard = everything unless the sampling is partitioned)
         release_table_shard();
-        const int num_shard = partitioned_sampling ? num_worker : 1;
+        const int num_shard = peer_pools ? num_worker : 1;
         require(num_shard <= GV_MAX_TABLE_SHARDS, "too many workers for sharded node2vec tables");
         std::vector<size_t> first_edge(num_shard + 1, m);
         first_edge[0] = 0;
@@ -662,7 +676,7 @@ struct Solver {
         table_shards.num_shard = num_shard;
         for (int r = 0; r <= num_shard; r++)
             table_shards.first_entry[r] = table_offsets[first_edge[r]];
-        const int mine = partitioned_sampling ? rank : 0;
+        const int mine = peer_pools ? rank : 0;
         const unsigned long long own = table_shards.first_entry[mine + 1] - table_shards.first_entry[mine];
         size_t free_bytes = 0, total_bytes = 0;
         GV_CHECK_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
@@ -756,7 +770,6 @@ struct Solver {
         bool complete = false;
         unsigned long long last_walk = 0;
         const uint64_t span_capacity = d_sampler_random.bytes / (size_t(kRandBatchSize) * sizeof(double));
-        const uint32_t share = partitioned_sampling ? num_worker : 1;
         while (!complete) {
             // walks still needed, judged from the emptiest block: the slowest block receives at most
             // 1 / num_block of the pairs, so 97 % of this estimate is certainly needed -- that many whole
@@ -784,23 +797,19 @@ struct Solver {
                     want = uint64_t(double(missing) * num_block / pairs_per_walk * 1.02) + 2 * walk_batch;
                     want = (want + walk_batch - 1) / walk_batch * walk_batch;
                 }
-                const uint32_t count = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, walk_chunk * share),
+                const uint32_t count = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, walk_chunk),
                                                                    in_span - done_in_span));
-                // this rank's slice of the round (everything unless the sampling is partitioned)
-                const uint32_t lo = uint32_t(uint64_t(count) * (partitioned_sampling ? rank : 0) / share);
-                const uint32_t hi = uint32_t(uint64_t(count) * (partitioned_sampling ? rank + 1 : 1) / share);
                 if (sample_mode == 2)
                     GV_CHECK_ABI(gv_cuda_biased_walk_sharded(&device_graph, &table_shards,
                                                              d_table_offsets.as<unsigned long long>(),
-                                                             d_sampler_random.as<double>(), hi - lo, L,
-                                                             done_in_span + lo, uint32_t(walks_per_buffer),
-                                                             kRandBatchSize, d_chains.as<gv_location_t>(),
-                                                             sample_stream));
+                                                             d_sampler_random.as<double>(), count, L, done_in_span,
+                                                             uint32_t(walks_per_buffer), kRandBatchSize,
+                                                             d_chains.as<gv_location_t>(), sample_stream));
                 else
-                    GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, d_sampler_random.as<double>(), hi - lo, L,
-                                                     done_in_span + lo, uint32_t(walks_per_buffer), kRandBatchSize,
+                    GV_CHECK_ABI(gv_cuda_random_walk(&device_graph, d_sampler_random.as<double>(), count, L,
+                                                     done_in_span, uint32_t(walks_per_buffer), kRandBatchSize,
                                                      d_chains.as<gv_location_t>(), sample_stream));
-                if (!partitioned_sampling) {
+                if (!peer_pools) {
                     GV_CHECK_ABI(gv_cuda_fill_pool(&params, d_chains.as<gv_location_t>(), count, walks_done,
                                                    pool_pointers[side].as<uint32_t *>(),
                                                    d_fill.as<unsigned long long>(),
@@ -808,41 +817,33 @@ struct Solver {
                                                    sample_stream));
                     stat_launches += num_partition == 1 ? 3 : 4;
                 } else {
-                    // stream order over the ranks is kept by exchanging per-block totals through peer
-                    // memory before anybody scatters
-                    GV_CHECK_ABI(gv_cuda_fill_count(&params, d_chains.as<gv_location_t>(), hi - lo,
+                    // some blocks of the slice live in a peer's pool: the same stable partition, but the pairs of
+                    // peer-owned blocks are staged locally and forwarded with coalesced stores over NVLink
+                    GV_CHECK_ABI(gv_cuda_fill_count(&params, d_chains.as<gv_location_t>(), count,
                                                     d_fill_scratch.ptr, d_totals.as<unsigned long long>(),
                                                     sample_stream));
-                    peer_barrier(d_totals.as<unsigned long long>());
+                    GV_CHECK_ABI(gv_cuda_fill_advance(num_block, d_totals.as<unsigned long long>(),
+                                                      d_fill.as<unsigned long long>(),
+                                                      d_bases.as<unsigned long long>(), sample_stream));
                     GV_CHECK_ABI(gv_cuda_fill_scatter_staged(
-                        &params, d_chains.as<gv_location_t>(), hi - lo, walks_done + lo,
+                        &params, d_chains.as<gv_location_t>(), count, walks_done,
                         pool_pointers[side].as<uint32_t *>(), d_bases.as<unsigned long long>(),
                         d_last_walk.as<unsigned long long>(), d_fill_scratch.ptr,
                         staged_scatter ? d_remote_blocks.as<unsigned char>() : nullptr, d_totals.as<unsigned long long>(),
                         d_stage.ptr, d_stage_offsets.as<unsigned long long>(), sample_stream));
-                    stat_launches += staged_scatter ? 9 : 7;
+                    stat_launches += staged_scatter ? 8 : 6;
                 }
                 GV_CHECK_CUDA(cudaMemcpyAsync(fill.data(), d_fill.ptr, num_block * sizeof(unsigned long long),
                                               cudaMemcpyDeviceToHost, sample_stream));
                 GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk),
                                               cudaMemcpyDeviceToHost, sample_stream));
                 GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
-                require(last_walk != ~0ull, "a peer rank did not reach the sampler exchange within 2 minutes");
                 done_in_span += count;
                 walks_done += count;
                 complete = true;
                 for (int b = 0; b < num_block; b++)
                     complete = complete && fill[b] >= slice;
             }
-        }
-        if (partitioned_sampling) {
-            // every rank's last scatter has been issued: one more exchange acts as the barrier after which
-            // the pools are complete everywhere, and carries the walk index that completed the last block
-            peer_barrier(nullptr);
-            GV_CHECK_CUDA(cudaMemcpyAsync(&last_walk, d_last_walk.ptr, sizeof(last_walk), cudaMemcpyDeviceToHost,
-                                          sample_stream));
-            GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
-            require(last_walk != ~0ull, "a peer rank did not reach the sampler exchange within 2 minutes");
         }
         // The reference stops at the end of the batch of walks that completed the last block; a
         // batch that runs past the current buffer pulls one more refill (only possible when
@@ -867,30 +868,33 @@ struct Solver {
         sampler_buffers[sampler_id] += needed_buffers;
     }
 
-    // one round of the peer exchange on the sample stream (gv_cuda_peer_exchange); totals == nullptr
-    // publishes zeros, i.e. a pure barrier
-    void peer_barrier(const unsigned long long *totals) {
-        GV_CHECK_ABI(gv_cuda_peer_exchange(rank, num_worker, num_partition, ++peer_round, totals,
+    // barrier over the ranks on the sample stream (flags in IPC-mapped peer memory, gv_cuda_peer_exchange):
+    // returns once every rank's sample stream has reached the same call
+    void peer_barrier() {
+        GV_CHECK_ABI(gv_cuda_peer_exchange(rank, num_worker, num_partition, ++peer_round, nullptr,
                                            d_peer_controls.as<unsigned long long *>(),
                                            reinterpret_cast<unsigned long long *>(static_cast<char *>(pool_arena.ptr) +
                                                                                   control_offset()),
-                                           d_fill.as<unsigned long long>(), d_bases.as<unsigned long long>(),
-                                           d_last_walk.as<unsigned long long>(), sample_stream));
+                                           d_barrier_scratch.as<unsigned long long>(),
+                                           d_barrier_scratch.as<unsigned long long>() + size_t(num_partition) * num_partition,
+                                           d_barrier_marker.as<unsigned long long>(), sample_stream));
+        unsigned long long marker = 0;
+        GV_CHECK_CUDA(cudaMemcpyAsync(&marker, d_barrier_marker.ptr, sizeof(marker), cudaMemcpyDeviceToHost,
+                                      sample_stream));
+        GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
+        require(marker != ~0ull, "a peer rank did not reach the sampler barrier within 2 minutes");
     }
 
-    // fill one side of the sample pools with all samplers (core/solver.h:614-628)
+    // fill one side of the sample pools with all samplers (core/solver.h:614-628).  Sampler i fills slice i of
+    // EVERY block from its own random stream, exactly as in the reference; with several ranks sampler i runs on
+    // rank i mod W and writes the blocks owned by other ranks into their pools over NVLink -- the samplers stay
+    // independent of one another, so the ranks only meet at the two barriers below.
     void fill_pool(int side) {
         GV_CHECK_CUDA(cudaSetDevice(device));
-        if (partitioned_sampling) {
-            // nobody may write into a pool that some rank is still training on: every rank gets here
-            // only after it finished the previous episode, so a barrier over the ranks is enough
-            peer_barrier(nullptr);
-            unsigned long long marker = 0;
-            GV_CHECK_CUDA(cudaMemcpyAsync(&marker, d_last_walk.ptr, sizeof(marker), cudaMemcpyDeviceToHost,
-                                          sample_stream));
-            GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
-            require(marker != ~0ull, "a peer rank did not reach the sampler barrier within 2 minutes");
-        }
+        // nobody may write into a pool that some rank is still training on: every rank gets here
+        // only after it finished the previous episode, so a barrier over the ranks is enough
+        if (peer_pools)
+            peer_barrier();
         cudaEvent_t begin, end;
         GV_CHECK_CUDA(cudaEventCreate(&begin));
         GV_CHECK_CUDA(cudaEventCreate(&end));
@@ -898,7 +902,8 @@ struct Solver {
         const uint64_t num_sample = pool_size();
         const uint64_t work_load = (num_sample + num_sampler - 1) / num_sampler;
         for (int i = 0; i < num_sampler; i++)
-            run_sampler(i, side, std::min(num_sample, work_load * i), std::min(num_sample, work_load * (i + 1)));
+            if (!peer_pools || i % num_worker == rank)
+                run_sampler(i, side, std::min(num_sample, work_load * i), std::min(num_sample, work_load * (i + 1)));
         GV_CHECK_CUDA(cudaEventRecord(end, sample_stream));
         GV_CHECK_CUDA(cudaEventSynchronize(end));
         float ms = 0;
@@ -906,6 +911,9 @@ struct Solver {
         stat_sample_seconds += ms * 1e-3;
         cudaEventDestroy(begin);
         cudaEventDestroy(end);
+        // the pools are complete once every rank's samplers have delivered
+        if (peer_pools)
+            peer_barrier();
     }
 
     // ---- host <-> device block movement (replaces Memory::gather/scatter + to_device/to_host) ----
@@ -1150,34 +1158,45 @@ struct Solver {
         const uint32_t *pool = pool_block(pool_id, head, g);
         const uint64_t per_batch_random = uint64_t(batch_size) * num_negative * 2;
         std::vector<float> lr(episode_size), loss(episode_size);
-        std::vector<cudaEvent_t> timers;
         int buffer = 0;
         // The stream is positional (one call for n batches == n calls for one batch), and a call is 4096 sequential
         // XORWOW streams however short it is: the randoms of the whole sub-episode are generated by ONE call when they
         // fit 2 GB (long calls are split by skip-ahead, gv_rng.cu) instead of one 4096-thread launch per chunk that the
-        // next train launch has to wait for.  GV_RNG_PER_CHUNK=1 keeps the per-chunk calls.
+        // next train launch has to wait for, and the negatives of the whole sub-episode are drawn from them by ONE
+        // gpu::Sample launch (the reference: one per batch, solver.h:1536-1539).  GV_RNG_PER_CHUNK=1 keeps the
+        // per-chunk calls.
         const uint64_t step_random = uint64_t(episode_size) * per_batch_random;
         const bool whole_step = num_negative > 0 && step_random * sizeof(double) <= (uint64_t(2) << 30) &&
                                 !getenv("GV_RNG_PER_CHUNK");
-        if (whole_step)
+        if (whole_step) {
             d_random_step.allocate(step_random * sizeof(double));
+            d_negatives_step.allocate(uint64_t(episode_size) * batch_size * num_negative * sizeof(uint32_t));
+        }
+        if (!step_timer[0]) {
+            GV_CHECK_CUDA(cudaEventCreate(&step_timer[0]));
+            GV_CHECK_CUDA(cudaEventCreate(&step_timer[1]));
+        }
         for (int reuse = 0; reuse < positive_reuse; reuse++) {
             for (int j = 0; j < episode_size; j++)
                 lr[j] = optimizer.lr_at(first_batch + (reuse * episode_size + j) * batch_stride, num_batch);
             GV_CHECK_CUDA(cudaMemcpyAsync(d_lr.ptr, lr.data(), episode_size * sizeof(float), cudaMemcpyHostToDevice,
                                           work_stream));
             GV_CHECK_CUDA(cudaMemsetAsync(d_loss.ptr, 0, episode_size * sizeof(float), work_stream));
-            if (whole_step) {  // random_free[0] / random_ready[0] guard the step buffer
+            if (whole_step) {  // random_free[0] / random_ready[0] guard the step buffers
                 GV_CHECK_CUDA(cudaStreamWaitEvent(random_stream, random_free[0], 0));
                 GV_CHECK_ABI(gv_rng_generate(worker_generator, d_random_step.as<double>(), step_random, random_stream));
-                stat_launches++;
+                GV_CHECK_ABI(gv_cuda_sample_negatives(negative_tables[g].as<gv_alias_entry_t>(), negative_counts[g],
+                                                      d_random_step.as<double>(),
+                                                      uint64_t(episode_size) * batch_size * num_negative,
+                                                      d_negatives_step.as<uint32_t>(), random_stream));
+                stat_launches += 2;
                 GV_CHECK_CUDA(cudaEventRecord(random_ready[0], random_stream));
                 GV_CHECK_CUDA(cudaStreamWaitEvent(work_stream, random_ready[0], 0));
             }
+            // device time of the pass's train launches: one event pair around all of them
+            GV_CHECK_CUDA(cudaEventRecord(step_timer[0], work_stream));
             for (int j0 = 0; j0 < episode_size; j0 += chunk_batches, buffer = (buffer + 1) % kRandomBuffers) {
                 const int count = std::min(chunk_batches, episode_size - j0);
-                const double *chunk_random = whole_step ? d_random_step.as<double>() + uint64_t(j0) * per_batch_random
-                                                        : d_random[buffer].as<double>();
                 // negatives: one curandGenerateUniformDouble(2 * B * k) per batch, like train_batch (solver.h:1536)
                 if (num_negative > 0 && !whole_step) {
                     GV_CHECK_CUDA(cudaStreamWaitEvent(random_stream, random_free[buffer], 0));
@@ -1190,10 +1209,6 @@ struct Solver {
                 }
                 // The loss is only needed for a batch whose successor logs it (one in log_frequency,
                 // core/solver.h:1541-1549): those batches get their own launch of the LOSS kernel.
-                cudaEvent_t begin, end;
-                GV_CHECK_CUDA(cudaEventCreate(&begin));
-                GV_CHECK_CUDA(cudaEventCreate(&end));
-                GV_CHECK_CUDA(cudaEventRecord(begin, work_stream));
                 for (int j = j0; j < j0 + count;) {
                     auto wants_loss = [&](int b) {
                         return (first_batch + (reuse * episode_size + b + 1) * batch_stride) % log_frequency == 0;
@@ -1202,9 +1217,11 @@ struct Solver {
                     int j1 = j + 1;
                     while (!with_loss && j1 < j0 + count && !wants_loss(j1))
                         j1++;
+                    const uint64_t first_negative = uint64_t(j) * batch_size * num_negative;
                     GV_CHECK_ABI(gv_cuda_train_block(
                         &matrices, pool + uint64_t(j) * batch_size * 2, uint64_t(j1 - j) * batch_size, num_negative,
-                        nullptr, chunk_random + uint64_t(j - j0) * per_batch_random,
+                        whole_step ? d_negatives_step.as<uint32_t>() + first_negative : nullptr,
+                        whole_step ? nullptr : d_random[buffer].as<double>() + uint64_t(j - j0) * per_batch_random,
                         negative_tables[g].as<gv_alias_entry_t>(), negative_counts[g],
                         capture_negatives ? d_negatives_out.as<uint32_t>() + uint64_t(j - j0) * batch_size * num_negative
                                           : nullptr,
@@ -1213,11 +1230,8 @@ struct Solver {
                     stat_launches++;
                     j = j1;
                 }
-                GV_CHECK_CUDA(cudaEventRecord(end, work_stream));
                 if (!whole_step)
                     GV_CHECK_CUDA(cudaEventRecord(random_free[buffer], work_stream));
-                timers.push_back(begin);
-                timers.push_back(end);
                 if (capture_negatives && reuse == positive_reuse - 1 && j0 + count == episode_size) {
                     last_negatives.resize(size_t(batch_size) * num_negative);
                     GV_CHECK_CUDA(cudaMemcpyAsync(last_negatives.data(),
@@ -1226,11 +1240,15 @@ struct Solver {
                                                   last_negatives.size() * 4, cudaMemcpyDeviceToHost, work_stream));
                 }
             }
+            GV_CHECK_CUDA(cudaEventRecord(step_timer[1], work_stream));
             if (whole_step)
                 GV_CHECK_CUDA(cudaEventRecord(random_free[0], work_stream));
             GV_CHECK_CUDA(cudaMemcpyAsync(loss.data(), d_loss.ptr, episode_size * sizeof(float),
                                           cudaMemcpyDeviceToHost, work_stream));
             GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+            float ms = 0;
+            GV_CHECK_CUDA(cudaEventElapsedTime(&ms, step_timer[0], step_timer[1]));
+            stat_kernel_seconds += ms * 1e-3;
             // the reference logs, at batch b, the mean loss of the batch trained before it (appendix A.8)
             for (int j = 0; j < episode_size; j++) {
                 const int this_batch = first_batch + (reuse * episode_size + j) * batch_stride;
@@ -1241,13 +1259,6 @@ struct Solver {
                 }
                 previous_batch_loss = loss[j] / batch_size;
             }
-        }
-        for (size_t i = 0; i < timers.size(); i += 2) {
-            float ms = 0;
-            GV_CHECK_CUDA(cudaEventElapsedTime(&ms, timers[i], timers[i + 1]));
-            stat_kernel_seconds += ms * 1e-3;
-            cudaEventDestroy(timers[i]);
-            cudaEventDestroy(timers[i + 1]);
         }
         stat_positive += double(positive_reuse) * episode_size * batch_size;
     }

@@ -66,6 +66,9 @@ struct TrainParams {
                 // 16 = interleaved mapping: warp w trains samples w, w + G, w + 2G ... (G = warps of the grid), so
                 //      that neighbouring pool entries run concurrently on different warps like the reference's
                 //      one-warp-per-sample grid (instance/gpu/graph.cuh:54-60); ignored with 8,
+                // 64 = SGD with the persistent kernels below (32 consecutive pool entries per warp, software
+                //      pipelining; faster, but a walk's samples no longer race the way the reference's do --
+                //      see train_sample_per_warp_kernel); flags 1 / 8 / 16 / 32 and hot_rows only act on those,
                 // 32 = rows are stored with the default write-back policy (st.global, what the reference's stores
                 //      compile to: the writing SM's L1 copy stays current) instead of st.global.cg
     unsigned int *work_counter;  // flags & 8: {next ticket, warps done}; both zero between launches
@@ -120,6 +123,19 @@ __device__ __forceinline__ void load_row(Row<DIM> &row, const float *base, int l
         if (lane_active<DIM>(p, lane))
             row.x[p] = l1 ? __ldca(reinterpret_cast<const float4 *>(base) + p * 32 + lane)
                           : __ldcg(reinterpret_cast<const float4 *>(base) + p * 32 + lane);
+        else
+            row.x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// a plain ld.global / st.global per lane: exactly the reference's memory policy (L1-cached loads, write-back stores;
+// SASS LDG.E.128 / STG.E.128 where the reference has LDG.E / STG.E)
+template<int DIM>
+__device__ __forceinline__ void load_row_plain(Row<DIM> &row, const float *base, int lane) {
+#pragma unroll
+    for (int p = 0; p < Row<DIM>::kPass; p++) {
+        if (lane_active<DIM>(p, lane))
+            row.x[p] = reinterpret_cast<const float4 *>(base)[p * 32 + lane];
         else
             row.x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -620,6 +636,90 @@ __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainPar
     release_work_counter(p, num_warp, lane);
 }
 
+
+// -----------------------------------------------------------------------------
+// The shipped SGD kernel: the reference's own launch geometry, because the result of Hogwild
+// training is a property of WHICH samples race, not only of the arithmetic.
+//
+// gpu::graph::train (instance/gpu/graph.cuh:36-95, launched <<<8192, 512>>> once per batch,
+// instance/graph.cuh:487) gives every sample of a batch its own warp: 16 consecutive pool entries per
+// 512-thread block, blocks dispatched in order, 4 blocks = 64 warps resident per SM.  At any moment
+// the samples in flight are a window of ~64 * #SM CONSECUTIVE pool entries, each read-modify-writing
+// its rows without atomics.  Consecutive pool entries come from the same random walk (pseudo shuffle,
+// instance/graph.cuh:427-447), a walk revisits a vertex two steps later with probability 1 / <degree>,
+// and of two concurrent updates of one row one is lost: on the Youtube-shaped graph the reference
+// loses ~10 % of the updates this way, and a kernel that trains a walk's samples one after another
+// (the persistent kernels above: 32 consecutive entries per warp) keeps them all -- measured on a
+// B200, 100 epochs: |vertex| +9.1 %, |context| -9.7 % against the unmodified reference however the
+// cache policy was set (profiles/r02_parity_sweep.md).  Within a row the arithmetic is identical.
+//
+// So this kernel keeps the reference's concurrency structure and memory policy and only changes how a
+// warp moves its bytes:
+//  * one warp = one sample, 16 warps per block, blocks in pool order, 64 warps per SM
+//    (__launch_bounds__(512, 4): 32 registers -- the reference's kernel has 30), one launch per batch
+//    (the launch boundary invalidates L1 like the reference's);
+//  * rows are read through L1 (ld.global.ca = the reference's plain loads) when they are needed -- the
+//    vertex row first, every target's context row right before its dot product -- and written back with
+//    plain stores right after the update, so the read-to-write window of every row is the reference's;
+//  * but a row is ONE 128-bit load / store per lane (a 128-d row = one 512-B transaction) held in
+//    registers, the dot product a butterfly reduction, the sigmoid ex2/rcp, the update 2 FMAs per
+//    element; the negatives are drawn by a pre-pass like the reference's gpu::Sample launch.
+// Latency is hidden by occupancy (64 warps x 1.5 KB in flight per SM), not by software pipelining.
+// -----------------------------------------------------------------------------
+constexpr int kSampleBlockThreads = 512;  // instance/gpu/graph.cuh: kThreadPerBlock = 512 -> 16 samples per block
+
+template<int DIM>
+constexpr int sample_blocks_per_sm() {
+    return Row<DIM>::kPass == 1 ? 4 : (Row<DIM>::kPass == 2 ? 2 : 1);
+}
+
+template<int DIM, bool LOSS>
+__global__ void __launch_bounds__(kSampleBlockThreads, sample_blocks_per_sm<DIM>())
+    train_sample_per_warp_kernel(const TrainParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t num_warp = gridDim.x * (blockDim.x >> 5);  // the host keeps launches below 2^32 samples
+    const uint32_t num_sample = uint32_t(p.num_sample);
+    const int k = p.num_negative;
+    // the reference's grid-stride loop (gpu/graph.cuh:54); one iteration unless the launch was capped
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < num_sample; i += num_warp) {
+        const uint2 pair = __ldg(p.pool + i);  // {tail, head}: one broadcast load per warp
+        const uint32_t batch = i / p.batch_size;
+        const float lr = __ldg(p.lr_per_batch + batch);
+        Row<DIM> v, c, unused;
+        load_row_plain<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane);
+        float sample_loss = 0.f;
+        for (int s = 0; s <= k; s++) {  // negatives first, then the positive (gpu/graph.cuh:62-71)
+            // negatives were drawn by gv_cuda_sample_negatives before this launch (gpu::Sample, solver.h:1536-1539)
+            const uint32_t tail = s < k ? __ldg(p.negatives + size_t(i) * k + s) : pair.x;
+            float *context = p.context + size_t(tail) * DIM;
+            load_row_plain<DIM>(c, context, lane);
+            const float prob = sigmoid(dot<DIM>(v, c));
+            float gradient, weight;
+            if (s == k) {
+                gradient = prob - 1;
+                weight = 1;
+                if (LOSS)
+                    sample_loss += weight * -logf(prob + kEpsilon);
+            } else {
+                gradient = prob;
+                weight = p.negative_weight;
+                if (LOSS)
+                    sample_loss += weight * -logf(1 - prob + kEpsilon);
+            }
+            backward<DIM, GV_OPT_SGD>(p.optimizer, lr, gradient, weight, v, c, unused, unused, unused, unused);
+            store_row<DIM>(c, context, lane, true);
+        }
+        store_row<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane, true);
+        if (LOSS && lane == 0) {
+            sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
+            if (p.loss_per_sample)
+                p.loss_per_sample[i] = sample_loss;
+            if (p.loss_per_batch)
+                atomicAdd(p.loss_per_batch + batch, sample_loss);
+        }
+    }
+}
+
 // gpu::Sample, base/alias_table.cuh:175-183
 __global__ void __launch_bounds__(256) sample_negatives_kernel(const gv_alias_entry_t *table, uint32_t count,
                                                                const double *random, unsigned long long num,
@@ -697,6 +797,32 @@ static unsigned int *work_counter_for(cudaStream_t stream) {
     return counter;
 }
 
+// grow-only device buffer for the negatives of one launch, per (device, stream): launches of a stream are serial
+static uint32_t *negative_scratch_for(cudaStream_t stream, unsigned long long count) {
+    static std::mutex mutex;
+    static std::map<std::pair<int, cudaStream_t>, std::pair<uint32_t *, unsigned long long>> buffers;
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess)
+        return nullptr;
+    std::lock_guard<std::mutex> lock(mutex);
+    auto &entry = buffers[{device, stream}];
+    if (entry.second < count) {
+        if (entry.first) {
+            cudaStreamSynchronize(stream);  // an earlier launch may still read the old buffer
+            cudaFree(entry.first);
+        }
+        entry = {nullptr, 0};
+        const unsigned long long capacity = count + count / 4;
+        if (cudaMalloc(&entry.first, capacity * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            entry.first = nullptr;
+            return nullptr;
+        }
+        entry.second = capacity;
+    }
+    return entry.first;
+}
+
 static int device_sm_count() {
     int device = 0, sms = 0;
     if (cudaGetDevice(&device) != cudaSuccess)
@@ -746,8 +872,57 @@ static int launch_sgd(const TrainParams &p, int num_warps, cudaStream_t stream) 
     return launch_train(train_sgd_kernel<DIM, K, false>, p, num_warps, stream);
 }
 
+
+// one warp per sample, 16 samples per block, blocks in pool order (the reference's <<<8192, 512>>> covers a batch of up
+// to 131 072 samples in one pass; longer launches simply get more blocks so that the order is kept)
+template<int DIM>
+static int launch_sample_per_warp(const TrainParams &p, int num_warps, cudaStream_t stream) {
+    int threads = kSampleBlockThreads;
+    unsigned long long blocks = (p.num_sample + threads / 32 - 1) / (threads / 32);
+    if (num_warps > 0) {  // tests: a fixed number of warps (1 = sequential) walking the pool with the grid stride
+        threads = num_warps >= kSampleBlockThreads / 32 ? kSampleBlockThreads : num_warps * 32;
+        blocks = (num_warps * 32 + threads - 1) / threads;
+    }
+    if (blocks > 0x7FFFFFFFull || p.num_sample > 0xFFFFFFFFull)
+        return fail("gv_cuda_train_block: too many samples for one launch");
+    TrainParams q = p;
+    if (!q.negatives && q.num_negative > 0) {
+        // gpu::Sample as its own launch (core/solver.h:1536-1539): into the caller's capture buffer, else a scratch
+        const unsigned long long count = q.num_sample * q.num_negative;
+        uint32_t *drawn = q.negatives_out ? q.negatives_out : negative_scratch_for(stream, count);
+        if (!drawn)
+            return fail("gv_cuda_train_block: cannot allocate the negative sample buffer");
+        unsigned long long draw_blocks = (count + 255) / 256;
+        draw_blocks = std::min<unsigned long long>(draw_blocks, (unsigned long long)device_sm_count() * 8);
+        GV_LAUNCH(int(draw_blocks), 256, 0, stream, sample_negatives_kernel)(q.negative_table, q.negative_count, q.random,
+                                                                            count, drawn);
+        GV_CUDA_OK(cudaGetLastError());
+        q.negatives = drawn;
+    } else if (q.negatives && q.negatives_out && q.num_negative > 0)
+        GV_CUDA_OK(cudaMemcpyAsync(q.negatives_out, q.negatives, q.num_sample * q.num_negative * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToDevice, stream));
+    void (*kernel)(const TrainParams) = (p.loss_per_sample || p.loss_per_batch)
+                                            ? train_sample_per_warp_kernel<DIM, true>
+                                            : train_sample_per_warp_kernel<DIM, false>;
+    static bool configured[2] = {false, false};
+    const int which = (p.loss_per_sample || p.loss_per_batch) ? 1 : 0;
+    if (!configured[which]) {
+        // the reference's kernel keeps 4 x 9 KB of shared memory per SM: ask for the same L1 / shared split, so that an
+        // L1 line lives about as long here as there (best effort -- a hint, not an error)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
+        cudaGetLastError();
+        configured[which] = true;
+    }
+    GV_LAUNCH(int(blocks), threads, 0, stream, kernel)(q);
+    GV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template<int DIM, int OPT>
 static int dispatch_loss(const TrainParams &p, int num_warps, cudaStream_t stream) {
+    // SGD: the reference's geometry (one warp per sample) unless the persistent kernels are asked for
+    if (OPT == GV_OPT_SGD && !(p.flags & 64))
+        return launch_sample_per_warp<DIM>(p, num_warps, stream);
     // the pipelined SGD kernel for the usual small k, when two samples' rows fit in registers
     if (OPT == GV_OPT_SGD && Row<DIM>::kPass <= 2 && !(p.flags & 4)) {
         switch (p.num_negative) {

@@ -37,7 +37,7 @@ enum { GV_OPT_SGD = 0, GV_OPT_MOMENTUM = 1, GV_OPT_ADAGRAD = 2, GV_OPT_RMSPROP =
 enum { GV_SCHEDULE_CONSTANT = 0, GV_SCHEDULE_LINEAR = 1, GV_SCHEDULE_CUSTOM = 2 };
 /* instance/graph.cuh:620-622 available models */
 enum { GV_MODEL_DEEPWALK = 0, GV_MODEL_LINE = 1, GV_MODEL_NODE2VEC = 2 };
-/* instance/knowledge_graph.cuh:575-577 available models (QuatE is not implemented) */
+/* instance/knowledge_graph.cuh:575-577 available models (all six are implemented) */
 enum { GV_KG_TRANSE = 0, GV_KG_DISTMULT = 1, GV_KG_COMPLEX = 2, GV_KG_SIMPLE = 3, GV_KG_ROTATE = 4, GV_KG_QUATE = 5 };
 
 /* Device-side view of core/optimizer.h Optimizer (the reference passes the whole C++
@@ -234,13 +234,17 @@ int gv_cuda_fill_pool(const gv_fill_params_t *params, const gv_location_t *chain
                       uint64_t first_walk, uint32_t *const *pool_blocks, unsigned long long *fill,
                       unsigned long long *last_walk, void *scratch, void *stream);
 
-/* The same pool fill split in two for sampling partitioned over several GPUs: every rank walks a
- * slice of the walks; gv_cuda_fill_count leaves the per-walk histogram in `scratch` and the slice's
- * per-block totals in `totals` [P*P]; the ranks exchange totals (gv_cuda_peer_exchange) and
- * gv_cuda_fill_scatter appends the slice's pairs behind those of the lower ranks (`bases` [P*P] =
- * slice offsets at which this rank's pairs start).  pool_blocks may point into peer GPUs' memory. */
+/* The same pool fill split in steps, for pools spread over several GPUs (sampler i of the reference runs on
+ * rank i mod W and writes slice i of every block, core/solver.h:617-625, into the pool of the rank that owns the
+ * block): gv_cuda_fill_count leaves the per-walk histogram in `scratch` and the round's per-block totals in
+ * `totals` [P*P]; gv_cuda_fill_advance turns them into the slice offsets `bases` [P*P] at which the round's pairs
+ * start (bases = fill, fill += totals); gv_cuda_fill_scatter[_staged] emits the pairs.  pool_blocks may point into
+ * peer GPUs' memory.  (gv_cuda_peer_exchange can stand in for gv_cuda_fill_advance when ONE sampler's walks are
+ * split over the ranks: it also adds the lower ranks' totals.) */
 int gv_cuda_fill_count(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk, void *scratch,
                        unsigned long long *totals, void *stream);
+int gv_cuda_fill_advance(int num_block, const unsigned long long *totals, unsigned long long *fill,
+                         unsigned long long *bases, void *stream);
 int gv_cuda_fill_scatter(const gv_fill_params_t *params, const gv_location_t *chains, uint32_t num_walk,
                          uint64_t first_walk, uint32_t *const *pool_blocks, const unsigned long long *bases,
                          unsigned long long *last_walk, void *scratch, void *stream);

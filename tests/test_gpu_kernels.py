@@ -101,11 +101,12 @@ def kernel_flags():
     set_flags(before)
 
 
-@pytest.mark.parametrize("flags", [16, 1 | 16 | 32, 1 | 32])
+@pytest.mark.parametrize("flags", [64 | 16, 64 | 1 | 16 | 32, 64 | 1 | 32, 64])
 @pytest.mark.parametrize("opt,k,dim,num_warps", [("SGD", 1, 128, 0), ("SGD", 1, 128, 5), ("SGD", 3, 64, 7),
                                                  ("Adam", 2, 128, 3), ("Momentum", 5, 32, 0)])
 def test_train_interleaved_mapping_race_free(kernel_flags, flags, opt, k, dim, num_warps):
-    """flags & 16: warp w trains the pool entries w, w + G, w + 2G ... (the reference's concurrency structure);
+    """The persistent kernels (flags & 64; without it SGD runs the one-warp-per-sample kernel, which every other SGD test
+    of this file covers).  flags & 16: warp w trains the pool entries w, w + G, w + 2G ...;
     flags & 32: write-back stores; flags & 1: every row through L1.  On a batch whose rows are all distinct the
     mapping and the cache policy cannot change the result; 2 999 samples leave a ragged last visit."""
     from gpu_util import run_train_block
@@ -124,7 +125,7 @@ def test_train_interleaved_mapping_race_free(kernel_flags, flags, opt, k, dim, n
     np.testing.assert_allclose(got["batch_loss"], expected_batch, rtol=1e-4)
 
 
-@pytest.mark.parametrize("flags", [16, 1 | 16 | 32])
+@pytest.mark.parametrize("flags", [64, 64 | 16, 64 | 1 | 16 | 32])
 def test_train_interleaved_single_warp_is_sequential(kernel_flags, flags):
     """one warp alone visits the pool in order in either mapping: collisions resolve as in the reference's loop"""
     from gpu_util import run_train_block

@@ -27,27 +27,32 @@ import bench  # noqa: E402
 from validate_parity import auc_of, make_split  # noqa: E402
 
 # name -> tunables (gv_cuda_set_tunable) + chunk_batches (solver option) + num_partition
+P = 64  # kernel_flags & 64: the persistent kernels (round 1's); without it SGD runs one warp per sample
 SETTINGS = {
+    # the shipped default: one warp per sample, one launch per batch, plain loads / stores (the reference's geometry)
+    "per_sample": dict(kernel_flags=0, chunk_batches=1),
+    "per_sample_chunk4": dict(kernel_flags=0, chunk_batches=4),
+    "per_sample_chunk16": dict(kernel_flags=0, chunk_batches=16),
     # round-1 shipped policy: hub rows through L1, everything else L2-only, 16 batches per launch
-    "r1_shipped": dict(hot_rows=128, kernel_flags=0, chunk_batches=16),
-    "l2_only": dict(hot_rows=0, kernel_flags=0, chunk_batches=16),
-    "hot128_chunk1": dict(hot_rows=128, kernel_flags=0, chunk_batches=1),
-    # the reference's memory policy: every row through L1, write-back stores; 1 or 16 batches per launch
-    "all_l1_chunk16": dict(hot_rows=0, kernel_flags=1, chunk_batches=16),
-    "all_l1_chunk1": dict(hot_rows=0, kernel_flags=1, chunk_batches=1),
-    "all_l1_wb_chunk16": dict(hot_rows=0, kernel_flags=1 | 32, chunk_batches=16),
-    "all_l1_wb_chunk1": dict(hot_rows=0, kernel_flags=1 | 32, chunk_batches=1),
-    # + the reference's concurrency structure: neighbouring pool entries on different warps
-    "interleaved_l2": dict(hot_rows=0, kernel_flags=16, chunk_batches=16),
-    "interleaved_hot128": dict(hot_rows=128, kernel_flags=16, chunk_batches=16),
-    "interleaved_all_l1_chunk16": dict(hot_rows=0, kernel_flags=1 | 16, chunk_batches=16),
-    "interleaved_all_l1_wb_chunk16": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=16),
-    "interleaved_all_l1_wb_chunk4": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=4),
-    "interleaved_all_l1_wb_chunk1": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=1),
-    "hot1024": dict(hot_rows=1024, kernel_flags=0, chunk_batches=16),
-    "hot8192": dict(hot_rows=8192, kernel_flags=0, chunk_batches=16),
-    "interleaved_hot1024": dict(hot_rows=1024, kernel_flags=16, chunk_batches=16),
-    "interleaved_all_l1_wb_chunk1_3cta": dict(hot_rows=0, kernel_flags=1 | 16 | 32, chunk_batches=1,
+    "r1_shipped": dict(hot_rows=128, kernel_flags=P, chunk_batches=16),
+    "l2_only": dict(hot_rows=0, kernel_flags=P, chunk_batches=16),
+    "hot128_chunk1": dict(hot_rows=128, kernel_flags=P, chunk_batches=1),
+    "hot1024": dict(hot_rows=1024, kernel_flags=P, chunk_batches=16),
+    "hot8192": dict(hot_rows=8192, kernel_flags=P, chunk_batches=16),
+    # the reference's memory policy on the persistent kernels: every row through L1, write-back stores
+    "all_l1_chunk16": dict(hot_rows=0, kernel_flags=P | 1, chunk_batches=16),
+    "all_l1_chunk1": dict(hot_rows=0, kernel_flags=P | 1, chunk_batches=1),
+    "all_l1_wb_chunk16": dict(hot_rows=0, kernel_flags=P | 1 | 32, chunk_batches=16),
+    "all_l1_wb_chunk1": dict(hot_rows=0, kernel_flags=P | 1 | 32, chunk_batches=1),
+    # + neighbouring pool entries on different warps (interleaved mapping)
+    "interleaved_l2": dict(hot_rows=0, kernel_flags=P | 16, chunk_batches=16),
+    "interleaved_hot128": dict(hot_rows=128, kernel_flags=P | 16, chunk_batches=16),
+    "interleaved_hot1024": dict(hot_rows=1024, kernel_flags=P | 16, chunk_batches=16),
+    "interleaved_all_l1_chunk16": dict(hot_rows=0, kernel_flags=P | 1 | 16, chunk_batches=16),
+    "interleaved_all_l1_wb_chunk16": dict(hot_rows=0, kernel_flags=P | 1 | 16 | 32, chunk_batches=16),
+    "interleaved_all_l1_wb_chunk4": dict(hot_rows=0, kernel_flags=P | 1 | 16 | 32, chunk_batches=4),
+    "interleaved_all_l1_wb_chunk1": dict(hot_rows=0, kernel_flags=P | 1 | 16 | 32, chunk_batches=1),
+    "interleaved_all_l1_wb_chunk1_3cta": dict(hot_rows=0, kernel_flags=P | 1 | 16 | 32, chunk_batches=1,
                                               train_blocks_per_sm=3),
 }
 
