@@ -9,9 +9,13 @@ episode_size * batch_size = 5e7 positive edges per GPU at the reference's Youtub
 (config/graph/line_youtube.yaml), while the samplers refill the other pool.  For N > 1 the script
 is launched by torchrun, one rank per GPU; the value is the whole job's edges per second with the
 time taken as the max over ranks of the device time (CUDA events on the solver's work stream).
+
+Other workloads (`--workload`): blogcatalog / toy (LINE, small graphs), node2vec_youtube (config/graph/
+node2vec_youtube.yaml with p = q = 0.25 on a degree-capped Youtube-shaped graph whose per-edge tables fit),
+friendster_lite (config/graph/line_friendster.yaml on a 1/16-scale Friendster-shaped graph from binary edge
+arrays), rotate_fb15k237 (config/knowledge_graph/rotate_fb15k-237.yaml, KnowledgeGraphSolver).
 """
 import argparse
-import ctypes
 import importlib.util
 import json
 import os
@@ -27,13 +31,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # config/graph/line_youtube.yaml
-YOUTUBE = dict(dim=128, lr=0.025, weight_decay=0.005, num_negative=1, batch_size=100000, episode_size=500,
-               model="LINE", negative_weight=5, augmentation_step=5, random_walk_length=40,
-               random_walk_batch_size=100)
+YOUTUBE = dict(solver="graph", dim=128, lr=0.025, weight_decay=0.005, num_negative=1, batch_size=100000,
+               episode_size=500, model="LINE", negative_weight=5, augmentation_step=5, random_walk_length=40,
+               random_walk_batch_size=100, p=1.0, q=1.0)
 WORKLOADS = {
     "youtube": dict(YOUTUBE, graph="youtube"),
     "blogcatalog": dict(YOUTUBE, graph="blogcatalog", augmentation_step=2),  # config/demo/quick_start.yaml
     "toy": dict(YOUTUBE, graph="toy", batch_size=1000, episode_size=20, augmentation_step=2, random_walk_length=10),
+    # config/graph/node2vec_youtube.yaml (augmentation 5 there too) with BASELINE.json's p = q = 0.25
+    "node2vec_youtube": dict(YOUTUBE, graph="youtube_capped", model="node2vec", p=0.25, q=0.25),
+    # config/graph/line_friendster.yaml: d=96 in the yaml, BASELINE.json quotes d=128; augmentation 2, episode 2500
+    "friendster_lite": dict(YOUTUBE, graph="friendster_lite", augmentation_step=2, episode_size=2500),
+    # config/knowledge_graph/rotate_fb15k-237.yaml
+    "rotate_fb15k237": dict(solver="kg", graph="fb15k-237", dim=2048, model="RotatE", lr=2e-6, weight_decay=0,
+                            num_negative=64, batch_size=100000, episode_size=1, margin=9.0, adversarial_temperature=2.0,
+                            l3_regularization=2e-3, sample_batch_size=2000),
 }
 
 
@@ -48,12 +60,38 @@ def graph_file(name):
     from graphvite_b200 import datasets
     path = "/tmp/gv_b200_%s.txt" % name
     if not os.path.exists(path):
-        num_vertex, num_edge = datasets.SHAPES[name]
-        u, v = datasets.power_law_edges(num_vertex, num_edge, max_degree=29000 if name == "youtube" else None)
+        u, v = datasets.named_edges(name)
         import pandas
         pandas.DataFrame({"u": u, "v": v}).to_csv(path + ".tmp", sep="\t", header=False, index=False)
         os.replace(path + ".tmp", path)
     return path
+
+
+def heldout_pairs(name, count=50000):
+    """Link-prediction evaluation set for a synthetic graph: `count` edges drawn from the SAME generative model with
+    another seed (label 1; they are held out in the sense that the training graph was drawn independently) and as
+    many uniformly random pairs (label 0).  Both arms are scored on it with the same function."""
+    from graphvite_b200 import datasets
+    u, v = datasets.named_edges(name, seed=20260923, num_edge=count)
+    rng = np.random.default_rng(7)
+    num_vertex = datasets.SHAPES[name][0]
+    a, b = rng.integers(0, num_vertex, count), rng.integers(0, num_vertex, count)
+    heads = np.concatenate([u, a])
+    tails = np.concatenate([v, b])
+    labels = np.concatenate([np.ones(count, dtype=np.int64), np.zeros(count, dtype=np.int64)])
+    return heads, tails, labels
+
+
+def quality(vertex, context, name2id, graph_name):
+    """Embedding norms and link-prediction AUC (score = <vertex[h], context[t]>, the LINE link predictor,
+    python/graphvite/application/network.py:45-75) of one trained model."""
+    from graphvite_b200.application import link_prediction_auc
+    heads, tails, labels = heldout_pairs(graph_name)
+    h = np.fromiter((name2id[str(x)] for x in heads), dtype=np.int64, count=len(heads))
+    t = np.fromiter((name2id[str(x)] for x in tails), dtype=np.int64, count=len(tails))
+    scores = np.einsum("ij,ij->i", vertex[h], context[t])
+    return {"vertex_norm": float(np.linalg.norm(vertex)), "context_norm": float(np.linalg.norm(context)),
+            "auc": float(link_prediction_auc(scores, labels))}
 
 
 class ClockSampler(object):
@@ -98,23 +136,113 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def workload_text(cfg, num_vertex, num_edge):
+    if cfg["solver"] == "kg":
+        return ("%s d=%d on %s-shaped knowledge graph (%d entities, %d triplets), Adam lr=%g, k=%d, B=%d, "
+                "episode_size=%d" % (cfg["model"], cfg["dim"], cfg["graph"], num_vertex, num_edge, cfg["lr"],
+                                     cfg["num_negative"], cfg["batch_size"], cfg["episode_size"]))
+    return ("%s d=%d on %s-shaped power-law graph (|V|=%d, %d edge lines), SGD lr=%g wd=%g, k=%d, B=%d, "
+            "episode_size=%d, augmentation_step=%d, walk length %d%s" %
+            (cfg["model"], cfg["dim"], cfg["graph"], num_vertex, num_edge, cfg["lr"], cfg["weight_decay"],
+             cfg["num_negative"], cfg["batch_size"], cfg["episode_size"], cfg["augmentation_step"],
+             cfg["random_walk_length"], ", p=%g q=%g" % (cfg["p"], cfg["q"]) if cfg["model"] == "node2vec" else ""))
+
+
+def metric_name(cfg):
+    if cfg["solver"] == "kg":
+        return "positive triplets/sec on FB15k-237 RotatE d=%d" % cfg["dim"]
+    names = {"youtube": "Youtube", "youtube_capped": "Youtube (degree-capped)", "friendster_lite": "Friendster/16"}
+    return "edges/sec on %s %s d=%d" % (names.get(cfg["graph"], cfg["graph"]), cfg["model"], cfg["dim"])
+
+
+def epochs_for(steps, world, num_partition, episode_size, batch_size, num_edge):
+    """num_epoch that makes train() run about `steps` sub-episodes per GPU in whole episodes (both arms use this)"""
+    per_episode = num_partition * num_partition * episode_size * batch_size
+    episodes = max(1, int(round(steps * world * episode_size * batch_size / per_episode)))
+    return max(1, int(np.ceil(episodes * per_episode / num_edge)) - 1), episodes * per_episode
+
+
+def reference_note_path(workload, gpus):
+    return "/tmp/gv_b200_reference_%s_n%d.json" % (workload, gpus)
+
+
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def make_solver(cfg, path, rank, world, local_rank, num_partition=0):
-    import graphvite_b200 as gv
+def load_graph(gv, cfg):
+    from graphvite_b200 import datasets
     graph = gv.graph.Graph()
-    graph.load(path, as_undirected=True)
+    if cfg["graph"] in datasets.BINARY_GRAPHS:  # no text file: integer edge arrays straight into the loader
+        u, v = datasets.named_edges(cfg["graph"])
+        graph.load_arrays(u, v, as_undirected=True)
+    else:
+        graph.load(graph_file(cfg["graph"]), as_undirected=True)
+    return graph
+
+
+def make_solver(cfg, graph, rank, world, local_rank, num_partition=0):
+    import graphvite_b200 as gv
     solver = gv.solver.GraphSolver(cfg["dim"], device_ids=[local_rank], rank=rank, world_size=world)
     solver.build(graph, gv.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), num_partition=num_partition,
                  num_negative=cfg["num_negative"], batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
-    return gv, graph, solver
+    return solver
 
 
 def train_kwargs(cfg, num_epoch):
     return dict(model=cfg["model"], num_epoch=num_epoch, augmentation_step=cfg["augmentation_step"],
                 random_walk_length=cfg["random_walk_length"], random_walk_batch_size=cfg["random_walk_batch_size"],
-                negative_weight=cfg["negative_weight"])
+                p=cfg["p"], q=cfg["q"], negative_weight=cfg["negative_weight"])
+
+
+def traffic_from_capture(kernel, num_partition, per_edge):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture -- only when the
+    capture is of THIS kernel at THIS partition count (profiles/r02_train_kernel.json lists its captures)."""
+    path = os.path.join(ROOT, "profiles", "r02_train_kernel.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed for round 2"
+    for capture in json.load(open(path)).get("captures", []):
+        if capture["kernel"] == kernel and capture["num_partition"] == num_partition:
+            note = ("dram__bytes_read+write.sum per launch of %d edges (%.0f B/edge vs %d algorithmic), git %s, %s" %
+                    (capture["edges_per_launch"], capture["dram_bytes_per_launch"] / capture["edges_per_launch"],
+                     per_edge, capture.get("git", "?"), capture.get("source", "")))
+            return capture["dram_bytes_per_launch"], note
+    return None, "no ncu capture of %s at num_partition=%d" % (kernel, num_partition)
+
+
+def multi_rank_parity(rank, world, local_rank):
+    """N > 1 only: toy inputs through the N-rank solver against the oracle's N-worker emulation (tests/
+    multi_rank_worker.py -- both sample pools after every episode bit-exact, embeddings rtol 1e-3): the node-embedding
+    solver with LINE (block rotation over NCCL, samplers delivering into peer pools over NVLink), node2vec (per-edge
+    tables sharded over the ranks) and the knowledge-graph solver (relation all-reduce).  The oracle is the checker
+    here, never the thing measured.  Returns {case: bool} for THIS rank."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    results = {}
+    try:
+        import multi_rank_worker as worker
+    except Exception as error:
+        return {"import": False, "error": str(error).splitlines()[0][:200]}
+    cases = [("line_P%d" % world, "graph", "LINE", world), ("line_P%d" % (2 * world), "graph", "LINE", 2 * world),
+             ("node2vec_P%d" % world, "graph", "node2vec", world), ("rotate_adam_P%d" % (2 * world), "kg", None, 2 * world)]
+    for name, kind, model, partitions in cases:
+        if partitions > 16:
+            continue
+        ok = True
+        try:
+            if kind == "graph":
+                os.environ["GV_TEST_MODEL"] = model
+                worker.run_graph(rank, world, local_rank, partitions)
+            else:
+                os.environ["GV_TEST_OPTIMIZER"] = "Adam"
+                worker.run_kg(rank, world, local_rank, partitions)
+        except BaseException as error:  # an assertion of the worker = a parity failure; report, keep going
+            ok = False
+            sys.stderr.write("parity self-check %s failed on rank %d: %s\n" % (name, rank, str(error)[:2000]))
+            if not isinstance(error, AssertionError):
+                results[name + "_error"] = str(error).splitlines()[0][:200] if str(error) else type(error).__name__
+        results[name] = ok
+        dist.barrier()
+    return results
 
 
 def run_ours(args, cfg):
@@ -135,6 +263,13 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(value):
+        if world == 1:
+            return value
+        t = torch.tensor([value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     origin = time.time()
 
     def progress(what):  # stderr only: if a multi-GPU run stalls, the log says in which phase
@@ -142,18 +277,20 @@ def run_ours(args, cfg):
             sys.stderr.write("[bench %7.2f s] rank %d: %s\n" % (time.time() - origin, rank, what))
             sys.stderr.flush()
 
-    if rank == 0:
-        path = graph_file(cfg["graph"])
+    import graphvite_b200 as gv
+    from graphvite_b200 import datasets
+    if rank == 0 and cfg["graph"] not in datasets.BINARY_GRAPHS:
+        graph_file(cfg["graph"])
     barrier()
-    path = graph_file(cfg["graph"])
-    progress("graph file ready, building the solver")
-    gv, graph, solver = make_solver(cfg, path, rank, world, local_rank, args.partitions)
+    graph = load_graph(gv, cfg)
+    progress("graph loaded, building the solver")
+    solver = make_solver(cfg, graph, rank, world, local_rank, args.partitions)
     progress("solver built (%d partitions)" % solver.num_partition)
     lib, handle = _lib.lib, solver._handle
     edges_per_step = cfg["episode_size"] * cfg["batch_size"]  # per GPU
     kw = train_kwargs(cfg, 4000)  # config/graph/line_youtube.yaml; far more epochs than we will run
     _lib.check(lib.gv_solver_train_begin(handle, kw["model"].encode(), kw["num_epoch"], 0, kw["augmentation_step"],
-                                         kw["random_walk_length"], kw["random_walk_batch_size"], 0, 1.0, 1.0, 1,
+                                         kw["random_walk_length"], kw["random_walk_batch_size"], 0, kw["p"], kw["q"], 1,
                                          0.75, float(kw["negative_weight"]), 1000))
     progress("train_begin done (tables, first pool, embeddings resident)")
     for _ in range(args.warmup):
@@ -170,35 +307,30 @@ def run_ours(args, cfg):
     progress("%d timed steps done" % args.steps)
     clocks = sampler.stop() if sampler else None
     after = solver.stats
-    if world > 1:
-        t = torch.tensor([seconds], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        seconds = float(t.item())
+    seconds = max_over_ranks(seconds)
     _lib.check(lib.gv_solver_train_end(handle))
-    norms = [float(np.linalg.norm(solver.vertex_embeddings)), float(np.linalg.norm(solver.context_embeddings))]
     value = args.steps * edges_per_step * world / seconds
 
     # roofline of the dominant kernel (the train kernel): algorithmic bytes / CUDA-event time of its launches
-    kernel_seconds = after["kernel_seconds"] - before["kernel_seconds"]
+    # (one event pair around the launches of a step on the solver's work stream: launch gaps count against us)
+    kernel_seconds = max_over_ranks(after["kernel_seconds"] - before["kernel_seconds"])
     positives = after["positives"] - before["positives"]
     per_edge = bytes_per_edge(cfg["dim"], cfg["num_negative"])
     achieved = positives * per_edge / kernel_seconds / 1e9
     peak, peak_kind = measured_peak()
     launches = int(after["launches"] - before["launches"])
-    # DRAM bytes of one launch of the same kernel from the committed `ncu --set full` capture
-    traffic, traffic_note = None, "no ncu capture committed"
-    capture = os.path.join(ROOT, "profiles", "r01_train_kernel.json")
-    if os.path.exists(capture) and cfg["dim"] == 128 and cfg["num_negative"] == 1:
-        info = json.load(open(capture))
-        traffic = info["dram_bytes_per_launch"]
-        traffic_note = ("dram__bytes_read+write.sum per launch of %d edges (%.0f B/edge vs %d algorithmic), %s" %
-                        (info["edges_per_launch"], info["dram_bytes_per_edge"], per_edge, info["source"]))
+    flags = int(lib.gv_cuda_get_tunable(b"kernel_flags"))
+    chunk_batches = solver.chunk_batches
+    kernel = ("gv::device::train_sgd_kernel<%d, %d>" if flags & 64 else "gv::device::train_sample_per_warp_kernel<%d>") % \
+        ((cfg["dim"], cfg["num_negative"]) if flags & 64 else (cfg["dim"],))
+    traffic, traffic_note = traffic_from_capture(kernel, solver.num_partition, per_edge)
+    num_partition = solver.num_partition
 
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": seconds / args.steps * 1e3, "roofline_gbs": achieved,
-                              "frac": achieved / peak, "gpu_launches": launches, "note": "profiling run, no e2e"}),
-                  flush=True)
+                              "frac": achieved / peak, "gpu_launches": launches, "kernel": kernel,
+                              "num_partition": num_partition, "note": "profiling run, no e2e"}), flush=True)
         solver.close()
         if world > 1:
             dist.barrier()
@@ -208,62 +340,181 @@ def run_ours(args, cfg):
     solver.close()  # collective teardown (IPC importers close before exporters free)
     del solver
     progress("steady-state solver closed, building the end-to-end solver")
-    gv2, graph2, solver2 = make_solver(cfg, path, rank, world, local_rank)
-    per_episode = edges_per_step * world * (solver2.num_partition // world) ** 2 * world  # edges per episode
-    episodes = max(1, int(round(args.steps * edges_per_step * world / per_episode)))
-    num_epoch = max(1, int(np.ceil(episodes * per_episode / graph2.num_edge)) - 1)
+    solver2 = make_solver(cfg, graph, rank, world, local_rank)
+    num_epoch, _ = epochs_for(args.steps, world, solver2.num_partition, cfg["episode_size"], cfg["batch_size"],
+                              graph.num_edge)
     barrier()
     start = time.time()
     solver2.train(**train_kwargs(cfg, num_epoch))
     barrier()
-    e2e_seconds = time.time() - start
+    e2e_seconds = max_over_ranks(time.time() - start)
     progress("end-to-end train() done")
-    if world > 1:
-        t = torch.tensor([e2e_seconds], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_seconds = float(t.item())
     e2e_edges = solver2.batch_id * cfg["batch_size"]
     e2e_steps = max(1, e2e_edges // (edges_per_step * world))
-    matrix_bytes = graph2.num_vertex * cfg["dim"] * 4
-    directed = 2 * graph2.num_edge
-    h2d = 2 * matrix_bytes + directed * (4 + 4 + 4 + 8 + 8) + graph2.num_vertex * 24
+    matrix_bytes = graph.num_vertex * cfg["dim"] * 4
+    directed = 2 * graph.num_edge
+    h2d = 2 * matrix_bytes + directed * (4 + 4 + 4 + 8 + 8) + graph.num_vertex * 24
     d2h = 2 * matrix_bytes
     e2e_stats = solver2.stats
+    model_quality = None
+    if rank == 0 and cfg["graph"] in datasets.SHAPES:
+        model_quality = quality(solver2.vertex_embeddings, solver2.context_embeddings, graph.name2id, cfg["graph"])
+        model_quality["num_epoch"] = num_epoch
 
     result = {
-        "metric": "edges/sec on Youtube LINE d=128", "value": value, "unit": "edges/s", "n_gpus": world,
+        "metric": metric_name(cfg), "value": value, "unit": "edges/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "impl": "graphvite_b200",
-        "config": {"workload": "LINE d=%d on %s-shaped power-law graph (|V|=%d, %d edge lines), SGD lr=%g wd=%g, "
-                               "k=%d, B=%d, episode_size=%d, augmentation_step=%d, walk length %d" %
-                               (cfg["dim"], cfg["graph"], graph2.num_vertex, graph2.num_edge, cfg["lr"],
-                                cfg["weight_decay"], cfg["num_negative"], cfg["batch_size"], cfg["episode_size"],
-                                cfg["augmentation_step"], cfg["random_walk_length"]),
-                   "num_partition": solver2.num_partition, "parallelism": "2-D block partition, %d GPU(s)" % world,
-                   "l2": "working set (2 x %.0f MB embeddings + %.0f MB pool block) >> 126 MB L2, no flush needed" %
-                         (matrix_bytes / 1e6, edges_per_step * 8 / 1e6)},
+        "config": {"workload": workload_text(cfg, graph.num_vertex, graph.num_edge), "num_partition": num_partition},
+        "parallelism": "2-D block partition, %d GPU(s), one process per GPU" % world,
+        "l2": "working set (2 x %.0f MB embedding blocks + %.0f MB pool block per GPU) >> 126 MB L2, no flush needed" %
+              (matrix_bytes / num_partition / 1e6, edges_per_step * 8 / 1e6),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_kind,
-                     "bytes_per_edge": per_edge, "kernel": "gv::device::train_sgd_kernel<%d, %d>" % (cfg["dim"], cfg["num_negative"]),
-                     "algorithmic_bytes_per_launch": per_edge * 16 * cfg["batch_size"],
-                     "kernel_edges_per_s": positives / kernel_seconds},
+                     "bytes_per_edge": per_edge, "kernel": kernel,
+                     "algorithmic_bytes_per_launch": per_edge * chunk_batches * cfg["batch_size"],
+                     "batches_per_launch": chunk_batches,
+                     "kernel_edges_per_s": positives / kernel_seconds,
+                     "timing": "CUDA events on the work stream around each step's train launches (gaps included), "
+                               "max over ranks"},
         "e2e": {"value": e2e_edges / e2e_seconds, "unit": "edges/s", "h2d_bytes_per_step": h2d / e2e_steps,
                 "d2h_bytes_per_step": d2h / e2e_steps, "seconds": e2e_seconds, "edges": e2e_edges,
-                "sampler_seconds": e2e_stats["sample_seconds"], "train_seconds": e2e_stats["train_seconds"]},
+                "num_epoch": num_epoch, "sampler_seconds": e2e_stats["sample_seconds"],
+                "train_seconds": e2e_stats["train_seconds"]},
         "gpu_launches": launches,
         "clocks": clocks,
-        "embedding_norms": norms,
+        "model_quality": model_quality,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # float parity on the driver's record: the reference arm (run just before on the same box) leaves its model's
+    # norms / AUC for the same num_epoch; rel_diff = (ours - reference) / reference
+    note = reference_note_path(args.workload, world)
+    if rank == 0 and model_quality and os.path.exists(note):
         try:
-            result["cpu_baseline"] = reference_baseline(cfg, path, 1, max(2, min(args.steps, 4)))
-        except Exception as error:  # the reference build is absent: report, do not hide
+            theirs = json.load(open(note))
+            if theirs.get("num_epoch") == num_epoch:
+                result["vs_reference_quality"] = {
+                    "reference": theirs,
+                    "vertex_norm_rel": model_quality["vertex_norm"] / theirs["vertex_norm"] - 1,
+                    "context_norm_rel": model_quality["context_norm"] / theirs["context_norm"] - 1,
+                    "auc_diff": model_quality["auc"] - theirs["auc"],
+                    "north_star": "norms within 1e-3 relative, AUC within 0.003"}
+        except (OSError, ValueError, KeyError):
+            pass
+    solver2.close()
+    del solver2
+    if world > 1 and not args.no_parity:
+        progress("multi-rank parity self-check against the oracle")
+        mine = multi_rank_parity(rank, world, local_rank)
+        names = sorted(k for k, v in mine.items() if isinstance(v, bool))
+        flags_mine = torch.tensor([1.0 if mine[k] else 0.0 for k in names], device="cuda", dtype=torch.float64)
+        dist.all_reduce(flags_mine, op=dist.ReduceOp.MIN)
+        result["parity"] = {k: bool(flags_mine[i].item() > 0.5) for i, k in enumerate(names)}
+        result["parity_ok"] = bool(names) and all(result["parity"].values())
+        result["parity_note"] = ("toy inputs, %d ranks vs the oracle's %d-worker emulation: pools bit-exact after "
+                                 "every episode, embeddings rtol 1e-3 (tests/multi_rank_worker.py); min over ranks" %
+                                 (world, world))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        child = run_reference_child(args, max(2, min(args.steps, 10)))
+        if "unavailable" in child:
             result["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": os.cpu_count(), "kind": "reference",
-                                      "sample": "unavailable: %s" % error}
+                                      "sample": "unavailable: %s" % child["unavailable"]}
+        else:
+            result["cpu_baseline"] = child["cpu_baseline"]
     if rank == 0:
         print(json.dumps(result), flush=True)
-    solver2.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# knowledge-graph workload (config #4): KnowledgeGraphSolver, RotatE d=2048, Adam
+# --------------------------------------------------------------------------------------------------
+def kg_bytes_per_positive(dim, k, num_moment, adversarial=True):
+    """negative rows once for the normaliser, once read-modify-write with their moments; the
+    positive head / tail / relation rows (+ moments) once each way."""
+    row = dim * 4
+    relation_row = row // 2  # RotatE: phases
+    states = 1 + num_moment
+    return ((k * row if adversarial else 0) + k * states * 2 * row + states * 2 * (2 * row + relation_row) +
+            12 + 8 * k + 4)
+
+
+def run_ours_kg(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import graphvite_b200 as gv
+    from graphvite_b200 import _lib, datasets
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    path = "/tmp/gv_b200_fb15k237.txt"
+    if rank == 0 and not os.path.exists(path):
+        datasets.synthetic_knowledge_graph_file("fb15k-237", path + ".tmp")
+        os.replace(path + ".tmp", path)
+    if world > 1:
+        dist.barrier()
+    graph = gv.graph.KnowledgeGraph()
+    graph.load(path)
+    solver = gv.solver.KnowledgeGraphSolver(cfg["dim"], device_ids=[local_rank], rank=rank, world_size=world)
+    solver.build(graph, gv.optimizer.Adam(cfg["lr"], cfg["weight_decay"]), num_partition=args.partitions,
+                 num_negative=cfg["num_negative"], batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
+    lib, handle = _lib.lib, solver._handle
+    _lib.check(lib.gv_kg_solver_train_begin(handle, cfg["model"].encode(), 1000, 0, 1.0, cfg["margin"],
+                                            cfg["l3_regularization"], cfg["sample_batch_size"], 1,
+                                            cfg["adversarial_temperature"], 100))
+    for _ in range(args.warmup):
+        assert lib.gv_kg_solver_train_episode(handle) == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    before = solver.stats
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    start = time.time()
+    for _ in range(args.steps):
+        assert lib.gv_kg_solver_train_episode(handle) == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    seconds = time.time() - start
+    after = solver.stats
+    clocks = sampler.stop() if sampler else None
+    positives = after["positives"] - before["positives"]
+    kernel_seconds = after["kernel_seconds"] - before["kernel_seconds"]
+    if world > 1:
+        t = torch.tensor([seconds, kernel_seconds], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds, kernel_seconds = float(t[0].item()), float(t[1].item())
+    _lib.check(lib.gv_kg_solver_train_end(handle))
+    per_positive = kg_bytes_per_positive(cfg["dim"], cfg["num_negative"], 2)
+    peak, peak_kind = measured_peak()
+    achieved = positives * per_positive / max(kernel_seconds, 1e-12) / 1e9
+    result = {
+        "metric": metric_name(cfg), "value": positives * world / seconds, "unit": "triplets/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "graphvite_b200",
+        "config": {"workload": workload_text(cfg, graph.num_vertex, graph.num_edge),
+                   "num_partition": solver.num_partition},
+        "step": "one episode = every rank's blocks of the tied-weight schedule, %d positives per rank" %
+                (positives // max(1, args.steps)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_kind, "bytes_per_positive": per_positive,
+                     "kernel": "gv::device::kg_train_kernel",
+                     "note": "algorithmic bytes; entity rows + 2 Adam moments of one rank's two blocks are %.0f MB, so "
+                             "part of the negative-row traffic is served by the 126 MB L2 (frac > 1 is possible)" %
+                             (2.0 * graph.num_vertex / max(1, solver.num_partition) * cfg["dim"] * 4 * 3 / 1e6)},
+        "gpu_launches": int(after["launches"] - before["launches"]),
+        "clocks": clocks,
+        "entity_norm": float(np.linalg.norm(solver.entity_embeddings)),
+    }
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    solver.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -293,64 +544,102 @@ def reference_train(cfg, path, num_gpu, steps):
     solver.build(graph, ref.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), 0, cfg["num_negative"],
                  cfg["batch_size"], cfg["episode_size"])
     P, E, B = solver.num_partition, solver.episode_size, solver.batch_size
-    per_episode = P * P * E * B
-    episodes = max(1, int(round(steps * num_gpu * E * B / per_episode)))
-    num_epoch = max(1, int(np.ceil(episodes * per_episode / graph.num_edge)) - 1)
+    num_epoch, _ = epochs_for(steps, num_gpu, P, E, B, graph.num_edge)
     kwargs = dict(model=cfg["model"], num_epoch=num_epoch, resume=False,
                   augmentation_step=cfg["augmentation_step"], random_walk_length=cfg["random_walk_length"],
-                  random_walk_batch_size=cfg["random_walk_batch_size"], negative_weight=cfg["negative_weight"],
-                  log_frequency=1 << 30)
+                  random_walk_batch_size=cfg["random_walk_batch_size"], p=cfg["p"], q=cfg["q"],
+                  negative_weight=cfg["negative_weight"], log_frequency=1 << 30)
     start = time.time()
     solver.train(**kwargs)
     seconds = time.time() - start
     num_batch = num_epoch * graph.num_edge // B
-    per_episode_batches = per_episode // B
+    per_episode_batches = P * P * E
     trained = -(-num_batch // per_episode_batches) * per_episode_batches * B
-    norms = [float(np.linalg.norm(solver.vertex_embeddings)), float(np.linalg.norm(solver.context_embeddings))]
     return {"edges": trained, "seconds": seconds, "num_sampler": solver.num_sampler, "num_worker": solver.num_worker,
-            "num_partition": P, "norms": norms, "graph": graph, "steps": trained // (E * B * num_gpu)}
+            "num_partition": P, "num_epoch": num_epoch, "graph": graph, "solver": solver,
+            "steps": trained // (E * B * num_gpu)}
 
 
-def reference_baseline(cfg, path, num_gpu, steps):
-    r = reference_train(cfg, path, num_gpu, steps)
-    return {"value": r["edges"] / r["seconds"], "unit": "edges/s", "cores": r["num_sampler"] + r["num_worker"],
-            "kind": "reference",
-            "sample": "reference GraphSolver.train(): %d edges (%d sub-episodes) in %.2f s wall, %d CPU sampler "
-                      "threads + %d GPU worker thread(s), host has %d logical cores" %
-                      (r["edges"], r["steps"], r["seconds"], r["num_sampler"], r["num_worker"], os.cpu_count())}
+def reference_child(args, cfg):
+    """Runs in its own process (the reference abort()s on every error, util/debug.h:30-38): one warm-up run, one
+    timed run, one JSON line."""
+    path = graph_file(cfg["graph"])
+    warm = reference_train(cfg, path, args.gpus, 1)  # CUDA context, page-in, first allocations
+    del warm
+    r = reference_train(cfg, path, args.gpus, args.steps)
+    value = r["edges"] / r["seconds"]
+    graph, solver = r["graph"], r["solver"]
+    cores = r["num_sampler"] + r["num_worker"]
+    sample = ("warmed GraphSolver.train() wall time for %d edges (%d sub-episodes per GPU, num_epoch %d), %d CPU "
+              "sampler threads + %d worker thread(s), host has %d logical cores" %
+              (r["edges"], r["steps"], r["num_epoch"], r["num_sampler"], r["num_worker"], os.cpu_count()))
+    from graphvite_b200 import datasets
+    model_quality = None
+    if cfg["graph"] in datasets.SHAPES:
+        model_quality = quality(np.array(solver.vertex_embeddings), np.array(solver.context_embeddings),
+                                graph.name2id, cfg["graph"])
+        model_quality["num_epoch"] = r["num_epoch"]
+        try:
+            json.dump(model_quality, open(reference_note_path(args.workload, args.gpus), "w"))
+        except OSError:
+            pass
+    print(json.dumps({
+        "metric": metric_name(cfg), "value": value, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] / max(1, r["steps"]) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": workload_text(cfg, graph.num_vertex, graph.num_edge),
+                   "num_partition": r["num_partition"]},
+        "steps_run": int(r["steps"]),
+        "warmup_note": "one untimed GraphSolver.train() of one episode in the same process (the reference has no "
+                       "step API; --warmup is echoed for the driver's bookkeeping)",
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "model_quality": model_quality,
+    }), flush=True)
+
+
+def run_reference_child(args, steps):
+    """Launch `bench.py --impl reference-child` and parse its line; a crash of the reference becomes
+    {"unavailable": <its last words>} instead of taking this process down."""
+    command = [sys.executable, os.path.abspath(__file__), "--impl", "reference-child", "--gpus", str(args.gpus),
+               "--steps", str(steps), "--warmup", str(args.warmup), "--workload", args.workload, "--watchdog", "0"]
+    env = dict(os.environ)
+    for name in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):  # one process drives all GPUs
+        env.pop(name, None)
+    try:
+        done = subprocess.run(command, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
+                              timeout=max(300, args.watchdog - 120 if args.watchdog else 1200))
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "the reference run did not finish in time"}
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log_dir):
+        with open(os.path.join(log_dir, "reference_stderr_n%d.log" % args.gpus), "w") as fout:
+            fout.write(done.stderr[-20000:])
+    for line in reversed(done.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                continue
+    words = [x for x in done.stderr.strip().splitlines() if x.strip()]
+    return {"unavailable": "reference process ended with code %d: %s" %
+                           (done.returncode, (words[-1] if words else "no output")[:300])}
 
 
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return  # the reference is one process driving all GPUs from threads
-    try:
-        path = graph_file(cfg["graph"])
-        reference_train(cfg, path, args.gpus, 1)  # warm-up: CUDA context, page-in, first allocations
-        r = reference_train(cfg, path, args.gpus, args.steps)
-    except Exception as error:
-        print(json.dumps({"impl": "reference", "unavailable": str(error).splitlines()[0][:200]}), flush=True)
+    if cfg["solver"] != "graph":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm is wired for the node-embedding "
+                          "workloads only"}), flush=True)
         return
-    value = r["edges"] / r["seconds"]
-    graph = r["graph"]
-    cores = r["num_sampler"] + r["num_worker"]
-    sample = ("GraphSolver.train() wall time for %d edges (%d sub-episodes per GPU), %d CPU sampler threads + %d "
-              "worker thread(s)" % (r["edges"], r["steps"], r["num_sampler"], r["num_worker"]))
-    print(json.dumps({
-        "metric": "edges/sec on Youtube LINE d=128", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
-        "steps": int(r["steps"]), "warmup": 1, "ms_per_step": r["seconds"] / max(1, r["steps"]) * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "impl": "reference",
-        "config": {"workload": "LINE d=%d on %s-shaped power-law graph (|V|=%d, %d edge lines), SGD lr=%g wd=%g, "
-                               "k=%d, B=%d, episode_size=%d, augmentation_step=%d, walk length %d" %
-                               (cfg["dim"], cfg["graph"], graph.num_vertex, graph.num_edge, cfg["lr"],
-                                cfg["weight_decay"], cfg["num_negative"], cfg["batch_size"], cfg["episode_size"],
-                                cfg["augmentation_step"], cfg["random_walk_length"]),
-                   "num_partition": r["num_partition"]},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "reference", "sample": sample},
-        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "embedding_norms": r["norms"],
-    }), flush=True)
+    child = run_reference_child(args, args.steps)
+    if "unavailable" in child:
+        print(json.dumps({"impl": "reference", "unavailable": child["unavailable"]}), flush=True)
+    else:
+        print(json.dumps(child), flush=True)
 
 
 def start_watchdog(seconds):
@@ -370,21 +659,28 @@ def main():
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=10)
     parser.add_argument("--warmup", type=int, default=3)
-    parser.add_argument("--impl", default="graphvite_b200", choices=["graphvite_b200", "reference"])
+    parser.add_argument("--impl", default="graphvite_b200", choices=["graphvite_b200", "reference", "reference-child"])
     parser.add_argument("--workload", default="youtube", choices=sorted(WORKLOADS))
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    parser.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity self-check (N > 1)")
     parser.add_argument("--partitions", type=int, default=0, help="num_partition (0 = auto; diagnosis only)")
     parser.add_argument("--watchdog", type=int, default=1500, help="abort after this many seconds (0 = never)")
     args = parser.parse_args()
     if args.watchdog > 0:
         start_watchdog(args.watchdog)
     cfg = WORKLOADS[args.workload]
+    if args.impl == "reference-child":
+        reference_child(args, cfg)
+        return
     if args.impl == "reference":
         run_reference(args, cfg)
         return
     try:
-        run_ours(args, cfg)
+        if cfg["solver"] == "kg":
+            run_ours_kg(args, cfg)
+        else:
+            run_ours(args, cfg)
     except BaseException:
         # leave at once: a rank that unwinds normally would first wait for its sampler thread, which may be waiting
         # for the peers -- torchrun only stops the other ranks once this process is gone

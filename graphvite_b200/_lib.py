@@ -138,6 +138,7 @@ SIGNATURES = {
     "gv_graph_as_undirected": (c_int, [c_void_p]),
     "gv_graph_normalization": (c_int, [c_void_p]),
     "gv_graph_id2name": (c_char_p, [c_void_p, c_uint64]),
+    "gv_graph_load_id_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int]),
     "gv_graph_name2id": (c_int64, [c_void_p, c_char_p]),
     "gv_graph_flatten": (c_uint64, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gv_graph_info": (c_int, [c_void_p, c_char_p, c_size_t]),

@@ -11,7 +11,7 @@
 #if defined(GV_EMULATE)
 
 // tests/emu/cuda_emu.h (force-included by the emulation build) provides GV_LAUNCH,
-// GV_DYNAMIC_SHARED, gv_named_barrier, gv_global_timer_ns, gv_fast_exp and gv_fast_divide.
+// GV_DYNAMIC_SHARED, gv_named_barrier, gv_global_timer_ns, gv_wait_for, gv_fast_exp and gv_fast_divide.
 
 #else
 
@@ -30,6 +30,11 @@ __device__ __forceinline__ unsigned long long gv_global_timer_ns() {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     return now;
+}
+
+// a scheduling fence on a loaded value: what follows is issued only once `value` has arrived
+__device__ __forceinline__ void gv_wait_for(float &value) {
+    asm volatile("" : "+f"(value)::"memory");
 }
 
 // ex2.approx / rcp.approx based (<= 2 ulp each)

@@ -307,6 +307,61 @@ void Graph::load_edges(const char *const *u_names, const char *const *v_names, c
         normalize();
 }
 
+// Binary edge arrays: the graph load_edges() would build from the edge list [(str(u[i]), str(v[i]))] -- internal ids
+// in order of first appearance, the same edge log, degrees, weights and line count (instance/graph.cuh:124-153,
+// 209-252) -- without creating or hashing 2 * count strings: a Friendster-sized edge list (1.8e9 lines) is read
+// from two uint32 arrays in one pass.  name2id stays empty (gv_graph_name2id answers from id_of_original).
+void Graph::load_id_edges(const uint32_t *u, const uint32_t *v, const float *weights, uint64_t count, bool undirected,
+                          bool normalized) {
+    clear();
+    as_undirected = undirected;
+    normalization = normalized;
+    uint32_t bound = 0;
+    for (uint64_t i = 0; i < count; i++)
+        bound = std::max(bound, std::max(u[i], v[i]));
+    id_of_original.assign(count ? size_t(bound) + 1 : 0, -1);
+    std::vector<uint32_t> original_of;
+    auto intern_id = [&](uint32_t original) {
+        int64_t &slot = id_of_original[original];
+        if (slot < 0) {
+            slot = int64_t(original_of.size());
+            original_of.push_back(original);
+        }
+        return uint32_t(slot);
+    };
+    const uint64_t directed = undirected ? 2 * count : count;
+    log_u.reserve(directed);
+    log_v.reserve(directed);
+    log_w.reserve(directed);
+    for (uint64_t i = 0; i < count; i++) {
+        const uint32_t a = intern_id(u[i]), b = intern_id(v[i]);
+        const float w = weights ? weights[i] : 1.f;
+        log_u.push_back(a);
+        log_v.push_back(b);
+        log_w.push_back(w);
+        if (undirected && a != b) {
+            log_u.push_back(b);
+            log_v.push_back(a);
+            log_w.push_back(w);
+        }
+    }
+    num_edge = count;
+    const size_t n = original_of.size();
+    degrees.assign(n, 0);
+    vertex_weights.assign(n, 0.f);
+    // weighted degrees accumulate in edge order per vertex, like add_edge's `vertex_weights[u] += w`
+    for (size_t e = 0; e < log_u.size(); e++) {
+        degrees[log_u[e]]++;
+        vertex_weights[log_u[e]] += log_w[e];
+    }
+    id2name.resize(n);
+    for (size_t i = 0; i < n; i++)
+        id2name[i] = std::to_string(original_of[i]);
+    flatten();
+    if (normalization)
+        normalize();
+}
+
 // Graph::save, instance/graph.cuh:260-277
 void Graph::save(const char *file_name, bool weighted, bool anonymous) {
     flatten();
@@ -428,8 +483,26 @@ const char *gv_graph_id2name(const gv_graph_t *graph, uint64_t id) {
 }
 
 int64_t gv_graph_name2id(const gv_graph_t *graph, const char *name) {
-    auto found = graph->graph.name2id.find(name);
-    return found == graph->graph.name2id.end() ? -1 : int64_t(found->second);
+    const Graph &g = graph->graph;
+    if (!g.id_of_original.empty()) {  // loaded from id arrays: the name is the decimal id
+        char *end = nullptr;
+        const unsigned long long original = strtoull(name, &end, 10);
+        if (!name[0] || *end || original >= g.id_of_original.size() || std::to_string(original) != name)
+            return -1;
+        return g.id_of_original[original];
+    }
+    auto found = g.name2id.find(name);
+    return found == g.name2id.end() ? -1 : int64_t(found->second);
+}
+
+int gv_graph_load_id_edges(gv_graph_t *graph, const uint32_t *u, const uint32_t *v, const float *weights,
+                           uint64_t num_edge, int as_undirected, int normalization) {
+    GV_TRY
+    if (num_edge && (!u || !v))
+        throw std::runtime_error("gv_graph_load_id_edges: null edge array");
+    graph->graph.load_id_edges(u, v, weights, num_edge, as_undirected != 0, normalization != 0);
+    return 0;
+    GV_CATCH(-1)
 }
 
 uint64_t gv_graph_flatten(gv_graph_t *graph, uint32_t *u, uint32_t *v, float *w, uint64_t *flat_offsets,

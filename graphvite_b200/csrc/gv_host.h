@@ -45,6 +45,10 @@ struct Graph {
                      const char *comment);  // WordGraph, instance/word_graph.cuh:75-166
     void load_edges(const char *const *u_names, const char *const *v_names, const float *weights, uint64_t count,
                     bool undirected, bool normalized);
+    // binary edge arrays (no text, no name hashing): vertex i is named by its decimal id
+    void load_id_edges(const uint32_t *u, const uint32_t *v, const float *weights, uint64_t count, bool undirected,
+                       bool normalized);
+    std::vector<int64_t> id_of_original;  // load_id_edges only: original id -> internal id (first-seen order), -1 = absent
     void save(const char *file_name, bool weighted, bool anonymous);
     bool has_dead_end() const;
     std::string info() const;

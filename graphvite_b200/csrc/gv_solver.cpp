@@ -1497,6 +1497,7 @@ struct Solver {
            << "\nnum_sampler=" << num_sampler << "\ngpu_memory_limit=" << gpu_memory_limit
            << "\ngpu_memory_cost=" << gpu_memory_cost << "\nnum_batch=" << num_batch << "\nbatch_id=" << batch_id
            << "\npool_id=" << pool_id << "\npartition_size=" << partition_size << "\nrank=" << rank
+           << "\nchunk_batches=" << chunk_batches
            << "\noptimizer_type=" << optimizer.type_name() << "\noptimizer_lr=" << optimizer.init_lr
            << "\noptimizer_weight_decay=" << optimizer.desc.weight_decay << "\n";
         return ss.str();

@@ -674,7 +674,7 @@ constexpr int sample_blocks_per_sm() {
 }
 
 template<int DIM, bool LOSS>
-__global__ void __launch_bounds__(kSampleBlockThreads, sample_blocks_per_sm<DIM>())
+__global__ void __launch_bounds__(1024, sample_blocks_per_sm<DIM>() / 2)
     train_sample_per_warp_kernel(const TrainParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t num_warp = gridDim.x * (blockDim.x >> 5);  // the host keeps launches below 2^32 samples
@@ -686,13 +686,25 @@ __global__ void __launch_bounds__(kSampleBlockThreads, sample_blocks_per_sm<DIM>
         const uint32_t batch = i / p.batch_size;
         const float lr = __ldg(p.lr_per_batch + batch);
         Row<DIM> v, c, unused;
-        load_row_plain<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane);
+        const bool l2_only = p.flags & 256;  // experiment: no L1 at all (ld.cg / st.cg)
+        if (l2_only)
+            load_row<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane, false);
+        else
+            load_row_plain<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane);
+        if (p.flags & 128) {
+            // experiment: the vertex row has arrived before the first context row is requested, as in the reference,
+            // whose copy loop into shared memory completes first (gpu/graph.cuh:58-59)
+            gv_wait_for(v.x[0].x);
+        }
         float sample_loss = 0.f;
         for (int s = 0; s <= k; s++) {  // negatives first, then the positive (gpu/graph.cuh:62-71)
             // negatives were drawn by gv_cuda_sample_negatives before this launch (gpu::Sample, solver.h:1536-1539)
             const uint32_t tail = s < k ? __ldg(p.negatives + size_t(i) * k + s) : pair.x;
             float *context = p.context + size_t(tail) * DIM;
-            load_row_plain<DIM>(c, context, lane);
+            if (l2_only)
+                load_row<DIM>(c, context, lane, false);
+            else
+                load_row_plain<DIM>(c, context, lane);
             const float prob = sigmoid(dot<DIM>(v, c));
             float gradient, weight;
             if (s == k) {
@@ -707,9 +719,9 @@ __global__ void __launch_bounds__(kSampleBlockThreads, sample_blocks_per_sm<DIM>
                     sample_loss += weight * -logf(1 - prob + kEpsilon);
             }
             backward<DIM, GV_OPT_SGD>(p.optimizer, lr, gradient, weight, v, c, unused, unused, unused, unused);
-            store_row<DIM>(c, context, lane, true);
+            store_row<DIM>(c, context, lane, !l2_only);
         }
-        store_row<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane, true);
+        store_row<DIM>(v, p.vertex + size_t(pair.y) * DIM, lane, !l2_only);
         if (LOSS && lane == 0) {
             sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
             if (p.loss_per_sample)
@@ -772,6 +784,8 @@ static int g_reserve_sms = getenv("GV_TRAIN_RESERVE_SMS") ? atoi(getenv("GV_TRAI
 // tiled, coalesced fill
 static int g_fill_per_walk = getenv("GV_FILL_PER_WALK") ? atoi(getenv("GV_FILL_PER_WALK")) : 0;
 static int g_sampler_max_ctas = getenv("GV_SAMPLER_MAX_CTAS") ? atoi(getenv("GV_SAMPLER_MAX_CTAS")) : 0;
+// threads per block of the one-warp-per-sample kernel (the reference: 512 = 16 samples per block, 64 warps per SM)
+static int g_sample_block_threads = getenv("GV_SAMPLE_BLOCK_THREADS") ? atoi(getenv("GV_SAMPLE_BLOCK_THREADS")) : 512;
 
 // -----------------------------------------------------------------------------
 // launch helpers
@@ -877,7 +891,11 @@ static int launch_sgd(const TrainParams &p, int num_warps, cudaStream_t stream) 
 // to 131 072 samples in one pass; longer launches simply get more blocks so that the order is kept)
 template<int DIM>
 static int launch_sample_per_warp(const TrainParams &p, int num_warps, cudaStream_t stream) {
-    int threads = kSampleBlockThreads;
+    // experiment knob: warps per block -> resident warps per SM (32 registers: floor(2048 / threads) blocks)
+    int threads = g_sample_block_threads >= 32 && g_sample_block_threads <= 1024 ? g_sample_block_threads / 32 * 32
+                                                                                 : kSampleBlockThreads;
+    if (Row<DIM>::kPass > 1)
+        threads = kSampleBlockThreads;
     unsigned long long blocks = (p.num_sample + threads / 32 - 1) / (threads / 32);
     if (num_warps > 0) {  // tests: a fixed number of warps (1 = sequential) walking the pool with the grid stride
         threads = num_warps >= kSampleBlockThreads / 32 ? kSampleBlockThreads : num_warps * 32;
@@ -1032,6 +1050,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_sampler_max_ctas = int(value);
     else if (key == "train_reserve_sms")
         g_reserve_sms = int(value);
+    else if (key == "sample_block_threads")
+        g_sample_block_threads = int(value);
     else
         return fail("unknown tunable `" + key + "`");
     return 0;
@@ -1051,6 +1071,8 @@ long gv_cuda_get_tunable(const char *name) {
         return g_sampler_max_ctas;
     if (key == "train_reserve_sms")
         return g_reserve_sms;
+    if (key == "sample_block_threads")
+        return g_sample_block_threads;
     fail("unknown tunable `" + key + "`");
     return -1;
 }

@@ -11,10 +11,27 @@ SHAPES = {
     "youtube": (1138499, 4945382),
     "blogcatalog": (10312, 333983),
     "toy": (300, 1500),
+    # the Youtube shape with hub degrees capped at ~2000: node2vec's per-edge alias tables take Sigma deg^2 x 8 B
+    # (209 GB on "youtube", which needs all 8 GPUs; 27 GB here, which fits one)
+    "youtube_capped": (1138499, 4945382),
+    # Friendster (65.6 M vertices, 1.806 G edge lines: BASELINE.json config 5) at 1/16 scale
+    "friendster_lite": (4100000, 112875000),
+    "friendster": (65600000, 1806000000),
 }
+MAX_DEGREE = {"youtube": 29000, "youtube_capped": 2000}
+# graphs that are only ever handed over as integer arrays (graph.Graph.load_arrays), never written as text
+BINARY_GRAPHS = {"friendster_lite", "friendster"}
 
 
-def power_law_edges(num_vertex, num_edge, exponent=2.1, seed=20260922, max_degree=None):
+def named_edges(name, seed=20260922, num_edge=None):
+    """Edge arrays (u, v) of the synthetic graph `name`; num_edge overrides the edge count (evaluation samples of
+    the same generative model)."""
+    num_vertex, edges = SHAPES[name]
+    return power_law_edges(num_vertex, edges if num_edge is None else num_edge, seed=seed,
+                           max_degree=MAX_DEGREE.get(name), cover=num_edge is None)
+
+
+def power_law_edges(num_vertex, num_edge, exponent=2.1, seed=20260922, max_degree=None, cover=True):
     """Chung-Lu style edge list: endpoints drawn proportionally to power-law weights.
 
     Returns int64 arrays (u, v) of length num_edge without self loops; every vertex id in
@@ -31,8 +48,9 @@ def power_law_edges(num_vertex, num_edge, exponent=2.1, seed=20260922, max_degre
     u = np.minimum(u, num_vertex - 1)
     v = np.minimum(v, num_vertex - 1)
     # the first num_vertex edges make sure every vertex appears: edge i touches vertex perm[i]
-    cover = min(num_vertex, num_edge)
-    u[:cover] = rng.permutation(num_vertex)[:cover]
+    if cover:
+        covered = min(num_vertex, num_edge)
+        u[:covered] = rng.permutation(num_vertex)[:covered]
     loops = u == v
     v[loops] = (v[loops] + 1 + rng.integers(0, num_vertex - 1, loops.sum())) % num_vertex
     return u.astype(np.int64), v.astype(np.int64)

@@ -97,6 +97,24 @@ class Graph(object):
         _lib.check(lib.gv_graph_load_edges(self._handle, u_names, v_names, weights, count, int(as_undirected),
                                            int(normalization)))
 
+    def load_arrays(self, u, v, weights=None, as_undirected=True, normalization=False):
+        """load_arrays(u, v, weights=None, as_undirected=True, normalization=False): binary edge list.
+        Not in the reference: the graph `load(edge_list=[(str(a), str(b)) ...])` would build (same ids, same edge
+        order, same counts) from integer numpy arrays, without materialising the names -- for inputs of Friendster's
+        size (1.8e9 edge lines) a Python list of tuples is not an option."""
+        import numpy as np
+        self._id2name = None
+        u = np.ascontiguousarray(u, dtype=np.uint32)
+        v = np.ascontiguousarray(v, dtype=np.uint32)
+        if u.shape != v.shape or u.ndim != 1:
+            raise ValueError("load_arrays(): u and v must be 1-D arrays of the same length")
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        if w is not None and w.shape != u.shape:
+            raise ValueError("load_arrays(): weights must match the edge arrays")
+        _lib.check(lib.gv_graph_load_id_edges(self._handle, u.ctypes.data, v.ctypes.data,
+                                              w.ctypes.data if w is not None else None, len(u), int(as_undirected),
+                                              int(normalization)))
+
     def save(self, file_name, weighted=True, anonymous=False):
         """save(file_name, weighted=True, anonymous=False): save the graph in edge-list format."""
         _lib.check(lib.gv_graph_save(self._handle, file_name.encode(), int(weighted), int(anonymous)))

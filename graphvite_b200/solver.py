@@ -311,7 +311,7 @@ _KG_FLOAT_ATTRIBUTES = {"negative_sample_exponent", "relation_lr_multiplier", "m
 _INT_ATTRIBUTES = {"num_partition", "num_negative", "num_epoch", "episode_size", "batch_size", "augmentation_step",
                    "random_walk_length", "random_walk_batch_size", "shuffle_base", "positive_reuse", "log_frequency",
                    "num_worker", "num_sampler", "gpu_memory_limit", "gpu_memory_cost", "num_batch", "batch_id",
-                   "pool_id", "partition_size", "rank"}
+                   "pool_id", "partition_size", "rank", "chunk_batches"}
 _FLOAT_ATTRIBUTES = {"negative_sample_exponent", "negative_weight", "p", "q"}
 
 __all__ = ["GraphSolver", "KnowledgeGraphSolver"]

@@ -342,6 +342,10 @@ int gv_graph_load_corpus(gv_graph_t *graph, const char *file_name, int window, i
 /* Graph::load_edge_list / load_weighted_edge_list (instance/graph.cuh:209-252); weights may be NULL */
 int gv_graph_load_edges(gv_graph_t *graph, const char *const *u_names, const char *const *v_names,
                         const float *weights, uint64_t num_edge, int as_undirected, int normalization);
+/* The same graph as gv_graph_load_edges on the edge list [(str(u[i]), str(v[i]))] -- first-seen ids, edge order,
+ * line count -- from two uint32 arrays (binary edge lists: Friendster-sized inputs without 3.6e9 strings). */
+int gv_graph_load_id_edges(gv_graph_t *graph, const uint32_t *u, const uint32_t *v, const float *weights,
+                           uint64_t num_edge, int as_undirected, int normalization);
 /* Graph::save (instance/graph.cuh:260-277) */
 int gv_graph_save(gv_graph_t *graph, const char *file_name, int weighted, int anonymous);
 uint64_t gv_graph_num_vertex(const gv_graph_t *graph);

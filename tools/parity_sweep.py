@@ -31,6 +31,18 @@ P = 64  # kernel_flags & 64: the persistent kernels (round 1's); without it SGD 
 SETTINGS = {
     # the shipped default: one warp per sample, one launch per batch, plain loads / stores (the reference's geometry)
     "per_sample": dict(kernel_flags=0, chunk_batches=1),
+    # ... with fewer resident warps per SM (threads per block -> floor(2048 / threads) blocks of 32-register threads)
+    "ps_w60": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=640),
+    "ps_w54": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=576),
+    "ps_w48": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=768),
+    "ps_w44": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=704),
+    # ... with the vertex row complete before the first context row is requested (the reference's copy loop)
+    "ps_serial_w64": dict(kernel_flags=128, chunk_batches=1),
+    "ps_serial_w54": dict(kernel_flags=128, chunk_batches=1, sample_block_threads=576),
+    "ps_serial_w48": dict(kernel_flags=128, chunk_batches=1, sample_block_threads=768),
+    # ... without L1 (how much of the residual is L1 staleness?)
+    "ps_l2only_w64": dict(kernel_flags=256, chunk_batches=1),
+    "ps_l2only_w48": dict(kernel_flags=256, chunk_batches=1, sample_block_threads=768),
     "per_sample_chunk4": dict(kernel_flags=0, chunk_batches=4),
     "per_sample_chunk16": dict(kernel_flags=0, chunk_batches=16),
     # round-1 shipped policy: hub rows through L1, everything else L2-only, 16 batches per launch
@@ -60,6 +72,7 @@ SETTINGS = {
 def apply(gv, setting):
     for name in ("hot_rows", "kernel_flags", "train_blocks_per_sm"):
         gv._clib.gv_cuda_set_tunable(name.encode(), int(setting.get(name, 0)))
+    gv._clib.gv_cuda_set_tunable(b"sample_block_threads", int(setting.get("sample_block_threads", 512)))
 
 
 def run_ours(gv, cfg, graph, test, epochs, setting, num_partition):
