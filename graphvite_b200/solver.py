@@ -145,6 +145,8 @@ class GraphSolver(object):
         raise AttributeError("'GraphSolver' object has no attribute '%s'" % name)
 
     def __repr__(self):
+        if not getattr(self, "_handle", None):
+            return "<GraphSolver (closed)>"
         buffer = ctypes.create_string_buffer(8192)
         lib.gv_solver_info(self._handle, buffer, len(buffer))
         return buffer.value.decode()
@@ -281,6 +283,8 @@ class KnowledgeGraphSolver(object):
         raise AttributeError("'KnowledgeGraphSolver' object has no attribute '%s'" % name)
 
     def __repr__(self):
+        if not getattr(self, "_handle", None):
+            return "<KnowledgeGraphSolver (closed)>"
         buffer = ctypes.create_string_buffer(8192)
         lib.gv_kg_solver_info(self._handle, buffer, len(buffer))
         return buffer.value.decode()
