@@ -40,6 +40,91 @@ def Application(type, *args, **kwargs):
     raise ValueError("Unknown application `%s` (this build ships `graph`, `word graph` and `knowledge graph`)" % type)
 
 
+def _resolve_gpus(gpus):
+    """The reference drives every listed GPU (`gpus: []` = all of them) from threads of one process
+    (core/solver.h:184-213).  Here one process drives one GPU and N processes form the N-GPU solver:
+      * under torchrun (WORLD_SIZE > 1) rank r takes gpus[r] (or GPU LOCAL_RANK for `gpus: []`) and the solver is
+        created with rank / world_size -- the YAML's `gpus: [0, 1, 2, 3]` then means what it means in the reference;
+      * in a single process a list of several GPUs is an error that says how to launch, never a silent truncation;
+        `gpus: []` on a multi-GPU box warns that only one GPU is used.
+    Returns (device_ids, extra solver kwargs)."""
+    gpus = list(gpus)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+        if gpus and len(gpus) != world:
+            raise ValueError("`gpus` lists %d devices but %d processes were launched: start one process per listed "
+                             "GPU (torchrun --nproc-per-node %d)" % (len(gpus), world, len(gpus)))
+        device = gpus[local] if gpus else local
+        torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        return [device], dict(rank=rank, world_size=world)
+    if len(gpus) > 1:
+        raise ValueError("gpus = %s: one process drives one GPU.  Launch one process per GPU -- `torchrun --nnodes=1 "
+                         "--nproc-per-node %d -m graphvite_b200.cmd run <config.yaml>` -- and the %d processes form the "
+                         "reference's %d-GPU solver (2-D block partition, NCCL block rotation)" %
+                         (gpus, len(gpus), len(gpus), len(gpus)))
+    if not gpus:
+        try:
+            import torch
+            count = torch.cuda.device_count()
+        except Exception:
+            count = 1
+        if count > 1:
+            logger.warning("`gpus: []` selects all %d GPUs in the reference; this process drives GPU 0 only -- launch "
+                           "with torchrun --nproc-per-node %d to train on all of them" % (count, count))
+    return gpus, {}
+
+
+def _tokenize(fmt, line):
+    """ApplicationMixin.tokenize (application.py:197-202) with the delimiters / comment of set_format"""
+    comment = fmt["comment"]
+    if comment and comment in line:
+        line = line[:line.index(comment)]
+    for delimiter in fmt["delimiters"]:
+        line = line.replace(delimiter, " ")
+    return line.split()
+
+
+class _Model(dict):
+    """What save_model pickles: a dict whose keys are also attributes, like the reference's EasyDict
+    (application.py:177-187), so that `model.solver.vertex_embeddings` works on either side's files."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+
+def _get_mapping(id2name, name2id):
+    """ApplicationMixin.get_mapping (application.py:189-195): stored row of every current name, or an error"""
+    mapping = np.empty(len(id2name), dtype=np.int64)
+    for i, name in enumerate(id2name):
+        if name not in name2id:
+            raise ValueError("Can't find the embedding for `%s`" % name)
+        mapping[i] = name2id[name]
+    return mapping
+
+
+def _hyperparameters(obj, names):
+    out = {}
+    for name in names:
+        try:
+            value = getattr(obj, name)
+        except Exception:
+            continue
+        if isinstance(value, (bool, int, float, str)):
+            out[name] = value
+    return out
+
+
 class GraphApplication(object):
     """GraphApplication(dim, gpus=[], cpu_per_gpu=auto, gpu_memory_limit=auto, float_type, index_type)
     (application.py:265-291)."""
@@ -53,8 +138,9 @@ class GraphApplication(object):
         self.graph = _graph.Graph(index_type)
         # application.py:283-286: num_sampler_per_worker = cpu_per_gpu - 1
         num_sampler_per_worker = auto if cpu_per_gpu == auto else cpu_per_gpu - 1
-        self.solver = _solver.GraphSolver(dim, float_type, index_type, self.gpus[:1], num_sampler_per_worker,
-                                          gpu_memory_limit, **kwargs)
+        device_ids, placement = _resolve_gpus(self.gpus)
+        self.solver = _solver.GraphSolver(dim, float_type, index_type, device_ids, num_sampler_per_worker,
+                                          gpu_memory_limit, **dict(placement, **kwargs))
 
     def set_format(self, delimiters=" \t\r\n", comment="#"):
         """application.py:64-76"""
@@ -94,15 +180,17 @@ class GraphApplication(object):
     # application.py:353-453, scored with the solver's own predict kernel instead of a torch module
     def link_prediction(self, H=None, T=None, Y=None, file_name=None, filter_H=None, filter_T=None,
                         filter_file=None):
+        fmt = getattr(self, "_format", dict(delimiters=" \t\r\n", comment="#"))
+
         def read(path, width):
             rows = []
             with open(path, "r") as fin:
-                for line in fin:
-                    tokens = line.split("#")[0].split()
+                for i, line in enumerate(fin):
+                    tokens = _tokenize(fmt, line)
                     if not tokens:
                         continue
                     if len(tokens) != width:
-                        raise ValueError("Invalid line `%s`" % line.strip())
+                        raise ValueError("Invalid line format at line %d in %s" % (i + 1, path))
                     rows.append(tokens)
             return rows
 
@@ -144,13 +232,16 @@ class GraphApplication(object):
             if not (X is None and Y is None):
                 raise ValueError("Evaluation data and file should not be provided at the same time")
             X, Y = [], []
+            fmt = getattr(self, "_format", dict(delimiters=" \t\r\n", comment="#"))
             with open(file_name, "r") as fin:
-                for line in fin:
-                    tokens = line.split("#")[0].split()
-                    if tokens:
-                        x, y = tokens
-                        X.append(x)
-                        Y.append(y)
+                for i, line in enumerate(fin):
+                    tokens = _tokenize(fmt, line)
+                    if not tokens:
+                        continue
+                    if len(tokens) != 2:
+                        raise ValueError("Invalid line format at line %d in %s" % (i + 1, file_name))
+                    X.append(tokens[0])
+                    Y.append(tokens[1])
         if X is None or Y is None:
             raise ValueError("Either evaluation data (X, Y) or a file name should be provided")
         name2id = self.graph.name2id
@@ -206,23 +297,28 @@ class GraphApplication(object):
 
     # application.py:145-187 / 131-143
     def save_model(self, file_name, save_hyperparameter=False):
-        objects = {"graph": {"name2id": dict(self.graph.name2id.items()), "id2name": list(self.graph.id2name)},
-                   "solver": {"vertex_embeddings": np.array(self.solver.vertex_embeddings),
-                              "context_embeddings": np.array(self.solver.context_embeddings)}}
+        model = _Model()
+        model.graph = _Model(name2id=dict(self.graph.name2id.items()), id2name=list(self.graph.id2name))
+        model.solver = _Model(vertex_embeddings=np.array(self.solver.vertex_embeddings),
+                              context_embeddings=np.array(self.solver.context_embeddings))
+        if save_hyperparameter:  # application.py:179-184: every int / float / str attribute
+            model.graph.update(_hyperparameters(self.graph, ("num_vertex", "num_edge", "as_undirected", "normalization")))
+            model.solver.update(_hyperparameters(self.solver, sorted(_solver._INT_ATTRIBUTES | _solver._FLOAT_ATTRIBUTES
+                                                                     | {"model", "resume", "dim"})))
+            optimizer = self.solver.optimizer
+            if optimizer is not None:
+                model.solver.optimizer = _Model(_hyperparameters(optimizer, [n for n in dir(optimizer)
+                                                                             if not n.startswith("_")]))
+                model.solver.optimizer.schedule = optimizer.schedule.type
         with open(file_name, "wb") as fout:
-            pickle.dump(objects, fout, protocol=pickle.HIGHEST_PROTOCOL)
+            pickle.dump(model, fout, protocol=pickle.HIGHEST_PROTOCOL)
 
     def load_model(self, file_name):
         with open(file_name, "rb") as fin:
-            objects = pickle.load(fin)
-        mapping = objects["graph"]["name2id"]
-        name2id = self.graph.name2id
-        for key in ("vertex_embeddings", "context_embeddings"):
-            view = getattr(self.solver, key)
-            stored = objects["solver"][key]
-            for name, old in mapping.items():
-                if name in name2id:
-                    view[name2id[name]] = stored[old]
+            model = pickle.load(fin)
+        mapping = _get_mapping(self.graph.id2name, model["graph"]["name2id"])  # raises on a missing name
+        self.solver.vertex_embeddings[:] = np.asarray(model["solver"]["vertex_embeddings"])[mapping]
+        self.solver.context_embeddings[:] = np.asarray(model["solver"]["context_embeddings"])[mapping]
         return self
 
 
@@ -252,8 +348,9 @@ class KnowledgeGraphApplication(object):
         self.gpu_memory_limit = gpu_memory_limit
         self.graph = _graph.KnowledgeGraph(index_type)
         num_sampler_per_worker = auto if cpu_per_gpu == auto else cpu_per_gpu - 1  # application.py:632-638
-        self.solver = _solver.KnowledgeGraphSolver(dim, float_type, index_type, self.gpus[:1], num_sampler_per_worker,
-                                                   gpu_memory_limit, **kwargs)
+        device_ids, placement = _resolve_gpus(self.gpus)
+        self.solver = _solver.KnowledgeGraphSolver(dim, float_type, index_type, device_ids, num_sampler_per_worker,
+                                                   gpu_memory_limit, **dict(placement, **kwargs))
 
     def set_format(self, delimiters=" \t\r\n", comment="#"):
         self._format = dict(delimiters=delimiters, comment=comment)

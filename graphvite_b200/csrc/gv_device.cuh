@@ -11,7 +11,7 @@
 #if defined(GV_EMULATE)
 
 // tests/emu/cuda_emu.h (force-included by the emulation build) provides GV_LAUNCH,
-// GV_DYNAMIC_SHARED, gv_named_barrier, gv_global_timer_ns, gv_wait_for, gv_fast_exp and gv_fast_divide.
+// GV_DYNAMIC_SHARED, gv_named_barrier, gv_global_timer_ns, gv_wait_for, gv_prefetch_l2, gv_fast_exp and gv_fast_divide.
 
 #else
 
@@ -35,6 +35,11 @@ __device__ __forceinline__ unsigned long long gv_global_timer_ns() {
 // a scheduling fence on a loaded value: what follows is issued only once `value` has arrived
 __device__ __forceinline__ void gv_wait_for(float &value) {
     asm volatile("" : "+f"(value)::"memory");
+}
+
+// bring the line holding `address` into L2 without waiting for it
+__device__ __forceinline__ void gv_prefetch_l2(const void *address) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(address));
 }
 
 // ex2.approx / rcp.approx based (<= 2 ulp each)

@@ -73,6 +73,7 @@ struct TrainParams {
                 //      compile to: the writing SM's L1 copy stays current) instead of st.global.cg
     unsigned int *work_counter;  // flags & 8: {next ticket, warps done}; both zero between launches
     uint32_t hot_rows;  // rows with a local id below this are loaded through L1 (.ca), the rest L2-only (.cg)
+    uint32_t prefetch_blocks;  // one-warp-per-sample kernel: index lines of the block this far ahead are pulled into L2
 };
 
 // Which 32-sample chunk a warp takes after `chunk`.  Static: the grid-stride successor.  Dynamic (work_counter):
@@ -680,6 +681,22 @@ __global__ void __launch_bounds__(1024, sample_blocks_per_sm<DIM>() / 2)
     const uint32_t num_warp = gridDim.x * (blockDim.x >> 5);  // the host keeps launches below 2^32 samples
     const uint32_t num_sample = uint32_t(p.num_sample);
     const int k = p.num_negative;
+    if (p.prefetch_blocks && threadIdx.x < 32) {
+        // The pool entries and negative ids are streamed once, so every warp would begin with a DRAM round trip before
+        // it can even ask for its vertex row.  The first warp of a block pulls the index lines of the block that runs
+        // `prefetch_blocks` later into L2: by then they are an L2 hit, the warp's rows are requested sooner, and a
+        // larger share of its lifetime is the read-modify-write window -- as in the reference, whose warps live 10 us
+        // and spend almost all of it between reading and writing their vertex row.
+        const unsigned long long first = (unsigned long long)(blockIdx.x + p.prefetch_blocks) * (blockDim.x >> 5);
+        const unsigned long long pool_bytes = (unsigned long long)(blockDim.x >> 5) * sizeof(uint2);
+        const unsigned long long negative_bytes = (unsigned long long)(blockDim.x >> 5) * k * sizeof(uint32_t);
+        if (first < num_sample) {
+            if (lane * 128ull < pool_bytes)
+                gv_prefetch_l2(reinterpret_cast<const char *>(p.pool + first) + lane * 128);
+            if (lane * 128ull < negative_bytes)
+                gv_prefetch_l2(reinterpret_cast<const char *>(p.negatives + first * k) + lane * 128);
+        }
+    }
     // the reference's grid-stride loop (gpu/graph.cuh:54); one iteration unless the launch was capped
     for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < num_sample; i += num_warp) {
         const uint2 pair = __ldg(p.pool + i);  // {tail, head}: one broadcast load per warp
@@ -786,6 +803,8 @@ static int g_fill_per_walk = getenv("GV_FILL_PER_WALK") ? atoi(getenv("GV_FILL_P
 static int g_sampler_max_ctas = getenv("GV_SAMPLER_MAX_CTAS") ? atoi(getenv("GV_SAMPLER_MAX_CTAS")) : 0;
 // threads per block of the one-warp-per-sample kernel (the reference: 512 = 16 samples per block, 64 warps per SM)
 static int g_sample_block_threads = getenv("GV_SAMPLE_BLOCK_THREADS") ? atoi(getenv("GV_SAMPLE_BLOCK_THREADS")) : 512;
+// one-warp-per-sample kernel: how many blocks ahead the index lines are prefetched into L2 (0 = off)
+static int g_sample_prefetch_blocks = getenv("GV_SAMPLE_PREFETCH_BLOCKS") ? atoi(getenv("GV_SAMPLE_PREFETCH_BLOCKS")) : 0;
 
 // -----------------------------------------------------------------------------
 // launch helpers
@@ -1023,6 +1042,7 @@ int gv_cuda_train_block(const gv_matrices_t *m, const uint32_t *pool, uint64_t n
     p.loss_per_batch = loss_per_batch;
     p.flags = g_kernel_flags;
     p.hot_rows = g_hot_rows;
+    p.prefetch_blocks = uint32_t(g_sample_prefetch_blocks);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     p.work_counter = (g_kernel_flags & 8) ? work_counter_for(s) : nullptr;
     switch (m->dim) {  // src/graphvite.cu:52-59 instantiates exactly these dimensions
@@ -1052,6 +1072,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_reserve_sms = int(value);
     else if (key == "sample_block_threads")
         g_sample_block_threads = int(value);
+    else if (key == "sample_prefetch_blocks")
+        g_sample_prefetch_blocks = int(value < 0 ? 0 : value);
     else
         return fail("unknown tunable `" + key + "`");
     return 0;
@@ -1073,6 +1095,8 @@ long gv_cuda_get_tunable(const char *name) {
         return g_reserve_sms;
     if (key == "sample_block_threads")
         return g_sample_block_threads;
+    if (key == "sample_prefetch_blocks")
+        return g_sample_prefetch_blocks;
     fail("unknown tunable `" + key + "`");
     return -1;
 }

@@ -36,6 +36,11 @@ SETTINGS = {
     "ps_w54": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=576),
     "ps_w48": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=768),
     "ps_w44": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=704),
+    # ... with the index lines prefetched into L2 N blocks ahead (592 blocks = one resident wave)
+    "ps_pf592": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=592),
+    "ps_pf1184": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=1184),
+    "ps_pf2368": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=2368),
+    "ps_pf1184_serial": dict(kernel_flags=128, chunk_batches=1, sample_prefetch_blocks=1184),
     # ... with the vertex row complete before the first context row is requested (the reference's copy loop)
     "ps_serial_w64": dict(kernel_flags=128, chunk_batches=1),
     "ps_serial_w54": dict(kernel_flags=128, chunk_batches=1, sample_block_threads=576),
@@ -73,6 +78,7 @@ def apply(gv, setting):
     for name in ("hot_rows", "kernel_flags", "train_blocks_per_sm"):
         gv._clib.gv_cuda_set_tunable(name.encode(), int(setting.get(name, 0)))
     gv._clib.gv_cuda_set_tunable(b"sample_block_threads", int(setting.get("sample_block_threads", 512)))
+    gv._clib.gv_cuda_set_tunable(b"sample_prefetch_blocks", int(setting.get("sample_prefetch_blocks", 0)))
 
 
 def run_ours(gv, cfg, graph, test, epochs, setting, num_partition):
