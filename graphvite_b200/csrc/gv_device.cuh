@@ -11,7 +11,7 @@
 #if defined(GV_EMULATE)
 
 // tests/emu/cuda_emu.h (force-included by the emulation build) provides GV_LAUNCH,
-// GV_DYNAMIC_SHARED, gv_named_barrier, gv_global_timer_ns, gv_wait_for, gv_prefetch_l2, gv_fast_exp and gv_fast_divide.
+// GV_DYNAMIC_SHARED, gv_named_barrier, gv_global_timer_ns, gv_wait_for, gv_load_again, gv_prefetch_l2, gv_fast_exp and gv_fast_divide.
 
 #else
 
@@ -35,6 +35,13 @@ __device__ __forceinline__ unsigned long long gv_global_timer_ns() {
 // a scheduling fence on a loaded value: what follows is issued only once `value` has arrived
 __device__ __forceinline__ void gv_wait_for(float &value) {
     asm volatile("" : "+f"(value)::"memory");
+}
+
+// a plain ld.global that the compiler may neither drop nor merge with an earlier load of the same address
+__device__ __forceinline__ float gv_load_again(const float *address) {
+    float value;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(value) : "l"(address) : "memory");
+    return value;
 }
 
 // bring the line holding `address` into L2 without waiting for it

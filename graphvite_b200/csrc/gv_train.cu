@@ -667,7 +667,16 @@ __global__ void __launch_bounds__(kBlockThreads) train_sgd_kernel(const TrainPar
 //    element; the negatives are drawn by a pre-pass like the reference's gpu::Sample launch.
 // Latency is hidden by occupancy (64 warps x 1.5 KB in flight per SM), not by software pipelining.
 // -----------------------------------------------------------------------------
-constexpr int kSampleBlockThreads = 512;  // instance/gpu/graph.cuh: kThreadPerBlock = 512 -> 16 samples per block
+constexpr int kSampleBlockThreads = 512;
+
+// an index load the compiler keeps where it is written (the reference loads head, negative and tail ids one after
+// another, each right before it is needed); `word` selects .x / .y of a {tail, head} pool entry
+__device__ __forceinline__ uint32_t gv_load_again_u32(const uint2 *entry, int word) {
+    return __float_as_uint(gv_load_again(reinterpret_cast<const float *>(entry) + word));
+}
+__device__ __forceinline__ uint32_t gv_load_again_u32(const uint32_t *entry, int) {
+    return __float_as_uint(gv_load_again(reinterpret_cast<const float *>(entry)));
+}  // instance/gpu/graph.cuh: kThreadPerBlock = 512 -> 16 samples per block
 
 template<int DIM>
 constexpr int sample_blocks_per_sm() {
@@ -749,6 +758,84 @@ __global__ void __launch_bounds__(1024, sample_blocks_per_sm<DIM>() / 2)
     }
 }
 
+
+// -----------------------------------------------------------------------------
+// kernel_flags & 512: the reference's memory TIMELINE as well as its geometry -- a measuring instrument, not a fast
+// path.  The reference's warp touches a row 128 bytes at a time (lane l owns elements l, l + 32, ..., base/vector.h:
+// 62-71, util/gpu.cuh:24-27) and its loops are not unrolled (SASS of gpu::graph::train: LDG; STS; BRA for the vertex
+// copy, LDG; LDS; FFMA; BRA for the dot product, LDG; LDS; ...; STS; STG; BRA for the update): every 128-byte segment
+// is a separate dependent round trip, the context row is read a second time in the backward loop, and a warp lives
+// ~10 us of which the vertex row's read-modify-write window is >80 %.  How long those windows are, relative to a
+// warp's lifetime, decides how many concurrent updates of a row are lost.  This variant reproduces that timeline with
+// the arithmetic of the kernels above; it runs at the reference kernel's own speed (~1e9 edges/s) and exists to show
+// that the residual between train_sample_per_warp_kernel and the reference is the timeline's.
+// -----------------------------------------------------------------------------
+template<int DIM, bool LOSS>
+__global__ void __launch_bounds__(kSampleBlockThreads, 4) train_reference_timeline_kernel(const TrainParams p) {
+    constexpr int N = DIM / 32;
+    const int lane = threadIdx.x & 31;
+    const uint32_t num_warp = gridDim.x * (blockDim.x >> 5);
+    const uint32_t num_sample = uint32_t(p.num_sample);
+    const int k = p.num_negative;
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < num_sample; i += num_warp) {
+        const uint32_t head = gv_load_again_u32(p.pool + i, 1);  // batch[sample_id * 2 + 1]
+        const uint32_t batch = i / p.batch_size;
+        const float lr = __ldg(p.lr_per_batch + batch);
+        float *vertex = p.vertex + size_t(head) * DIM;
+        float v[N];
+#pragma unroll 1
+        for (int j = 0; j < N; j++) {  // vertex_buffer = vertex: one segment per round trip
+            v[j] = gv_load_again(vertex + lane + 32 * j);
+            gv_wait_for(v[j]);
+        }
+        float sample_loss = 0.f;
+        for (int s = 0; s <= k; s++) {
+            const uint32_t tail = s < k ? gv_load_again_u32(p.negatives + size_t(i) * k + s, 0)
+                                        : gv_load_again_u32(p.pool + i, 0);
+            float *context = p.context + size_t(tail) * DIM;
+            float acc = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < N; j++) {  // LINE::forward: the dot product, segment by segment
+                float c = gv_load_again(context + lane + 32 * j);
+                gv_wait_for(c);
+                acc = fmaf(v[j], c, acc);
+            }
+            const float prob = sigmoid(warp_sum(acc));
+            float gradient, weight;
+            if (s == k) {
+                gradient = prob - 1;
+                weight = 1;
+                if (LOSS)
+                    sample_loss += weight * -logf(prob + kEpsilon);
+            } else {
+                gradient = prob;
+                weight = p.negative_weight;
+                if (LOSS)
+                    sample_loss += weight * -logf(1 - prob + kEpsilon);
+            }
+            const float scale = lr * weight;
+            const float alpha = 1.f - scale * p.optimizer.weight_decay, beta = scale * gradient;
+#pragma unroll 1
+            for (int j = 0; j < N; j++) {  // LINE::backward: the context row is read again (an L1 hit), then written
+                const float c = gv_load_again(context + lane + 32 * j);
+                const float vv = v[j];
+                v[j] = fmaf(-beta, c, alpha * vv);
+                context[lane + 32 * j] = fmaf(-beta, vv, alpha * c);
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < N; j++)  // vertex = vertex_buffer
+            vertex[lane + 32 * j] = v[j];
+        if (LOSS && lane == 0) {
+            sample_loss = sample_loss / (1 + k * p.negative_weight);
+            if (p.loss_per_sample)
+                p.loss_per_sample[i] = sample_loss;
+            if (p.loss_per_batch)
+                atomicAdd(p.loss_per_batch + batch, sample_loss);
+        }
+    }
+}
+
 // gpu::Sample, base/alias_table.cuh:175-183
 __global__ void __launch_bounds__(256) sample_negatives_kernel(const gv_alias_entry_t *table, uint32_t count,
                                                                const double *random, unsigned long long num,
@@ -803,8 +890,9 @@ static int g_fill_per_walk = getenv("GV_FILL_PER_WALK") ? atoi(getenv("GV_FILL_P
 static int g_sampler_max_ctas = getenv("GV_SAMPLER_MAX_CTAS") ? atoi(getenv("GV_SAMPLER_MAX_CTAS")) : 0;
 // threads per block of the one-warp-per-sample kernel (the reference: 512 = 16 samples per block, 64 warps per SM)
 static int g_sample_block_threads = getenv("GV_SAMPLE_BLOCK_THREADS") ? atoi(getenv("GV_SAMPLE_BLOCK_THREADS")) : 512;
-// one-warp-per-sample kernel: how many blocks ahead the index lines are prefetched into L2 (0 = off)
-static int g_sample_prefetch_blocks = getenv("GV_SAMPLE_PREFETCH_BLOCKS") ? atoi(getenv("GV_SAMPLE_PREFETCH_BLOCKS")) : 0;
+// one-warp-per-sample kernel: how many blocks ahead the index lines are prefetched into L2 (0 = off; 592 = one
+// resident wave of 148 SMs x 4 blocks, the setting closest to the reference in profiles/r02_parity4_*.jsonl)
+static int g_sample_prefetch_blocks = getenv("GV_SAMPLE_PREFETCH_BLOCKS") ? atoi(getenv("GV_SAMPLE_PREFETCH_BLOCKS")) : 592;
 
 // -----------------------------------------------------------------------------
 // launch helpers
@@ -938,11 +1026,17 @@ static int launch_sample_per_warp(const TrainParams &p, int num_warps, cudaStrea
     } else if (q.negatives && q.negatives_out && q.num_negative > 0)
         GV_CUDA_OK(cudaMemcpyAsync(q.negatives_out, q.negatives, q.num_sample * q.num_negative * sizeof(uint32_t),
                                    cudaMemcpyDeviceToDevice, stream));
-    void (*kernel)(const TrainParams) = (p.loss_per_sample || p.loss_per_batch)
-                                            ? train_sample_per_warp_kernel<DIM, true>
-                                            : train_sample_per_warp_kernel<DIM, false>;
-    static bool configured[2] = {false, false};
-    const int which = (p.loss_per_sample || p.loss_per_batch) ? 1 : 0;
+    const bool timeline = (p.flags & 512) && DIM % 32 == 0;
+    void (*kernel)(const TrainParams) =
+        (p.loss_per_sample || p.loss_per_batch)
+            ? (timeline ? train_reference_timeline_kernel<DIM, true> : train_sample_per_warp_kernel<DIM, true>)
+            : (timeline ? train_reference_timeline_kernel<DIM, false> : train_sample_per_warp_kernel<DIM, false>);
+    static bool configured[4] = {false, false, false, false};
+    const int which = ((p.loss_per_sample || p.loss_per_batch) ? 1 : 0) + (timeline ? 2 : 0);
+    if (timeline && num_warps <= 0 && threads != kSampleBlockThreads) {
+        threads = kSampleBlockThreads;
+        blocks = (p.num_sample + threads / 32 - 1) / (threads / 32);
+    }
     if (!configured[which]) {
         // the reference's kernel keeps 4 x 9 KB of shared memory per SM: ask for the same L1 / shared split, so that an
         // L1 line lives about as long here as there (best effort -- a hint, not an error)

@@ -31,17 +31,15 @@ class NoClocks(object):  # nvidia-smi is not here
         return {"sm_mhz": 0, "sm_max_mhz": 0, "reasons": []}
 
 
-def make_solver(cfg, path, rank, world, local_rank, num_partition=0):
+def make_solver(cfg, graph, rank, world, local_rank, num_partition=0):
     """bench.make_solver with the exchange moved to host buffers over gloo (emulated device memory is host memory)"""
     import graphvite_b200 as gv
-    graph = gv.graph.Graph()
-    graph.load(path, as_undirected=True)
     solver = gv.solver.GraphSolver(cfg["dim"], device_ids=[0], rank=rank, world_size=world)
     if world > 1:
         distributed.attach(solver, None)
     solver.build(graph, gv.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), num_partition=num_partition,
                  num_negative=cfg["num_negative"], batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
-    return gv, graph, solver
+    return solver
 
 
 bench.ClockSampler = NoClocks

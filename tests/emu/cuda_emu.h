@@ -131,6 +131,7 @@ unsigned long long gv_global_timer_ns();
 inline float gv_fast_exp(float x) {
     return expf(x);
 }
+inline float gv_load_again(const float *address) { return *address; }
 inline void gv_prefetch_l2(const void *) {}
 inline void gv_wait_for(float &) {}  // a scheduling fence on the GPU; nothing to wait for here
 inline float gv_fast_divide(float a, float b) {

@@ -42,3 +42,7 @@ def test_bench_flow_under_emulation(world):
     assert line["e2e"]["value"] > 0 and line["e2e"]["edges"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert "end-to-end train() done" in result.stderr
+    assert line["model_quality"]["auc"] > 0 and line["model_quality"]["vertex_norm"] > 0
+    if world > 1:  # the multi-rank parity self-check against the oracle's N-worker emulation ran and passed
+        assert line["parity_ok"] is True, line.get("parity")
+        assert set(line["parity"]) >= {"line_P2", "line_P4", "node2vec_P2", "rotate_adam_P4"}

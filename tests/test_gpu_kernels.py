@@ -139,6 +139,27 @@ def test_train_interleaved_single_warp_is_sequential(kernel_flags, flags):
     compare(got, v, c, m, loss)
 
 
+@pytest.mark.parametrize("dim,k,num_warps", [(128, 1, 0), (128, 1, 1), (64, 3, 5), (512, 2, 0)])
+def test_train_reference_timeline_variant(kernel_flags, dim, k, num_warps):
+    """kernel_flags & 512: the one-warp-per-sample kernel with the reference's 128-byte-segment access timeline
+    (a measuring instrument for the Hogwild parity study): same arithmetic, so race-free batches and the
+    single-warp sequential order match the oracle like every other kernel"""
+    from gpu_util import run_train_block
+    kernel_flags(512)
+    optimizer = O.OPTIMIZERS["SGD"]
+    if num_warps == 1:
+        n = 257
+        vertex, context, ms, batch, negatives = make_problem(dim, n, k, 40, 50, seed=dim + k)
+    else:
+        n = 2999
+        vertex, context, ms, batch, negatives = make_problem(dim, n, k, n, n * (k + 1), seed=dim + k, unique=True)
+    lr = np.array([optimizer[1], optimizer[1] * 0.5, optimizer[1] * 0.25], dtype=np.float32)
+    v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives.reshape(n, k), optimizer, 5.0, lr, 1000)
+    got = run_train_block(dim, vertex, context, ms, batch, negatives, optimizer, 5.0, lr=lr, batch_size=1000,
+                          num_warps=num_warps)
+    compare(got, v, c, m, loss)
+
+
 def test_train_large_k_shared_memory_opt_in():
     """k = 200 needs > 48 KB of dynamic shared memory for the id staging"""
     from gpu_util import run_train_block

@@ -31,6 +31,7 @@ P = 64  # kernel_flags & 64: the persistent kernels (round 1's); without it SGD 
 SETTINGS = {
     # the shipped default: one warp per sample, one launch per batch, plain loads / stores (the reference's geometry)
     "per_sample": dict(kernel_flags=0, chunk_batches=1),
+    "shipped": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=592),
     # ... with fewer resident warps per SM (threads per block -> floor(2048 / threads) blocks of 32-register threads)
     "ps_w60": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=640),
     "ps_w54": dict(kernel_flags=0, chunk_batches=1, sample_block_threads=576),
@@ -41,6 +42,8 @@ SETTINGS = {
     "ps_pf1184": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=1184),
     "ps_pf2368": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=2368),
     "ps_pf1184_serial": dict(kernel_flags=128, chunk_batches=1, sample_prefetch_blocks=1184),
+    # ... with the reference's access timeline (128-byte segments, one dependent round trip each): a measuring variant
+    "ps_timeline": dict(kernel_flags=512, chunk_batches=1),
     # ... with the vertex row complete before the first context row is requested (the reference's copy loop)
     "ps_serial_w64": dict(kernel_flags=128, chunk_batches=1),
     "ps_serial_w54": dict(kernel_flags=128, chunk_batches=1, sample_block_threads=576),
