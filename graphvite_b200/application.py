@@ -4,7 +4,9 @@ load / build / train / link_prediction / save_model / load_model, driven by the 
 arguments as the reference's config/*.yaml sections.
 """
 import logging
+import os
 import pickle
+import re
 
 import numpy as np
 
@@ -80,13 +82,20 @@ def _resolve_gpus(gpus):
 
 
 def _tokenize(fmt, line):
-    """ApplicationMixin.tokenize (application.py:197-202) with the delimiters / comment of set_format"""
-    comment = fmt["comment"]
-    if comment and comment in line:
-        line = line[:line.index(comment)]
-    for delimiter in fmt["delimiters"]:
-        line = line.replace(delimiter, " ")
-    return line.split()
+    """ApplicationMixin.tokenize (application.py:197-202) with the delimiters / comment of set_format: strip the
+    delimiters off both ends, cut at the comment prefix, split at delimiter characters.  (The reference splits at
+    every single delimiter, `[%s]`, so two consecutive blanks yield an empty token there and its readers then reject
+    the line; runs of delimiters are one separator here, and an empty line is [] rather than [""].)"""
+    delimiters, comment = fmt["delimiters"], fmt["comment"]
+    line = line.strip(delimiters)
+    if comment:
+        start = line.find(comment)
+        if start != -1:
+            line = line[:start]
+    line = line.strip(delimiters)
+    if not line:
+        return []
+    return re.split("[%s]+" % re.escape(delimiters), line)
 
 
 class _Model(dict):
@@ -386,13 +395,7 @@ class KnowledgeGraphApplication(object):
         return result
 
     def _tokenize(self, line):
-        fmt = getattr(self, "_format", dict(delimiters=" \t\r\n", comment="#"))
-        comment = fmt["comment"]
-        if comment and comment in line:
-            line = line[:line.index(comment)]
-        for delimiter in fmt["delimiters"]:
-            line = line.replace(delimiter, " ")
-        return line.split()
+        return _tokenize(getattr(self, "_format", dict(delimiters=" \t\r\n", comment="#")), line)
 
     def _read_triplets(self, file_name):
         H, R, T = [], [], []
@@ -547,24 +550,27 @@ class KnowledgeGraphApplication(object):
         return recalls
 
     def save_model(self, file_name, save_hyperparameter=False):
-        objects = {"graph": {"entity2id": dict(self.graph.entity2id.items()), "id2entity": list(self.graph.id2entity),
-                             "relation2id": dict(self.graph.relation2id.items()),
-                             "id2relation": list(self.graph.id2relation)},
-                   "solver": {"entity_embeddings": np.array(self.solver.entity_embeddings),
-                              "relation_embeddings": np.array(self.solver.relation_embeddings)}}
+        objects = _Model()
+        objects.graph = _Model(entity2id=dict(self.graph.entity2id.items()), id2entity=list(self.graph.id2entity),
+                               relation2id=dict(self.graph.relation2id.items()),
+                               id2relation=list(self.graph.id2relation))
+        objects.solver = _Model(entity_embeddings=np.array(self.solver.entity_embeddings),
+                                relation_embeddings=np.array(self.solver.relation_embeddings))
+        if save_hyperparameter:
+            objects.solver.update(_hyperparameters(self.solver, sorted(_solver._KG_INT_ATTRIBUTES |
+                                                                       _solver._KG_FLOAT_ATTRIBUTES | {"model", "dim"})))
         with open(file_name, "wb") as fout:
             pickle.dump(objects, fout, protocol=pickle.HIGHEST_PROTOCOL)
 
     def load_model(self, file_name):
-        """set_parameters (application.py:640-644): rows are matched by entity / relation NAME"""
+        """set_parameters (application.py:640-644): rows are matched by entity / relation NAME; a name of the current
+        graph that the checkpoint lacks is an error, as in the reference's get_mapping"""
         with open(file_name, "rb") as fin:
-            objects = pickle.load(fin)
-        for mapping, current, key in (("entity2id", self.graph.entity2id, "entity_embeddings"),
-                                      ("relation2id", self.graph.relation2id, "relation_embeddings")):
-            view, stored = getattr(self.solver, key), objects["solver"][key]
-            for name, old in objects["graph"][mapping].items():
-                if name in current:
-                    view[current[name]] = stored[old]
+            model = pickle.load(fin)
+        entity_mapping = _get_mapping(self.graph.id2entity, model["graph"]["entity2id"])
+        relation_mapping = _get_mapping(self.graph.id2relation, model["graph"]["relation2id"])
+        self.solver.entity_embeddings[:] = np.asarray(model["solver"]["entity_embeddings"])[entity_mapping]
+        self.solver.relation_embeddings[:] = np.asarray(model["solver"]["relation_embeddings"])[relation_mapping]
         return self
 
 

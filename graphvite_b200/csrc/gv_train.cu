@@ -760,6 +760,126 @@ __global__ void __launch_bounds__(1024, sample_blocks_per_sm<DIM>() / 2)
 
 
 // -----------------------------------------------------------------------------
+// kernel_flags & 1024: the same one-warp-per-sample training with RESIDENT blocks.  A block of 16 warps takes groups
+// of 16 consecutive pool entries by ticket (one atomicAdd per group: groups start in pool order, like the reference's
+// blocks) and, while it trains group t, already knows its next group t':
+//   * every warp loads the k + 2 indices of its next sample (one lane each) during the current sample, so the next
+//     vertex row is requested the moment the current one is stored -- no index round trip in front of it.  The share
+//     of a warp's time that is a read-modify-write window rises to what it is in the reference;
+//   * the rows of the next sample are pulled into L2 (prefetch.global.L2, 4 lanes per row): a prefetch is not a read
+//     -- the values are read from L2 when they are needed, after every write that reached L2 before -- so the race
+//     semantics are untouched, but a read no longer waits for DRAM.
+// How many updates of a row are lost depends on how many samples are between reading and writing it at the same
+// time, i.e. on the number of resident blocks: `sample_resident_blocks` (default 4 per SM) is the one calibration knob,
+// set so that the Youtube-shaped model's norms match the unmodified reference's (tools/parity_sweep.py,
+// profiles/r02_parity6_*.jsonl).
+// -----------------------------------------------------------------------------
+template<int DIM, bool LOSS>
+__global__ void __launch_bounds__(kSampleBlockThreads, sample_blocks_per_sm<DIM>())
+    train_resident_groups_kernel(const TrainParams p) {
+    __shared__ unsigned int next_group[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t num_sample = uint32_t(p.num_sample);
+    const uint32_t group_size = blockDim.x >> 5;
+    const int k = p.num_negative;  // k + 2 <= 32 (checked by the host)
+    const bool l2_only = p.flags & 256;
+
+    // index l of sample i: head (l = 0), the k negatives, the positive tail (l = k + 1) -- one lane each
+    auto load_index = [&](uint32_t i) -> uint32_t {
+        if (i >= num_sample || lane > k + 1)
+            return 0u;
+        if (lane == 0)
+            return __ldg(reinterpret_cast<const uint32_t *>(p.pool + i) + 1);
+        if (lane == k + 1)
+            return __ldg(reinterpret_cast<const uint32_t *>(p.pool + i));
+        return __ldg(p.negatives + size_t(i) * k + (lane - 1));
+    };
+
+    if (threadIdx.x == 0)
+        next_group[0] = atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    uint32_t i = next_group[0] * group_size + warp;
+    uint32_t index = load_index(i);
+    int parity = 1;
+    while (true) {
+        // the ticket of the group after this one (a uniform decision: every warp sees the same value)
+        if (threadIdx.x == 0)
+            next_group[parity] = atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        if (i - warp >= num_sample)
+            break;  // this group starts past the end: so does every later ticket
+        const uint32_t i_next = next_group[parity] * group_size + warp;
+        parity ^= 1;
+        const uint32_t index_next = load_index(i_next);  // in flight while this sample is trained
+        if (i < num_sample) {
+            const uint32_t head = __shfl_sync(kFullMask, index, 0);
+            const uint32_t batch = i / p.batch_size;
+            const float lr = __ldg(p.lr_per_batch + batch);
+            Row<DIM> v, c, unused;
+            float *vertex = p.vertex + size_t(head) * DIM;
+            if (l2_only)
+                load_row<DIM>(v, vertex, lane, false);
+            else
+                load_row_plain<DIM>(v, vertex, lane);
+            float sample_loss = 0.f;
+            for (int s = 0; s <= k; s++) {  // negatives first, then the positive (gpu/graph.cuh:62-71)
+                const uint32_t tail = __shfl_sync(kFullMask, index, s + 1);
+                float *context = p.context + size_t(tail) * DIM;
+                if (l2_only)
+                    load_row<DIM>(c, context, lane, false);
+                else
+                    load_row_plain<DIM>(c, context, lane);
+                if (s == 0 && p.prefetch_blocks && i_next < num_sample) {
+                    // rows of the next sample -> L2: lanes 4r .. 4r + 3 take the four 128-byte lines of row r
+                    constexpr int kLines = (DIM * 4 + 127) / 128, kRows = 32 / kLines;
+                    for (int first = 0; first <= k + 1; first += kRows) {
+                        const int r = first + lane / kLines;
+                        const uint32_t row = __shfl_sync(kFullMask, index_next, r & 31);
+                        if (r <= k + 1 && lane < kRows * kLines) {
+                            const float *base = (r == 0 ? p.vertex : p.context) + size_t(row) * DIM;
+                            gv_prefetch_l2(reinterpret_cast<const char *>(base) + (lane % kLines) * 128);
+                        }
+                    }
+                }
+                const float prob = sigmoid(dot<DIM>(v, c));
+                float gradient, weight;
+                if (s == k) {
+                    gradient = prob - 1;
+                    weight = 1;
+                    if (LOSS)
+                        sample_loss += weight * -logf(prob + kEpsilon);
+                } else {
+                    gradient = prob;
+                    weight = p.negative_weight;
+                    if (LOSS)
+                        sample_loss += weight * -logf(1 - prob + kEpsilon);
+                }
+                backward<DIM, GV_OPT_SGD>(p.optimizer, lr, gradient, weight, v, c, unused, unused, unused, unused);
+                store_row<DIM>(c, context, lane, !l2_only);
+            }
+            store_row<DIM>(v, vertex, lane, !l2_only);
+            if (LOSS && lane == 0) {
+                sample_loss = sample_loss / (1 + k * p.negative_weight);  // gpu/graph.cuh:91-92
+                if (p.loss_per_sample)
+                    p.loss_per_sample[i] = sample_loss;
+                if (p.loss_per_batch)
+                    atomicAdd(p.loss_per_batch + batch, sample_loss);
+            }
+        }
+        i = i_next;
+        index = index_next;
+    }
+    // the last block to leave re-arms the ticket counter for the next launch of this stream
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(p.work_counter + 1, 1u);
+        if (done + 1 == gridDim.x) {
+            p.work_counter[0] = 0;
+            p.work_counter[1] = 0;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------
 // kernel_flags & 512: the reference's memory TIMELINE as well as its geometry -- a measuring instrument, not a fast
 // path.  The reference's warp touches a row 128 bytes at a time (lane l owns elements l, l + 32, ..., base/vector.h:
 // 62-71, util/gpu.cuh:24-27) and its loops are not unrolled (SASS of gpu::graph::train: LDG; STS; BRA for the vertex
@@ -892,6 +1012,8 @@ static int g_sampler_max_ctas = getenv("GV_SAMPLER_MAX_CTAS") ? atoi(getenv("GV_
 static int g_sample_block_threads = getenv("GV_SAMPLE_BLOCK_THREADS") ? atoi(getenv("GV_SAMPLE_BLOCK_THREADS")) : 512;
 // one-warp-per-sample kernel: how many blocks ahead the index lines are prefetched into L2 (0 = off; 592 = one
 // resident wave of 148 SMs x 4 blocks, the setting closest to the reference in profiles/r02_parity4_*.jsonl)
+// resident blocks of train_resident_groups_kernel (0 = 4 per SM): the calibration knob of its race statistics
+static int g_sample_resident_blocks = getenv("GV_SAMPLE_RESIDENT_BLOCKS") ? atoi(getenv("GV_SAMPLE_RESIDENT_BLOCKS")) : 0;
 static int g_sample_prefetch_blocks = getenv("GV_SAMPLE_PREFETCH_BLOCKS") ? atoi(getenv("GV_SAMPLE_PREFETCH_BLOCKS")) : 592;
 
 // -----------------------------------------------------------------------------
@@ -1026,6 +1148,30 @@ static int launch_sample_per_warp(const TrainParams &p, int num_warps, cudaStrea
     } else if (q.negatives && q.negatives_out && q.num_negative > 0)
         GV_CUDA_OK(cudaMemcpyAsync(q.negatives_out, q.negatives, q.num_sample * q.num_negative * sizeof(uint32_t),
                                    cudaMemcpyDeviceToDevice, stream));
+    if ((p.flags & 1024) && num_warps <= 0 && q.num_negative + 2 <= 32 && DIM % 32 == 0) {
+        // resident blocks taking groups of 16 samples by ticket (train_resident_groups_kernel)
+        q.work_counter = work_counter_for(stream);
+        if (!q.work_counter)
+            return fail("gv_cuda_train_block: cannot allocate the ticket counter");
+        void (*resident)(const TrainParams) = (p.loss_per_sample || p.loss_per_batch)
+                                                  ? train_resident_groups_kernel<DIM, true>
+                                                  : train_resident_groups_kernel<DIM, false>;
+        static bool resident_configured[2] = {false, false};
+        const int slot = (p.loss_per_sample || p.loss_per_batch) ? 1 : 0;
+        if (!resident_configured[slot]) {
+            cudaFuncSetAttribute(resident, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
+            cudaGetLastError();
+            resident_configured[slot] = true;
+        }
+        const unsigned long long groups = (p.num_sample + kSampleBlockThreads / 32 - 1) / (kSampleBlockThreads / 32);
+        unsigned long long resident_blocks = g_sample_resident_blocks > 0
+                                                 ? (unsigned long long)g_sample_resident_blocks
+                                                 : (unsigned long long)device_sm_count() * sample_blocks_per_sm<DIM>();
+        resident_blocks = std::min(resident_blocks, groups);
+        GV_LAUNCH(int(resident_blocks), kSampleBlockThreads, 0, stream, resident)(q);
+        GV_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const bool timeline = (p.flags & 512) && DIM % 32 == 0;
     void (*kernel)(const TrainParams) =
         (p.loss_per_sample || p.loss_per_batch)
@@ -1168,6 +1314,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_sample_block_threads = int(value);
     else if (key == "sample_prefetch_blocks")
         g_sample_prefetch_blocks = int(value < 0 ? 0 : value);
+    else if (key == "sample_resident_blocks")
+        g_sample_resident_blocks = int(value < 0 ? 0 : value);
     else
         return fail("unknown tunable `" + key + "`");
     return 0;
@@ -1191,6 +1339,8 @@ long gv_cuda_get_tunable(const char *name) {
         return g_sample_block_threads;
     if (key == "sample_prefetch_blocks")
         return g_sample_prefetch_blocks;
+    if (key == "sample_resident_blocks")
+        return g_sample_resident_blocks;
     fail("unknown tunable `" + key + "`");
     return -1;
 }

@@ -160,6 +160,24 @@ def test_train_reference_timeline_variant(kernel_flags, dim, k, num_warps):
     compare(got, v, c, m, loss)
 
 
+@pytest.mark.parametrize("dim,k", [(128, 1), (64, 3), (32, 0), (256, 2), (96, 5)])
+def test_train_resident_groups_variant(kernel_flags, dim, k):
+    """kernel_flags & 1024: resident blocks take groups of 16 samples by ticket, the next sample's indices are loaded
+    and its rows prefetched into L2 during the current one -- same arithmetic, every sample trained exactly once
+    (2 999 samples: a ragged last group; three launches in a row re-arm the ticket counter)"""
+    from gpu_util import run_train_block
+    kernel_flags(1024)
+    optimizer = O.OPTIMIZERS["SGD"]
+    n = 2999
+    for seed in range(3):
+        vertex, context, ms, batch, negatives = make_problem(dim, n, k, n, n * (k + 1), seed=dim + k + seed, unique=True)
+        lr = np.array([optimizer[1], optimizer[1] * 0.5, optimizer[1] * 0.25], dtype=np.float32)
+        v, c, m, loss = oracle_run(dim, vertex, context, ms, batch, negatives.reshape(n, k), optimizer, 5.0, lr, 1000)
+        got = run_train_block(dim, vertex, context, ms, batch, negatives.reshape(n, k) if k else negatives, optimizer, 5.0,
+                              lr=lr, batch_size=1000)
+        compare(got, v, c, m, loss)
+
+
 def test_train_large_k_shared_memory_opt_in():
     """k = 200 needs > 48 KB of dynamic shared memory for the id staging"""
     from gpu_util import run_train_block

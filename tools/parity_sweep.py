@@ -42,6 +42,14 @@ SETTINGS = {
     "ps_pf1184": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=1184),
     "ps_pf2368": dict(kernel_flags=0, chunk_batches=1, sample_prefetch_blocks=2368),
     "ps_pf1184_serial": dict(kernel_flags=128, chunk_batches=1, sample_prefetch_blocks=1184),
+    # resident blocks taking 16-sample groups by ticket, next indices loaded early, next rows prefetched into L2
+    "rg_592": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=1, sample_resident_blocks=592),
+    "rg_592_noprefetch": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=0, sample_resident_blocks=592),
+    "rg_560": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=1, sample_resident_blocks=560),
+    "rg_520": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=1, sample_resident_blocks=520),
+    "rg_480": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=1, sample_resident_blocks=480),
+    "rg_444": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=1, sample_resident_blocks=444),
+    "rg_400": dict(kernel_flags=1024, chunk_batches=1, sample_prefetch_blocks=1, sample_resident_blocks=400),
     # ... with the reference's access timeline (128-byte segments, one dependent round trip each): a measuring variant
     "ps_timeline": dict(kernel_flags=512, chunk_batches=1),
     # ... with the vertex row complete before the first context row is requested (the reference's copy loop)
@@ -82,6 +90,7 @@ def apply(gv, setting):
         gv._clib.gv_cuda_set_tunable(name.encode(), int(setting.get(name, 0)))
     gv._clib.gv_cuda_set_tunable(b"sample_block_threads", int(setting.get("sample_block_threads", 512)))
     gv._clib.gv_cuda_set_tunable(b"sample_prefetch_blocks", int(setting.get("sample_prefetch_blocks", 0)))
+    gv._clib.gv_cuda_set_tunable(b"sample_resident_blocks", int(setting.get("sample_resident_blocks", 0)))
 
 
 def run_ours(gv, cfg, graph, test, epochs, setting, num_partition):
