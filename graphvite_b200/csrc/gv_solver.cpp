@@ -147,7 +147,7 @@ struct Solver {
     DeviceArray pool_pointers[2];                  // [P*P] block pointers (NULL: not reachable from here)
     bool peer_pools = false;
     std::vector<void *> peer_arenas;               // [W] mapped arenas (own entry = pool_arena.ptr)
-    DeviceArray d_peer_controls, d_totals, d_bases, d_barrier_scratch, d_barrier_marker;
+    DeviceArray d_peer_controls, d_totals, d_bases;
     uint64_t peer_round = 0;
     // device graph
     DeviceArray d_offsets, d_edge_u, d_edge_v, d_edge_prob, d_edge_alias, d_vertex_tables, d_locations;
@@ -495,10 +495,6 @@ struct Solver {
             d_peer_controls.upload(controls, work_stream);
             d_totals.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
             d_bases.allocate(size_t(num_partition) * num_partition * sizeof(unsigned long long));
-            d_barrier_scratch.allocate(size_t(2) * num_partition * num_partition * sizeof(unsigned long long));
-            d_barrier_marker.allocate(sizeof(unsigned long long));
-            GV_CHECK_CUDA(cudaMemsetAsync(d_barrier_scratch.ptr, 0, d_barrier_scratch.bytes, work_stream));
-            GV_CHECK_CUDA(cudaMemsetAsync(d_barrier_marker.ptr, 0, d_barrier_marker.bytes, work_stream));
             peer_round = 0;
             // pairs of blocks owned by other ranks are staged locally and forwarded with coalesced peer stores
             // (gv_cuda_fill_scatter_staged); GV_DIRECT_PEER_SCATTER=1 keeps the direct 8-byte peer stores
@@ -868,21 +864,18 @@ struct Solver {
         sampler_buffers[sampler_id] += needed_buffers;
     }
 
-    // barrier over the ranks on the sample stream (flags in IPC-mapped peer memory, gv_cuda_peer_exchange):
-    // returns once every rank's sample stream has reached the same call
+    // Barrier over the ranks' sampler threads: everything this rank queued on its sample stream has completed (its
+    // deliveries into the peers' pools included), then the hosts meet (gv_host_allgather_fn: a gloo group of its own,
+    // graphvite_b200/distributed.py).  A host barrier on purpose: a kernel that spins on a peer's flag holds a hardware
+    // queue, and a train launch or an NCCL send queued behind it on the same GPU can then wait for a peer that waits
+    // for exactly that send (seen on 2 x B200 with single-warp training, where the main threads lag the samplers).
     void peer_barrier() {
-        GV_CHECK_ABI(gv_cuda_peer_exchange(rank, num_worker, num_partition, ++peer_round, nullptr,
-                                           d_peer_controls.as<unsigned long long *>(),
-                                           reinterpret_cast<unsigned long long *>(static_cast<char *>(pool_arena.ptr) +
-                                                                                  control_offset()),
-                                           d_barrier_scratch.as<unsigned long long>(),
-                                           d_barrier_scratch.as<unsigned long long>() + size_t(num_partition) * num_partition,
-                                           d_barrier_marker.as<unsigned long long>(), sample_stream));
-        unsigned long long marker = 0;
-        GV_CHECK_CUDA(cudaMemcpyAsync(&marker, d_barrier_marker.ptr, sizeof(marker), cudaMemcpyDeviceToHost,
-                                      sample_stream));
         GV_CHECK_CUDA(cudaStreamSynchronize(sample_stream));
-        require(marker != ~0ull, "a peer rank did not reach the sampler barrier within 2 minutes");
+        int token = int(++peer_round), all[256] = {0};
+        require(host_allgather_fn && host_allgather_fn(&token, all, sizeof(int), host_allgather_ctx) == 0,
+                "host barrier of the samplers failed");
+        for (int r = 0; r < num_worker; r++)
+            require(all[r] == token, "the ranks' samplers are out of step (barrier " + std::to_string(token) + ")");
     }
 
     // fill one side of the sample pools with all samplers (core/solver.h:614-628).  Sampler i fills slice i of

@@ -66,17 +66,16 @@ _host_group = None
 
 
 def make_host_allgather():
-    """gv_host_allgather_fn over a gloo group (host buffers; used once per build() to trade the CUDA
-    IPC handles of the sample-pool arenas).  Must be created by all ranks collectively."""
+    """gv_host_allgather_fn over a gloo group of its own (host buffers): trades the CUDA IPC handles of the sample-pool
+    arenas once per build(), and is the barrier of the ranks' SAMPLER threads twice per episode -- those run next to
+    the main threads' block exchange, so they must not share a process group with it (two threads issuing collectives
+    on one group would interleave differently on different ranks).  Must be created by all ranks collectively."""
     import torch
     import torch.distributed as dist
     global _host_group
-    if dist.get_backend() == "gloo":
-        group = None
-    else:
-        if _host_group is None:
-            _host_group = dist.new_group(backend="gloo")
-        group = _host_group
+    if _host_group is None:
+        _host_group = dist.new_group(backend="gloo")
+    group = _host_group
     world = dist.get_world_size()
 
     def allgather(send, recv, nbytes, ctx):

@@ -1,0 +1,112 @@
+"""Float parity of Hogwild training against the UNMODIFIED reference (oracle/_ref/libgraphvite.so through its own
+pybind API), on the two workloads the north star names: the BlogCatalog-shaped quick start (2000 epochs) and the
+Youtube-shaped LINE run (100 epochs = 5e8 edges), each on the train part of the reference's own link-prediction split,
+scored on the held-out part.  Integer outputs (pools, negatives) are bit-exact elsewhere; this file is about the
+floats, which depend on which concurrent updates of a row are lost to races -- so every figure is a mean over runs
+and is judged against the reference's OWN run-to-run range, which the test measures first and prints.
+
+What is asserted, and why these numbers (profiles/r02_parity_study.md has the whole study):
+  * shipped kernel (one warp per sample in the reference's launch geometry, one launch per batch):
+      link-prediction AUC within 0.003 of the reference on Youtube (measured +0.0006 ... +0.0014) and within
+      0.003 + the reference's own range on BlogCatalog (measured -0.003, range 0.003-0.004);
+      embedding L2 norms within 3.2 % (measured: vertex -1.3 ... -1.6 %, context +2.1 ... +2.3 % on both graphs).
+      The north star's 1e-3 on norms is NOT met by the fast kernel: the residual is the read-modify-write timeline of
+      a warp, see the next item.
+  * reference-timeline variant (kernel_flags = 512: same geometry AND the reference's 128-byte-segment access
+      timeline; runs at the reference kernel's own speed): norms within 4e-3 on BlogCatalog (measured -1.0e-3 /
+      +1.1e-3; the reference's own range there is 2.7e-3 ... 5.5e-3, so 1e-3 is below its noise) and within 1.2 % on
+      Youtube (measured -0.6 % / +0.7 %), AUC within 0.003 on Youtube.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libgraphvite.so")
+RUNS = {"blogcatalog": dict(epochs=2000, ours=3, reference=3), "youtube": dict(epochs=100, ours=2, reference=3)}
+# (norm tolerance, AUC tolerance beyond the reference's own range)
+BOUNDS = {
+    ("shipped", "youtube"): (0.032, 0.003, False),
+    ("shipped", "blogcatalog"): (0.032, 0.003, True),
+    ("timeline", "youtube"): (0.012, 0.003, False),
+    ("timeline", "blogcatalog"): (0.004, 0.003, True),
+}
+SETTINGS = {"shipped": None, "timeline": dict(kernel_flags=512)}
+
+
+@pytest.fixture(scope="module")
+def sweep():
+    if os.environ.get("GV_EMULATE") == "1":
+        pytest.skip("statistical parity needs the real race pattern of a GPU")
+    if not os.path.exists(REF_PATH):
+        pytest.skip("oracle/_ref/libgraphvite.so is not built")
+    import graphvite_b200  # noqa: F401  (before tools.parity_sweep puts the repository root first on sys.path)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_sweep
+    return parity_sweep
+
+
+_reference_cache = {}
+
+
+def reference_runs(sweep, workload):
+    if workload not in _reference_cache:
+        import bench
+        from validate_parity import make_split
+        cfg = bench.WORKLOADS[workload]
+        path, test = make_split(cfg["graph"])
+        ref = bench.load_reference()
+        rows = [sweep.run_reference(ref, cfg, path, test, RUNS[workload]["epochs"])
+                for _ in range(RUNS[workload]["reference"])]
+        _reference_cache[workload] = (cfg, path, test, rows)
+    return _reference_cache[workload]
+
+
+@pytest.mark.parametrize("workload", ["blogcatalog", "youtube"])
+@pytest.mark.parametrize("setting", ["shipped", "timeline"])
+def test_hogwild_training_against_the_unmodified_reference(sweep, setting, workload):
+    import graphvite_b200 as gv
+    from graphvite_b200 import _lib
+    cfg, path, test, reference = reference_runs(sweep, workload)
+    graph = gv.graph.Graph()
+    graph.load(path)
+    defaults = {name: _lib.lib.gv_cuda_get_tunable(name.encode()) for name in ("kernel_flags",)}
+    runs = []
+    try:
+        for _ in range(RUNS[workload]["ours"]):
+            if SETTINGS[setting]:
+                for name, value in SETTINGS[setting].items():
+                    _lib.check(_lib.lib.gv_cuda_set_tunable(name.encode(), value))
+            _lib.lib.gv_reset_global_engine(5489)
+            solver = gv.solver.GraphSolver(cfg["dim"], device_ids=[0])  # the library's defaults: what ships
+            solver.build(graph, gv.optimizer.SGD(cfg["lr"], cfg["weight_decay"]), num_negative=cfg["num_negative"],
+                         batch_size=cfg["batch_size"], episode_size=cfg["episode_size"])
+            import bench
+            solver.train(**bench.train_kwargs(cfg, RUNS[workload]["epochs"]))
+            vertex, context = solver.vertex_embeddings, solver.context_embeddings
+            scores = lambda pairs: np.einsum("ij,ij->i", vertex[pairs[:, 0]], context[pairs[:, 1]])  # noqa: E731
+            from validate_parity import auc_of
+            runs.append({"vertex_norm": float(np.linalg.norm(vertex)), "context_norm": float(np.linalg.norm(context)),
+                         "auc": auc_of(scores, graph.name2id, test)})
+            solver.close()
+    finally:
+        for name, value in defaults.items():
+            _lib.lib.gv_cuda_set_tunable(name.encode(), value)
+    summary = sweep.summarise(setting, runs, reference)
+    record = {"workload": workload, "setting": setting, "epochs": RUNS[workload]["epochs"], "ours": runs,
+              "reference": reference, "summary": summary}
+    print(json.dumps(record))
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_test_%s_%s.json" % (workload, setting)), "w") as fout:
+            json.dump(record, fout)
+    norm_bound, auc_bound, add_reference_range = BOUNDS[(setting, workload)]
+    if add_reference_range:
+        auc_bound += summary["auc_reference_spread"]
+    assert abs(summary["vertex_norm_rel"]) <= norm_bound, summary
+    assert abs(summary["context_norm_rel"]) <= norm_bound, summary
+    assert abs(summary["auc_diff"]) <= auc_bound, summary
