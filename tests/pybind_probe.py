@@ -60,6 +60,30 @@ def main():
     optimizers["Optimizer(0.5)"] = m.optimizer.Optimizer(0.5).lr
     optimizers["LRSchedule"] = m.optimizer.LRSchedule("linear").type
     out["optimizers"] = optimizers
+    out["backend"] = getattr(m, "__backend__", "reference")
+    out["gib2"] = m.GiB(2)
+    if out["backend"] != "reference":  # errors are exceptions in our module (the reference abort()s the process)
+        try:
+            m.optimizer.LRSchedule("cosine")
+            out["bad_schedule"] = "accepted"
+        except (ValueError, RuntimeError) as error:
+            out["bad_schedule"] = type(error).__name__
+        try:
+            import torch
+            have_gpu = torch.cuda.is_available()
+        except Exception:
+            have_gpu = False
+        if not have_gpu:
+            try:
+                m.solver.GraphSolver_128_f_j([0], 0, 0)
+                out["solver_without_gpu"] = "constructed"
+            except RuntimeError as error:
+                out["solver_without_gpu"] = "RuntimeError"
+        try:
+            m.solver.GraphSolver_128_f_j([0, 1], 0, 0)
+            out["two_devices"] = "constructed"
+        except RuntimeError as error:
+            out["two_devices"] = str(error)[:200]
     print(json.dumps(out))
 
 
