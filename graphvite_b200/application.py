@@ -42,13 +42,14 @@ def Application(type, *args, **kwargs):
     raise ValueError("Unknown application `%s` (this build ships `graph`, `word graph` and `knowledge graph`)" % type)
 
 
-def _resolve_gpus(gpus):
+def _resolve_gpus(gpus, knowledge_graph=False):
     """The reference drives every listed GPU (`gpus: []` = all of them) from threads of one process
     (core/solver.h:184-213).  Here one process drives one GPU and N processes form the N-GPU solver:
       * under torchrun (WORLD_SIZE > 1) rank r takes gpus[r] (or GPU LOCAL_RANK for `gpus: []`) and the solver is
         created with rank / world_size -- the YAML's `gpus: [0, 1, 2, 3]` then means what it means in the reference;
-      * in a single process a list of several GPUs is an error that says how to launch, never a silent truncation;
-        `gpus: []` on a multi-GPU box warns that only one GPU is used.
+      * in a single process the whole list is handed to GraphSolver, whose front end starts one worker process per
+        listed GPU (`gpus: []` = every visible GPU); the knowledge-graph solver has no such front end and refuses a
+        list with the torchrun instructions.  Never a silent truncation.
     Returns (device_ids, extra solver kwargs)."""
     gpus = list(gpus)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -64,20 +65,21 @@ def _resolve_gpus(gpus):
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
         return [device], dict(rank=rank, world_size=world)
-    if len(gpus) > 1:
-        raise ValueError("gpus = %s: one process drives one GPU.  Launch one process per GPU -- `torchrun --nnodes=1 "
-                         "--nproc-per-node %d -m graphvite_b200.cmd run <config.yaml>` -- and the %d processes form the "
-                         "reference's %d-GPU solver (2-D block partition, NCCL block rotation)" %
-                         (gpus, len(gpus), len(gpus), len(gpus)))
-    if not gpus:
+    if not gpus and not knowledge_graph:
+        # `gpus: []` = all GPUs (core/solver.h:186-191)
         try:
             import torch
             count = torch.cuda.device_count()
         except Exception:
             count = 1
         if count > 1:
-            logger.warning("`gpus: []` selects all %d GPUs in the reference; this process drives GPU 0 only -- launch "
-                           "with torchrun --nproc-per-node %d to train on all of them" % (count, count))
+            gpus = list(range(count))
+    if len(gpus) > 1 and knowledge_graph:
+        raise ValueError("gpus = %s: the knowledge-graph solver drives one GPU per process.  Launch one process per GPU "
+                         "-- `torchrun --nnodes=1 --nproc-per-node %d -m graphvite_b200.cmd run <config.yaml>` -- and "
+                         "the %d processes form the reference's %d-GPU solver" % (gpus, len(gpus), len(gpus), len(gpus)))
+    # several GPUs for a GraphSolver in one process: the solver front end starts one worker process per GPU
+    # (graphvite_b200/multi.py)
     return gpus, {}
 
 
@@ -357,7 +359,7 @@ class KnowledgeGraphApplication(object):
         self.gpu_memory_limit = gpu_memory_limit
         self.graph = _graph.KnowledgeGraph(index_type)
         num_sampler_per_worker = auto if cpu_per_gpu == auto else cpu_per_gpu - 1  # application.py:632-638
-        device_ids, placement = _resolve_gpus(self.gpus)
+        device_ids, placement = _resolve_gpus(self.gpus, knowledge_graph=True)
         self.solver = _solver.KnowledgeGraphSolver(dim, float_type, index_type, device_ids, num_sampler_per_worker,
                                                    gpu_memory_limit, **dict(placement, **kwargs))
 

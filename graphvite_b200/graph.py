@@ -2,6 +2,7 @@
 include/instance/graph.cuh:62-277) and graphvite.graph.KnowledgeGraph (bind.h:237-314 over
 include/instance/knowledge_graph.cuh:67-284)."""
 import ctypes
+import os
 
 from . import _lib
 from .base import cfg, dtype
@@ -52,6 +53,7 @@ class Graph(object):
             raise ValueError("Can't find an instantiation of Graph with index_type = %s" % (index_type,))
         self._handle = lib.gv_graph_create()
         self._id2name = None
+        self._recipe = None  # how this graph was loaded: lets the workers of a multi-GPU solver load it again
 
     def __del__(self):
         handle, self._handle = getattr(self, "_handle", None), None
@@ -84,6 +86,9 @@ class Graph(object):
             path = source if isinstance(source, bytes) else source.encode()
             _lib.check(lib.gv_graph_load_file(self._handle, path, int(as_undirected), int(normalization),
                                               delimiters.encode(), comment.encode()))
+            self._recipe = ("file", os.path.abspath(source if isinstance(source, str) else source.decode()),
+                            dict(as_undirected=as_undirected, normalization=normalization, delimiters=delimiters,
+                                 comment=comment))
             return
         if "delimiters" in params or "comment" in params:
             raise TypeError("load(): incompatible function arguments")
@@ -96,6 +101,7 @@ class Graph(object):
             weights = (ctypes.c_float * count)(*[float(e[2]) for e in edges])
         _lib.check(lib.gv_graph_load_edges(self._handle, u_names, v_names, weights, count, int(as_undirected),
                                            int(normalization)))
+        self._recipe = ("edges", [tuple(e) for e in edges], dict(as_undirected=as_undirected, normalization=normalization))
 
     def load_arrays(self, u, v, weights=None, as_undirected=True, normalization=False):
         """load_arrays(u, v, weights=None, as_undirected=True, normalization=False): binary edge list.
@@ -114,6 +120,7 @@ class Graph(object):
         _lib.check(lib.gv_graph_load_id_edges(self._handle, u.ctypes.data, v.ctypes.data,
                                               w.ctypes.data if w is not None else None, len(u), int(as_undirected),
                                               int(normalization)))
+        self._recipe = ("arrays", u, v, w, dict(as_undirected=as_undirected, normalization=normalization))
 
     def save(self, file_name, weighted=True, anonymous=False):
         """save(file_name, weighted=True, anonymous=False): save the graph in edge-list format."""

@@ -2,6 +2,7 @@
 include/instance/graph.cuh:587-813 and include/core/solver.h).  One process drives one GPU;
 several processes (torchrun) form the reference's multi-GPU solver, see `distributed.py`."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -19,7 +20,16 @@ class GraphSolver(object):
     num_sampler_per_worker=auto, gpu_memory_limit=auto)
 
     Extra keyword arguments (not in the reference): rank, world_size for one-process-per-GPU runs.
+    Several `device_ids` in one process (the reference's multi-GPU signature, core/solver.h:184-213) return a front
+    end that starts one worker process per listed GPU (`graphvite_b200/multi.py`).
     """
+
+    def __new__(cls, dim, float_type=None, index_type=None, device_ids=(), *args, **kwargs):
+        if cls is GraphSolver and len(list(device_ids)) > 1 and kwargs.get("world_size", 1) == 1 and \
+                int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            from .multi import SpawnedGraphSolver
+            return SpawnedGraphSolver(dim, float_type, index_type, device_ids, *args, **kwargs)
+        return super(GraphSolver, cls).__new__(cls)
 
     def __init__(self, dim, float_type=None, index_type=None, device_ids=(), num_sampler_per_worker=auto,
                  gpu_memory_limit=auto, rank=0, world_size=1):

@@ -8,13 +8,15 @@ import pytest
 from graphvite_b200 import application as A
 
 
-def test_several_gpus_in_one_process_is_an_error_that_says_how_to_launch(monkeypatch):
+def test_gpu_lists_are_never_truncated(monkeypatch):
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    with pytest.raises(ValueError, match="torchrun"):
-        A._resolve_gpus([0, 1, 2, 3])
+    # node embeddings: the whole list reaches GraphSolver, whose front end starts one worker process per GPU
+    assert A._resolve_gpus([0, 1, 2, 3]) == ([0, 1, 2, 3], {})
     assert A._resolve_gpus([2]) == ([2], {})
-    device_ids, extra = A._resolve_gpus([])  # reference: all GPUs; here: GPU 0 (+ a warning on a multi-GPU box)
-    assert device_ids == [] and extra == {}
+    # knowledge graphs: one GPU per process, several need torchrun -- said loudly
+    with pytest.raises(ValueError, match="torchrun"):
+        A._resolve_gpus([0, 1], knowledge_graph=True)
+    assert A._resolve_gpus([], knowledge_graph=True) == ([], {})
 
 
 def test_gpu_list_must_match_the_number_of_launched_processes(monkeypatch):
