@@ -380,10 +380,15 @@ struct Solver {
         };
         num_partition = _num_partition;
         if (num_partition == 0) {
-            for (num_partition = min_partition; num_partition < kMaxPartition; num_partition += min_partition)
+            // With one worker every block stays resident in HBM (no host paging, section 3 of DESIGN.md), so more
+            // partitions never lower the demand of a single GPU: P = 1, and only the pools can shrink below.
+            const int last = num_worker == 1 ? min_partition + 1 : kMaxPartition;
+            for (num_partition = min_partition; num_partition < last; num_partition += min_partition)
                 if (memory_demand(num_partition, _episode_size ? _episode_size : auto_episode(num_partition)) <
                     gpu_memory_limit)
                     break;
+            if (num_worker == 1)
+                num_partition = min_partition;
         } else
             require(num_partition >= min_partition,
                     "#partition should be no less than " + std::to_string(min_partition));
@@ -394,7 +399,11 @@ struct Solver {
         while (episode_size > 1 && memory_demand(num_partition, episode_size) >= gpu_memory_limit)
             episode_size /= 2;
         gpu_memory_cost = memory_demand(num_partition, episode_size);
-        require(gpu_memory_cost < gpu_memory_limit, "Can't satisfy the specified GPU memory limit");
+        require(gpu_memory_cost < gpu_memory_limit,
+                "Can't satisfy the specified GPU memory limit: " + std::to_string(gpu_memory_cost >> 20) + " MiB needed (" +
+                    std::to_string(num_partition) + " partition(s), every block resident on its GPU), " +
+                    std::to_string(gpu_memory_limit >> 20) + " MiB allowed" +
+                    (num_worker == 1 ? "; embeddings larger than one GPU need more GPUs (one process per GPU)" : ""));
 
         partitions = partition_vertices(graph->vertex_weights, num_partition);
         partition_size = 0;

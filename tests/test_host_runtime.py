@@ -280,3 +280,33 @@ def test_bulk_engine_is_std_mt19937(seed, bulk):
     uniform_int_distribution -- compared inside the library against libstdc++ itself."""
     from graphvite_b200 import _lib
     assert _lib.lib.gv_engine_self_check(seed, bulk) == 0
+
+
+def test_binary_edge_arrays_load_like_the_equivalent_edge_list(tmp_path):
+    """Graph.load_arrays (gv_graph_load_id_edges) builds what load(edge_list=[(str(u), str(v)) ...]) builds -- first-seen
+    ids, edge order, counts, weights -- without materialising names: byte-identical save(), same name <-> id maps."""
+    import graphvite_b200 as gv
+    rng = np.random.RandomState(5)
+    u = rng.randint(0, 50, 400)
+    v = rng.randint(0, 50, 400)
+    w = (rng.rand(400) + 0.5).astype(np.float32)
+    for undirected in (True, False):
+        for weights in (None, w):
+            for normalization in (False, True):
+                a, b = gv.graph.Graph(), gv.graph.Graph()
+                a.load_arrays(u, v, weights, as_undirected=undirected, normalization=normalization)
+                edges = [(str(x), str(y)) for x, y in zip(u, v)] if weights is None else \
+                    [(str(x), str(y), float(z)) for x, y, z in zip(u, v, w)]
+                b.load(edges, as_undirected=undirected, normalization=normalization)
+                assert (a.num_vertex, a.num_edge) == (b.num_vertex, b.num_edge)
+                assert a.id2name == b.id2name
+                for name in ("0", "17", "49", "50", "x", "07", ""):
+                    assert a.name2id.get(name) == b.name2id.get(name), name
+                a.save(str(tmp_path / "a.txt"))
+                b.save(str(tmp_path / "b.txt"))
+                assert (tmp_path / "a.txt").read_bytes() == (tmp_path / "b.txt").read_bytes()
+    empty = gv.graph.Graph()
+    empty.load_arrays(np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
+    assert empty.num_vertex == 0 and empty.num_edge == 0
+    with pytest.raises(ValueError):
+        empty.load_arrays(np.zeros(3), np.zeros(4))
