@@ -35,6 +35,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "gv_common.h"
@@ -49,6 +50,14 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr float kEps = 1e-15f;  // util/common.h:28
 constexpr int kCtaThreads = 256;
 constexpr int kPass1Batch = 4;  // targets per barrier in the normaliser pass
+
+// tunable `kg_flags` (gv_cuda_set_tunable; environment GV_KG_FLAGS gives the initial value).
+// bit 0: IEEE square roots, divisions and sincosf() in the train kernel instead of the MUFU / gv_sincos versions
+// bit 1: no L2 prefetch of the negative rows ahead of their targets
+int &kg_flags() {
+    static int flags = getenv("GV_KG_FLAGS") ? atoi(getenv("GV_KG_FLAGS")) : 0;
+    return flags;
+}
 
 struct KgParams {
     int dim;
@@ -69,6 +78,7 @@ struct KgParams {
     uint32_t batch_size;
     float relation_lr_multiplier, margin_or_l3, temperature;
     float *loss_per_sample, *loss_per_batch;
+    int flags;  // kg_flags
 };
 
 // ---- a thread's N floats of a row: N / U vector units of U floats (128-, 64- or 32-bit accesses) ------------
@@ -152,7 +162,36 @@ struct Opt {
     float lr, wd, a, b, eps;
 };
 
-template<int NM>
+// ---- math policy ------------------------------------------------------------------------------------
+// FAST (the default, `kg_flags` bit 0 clear): square roots and divisions of the update rules are single MUFU
+// instructions (<= 2 ulp each) and RotatE's rotation is gv_sincos (<= 1.6 ulp, no slow path), evaluated ONCE per
+// target and shared by the logit and the gradient.  The IEEE versions nvcc emits for `/`, sqrtf() and sincosf() are
+// 8-40 instructions each with a divergent slow path per call site; with them the RotatE / Adam kernel executes ~2 000
+// instructions per thread and target and is bound by instruction issue at one 256-thread group per SM (0.22 of the
+// HBM roofline, even with every row in L2 -- profiles/r02_bench/bench_rotate_n4.json).  !FAST keeps that code.
+template<bool FAST>
+__device__ __forceinline__ float kg_sqrt(float x) {
+    if constexpr (FAST)
+        return gv_fast_sqrt(x);
+    else
+        return sqrtf(x);
+}
+template<bool FAST>
+__device__ __forceinline__ float kg_divide(float a, float b) {
+    if constexpr (FAST)
+        return a * gv_fast_rcp(b);
+    else
+        return a / b;
+}
+template<bool FAST>
+__device__ __forceinline__ void kg_sincos(float x, float *sine, float *cosine) {
+    if constexpr (FAST)
+        gv_sincos(x, sine, cosine);
+    else
+        sincosf(x, sine, cosine);
+}
+
+template<int NM, bool FAST>
 __device__ __forceinline__ float step(const Opt &o, float parameter, float gradient, float &m1, float &m2,
                                       float weight) {
     if constexpr (NM == 0)
@@ -161,7 +200,7 @@ __device__ __forceinline__ float step(const Opt &o, float parameter, float gradi
     if constexpr (NM == 2) {
         m1 = o.a * m1 + (1 - o.a) * regularized;
         m2 = o.b * m2 + (1 - o.b) * regularized * regularized;
-        return o.lr * m1 / (sqrtf(m2) + o.eps);
+        return kg_divide<FAST>(o.lr * m1, kg_sqrt<FAST>(m2) + o.eps);
     }
     if (o.type == GV_OPT_MOMENTUM) {
         m1 = o.a * m1 + (1 - o.a) * regularized;
@@ -169,15 +208,24 @@ __device__ __forceinline__ float step(const Opt &o, float parameter, float gradi
     }
     if (o.type == GV_OPT_ADAGRAD) {
         m1 += regularized * regularized;
-        return o.lr * regularized / (sqrtf(m1) + o.eps);
+        return kg_divide<FAST>(o.lr * regularized, kg_sqrt<FAST>(m1) + o.eps);
     }
     m1 = o.a * m1 + (1 - o.a) * regularized * regularized;  // RMSprop
-    return o.lr * regularized / sqrtf(m1 + o.eps);
+    if constexpr (FAST)
+        return o.lr * regularized * gv_fast_rsqrt(m1 + o.eps);
+    else
+        return o.lr * regularized / sqrtf(m1 + o.eps);
 }
 
 // util/math.h:30-44 (precise exponentials: the loss and the adversarial weights are compared with the reference)
+template<bool FAST>
 __device__ __forceinline__ float sigmoid(float x) {
-    return x > 0 ? 1 / (1 + expf(-x)) : expf(x) / (expf(x) + 1);
+    if constexpr (FAST) {  // one exponential, one MUFU.RCP: the same two branches of util/math.h
+        const float e = expf(-fabsf(x));
+        const float inverse = gv_fast_rcp(1 + e);
+        return x > 0 ? inverse : e * inverse;
+    } else
+        return x > 0 ? 1 / (1 + expf(-x)) : expf(x) / (expf(x) + 1);
 }
 __device__ __forceinline__ float safe_exp(float x) {
     return expf(fminf(fmaxf(x, -80.f), 80.f));
@@ -209,7 +257,7 @@ struct Relation {
 
 // Model::forward restricted to a thread's slice (model/knowledge_graph.h:44-49,117-123,208-223,359-366,
 // 453-468); the caller sums over the group and applies `margin - sum` for TransE / RotatE.
-template<int E, int MODEL>
+template<int E, int MODEL, bool FAST>
 __device__ __forceinline__ float partial_logit(const float (&h)[E], const float (&t)[E],
                                                const float (&r)[Geometry<E, MODEL>::RV]) {
     float output = 0.f;
@@ -238,21 +286,22 @@ __device__ __forceinline__ float partial_logit(const float (&h)[E], const float 
             const float h_r = h[i * 4], h_i = h[i * 4 + 1], h_j = h[i * 4 + 2], h_k = h[i * 4 + 3];
             const float r_r = r[i * 4], r_i = r[i * 4 + 1], r_j = r[i * 4 + 2], r_k = r[i * 4 + 3];
             const float t_r = t[i * 4], t_i = t[i * 4 + 1], t_j = t[i * 4 + 2], t_k = t[i * 4 + 3];
-            const float r_norm = sqrtf(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
+            const float r_norm = kg_sqrt<FAST>(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
             const float product_r = h_r * r_r - h_i * r_i - h_j * r_j - h_k * r_k;
             const float product_i = h_r * r_i + h_i * r_r + h_j * r_k - h_k * r_j;
             const float product_j = h_r * r_j - h_i * r_k + h_j * r_r + h_k * r_i;
             const float product_k = h_r * r_k + h_i * r_j - h_j * r_i + h_k * r_r;
-            output += (product_r * t_r + product_i * t_i + product_j * t_j + product_k * t_k) / (r_norm + kEps);
+            output += kg_divide<FAST>(product_r * t_r + product_i * t_i + product_j * t_j + product_k * t_k,
+                                      r_norm + kEps);
         }
     } else {  // RotatE
 #pragma unroll
         for (int i = 0; i < E / 2; i++) {
             float r_re, r_im;
-            sincosf(r[i], &r_im, &r_re);
+            kg_sincos<FAST>(r[i], &r_im, &r_re);
             const float distance_re = h[i * 2] * r_re - h[i * 2 + 1] * r_im - t[i * 2];
             const float distance_im = h[i * 2] * r_im + h[i * 2 + 1] * r_re - t[i * 2 + 1];
-            output += sqrtf(distance_re * distance_re + distance_im * distance_im);
+            output += kg_sqrt<FAST>(distance_re * distance_re + distance_im * distance_im);
         }
     }
     return output;
@@ -260,7 +309,7 @@ __device__ __forceinline__ float partial_logit(const float (&h)[E], const float 
 
 // RotatE with the relation's rotation (cos, sin of its phases) already evaluated: the relation row does not change
 // during the normaliser pass, so its sincosf are hoisted out of the k targets (same values, same order of operations)
-template<int E>
+template<int E, bool FAST>
 __device__ __forceinline__ float partial_logit_rotated(const float (&h)[E], const float (&t)[E],
                                                        const float (&r_re)[E / 2], const float (&r_im)[E / 2]) {
     float output = 0.f;
@@ -268,7 +317,7 @@ __device__ __forceinline__ float partial_logit_rotated(const float (&h)[E], cons
     for (int i = 0; i < E / 2; i++) {
         const float distance_re = h[i * 2] * r_re[i] - h[i * 2 + 1] * r_im[i] - t[i * 2];
         const float distance_im = h[i * 2] * r_im[i] + h[i * 2 + 1] * r_re[i] - t[i * 2 + 1];
-        output += sqrtf(distance_re * distance_re + distance_im * distance_im);
+        output += kg_sqrt<FAST>(distance_re * distance_re + distance_im * distance_im);
     }
     return output;
 }
@@ -277,20 +326,22 @@ __device__ __forceinline__ float partial_logit_rotated(const float (&h)[E], cons
 // (model/knowledge_graph.h:51-108,125-190,225-340,368-433,470-575).  ALIAS: head and tail are the SAME
 // row of the same matrix; every tail access then goes to the head slice (and its moments), which
 // reproduces the reference's two successive read-modify-writes of one memory location.
-template<int E, int MODEL, int NM, bool ALIAS>
+// `rotation_re / rotation_im` (RotatE with FAST only): cos / sin of R.v as the logit of this target used them.
+template<int E, int MODEL, int NM, bool ALIAS, bool FAST>
 __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Relation<E, MODEL, NM> &R, const Opt &o,
                                          float margin_or_l3, float gradient, float relation_lr_multiplier,
-                                         float weight) {
+                                         float weight, const float (&rotation_re)[E / 2],
+                                         const float (&rotation_im)[E / 2]) {
     Slice<E, NM> &T = ALIAS ? H : Tin;
     if constexpr (MODEL == GV_KG_TRANSE) {
 #pragma unroll
         for (int i = 0; i < E; i++) {
             const float h = H.v[i], t = T.v[i], r = R.v[i];
             const float s = h + r - t > 0 ? 1.f : -1.f;
-            H.v[i] -= step<NM>(o, h, -gradient * s, H.m1[NM >= 1 ? i : 0], H.m2[NM >= 2 ? i : 0], weight);
-            T.v[i] -= step<NM>(o, t, gradient * s, T.m1[NM >= 1 ? i : 0], T.m2[NM >= 2 ? i : 0], weight);
+            H.v[i] -= step<NM, FAST>(o, h, -gradient * s, H.m1[NM >= 1 ? i : 0], H.m2[NM >= 2 ? i : 0], weight);
+            T.v[i] -= step<NM, FAST>(o, t, gradient * s, T.m1[NM >= 1 ? i : 0], T.m2[NM >= 2 ? i : 0], weight);
             R.v[i] -= relation_lr_multiplier *
-                      step<NM>(o, r, -gradient * s, R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+                      step<NM, FAST>(o, r, -gradient * s, R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
         }
     } else if constexpr (MODEL == GV_KG_DISTMULT || MODEL == GV_KG_SIMPLE) {
         const float l3 = margin_or_l3 * 3;
@@ -298,11 +349,11 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
         for (int i = 0; i < E; i++) {
             const int j = MODEL == GV_KG_SIMPLE ? (i ^ 1) : i;
             const float h = H.v[i], t = T.v[j], r = R.v[i];
-            H.v[i] -= step<NM>(o, h, gradient * r * t + l3 * fabsf(h) * h, H.m1[NM >= 1 ? i : 0],
+            H.v[i] -= step<NM, FAST>(o, h, gradient * r * t + l3 * fabsf(h) * h, H.m1[NM >= 1 ? i : 0],
                                H.m2[NM >= 2 ? i : 0], weight);
-            T.v[j] -= step<NM>(o, t, gradient * h * r + l3 * fabsf(t) * t, T.m1[NM >= 1 ? j : 0],
+            T.v[j] -= step<NM, FAST>(o, t, gradient * h * r + l3 * fabsf(t) * t, T.m1[NM >= 1 ? j : 0],
                                T.m2[NM >= 2 ? j : 0], weight);
-            R.v[i] -= relation_lr_multiplier * step<NM>(o, r, gradient * h * t + l3 * fabsf(r) * r,
+            R.v[i] -= relation_lr_multiplier * step<NM, FAST>(o, r, gradient * h * t + l3 * fabsf(r) * r,
                                                         R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
         }
     } else if constexpr (MODEL == GV_KG_COMPLEX) {
@@ -314,21 +365,21 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
             const float r_re = R.v[re], r_im = R.v[im];
             const float h_re_grad = gradient * (r_re * t_re + r_im * t_im);
             const float h_im_grad = gradient * (-r_im * t_re + r_re * t_im);
-            H.v[re] -= step<NM>(o, h_re, h_re_grad + l3 * fabsf(h_re) * h_re, H.m1[NM >= 1 ? re : 0],
+            H.v[re] -= step<NM, FAST>(o, h_re, h_re_grad + l3 * fabsf(h_re) * h_re, H.m1[NM >= 1 ? re : 0],
                                 H.m2[NM >= 2 ? re : 0], weight);
-            H.v[im] -= step<NM>(o, h_im, h_im_grad + l3 * fabsf(h_im) * h_im, H.m1[NM >= 1 ? im : 0],
+            H.v[im] -= step<NM, FAST>(o, h_im, h_im_grad + l3 * fabsf(h_im) * h_im, H.m1[NM >= 1 ? im : 0],
                                 H.m2[NM >= 2 ? im : 0], weight);
             const float t_re_grad = gradient * (h_re * r_re - h_im * r_im);
             const float t_im_grad = gradient * (h_re * r_im + h_im * r_re);
-            T.v[re] -= step<NM>(o, t_re, t_re_grad + l3 * fabsf(t_re) * t_re, T.m1[NM >= 1 ? re : 0],
+            T.v[re] -= step<NM, FAST>(o, t_re, t_re_grad + l3 * fabsf(t_re) * t_re, T.m1[NM >= 1 ? re : 0],
                                 T.m2[NM >= 2 ? re : 0], weight);
-            T.v[im] -= step<NM>(o, t_im, t_im_grad + l3 * fabsf(t_im) * t_im, T.m1[NM >= 1 ? im : 0],
+            T.v[im] -= step<NM, FAST>(o, t_im, t_im_grad + l3 * fabsf(t_im) * t_im, T.m1[NM >= 1 ? im : 0],
                                 T.m2[NM >= 2 ? im : 0], weight);
             const float r_re_grad = gradient * (h_re * t_re + h_im * t_im);
             const float r_im_grad = gradient * (-h_im * t_re + h_re * t_im);
-            R.v[re] -= relation_lr_multiplier * step<NM>(o, r_re, r_re_grad + l3 * fabsf(r_re) * r_re,
+            R.v[re] -= relation_lr_multiplier * step<NM, FAST>(o, r_re, r_re_grad + l3 * fabsf(r_re) * r_re,
                                                          R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
-            R.v[im] -= relation_lr_multiplier * step<NM>(o, r_im, r_im_grad + l3 * fabsf(r_im) * r_im,
+            R.v[im] -= relation_lr_multiplier * step<NM, FAST>(o, r_im, r_im_grad + l3 * fabsf(r_im) * r_im,
                                                          R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
         }
     } else if constexpr (MODEL == GV_KG_QUATE) {  // model/knowledge_graph.h:620-674 (and the moment overloads)
@@ -339,8 +390,8 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
             const float h_r = H.v[q], h_i = H.v[q + 1], h_j = H.v[q + 2], h_k = H.v[q + 3];
             const float r_r = R.v[q], r_i = R.v[q + 1], r_j = R.v[q + 2], r_k = R.v[q + 3];
             const float t_r = T.v[q], t_i = T.v[q + 1], t_j = T.v[q + 2], t_k = T.v[q + 3];
-            const float r_norm = sqrtf(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
-            const float grad = gradient / (r_norm + kEps);
+            const float r_norm = kg_sqrt<FAST>(r_r * r_r + r_i * r_i + r_j * r_j + r_k * r_k);
+            const float grad = kg_divide<FAST>(gradient, r_norm + kEps);
             const float head_grad[4] = {grad * (r_r * t_r + r_i * t_i + r_j * t_j + r_k * t_k),
                                         grad * (-r_i * t_r + r_r * t_i - r_k * t_j + r_j * t_k),
                                         grad * (-r_j * t_r + r_k * t_i + r_r * t_j - r_i * t_k),
@@ -348,7 +399,7 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
             const float head_old[4] = {h_r, h_i, h_j, h_k};
 #pragma unroll
             for (int c = 0; c < 4; c++)
-                H.v[q + c] -= step<NM>(o, head_old[c], head_grad[c] + l3 * fabsf(head_old[c]) * head_old[c],
+                H.v[q + c] -= step<NM, FAST>(o, head_old[c], head_grad[c] + l3 * fabsf(head_old[c]) * head_old[c],
                                        H.m1[NM >= 1 ? q + c : 0], H.m2[NM >= 2 ? q + c : 0], weight);
             const float tail_grad[4] = {grad * (h_r * r_r - h_i * r_i - h_j * r_j - h_k * r_k),
                                         grad * (h_r * r_i + h_i * r_r + h_j * r_k - h_k * r_j),
@@ -357,7 +408,7 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
             const float tail_old[4] = {t_r, t_i, t_j, t_k};
 #pragma unroll
             for (int c = 0; c < 4; c++)
-                T.v[q + c] -= step<NM>(o, tail_old[c], tail_grad[c] + l3 * fabsf(tail_old[c]) * tail_old[c],
+                T.v[q + c] -= step<NM, FAST>(o, tail_old[c], tail_grad[c] + l3 * fabsf(tail_old[c]) * tail_old[c],
                                        T.m1[NM >= 1 ? q + c : 0], T.m2[NM >= 2 ? q + c : 0], weight);
             const float relation_grad[4] = {grad * (h_r * t_r + h_i * t_i + h_j * t_j + h_k * t_k),
                                             grad * (-h_i * t_r + h_r * t_i + h_k * t_j - h_j * t_k),
@@ -367,7 +418,7 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
 #pragma unroll
             for (int c = 0; c < 4; c++)
                 R.v[q + c] -= relation_lr_multiplier *
-                              step<NM>(o, relation_old[c],
+                              step<NM, FAST>(o, relation_old[c],
                                        relation_grad[c] + l3 * fabsf(relation_old[c]) * relation_old[c],
                                        R.m1[NM >= 1 ? q + c : 0], R.m2[NM >= 2 ? q + c : 0], weight);
         }
@@ -377,21 +428,25 @@ __device__ __forceinline__ void backward(Slice<E, NM> &H, Slice<E, NM> &Tin, Rel
             const int re = i * 2, im = i * 2 + 1;
             const float phase = R.v[i];
             float r_re, r_im;
-            sincosf(phase, &r_im, &r_re);
+            if constexpr (FAST)
+                r_re = rotation_re[i], r_im = rotation_im[i];
+            else
+                sincosf(phase, &r_im, &r_re);
             const float h_re = H.v[re], h_im = H.v[im], t_re = T.v[re], t_im = T.v[im];
             const float distance_re = h_re * r_re - h_im * r_im - t_re;
             const float distance_im = h_re * r_im + h_im * r_re - t_im;
-            const float grad = gradient / (sqrtf(distance_re * distance_re + distance_im * distance_im) + kEps);
+            const float grad =
+                kg_divide<FAST>(gradient, kg_sqrt<FAST>(distance_re * distance_re + distance_im * distance_im) + kEps);
             const float head_re_grad = -grad * (distance_re * r_re + distance_im * r_im);
             const float head_im_grad = -grad * (-distance_re * r_im + distance_im * r_re);
-            H.v[re] -= step<NM>(o, h_re, head_re_grad, H.m1[NM >= 1 ? re : 0], H.m2[NM >= 2 ? re : 0], weight);
-            H.v[im] -= step<NM>(o, h_im, head_im_grad, H.m1[NM >= 1 ? im : 0], H.m2[NM >= 2 ? im : 0], weight);
-            T.v[re] -= step<NM>(o, t_re, grad * distance_re, T.m1[NM >= 1 ? re : 0], T.m2[NM >= 2 ? re : 0], weight);
-            T.v[im] -= step<NM>(o, t_im, grad * distance_im, T.m1[NM >= 1 ? im : 0], T.m2[NM >= 2 ? im : 0], weight);
+            H.v[re] -= step<NM, FAST>(o, h_re, head_re_grad, H.m1[NM >= 1 ? re : 0], H.m2[NM >= 2 ? re : 0], weight);
+            H.v[im] -= step<NM, FAST>(o, h_im, head_im_grad, H.m1[NM >= 1 ? im : 0], H.m2[NM >= 2 ? im : 0], weight);
+            T.v[re] -= step<NM, FAST>(o, t_re, grad * distance_re, T.m1[NM >= 1 ? re : 0], T.m2[NM >= 2 ? re : 0], weight);
+            T.v[im] -= step<NM, FAST>(o, t_im, grad * distance_im, T.m1[NM >= 1 ? im : 0], T.m2[NM >= 2 ? im : 0], weight);
             const float relation_grad = -grad * (distance_re * (h_re * -r_im + h_im * -r_re) +
                                                  distance_im * (h_re * r_re + h_im * -r_im));
             R.v[i] -= relation_lr_multiplier *
-                      step<NM>(o, phase, relation_grad, R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
+                      step<NM, FAST>(o, phase, relation_grad, R.m1[NM >= 1 ? i : 0], R.m2[NM >= 2 ? i : 0], weight);
         }
     }
 }
@@ -475,7 +530,7 @@ __device__ __forceinline__ uint32_t uniform_negative(uint32_t count, double rand
 // The train kernel.  E floats per thread, NM moments per row.
 // Dynamic shared memory per group: 2 * kPass1Batch * warps floats (sums) + num_negative ids.
 // -----------------------------------------------------------------------------
-template<int E, int MODEL, int NM>
+template<int E, int MODEL, int NM, bool FAST>
 __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p) {
     GV_DYNAMIC_SHARED(unsigned char, shared_bytes);
     using G = Geometry<E, MODEL>;
@@ -511,6 +566,11 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
     o.a = p.optimizer.a;
     o.b = p.optimizer.b;
     o.eps = p.optimizer.epsilon;
+
+    // L2 prefetch geometry (see prefetch_row): this thread's array (0 = row, 1 / 2 = moments) and 128-byte line
+    const bool l2_prefetch = !(p.flags & 2);
+    const int row_lines = (p.dim * 4 + 127) / 128;
+    const int prefetch_array = c / row_lines, prefetch_line = c % row_lines;
 
     const unsigned long long first = (unsigned long long)blockIdx.x * groups_per_cta + g.id_in_cta;
     const unsigned long long stride = (unsigned long long)gridDim.x * groups_per_cta;
@@ -571,6 +631,32 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
             }
         };
 
+        // The negative rows of a sample are scattered 8-KB reads whose ids are known from the start, and one group per
+        // SM has only the next target's row in flight (NX below): rows further ahead are pulled into L2 -- the row
+        // and its moments are (1 + NM) * row_lines 128-byte lines, one per thread (always fewer than the group has
+        // threads).  A prefetch is not a read: the values are loaded when the target is reached.
+        auto prefetch_row = [&](int s, int arrays) {
+            if (!l2_prefetch || s >= k || prefetch_array >= arrays)
+                return;
+            const uint32_t negative = negative_ids[s];
+            const bool is_head = negative < p.num_head;
+            const size_t row = size_t(is_head ? negative : negative - p.num_head) * dim;
+            const float *base = prefetch_array == 0 ? (is_head ? p.head : p.tail)
+                                : prefetch_array == 1 ? (is_head ? p.head_m1 : p.tail_m1)
+                                                      : (is_head ? p.head_m2 : p.tail_m2);
+            gv_prefetch_row_line(reinterpret_cast<const char *>(base + row) + prefetch_line * 128);
+        };
+        auto prefetch_row_of = [&](int s) {  // values only, line prefetch_line of target s
+            if (!l2_prefetch || s >= k)
+                return;
+            const uint32_t negative = negative_ids[s];
+            const bool is_head = negative < p.num_head;
+            const float *row = (is_head ? p.head : p.tail) + size_t(is_head ? negative : negative - p.num_head) * dim;
+            gv_prefetch_row_line(reinterpret_cast<const char *>(row) + prefetch_line * 128);
+        };
+        prefetch_row(0, 1 + NM);  // pass 2 starts with these; pass 1 (values only) runs in between
+        prefetch_row(1, 1 + NM);
+
         // pass 1: normaliser of the self-adversarial weights (gpu/knowledge_graph.cuh:59-77).  The k logits are
         // independent of each other: kPass1Batch targets are loaded together (that many rows in flight per
         // thread) and reduced with one barrier; the normaliser is still accumulated in target order.
@@ -580,10 +666,14 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
             if (adversarial) {
 #pragma unroll
                 for (int i = 0; i < E / 2; i++)
-                    sincosf(R.v[i], &rotation_im[i], &rotation_re[i]);
+                    kg_sincos<FAST>(R.v[i], &rotation_im[i], &rotation_re[i]);
             }
         if (adversarial)
             for (int s0 = 0; s0 < k; s0 += kPass1Batch) {
+                // the rows of the NEXT batch of targets -> L2: thread c takes line (c % row_lines) of target
+                // s0 + kPass1Batch + c / row_lines
+                if (prefetch_array < kPass1Batch)
+                    prefetch_row_of(s0 + kPass1Batch + prefetch_array);
                 float partial[kPass1Batch];
 #pragma unroll
                 for (int b = 0; b < kPass1Batch; b++) {
@@ -605,9 +695,9 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                         } else
                             load_vec<E, G::UE>(t, p.tail + size_t(tail_id) * dim + slice, slice_stride);
                         if constexpr (MODEL == GV_KG_ROTATE)
-                            partial[b] = partial_logit_rotated<E>(h, t, rotation_re, rotation_im);
+                            partial[b] = partial_logit_rotated<E, FAST>(h, t, rotation_re, rotation_im);
                         else
-                            partial[b] = partial_logit<E, MODEL>(h, t, R.v);
+                            partial[b] = partial_logit<E, MODEL, FAST>(h, t, R.v);
                     }
                 }
                 g.sum_many<kPass1Batch>(partial);
@@ -617,7 +707,7 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                         const float logit = finish_logit<MODEL>(partial[b], p.margin_or_l3);
                         if (s0 + b == 0)
                             bias = logit;
-                        normalizer += safe_exp((logit - bias) / p.temperature);
+                        normalizer += safe_exp(kg_divide<FAST>(logit - bias, p.temperature));
                     }
             }
 
@@ -657,6 +747,7 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
                     load_slice<E, NM>(WT, p.tail, p.tail_m1, p.tail_m2, tail_offset, slice_stride, active);
             }
             next_valid = false;
+            prefetch_row(s + 2, 1 + NM);  // two targets ahead -> L2; the next one -> registers:
             if (s + 1 < k && cached) {  // target s + 1 is a negative: exactly one of its rows may be uncached
                 uint32_t next_head, next_tail;
                 target(s + 1, next_head, next_tail);
@@ -682,30 +773,43 @@ __global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p)
             }
 
             float partial = 0.f;
-            if (active)
-                partial = alias ? partial_logit<E, MODEL>(WH.v, WH.v, R.v) : partial_logit<E, MODEL>(WH.v, WT.v, R.v);
+            if constexpr (MODEL == GV_KG_ROTATE && FAST) {
+                // the rotation of this target's relation row, once: the logit and the gradient use the same values
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < E / 2; i++)
+                        gv_sincos(R.v[i], &rotation_im[i], &rotation_re[i]);
+                    partial = alias ? partial_logit_rotated<E, FAST>(WH.v, WH.v, rotation_re, rotation_im)
+                                    : partial_logit_rotated<E, FAST>(WH.v, WT.v, rotation_re, rotation_im);
+                }
+            } else if (active)
+                partial = alias ? partial_logit<E, MODEL, FAST>(WH.v, WH.v, R.v)
+                                : partial_logit<E, MODEL, FAST>(WH.v, WT.v, R.v);
             const float logit = finish_logit<MODEL>(g.sum(partial), p.margin_or_l3);
-            const float prob = sigmoid(logit);
+            const float prob = sigmoid<FAST>(logit);
             float gradient, weight;
             if (s == k) {
                 gradient = prob - 1;
                 weight = 1;
-                sample_loss += weight * -logf(prob + kEps);
+                if (c == 0)  // the loss is reported by the group's first thread only
+                    sample_loss += weight * -logf(prob + kEps);
             } else {
                 gradient = prob;
                 if (adversarial)
-                    weight = fminf(safe_exp((logit - bias) / p.temperature) / normalizer, 1.f);
+                    weight = fminf(kg_divide<FAST>(safe_exp(kg_divide<FAST>(logit - bias, p.temperature)), normalizer),
+                                   1.f);
                 else
                     weight = float(1.0 / k);
-                sample_loss += weight * -logf(1 - prob + kEps);
+                if (c == 0)
+                    sample_loss += weight * -logf(1 - prob + kEps);
             }
             if (active) {
                 if (alias)
-                    backward<E, MODEL, NM, true>(WH, WH, R, o, p.margin_or_l3, gradient, p.relation_lr_multiplier,
-                                                 weight);
+                    backward<E, MODEL, NM, true, FAST>(WH, WH, R, o, p.margin_or_l3, gradient,
+                                                       p.relation_lr_multiplier, weight, rotation_re, rotation_im);
                 else
-                    backward<E, MODEL, NM, false>(WH, WT, R, o, p.margin_or_l3, gradient, p.relation_lr_multiplier,
-                                                  weight);
+                    backward<E, MODEL, NM, false, FAST>(WH, WT, R, o, p.margin_or_l3, gradient,
+                                                        p.relation_lr_multiplier, weight, rotation_re, rotation_im);
             }
             if (head_source == 1)
                 PH = WH;
@@ -779,7 +883,7 @@ __global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *he
             load_vec<E, G::UE>(t, tail + size_t(tail_id) * dim + size_t(c) * G::UE, size_t(chunks) * G::UE);
             load_vec<G::RV, G::URV>(r, relation + size_t(relation_id) * dim + size_t(c) * G::URV,
                                     size_t(chunks) * G::URV);
-            partial = partial_logit<E, MODEL>(h, t, r);
+            partial = partial_logit<E, MODEL, false>(h, t, r);
         }
         const float logit = finish_logit<MODEL>(g.sum(partial), margin);
         if (c == 0)
@@ -795,15 +899,23 @@ int floats_per_thread(int dim, int model) {
     return 2;
 }
 
+template<int E, int MODEL, bool FAST>
+cudaError_t launch_train_math(const KgParams &p, int num_moment, dim3 grid, dim3 block, size_t shared,
+                              cudaStream_t s) {
+    if (num_moment == 0)
+        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 0, FAST>)(p);
+    else if (num_moment == 1)
+        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 1, FAST>)(p);
+    else
+        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 2, FAST>)(p);
+    return cudaGetLastError();
+}
+
 template<int E, int MODEL>
 cudaError_t launch_train_nm(const KgParams &p, int num_moment, dim3 grid, dim3 block, size_t shared, cudaStream_t s) {
-    if (num_moment == 0)
-        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 0>)(p);
-    else if (num_moment == 1)
-        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 1>)(p);
-    else
-        GV_LAUNCH(grid, block, shared, s, kg_train_kernel<E, MODEL, 2>)(p);
-    return cudaGetLastError();
+    if (kg_flags() & 1)  // IEEE sqrt / division / sincosf
+        return launch_train_math<E, MODEL, false>(p, num_moment, grid, block, shared, s);
+    return launch_train_math<E, MODEL, true>(p, num_moment, grid, block, shared, s);
 }
 
 template<int E>
@@ -863,6 +975,14 @@ int check_geometry(const char *who, int dim, int model, int &E, int &group_threa
 }  // namespace
 
 }  // namespace device
+
+int kg_kernel_flags() {
+    return device::kg_flags();
+}
+void set_kg_kernel_flags(int value) {
+    device::kg_flags() = value;
+}
+
 }  // namespace gv
 
 using namespace gv;
@@ -914,6 +1034,7 @@ int gv_cuda_kg_train_block(const gv_kg_matrices_t *m, int model, const uint32_t 
     p.temperature = adversarial_temperature;
     p.loss_per_sample = loss_per_sample;
     p.loss_per_batch = loss_per_batch;
+    p.flags = kg_flags();
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int device = 0, num_sm = 0;

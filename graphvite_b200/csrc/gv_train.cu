@@ -1316,6 +1316,8 @@ int gv_cuda_set_tunable(const char *name, long value) {
         g_sample_prefetch_blocks = int(value < 0 ? 0 : value);
     else if (key == "sample_resident_blocks")
         g_sample_resident_blocks = int(value < 0 ? 0 : value);
+    else if (key == "kg_flags")
+        set_kg_kernel_flags(int(value));
     else
         return fail("unknown tunable `" + key + "`");
     return 0;
@@ -1341,6 +1343,8 @@ long gv_cuda_get_tunable(const char *name) {
         return g_sample_prefetch_blocks;
     if (key == "sample_resident_blocks")
         return g_sample_resident_blocks;
+    if (key == "kg_flags")
+        return kg_kernel_flags();
     fail("unknown tunable `" + key + "`");
     return -1;
 }

@@ -133,9 +133,21 @@ inline float gv_fast_exp(float x) {
 }
 inline float gv_load_again(const float *address) { return *address; }
 inline void gv_prefetch_l2(const void *) {}
+inline void gv_prefetch_row_line(const void *address) {  // checked: must lie inside a live allocation
+    (void)*static_cast<const volatile unsigned char *>(address);
+}
 inline void gv_wait_for(float &) {}  // a scheduling fence on the GPU; nothing to wait for here
 inline float gv_fast_divide(float a, float b) {
     return a / b;
+}
+inline float gv_fast_rcp(float x) {
+    return 1.f / x;
+}
+inline float gv_fast_sqrt(float x) {
+    return sqrtf(x);
+}
+inline float gv_fast_rsqrt(float x) {
+    return 1.f / sqrtf(x);
 }
 
 // ---- synchronisation ------------------------------------------------------------------------------
