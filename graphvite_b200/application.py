@@ -47,9 +47,8 @@ def _resolve_gpus(gpus, knowledge_graph=False):
     (core/solver.h:184-213).  Here one process drives one GPU and N processes form the N-GPU solver:
       * under torchrun (WORLD_SIZE > 1) rank r takes gpus[r] (or GPU LOCAL_RANK for `gpus: []`) and the solver is
         created with rank / world_size -- the YAML's `gpus: [0, 1, 2, 3]` then means what it means in the reference;
-      * in a single process the whole list is handed to GraphSolver, whose front end starts one worker process per
-        listed GPU (`gpus: []` = every visible GPU); the knowledge-graph solver has no such front end and refuses a
-        list with the torchrun instructions.  Never a silent truncation.
+      * in a single process the whole list is handed to the solver, whose front end starts one worker process per
+        listed GPU (`gpus: []` = every visible GPU).  Never a silent truncation.
     Returns (device_ids, extra solver kwargs)."""
     gpus = list(gpus)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -65,7 +64,7 @@ def _resolve_gpus(gpus, knowledge_graph=False):
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
         return [device], dict(rank=rank, world_size=world)
-    if not gpus and not knowledge_graph:
+    if not gpus:
         # `gpus: []` = all GPUs (core/solver.h:186-191)
         try:
             import torch
@@ -74,12 +73,7 @@ def _resolve_gpus(gpus, knowledge_graph=False):
             count = 1
         if count > 1:
             gpus = list(range(count))
-    if len(gpus) > 1 and knowledge_graph:
-        raise ValueError("gpus = %s: the knowledge-graph solver drives one GPU per process.  Launch one process per GPU "
-                         "-- `torchrun --nnodes=1 --nproc-per-node %d -m graphvite_b200.cmd run <config.yaml>` -- and "
-                         "the %d processes form the reference's %d-GPU solver" % (gpus, len(gpus), len(gpus), len(gpus)))
-    # several GPUs for a GraphSolver in one process: the solver front end starts one worker process per GPU
-    # (graphvite_b200/multi.py)
+    # several GPUs in one process: the solver front end starts one worker process per GPU (graphvite_b200/multi.py)
     return gpus, {}
 
 

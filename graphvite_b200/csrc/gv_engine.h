@@ -2,13 +2,23 @@
 // bulk path for the one place that draws hundreds of millions of numbers: init_embeddings
 // (std::uniform_real_distribution<float>(a, b)(engine) for every element, instance/graph.cuh:724-731).
 // fill_uniform() produces bit for bit what that loop produces with libstdc++ (gv_engine_self_check() compares the two;
-// tests/test_host_runtime.py).
+// tests/test_host_runtime.py).  The stream is sequential by definition, but the generator is linear over GF(2):
+// jump(l) skips kJumpBlocks * 2^l * 624 draws in ~1 ms (gv_mt_jump.h, tools/mt_jump_poly.py), so fill_uniform() cuts a
+// long request into one contiguous piece per thread, and every thread advances its copy of the engine to its piece -- 1.46e8 draws (Youtube,
+// d = 128) are 0.17 s on one core and sit on the critical path of GraphSolver.train().
 #pragma once
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <emmintrin.h>  // SSE2, baseline x86-64
+#include <thread>
+#include <vector>
+
+#include "gv_mt_jump.h"
 
 namespace gv {
 
@@ -35,7 +45,78 @@ public:
     }
 
     // out[i] = std::uniform_real_distribution<float>(a, b)(*this), i = 0 .. n-1
-    void fill_uniform(float *out, size_t n, float a, float b) {
+    // `threads` = 0: as many as the machine has (at most 16); requests shorter than two spans stay on this thread
+    void fill_uniform(float *out, size_t n, float a, float b, int threads = 0) {
+        const size_t span = size_t(kJumpBlocks) * kN;
+        if (threads == 0)
+            threads = int(std::min<unsigned>(16, std::max<unsigned>(1, std::thread::hardware_concurrency())));
+        const size_t spans = (n + span - 1) / span;
+        if (threads <= 1 || spans < 2) {
+            fill_uniform_sequential(out, n, a, b);
+            return;
+        }
+        // thread t generates the draws of spans [first(t), first(t + 1)) from a copy of the engine that it advances
+        // to its first span itself (one jump per set bit of first(t)): nothing is sequential but the draws of a thread
+        const size_t workers = std::min<size_t>(size_t(threads), spans);
+        std::vector<Mt19937> engines(workers, *this);
+        auto first_span = [&](size_t t) { return t * spans / workers; };
+        auto work = [&](size_t t) {
+            engines[t].skip_spans(first_span(t));
+            const size_t begin = first_span(t) * span, end = std::min(n, first_span(t + 1) * span);
+            engines[t].fill_uniform_sequential(out + begin, end - begin, a, b);
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < workers; t++)
+            pool.emplace_back(work, t);
+        work(0);
+        for (auto &thread : pool)
+            thread.join();
+        *this = engines[workers - 1];
+    }
+
+    // this engine after count * kJumpBlocks * 624 more draws
+    void skip_spans(size_t count) {
+        for (int level = 0; level < kJumpLevels - 1; level++)
+            if ((count >> level) & 1)
+                jump(level);
+        for (size_t rest = count >> (kJumpLevels - 1); rest > 0; rest--)
+            jump(kJumpLevels - 1);
+    }
+
+    // this engine after kJumpBlocks * 2^level * 624 more draws (the position inside the current block is kept)
+    void jump(int level) {
+        // Horner over the window (x_k .. x_{k+623}) sliding through one long buffer: h <- T h is one step of the
+        // recurrence appended behind the window, h <- h + s adds the start block to the window
+        const uint32_t *polynomial = kJumpPolynomial[level];
+        int degree = 19936;
+        while (degree > 0 && !((polynomial[degree >> 5] >> (degree & 31)) & 1u))
+            degree--;
+        std::vector<uint32_t> buffer(size_t(kN) + size_t(degree) + 8, 0u);
+        uint32_t *window = buffer.data();
+        for (int i = degree; i >= 0; i--) {
+            if (i != degree) {  // h <- T h
+                window[kN] = twist1(window[0], window[1], window[kM]);
+                window++;
+            }
+            if ((polynomial[i >> 5] >> (i & 31)) & 1u) {
+                int j = 0;
+                for (; j + 4 <= kN; j += 4)
+                    _mm_storeu_si128(reinterpret_cast<__m128i *>(window + j),
+                                     _mm_xor_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(window + j)),
+                                                   _mm_loadu_si128(reinterpret_cast<const __m128i *>(state + j))));
+                for (; j < kN; j++)
+                    window[j] ^= state[j];
+            }
+        }
+        // the window now starts one block before the target; the 31 low bits of its first word are not part of the
+        // 19937-bit state and are undefined: one ordinary block update produces the target block from valid bits only
+        const int position = index;
+        std::memcpy(state, window, kN * sizeof(uint32_t));
+        twist();
+        index = position;
+    }
+
+    void fill_uniform_sequential(float *out, size_t n, float a, float b) {
         const float range = b - a;
         size_t done = 0;
         while (done < n) {

@@ -1039,8 +1039,19 @@ struct Solver {
             const int tail = g * num_worker + rank;
             const auto &ids = partitions[tail];
             std::vector<float> weights(ids.size());
-            for (size_t i = 0; i < ids.size(); i++)
-                weights[i] = std::pow(graph->vertex_weights[ids[i]], negative_sample_exponent);
+            {  // elementwise powf, 30 ns each: a few threads for a million vertices
+                const size_t threads = ids.size() < 100000 ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+                auto range = [&](size_t t) {
+                    for (size_t i = ids.size() * t / threads; i < ids.size() * (t + 1) / threads; i++)
+                        weights[i] = std::pow(graph->vertex_weights[ids[i]], negative_sample_exponent);
+                };
+                std::vector<std::thread> pool;
+                for (size_t t = 1; t < threads; t++)
+                    pool.emplace_back(range, t);
+                range(0);
+                for (auto &thread : pool)
+                    thread.join();
+            }
             std::vector<float> prob(ids.size());
             std::vector<uint32_t> alias(ids.size());
             build_alias<uint32_t>(weights.data(), weights.size(), prob.data(), alias.data());
@@ -1057,7 +1068,20 @@ struct Solver {
         // x = init(seed) for every element, in row-major order -- drawn in bulk (gv_engine.h), same values
         std::uniform_real_distribution<float> init(-0.5 / dim, 0.5 / dim);
         g_engine.fill_uniform(vertex_host.data(), vertex_host.size(), init.a(), init.b());
-        std::fill(context_host.begin(), context_host.end(), 0.f);
+        zero_matrix(context_host);
+    }
+
+    // m = 0 on a few threads (583 MB per matrix at Youtube size: 60 ms on one core)
+    static void zero_matrix(std::vector<float> &m) {
+        const size_t threads = m.size() < (size_t(1) << 24) ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < threads; t++)
+            pool.emplace_back([&m, t, threads]() {
+                std::memset(m.data() + m.size() * t / threads, 0, (m.size() * (t + 1) / threads - m.size() * t / threads) * sizeof(float));
+            });
+        std::memset(m.data(), 0, m.size() / threads * sizeof(float));
+        for (auto &thread : pool)
+            thread.join();
     }
 
     // ---- GraphSolver::train prologue + SolverMixin::train up to the first pool fill ----
@@ -1111,28 +1135,42 @@ struct Solver {
             initializer = std::thread([this]() {
                 init_embeddings();
                 for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
-                    std::fill(m->begin(), m->end(), 0.f);
+                    zero_matrix(*m);
             });
             batch_id = 0;
         }
         num_batch = int(batch_id + uint64_t(num_epoch) * graph->num_edge / batch_size);
+        // the negative tables (powf + Vose per owned tail partition, uploaded on the work stream) are independent of
+        // the samplers' tables and pools (sample stream): built next to them
+        std::exception_ptr negative_error;
+        std::thread negatives([this, &negative_error]() {
+            try {
+                GV_CHECK_CUDA(cudaSetDevice(device));
+                build_negative_tables();
+            } catch (...) {
+                negative_error = std::current_exception();
+            }
+        });
         try {
             prepare_sampling();
             phase.mark("sampler tables + graph upload");
-            build_negative_tables();
-            phase.mark("negative tables");
             stat_positive = stat_kernel_seconds = stat_train_seconds = stat_sample_seconds = 0;
             stat_launches = 0;
             fill_pool(pool_id ^ 1);
             phase.mark("first pool fill");
         } catch (...) {
+            negatives.join();
             if (initializer.joinable())
                 initializer.join();
             throw;
         }
+        negatives.join();
+        phase.mark("negative tables (rest)");
         if (initializer.joinable())
             initializer.join();
         phase.mark("init embeddings (rest)");
+        if (negative_error)
+            std::rethrow_exception(negative_error);
         load_blocks(!resume);
         phase.mark("embedding upload");
         if (capture_negatives)
@@ -1595,6 +1633,31 @@ int gv_engine_self_check(uint32_t seed, uint64_t bulk) {
             return 3;
         if (reference() != ours())
             return 4;
+    }
+    // skip_spans(5) = levels 0 and 2 = 5 * kJumpBlocks * 624 draws, from a position in the middle of a block
+    if (bulk >= 1000) {
+        gv::Mt19937 jumped = ours, stepped = ours;
+        jumped.skip_spans(5);
+        for (uint64_t i = 0; i < uint64_t(gv::kJumpBlocks) * 624 * 5; i++)
+            stepped();
+        for (int i = 0; i < 2000; i++)
+            if (jumped() != stepped())
+                return 5;
+    }
+    // the multi-threaded fill (spans of kJumpBlocks * 624 draws) against the sequential one, engine state included
+    if (bulk >= 1000) {
+        const uint64_t n = uint64_t(gv::kJumpBlocks) * 624 * 6 + bulk;
+        for (int threads : {2, 5}) {
+            gv::Mt19937 sequential = ours, parallel = ours;
+            std::vector<float> expected(n), got(n);
+            sequential.fill_uniform(expected.data(), n, -0.25f, 0.75f, 1);
+            parallel.fill_uniform(got.data(), n, -0.25f, 0.75f, threads);
+            if (memcmp(expected.data(), got.data(), n * sizeof(float)) != 0)
+                return 6;
+            for (int i = 0; i < 700; i++)
+                if (sequential() != parallel())
+                    return 7;
+        }
     }
     return 0;
 }

@@ -183,6 +183,7 @@ class KnowledgeGraph(object):
             raise ValueError("Can't find an instantiation of KnowledgeGraph with index_type = %s" % (index_type,))
         self._handle = lib.gv_kgraph_create()
         self._names = None
+        self._recipe = None  # how this graph was loaded: lets the workers of a multi-GPU solver load it again
 
     def __del__(self):
         handle, self._handle = getattr(self, "_handle", None), None
@@ -195,6 +196,7 @@ class KnowledgeGraph(object):
         load(triplet_list, normalization=False)
         load(weighted_triplet_list, normalization=False)"""
         self._names = None
+        self._recipe = None
         names = ["file_name", "normalization", "delimiters", "comment"]
         for alias in ("triplet_list", "weighted_triplet_list"):
             if alias in kwargs:
@@ -214,6 +216,8 @@ class KnowledgeGraph(object):
             path = source if isinstance(source, bytes) else source.encode()
             _lib.check(lib.gv_kgraph_load_file(self._handle, path, int(normalization), delimiters.encode(),
                                                comment.encode()))
+            self._recipe = ("kg_file", os.path.abspath(source if isinstance(source, str) else source.decode()),
+                            dict(normalization=normalization, delimiters=delimiters, comment=comment))
             return
         if "delimiters" in params or "comment" in params:
             raise TypeError("load(): incompatible function arguments")
@@ -225,6 +229,7 @@ class KnowledgeGraph(object):
             weights = (ctypes.c_float * count)(*[float(t[3]) for t in triplets])
         _lib.check(lib.gv_kgraph_load_triplets(self._handle, columns[0], columns[1], columns[2], weights, count,
                                                int(normalization)))
+        self._recipe = ("kg_triplets", [tuple(t) for t in triplets], dict(normalization=normalization))
 
     def save(self, file_name, anonymous=False):
         """save(file_name, anonymous=False): save the graph in triplet-list format (head, tail, relation)."""

@@ -185,7 +185,18 @@ class KnowledgeGraphSolver(object):
     Knowledge graph embedding solver (reference include/bind.h:516-639 over
     include/instance/knowledge_graph.cuh:531-677).  Models: TransE, DistMult, ComplEx, SimplE, RotatE, QuatE.
     Extra keyword arguments (not in the reference): rank, world_size for one-process-per-GPU runs.
+    Several `device_ids` in one process (the reference's signature, core/solver.h:184-213) return a front end that
+    starts one worker process per listed GPU (`graphvite_b200/multi.py`).
     """
+
+    def __new__(cls, dim, float_type=None, index_type=None, device_ids=(), *args, **kwargs):
+        if cls is KnowledgeGraphSolver and len(list(device_ids)) > 1 and kwargs.get("world_size", 1) == 1 and \
+                int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            if dim not in _KG_DIMS:
+                raise ValueError("Can't find an instantiation of KnowledgeGraphSolver with dim = %s" % (dim,))
+            from .multi import SpawnedKnowledgeGraphSolver
+            return SpawnedKnowledgeGraphSolver(dim, float_type, index_type, device_ids, *args, **kwargs)
+        return super(KnowledgeGraphSolver, cls).__new__(cls)
 
     def __init__(self, dim, float_type=None, index_type=None, device_ids=(), num_sampler_per_worker=auto,
                  gpu_memory_limit=auto, rank=0, world_size=1):

@@ -13,10 +13,9 @@ def test_gpu_lists_are_never_truncated(monkeypatch):
     # node embeddings: the whole list reaches GraphSolver, whose front end starts one worker process per GPU
     assert A._resolve_gpus([0, 1, 2, 3]) == ([0, 1, 2, 3], {})
     assert A._resolve_gpus([2]) == ([2], {})
-    # knowledge graphs: one GPU per process, several need torchrun -- said loudly
-    with pytest.raises(ValueError, match="torchrun"):
-        A._resolve_gpus([0, 1], knowledge_graph=True)
-    assert A._resolve_gpus([], knowledge_graph=True) == ([], {})
+    # knowledge graphs: the same -- KnowledgeGraphSolver has the front end too
+    assert A._resolve_gpus([0, 1], knowledge_graph=True) == ([0, 1], {})
+    assert A._resolve_gpus([], knowledge_graph=True) == ([], {})  # no GPU here: `[]` stays the solver's default
 
 
 def test_gpu_list_must_match_the_number_of_launched_processes(monkeypatch):
