@@ -48,12 +48,18 @@ namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr float kEps = 1e-15f;  // util/common.h:28
-constexpr int kCtaThreads = 256;
+constexpr int kCtaThreads = 256;  // groups are packed into CTAs of this size ...
+constexpr int kMaxGroupThreads = 512;  // ... except a group of 4-float threads at d = 2048 (kg_flags bit 2), a CTA of its own
+template<int E>
+constexpr int max_cta_threads() {
+    return E == 8 ? kCtaThreads : kMaxGroupThreads;
+}
 constexpr int kPass1Batch = 4;  // targets per barrier in the normaliser pass
 
 // tunable `kg_flags` (gv_cuda_set_tunable; environment GV_KG_FLAGS gives the initial value).
 // bit 0: IEEE square roots, divisions and sincosf() in the train kernel instead of the MUFU / gv_sincos versions
 // bit 1: no L2 prefetch of the negative rows ahead of their targets
+// bit 2: 4 floats per thread also for rows of 1024 .. 2048 floats (groups of up to 512 threads)
 int &kg_flags() {
     static int flags = getenv("GV_KG_FLAGS") ? atoi(getenv("GV_KG_FLAGS")) : 0;
     return flags;
@@ -531,7 +537,7 @@ __device__ __forceinline__ uint32_t uniform_negative(uint32_t count, double rand
 // Dynamic shared memory per group: 2 * kPass1Batch * warps floats (sums) + num_negative ids.
 // -----------------------------------------------------------------------------
 template<int E, int MODEL, int NM, bool FAST>
-__global__ void __launch_bounds__(kCtaThreads) kg_train_kernel(const KgParams p) {
+__global__ void __launch_bounds__(max_cta_threads<E>()) kg_train_kernel(const KgParams p) {
     GV_DYNAMIC_SHARED(unsigned char, shared_bytes);
     using G = Geometry<E, MODEL>;
     const int chunks = p.dim / E;                       // active threads of a group
@@ -891,8 +897,11 @@ __global__ void __launch_bounds__(kCtaThreads) kg_predict_kernel(const float *he
     }
 }
 
-int floats_per_thread(int dim, int model) {
-    if (dim % 8 == 0 && dim >= 256)
+int floats_per_thread(int dim, int model, bool train) {
+    // kg_flags bit 2 (train kernel only): 4 floats per thread for the largest rows as well -- twice the warps per
+    // sample (16 per SM at d = 2048), half the registers and instructions per thread
+    const bool narrow = train && (kg_flags() & 4) && dim / 4 <= kMaxGroupThreads;
+    if (dim % 8 == 0 && dim >= 256 && !narrow)
         return 8;
     if (dim % 4 == 0 && (dim >= 64 || model == GV_KG_QUATE))  // a quaternion never straddles two threads
         return 4;
@@ -956,18 +965,18 @@ cudaError_t launch_predict(int model, const float *head, const float *tail, cons
     return cudaGetLastError();
 }
 
-int check_geometry(const char *who, int dim, int model, int &E, int &group_threads) {
+int check_geometry(const char *who, int dim, int model, int &E, int &group_threads, bool train = false) {
     if (model < GV_KG_TRANSE || model > GV_KG_QUATE)
         return fail(std::string(who) + ": unknown model");
     if (dim < 2 || dim % 2 != 0 || dim > 2048)
         return fail(std::string(who) + ": dim must be even and at most 2048");
     if (model == GV_KG_QUATE && dim % 4 != 0)
         return fail(std::string(who) + ": QuatE needs a dimension divisible by 4");
-    E = floats_per_thread(dim, model);
+    E = floats_per_thread(dim, model, train);
     if (dim % E != 0)
         return fail(std::string(who) + ": dim must be a multiple of " + std::to_string(E));
     group_threads = (dim / E + 31) / 32 * 32;
-    if (group_threads > kCtaThreads)
+    if (group_threads > (train && E != 8 ? kMaxGroupThreads : kCtaThreads))
         return fail(std::string(who) + ": dim too large for one CTA");
     return 0;
 }
@@ -1003,7 +1012,7 @@ int gv_cuda_kg_train_block(const gv_kg_matrices_t *m, int model, const uint32_t 
     if (num_negative < 0 || (num_negative > 0 && !negatives && (!random || negative_count == 0)))
         return fail("gv_cuda_kg_train_block: negatives need either ids or a random stream and a count");
     int E, group_threads;
-    if (check_geometry("gv_cuda_kg_train_block", m->dim, model, E, group_threads))
+    if (check_geometry("gv_cuda_kg_train_block", m->dim, model, E, group_threads, true))
         return -1;
     const int type = optimizer->type;
     const int num_moment = type == GV_OPT_SGD ? 0 : (type == GV_OPT_ADAM ? 2 : 1);
@@ -1041,7 +1050,7 @@ int gv_cuda_kg_train_block(const gv_kg_matrices_t *m, int model, const uint32_t 
     GV_CUDA_OK(cudaGetDevice(&device));
     GV_CUDA_OK(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, device));
     // num_group == 1: one group, samples in order (the parity tests); 0: fill the device
-    const int groups_per_cta = num_group == 1 ? 1 : kCtaThreads / group_threads;
+    const int groups_per_cta = num_group == 1 ? 1 : std::max(1, kCtaThreads / group_threads);
     const dim3 block(groups_per_cta * group_threads);
     const size_t per_group =
         size_t(2) * kPass1Batch * (group_threads / 32) * sizeof(float) + size_t(num_negative) * sizeof(uint32_t);

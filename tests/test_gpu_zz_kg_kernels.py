@@ -343,21 +343,23 @@ def test_multi_warp_groups_with_every_batching_remainder(dim, k):
     np.testing.assert_allclose(got["hm2"], m[2], **TOLERANCE)
 
 
-@pytest.mark.parametrize("model,opt", [("RotatE", "Adam"), ("RotatE", "SGD"), ("QuatE", "AdaGrad"), ("TransE", "RMSprop")])
-def test_ieee_math_variant(model, opt):
-    """`kg_flags` bit 0 selects the kernel instantiation with IEEE sqrt / division / sincosf() (the default uses one
-    MUFU instruction each and gv_sincos): both follow the oracle, and they agree with each other far inside the
-    tolerance (<= 2 ulp per operation)"""
+@pytest.mark.parametrize("model,opt,dim", [("RotatE", "Adam", 256), ("RotatE", "SGD", 256), ("QuatE", "AdaGrad", 256),
+                                           ("TransE", "RMSprop", 256), ("RotatE", "Adam", 2048)])
+def test_kernel_variants_agree(model, opt, dim):
+    """`kg_flags` selects instantiations of the train kernel: bit 0 = IEEE sqrt / division / sincosf() (the default uses
+    one MUFU instruction each and gv_sincos), bit 1 = no L2 prefetch of the negative rows, bit 2 = 4 floats per thread
+    (a 512-thread group at d = 2048).  All follow the oracle, and the math variants agree with each other far inside
+    the tolerance (<= 2 ulp per operation)"""
     from graphvite_b200 import _lib
     optimizer = O.OPTIMIZERS[opt]
     nm = num_moment_of(optimizer)
-    dim, n, k, rows = 256, 40, 5, 30
-    entity, relation, ms, batch, negatives = make_problem(dim, n, k, rows, 4, 77, nm)
+    n, k, rows = 40, 5, 30
+    entity, relation, ms, batch, negatives = make_problem(dim, n, k, rows, 4, 77, nm, scale=0.2 if dim >= 512 else 1.0)
     margin_or_l3 = 6.0 if model in ("TransE", "RotatE") else 2e-3
     e, r, m, loss = oracle_shared(model, dim, entity, relation, ms, batch, negatives, optimizer, 1.5, margin_or_l3, 1.0)
     results = {}
     try:
-        for flags in (0, 1):
+        for flags in (0, 1, 2, 4):
             _lib.check(_lib.lib.gv_cuda_set_tunable(b"kg_flags", flags))
             assert _lib.lib.gv_cuda_get_tunable(b"kg_flags") == flags
             got = run_kg_train(model, dim, entity, None, relation, ms, batch, negatives, optimizer, rows, 1.5,
@@ -370,3 +372,4 @@ def test_ieee_math_variant(model, opt):
         _lib.lib.gv_cuda_set_tunable(b"kg_flags", 0)
     np.testing.assert_allclose(results[0]["head"], results[1]["head"], rtol=2e-4, atol=2e-6)
     np.testing.assert_allclose(results[0]["relation"], results[1]["relation"], rtol=2e-4, atol=2e-6)
+    np.testing.assert_array_equal(results[0]["head"], results[2]["head"])  # a prefetch is not a read
