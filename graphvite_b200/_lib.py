@@ -116,6 +116,9 @@ SIGNATURES = {
     "gv_cuda_kg_relation_delta": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "gv_cuda_kg_relation_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "gv_cuda_move_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p]),
+    "gv_cuda_fill_float": (c_int, [c_void_p, c_uint64, ctypes.c_float, c_void_p]),
+    "gv_cuda_fill_identity": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "gv_cuda_expand_sources": (c_int, [c_void_p, ctypes.c_uint32, c_void_p, c_void_p]),
     "gv_cuda_fill_count": (c_int, [P(FillParams), c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "gv_cuda_fill_scatter": (c_int, [P(FillParams), c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),

@@ -11,6 +11,10 @@
 // =============================================================================
 #include "gv_host.h"
 
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +22,7 @@
 #include <functional>
 #include <deque>
 #include <sstream>
+#include <thread>
 
 namespace gv {
 
@@ -82,22 +87,28 @@ void Graph::clear() {
     *this = Graph();
 }
 
-uint32_t Graph::intern(const std::string &name) {
-    auto found = name2id.find(name);
-    if (found != name2id.end())
-        return found->second;
-    const uint32_t id = uint32_t(id2name.size());
-    name2id.emplace(name, id);
-    id2name.push_back(name);
-    vertex_weights.push_back(0.f);
-    degrees.push_back(0);
+uint32_t Graph::intern(const char *name, size_t length, uint64_t hash) {
+    bool created;
+    const uint32_t id = names.intern(name, length, hash, id2name, created);
+    if (created) {
+        vertex_weights.push_back(0.f);
+        degrees.push_back(0);
+    }
     return id;
+}
+
+uint32_t Graph::intern(const std::string &name) {
+    return intern(name.data(), name.size(), NameTable::hash(name.data(), name.size()));
 }
 
 // Graph::add_edge, instance/graph.cuh:124-153
 void Graph::add_edge(const std::string &u_name, const std::string &v_name, float w) {
     const uint32_t u = intern(u_name);
     const uint32_t v = intern(v_name);
+    add_edge_ids(u, v, w);
+}
+
+void Graph::add_edge_ids(uint32_t u, uint32_t v, float w) {
     log_u.push_back(u);
     log_v.push_back(v);
     log_w.push_back(w);
@@ -123,17 +134,41 @@ void Graph::flatten() {
     offsets.assign(n + 1, 0);
     for (size_t v = 0; v < n; v++)
         offsets[v + 1] = offsets[v] + degrees[v];
-    std::vector<uint64_t> cursor(offsets.begin(), offsets.end() - 1);
     edge_u.resize(m);
     edge_v.resize(m);
     edge_w.resize(m);
-    for (size_t e = 0; e < m; e++) {
-        const uint64_t slot = cursor[log_u[e]]++;
-        edge_u[slot] = log_u[e];
-        edge_v[slot] = log_v[e];
-        edge_w[slot] = log_w[e];
+    // A stable counting sort of the edge log by source vertex.  The scatter is random over the whole output, so big
+    // logs are split by vertex range: thread t scans the log and places the edges whose source lies in its range
+    // (ranges of about equal edge count) -- sequential reads, writes confined to 1/T of the arrays, same result.
+    const size_t threads = m < (size_t(1) << 22) ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<uint64_t> cursor(offsets.begin(), offsets.end() - 1);
+    auto place = [&](uint32_t first, uint32_t last) {  // sources in [first, last)
+        for (size_t e = 0; e < m; e++) {
+            const uint32_t u = log_u[e];
+            if (u < first || u >= last)
+                continue;
+            const uint64_t slot = cursor[u]++;
+            edge_u[slot] = u;
+            edge_v[slot] = log_v[e];
+            edge_w[slot] = log_w[e];
+        }
+    };
+    if (threads == 1)
+        place(0, uint32_t(n));
+    else {
+        std::vector<uint32_t> bound(threads + 1, uint32_t(n));
+        bound[0] = 0;
+        for (size_t t = 1; t < threads; t++)
+            bound[t] = uint32_t(std::lower_bound(offsets.begin(), offsets.end(), uint64_t(m) * t / threads) - offsets.begin());
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < threads; t++)
+            pool.emplace_back(place, bound[t], bound[t + 1]);
+        place(bound[0], bound[1]);
+        for (auto &thread : pool)
+            thread.join();
     }
     flattened = true;
+    uniform_cache = -1;
 }
 
 // Graph::normalize, instance/graph.cuh:103-121
@@ -151,55 +186,142 @@ void Graph::normalize() {
         }
         vertex_weights[u] = weight;
     }
+    uniform_cache = -1;
     // the edge log is no longer consulted once flattened
 }
 
-// Graph::load_file, instance/graph.cuh:163-201
+// Graph::load_file, instance/graph.cuh:163-201.  Same lines, tokens, ids and errors as the fgets / strtok-style loop
+// it replaces; the file is read in large chunks, a batch of lines is tokenised and its names hashed (prefetching their
+// table slots) before the batch is resolved in order.
 void Graph::load_file(const char *file_name, bool undirected, bool normalized, const char *delimiters,
                       const char *comment) {
     clear();
     as_undirected = undirected;
     normalization = normalized;
-    FILE *fin = fopen(file_name, "r");
+    FILE *fin = fopen(file_name, "rb");
     if (!fin)
         throw std::runtime_error(std::string("File `") + file_name + "` doesn't exist");
-    const size_t kMaxLineLength = size_t(1) << 22;  // util/common.h:30
-    std::vector<char> line(kMaxLineLength);
+    struct {  // GV_LOG=2: phase timings on stderr
+        std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+        bool on = getenv("GV_LOG") != nullptr && atoi(getenv("GV_LOG")) >= 2;
+        void mark(const char *what) {
+            if (on) {
+                const auto now = std::chrono::steady_clock::now();
+                fprintf(stderr, "[gv] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - last).count());
+                last = now;
+            }
+        }
+    } phase;
+    bool is_delimiter[256] = {false};
+    for (const char *d = delimiters; *d; d++)
+        is_delimiter[uint8_t(*d)] = true;
     const size_t comment_length = strlen(comment);
-    std::string names[2];
-    for (size_t line_no = 1; fgets(line.data(), int(kMaxLineLength), fin); line_no++) {
-        if (comment_length) {
-            char *cut = strstr(line.data(), comment);
-            if (cut)
-                *cut = 0;
+    struct Pending {
+        const char *u, *v;
+        uint32_t u_length, v_length;
+        uint64_t u_hash, v_hash;
+        float w;
+    };
+    constexpr size_t kBatch = 64;
+    Pending pending[kBatch];
+    size_t num_pending = 0;
+    uint32_t ids[kBatch][2];
+    auto resolve = [&]() {
+        // ids in order of first appearance, then the per-vertex counters (scattered too: fetched ahead of their use)
+        for (size_t i = 0; i < num_pending; i++) {
+            const Pending &edge = pending[i];
+            ids[i][0] = intern(edge.u, edge.u_length, edge.u_hash);
+            ids[i][1] = intern(edge.v, edge.v_length, edge.v_hash);
+            __builtin_prefetch(&degrees[ids[i][0]], 1);
+            __builtin_prefetch(&vertex_weights[ids[i][0]], 1);
+            if (as_undirected) {
+                __builtin_prefetch(&degrees[ids[i][1]], 1);
+                __builtin_prefetch(&vertex_weights[ids[i][1]], 1);
+            }
         }
-        int num_token = 0;
-        float w = 1;
-        bool bad = false;
-        for (char *cursor = line.data(); *cursor;) {
-            cursor += strspn(cursor, delimiters);
-            if (!*cursor)
-                break;
-            const size_t length = strcspn(cursor, delimiters);
-            if (num_token < 2)
-                names[num_token].assign(cursor, length);
-            else if (num_token == 2)
-                w = float(atof(std::string(cursor, length).c_str()));
-            else
-                bad = true;
-            num_token++;
-            cursor += length;
+        for (size_t i = 0; i < num_pending; i++)
+            add_edge_ids(ids[i][0], ids[i][1], pending[i].w);
+        num_pending = 0;
+    };
+    {  // room for the edge log: ~12 bytes per line in a typical edge list
+        struct stat status;
+        if (fstat(fileno(fin), &status) == 0 && status.st_size > 0) {
+            const size_t lines = size_t(status.st_size) / 10, directed = lines * (undirected ? 2 : 1);
+            log_u.reserve(directed);
+            log_v.reserve(directed);
+            log_w.reserve(directed);
         }
-        if (num_token == 0)
-            continue;
-        if (num_token < 2 || bad) {
-            fclose(fin);
-            throw std::runtime_error("Invalid format at line " + std::to_string(line_no));
+    }
+    const size_t kChunk = size_t(64) << 20;
+    std::vector<char> buffer(kChunk + 1);
+    size_t held = 0, line_no = 0;  // bytes of an incomplete line carried over from the previous chunk
+    bool at_end = false;
+    while (!at_end) {
+        if (held == buffer.size() - 1)  // a line longer than the buffer
+            buffer.resize(buffer.size() * 2);
+        const size_t got = fread(buffer.data() + held, 1, buffer.size() - 1 - held, fin);
+        at_end = got == 0;
+        const size_t filled = held + got;
+        const char *cursor = buffer.data(), *limit = buffer.data() + filled;
+        while (cursor < limit) {
+            const char *newline = static_cast<const char *>(memchr(cursor, '\n', size_t(limit - cursor)));
+            if (!newline && !at_end)
+                break;  // the rest of this line is in the next chunk
+            const char *line_end = newline ? newline + 1 : limit;  // fgets keeps the newline: it is part of the line
+            line_no++;
+            const char *end = line_end;
+            if (const void *nul = memchr(cursor, 0, size_t(end - cursor)))  // a C string ends at its first NUL
+                end = static_cast<const char *>(nul);
+            if (comment_length) {
+                const void *cut = memmem(cursor, size_t(end - cursor), comment, comment_length);
+                if (cut)
+                    end = static_cast<const char *>(cut);
+            }
+            int num_token = 0;
+            bool bad = false;
+            Pending edge;
+            edge.w = 1;
+            for (const char *c = cursor; c < end;) {
+                while (c < end && is_delimiter[uint8_t(*c)])
+                    c++;
+                if (c == end)
+                    break;
+                const char *token = c;
+                while (c < end && !is_delimiter[uint8_t(*c)])
+                    c++;
+                if (num_token == 0)
+                    edge.u = token, edge.u_length = uint32_t(c - token);
+                else if (num_token == 1)
+                    edge.v = token, edge.v_length = uint32_t(c - token);
+                else if (num_token == 2)
+                    edge.w = float(atof(std::string(token, size_t(c - token)).c_str()));
+                else
+                    bad = true;
+                num_token++;
+            }
+            cursor = line_end;
+            if (num_token == 0)
+                continue;
+            if (num_token < 2 || bad) {
+                fclose(fin);
+                throw std::runtime_error("Invalid format at line " + std::to_string(line_no));
+            }
+            edge.u_hash = NameTable::hash(edge.u, edge.u_length);
+            edge.v_hash = NameTable::hash(edge.v, edge.v_length);
+            names.prefetch(edge.u_hash);
+            names.prefetch(edge.v_hash);
+            pending[num_pending++] = edge;
+            if (num_pending == kBatch)
+                resolve();
         }
-        add_edge(names[0], names[1], w);
+        resolve();  // the names point into the buffer, which is about to move
+        held = size_t(limit - cursor);
+        memmove(buffer.data(), cursor, held);
     }
     fclose(fin);
+    phase.mark("graph file: parse + intern");
     flatten();
+    phase.mark("graph file: flatten");
     if (normalization)
         normalize();
 }
@@ -258,9 +380,9 @@ void Graph::load_corpus(const char *file_name, int window, int min_count, bool n
     while (fgets(line.data(), int(kMaxLineLength), fin)) {
         sentence.clear();
         for_each_word([&](const std::string &word) {
-            auto found = name2id.find(word);
-            if (found != name2id.end())
-                sentence.push_back(found->second);
+            const uint32_t found = names.find(word, id2name);
+            if (found != NameTable::kNone)
+                sentence.push_back(found);
         });
         for (size_t i = 0; i < sentence.size(); i++)
             for (int j = 1; j <= window && i + j < sentence.size(); j++) {
@@ -380,6 +502,26 @@ void Graph::save(const char *file_name, bool weighted, bool anonymous) {
     fclose(fout);
 }
 
+bool Graph::uniform_edge_table(float &probability) {
+    flatten();
+    if (uniform_cache < 0) {
+        const size_t m = edge_w.size();
+        bool uniform = m > 0;
+        for (size_t e = 1; e < m && uniform; e++)
+            uniform = edge_w[e] == edge_w[0];
+        if (uniform) {
+            double norm = 0;  // AliasTable::build's own normaliser (base/alias_table.cuh:92), same order of additions
+            for (size_t e = 0; e < m; e++)
+                norm += edge_w[e];
+            norm = norm / m;
+            uniform_probability = float(double(edge_w[0]) / norm);
+        }
+        uniform_cache = uniform ? 1 : 0;
+    }
+    probability = uniform_probability;
+    return uniform_cache == 1;
+}
+
 bool Graph::has_dead_end() const {
     for (size_t v = 0; v < degrees.size(); v++)
         if (degrees[v] == 0)
@@ -491,8 +633,8 @@ int64_t gv_graph_name2id(const gv_graph_t *graph, const char *name) {
             return -1;
         return g.id_of_original[original];
     }
-    auto found = g.name2id.find(name);
-    return found == g.name2id.end() ? -1 : int64_t(found->second);
+    const uint32_t found = g.names.find(name, strlen(name), gv::NameTable::hash(name, strlen(name)), g.id2name);
+    return found == gv::NameTable::kNone ? -1 : int64_t(found);
 }
 
 int gv_graph_load_id_edges(gv_graph_t *graph, const uint32_t *u, const uint32_t *v, const float *weights,

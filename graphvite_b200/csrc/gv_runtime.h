@@ -105,6 +105,57 @@ struct DeviceArray {
     }
 };
 
+// Host -> device copies of large PAGEABLE arrays (the graph's std::vectors).  cudaMemcpyAsync from pageable memory
+// measured 1.4 GB/s on the B200 boxes (89 MB of CSR in 64 ms inside train()); here the bytes go through two page-locked
+// staging buffers -- the CPU copies chunk i + 1 while the DMA engine moves chunk i.
+struct StagedUploader {
+    static constexpr size_t kChunk = size_t(8) << 20;
+    void *staging[2] = {nullptr, nullptr};
+    cudaEvent_t moved[2] = {nullptr, nullptr};
+    StagedUploader() {}
+    StagedUploader(const StagedUploader &) = delete;
+    StagedUploader &operator=(const StagedUploader &) = delete;
+    ~StagedUploader() { release(); }
+    void release() {
+        for (int i = 0; i < 2; i++) {
+            if (staging[i])
+                cudaFreeHost(staging[i]);
+            if (moved[i])
+                cudaEventDestroy(moved[i]);
+            staging[i] = nullptr;
+            moved[i] = nullptr;
+        }
+    }
+    // dst (device) <- src (host, any memory); returns when the bytes have left `src` and are queued on `stream`
+    void copy(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+        if (bytes < kChunk) {
+            GV_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(stream));
+            return;
+        }
+        for (int i = 0; i < 2; i++)
+            if (!staging[i]) {
+                GV_CHECK_CUDA(cudaMallocHost(&staging[i], kChunk));
+                GV_CHECK_CUDA(cudaEventCreateWithFlags(&moved[i], cudaEventDisableTiming));
+            }
+        int which = 0;
+        for (size_t done = 0; done < bytes; done += kChunk, which ^= 1) {
+            const size_t n = std::min(kChunk, bytes - done);
+            GV_CHECK_CUDA(cudaEventSynchronize(moved[which]));  // the copy that last used this buffer (none: returns at once)
+            memcpy(staging[which], static_cast<const char *>(src) + done, n);
+            GV_CHECK_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + done, staging[which], n, cudaMemcpyHostToDevice, stream));
+            GV_CHECK_CUDA(cudaEventRecord(moved[which], stream));
+        }
+        GV_CHECK_CUDA(cudaStreamSynchronize(stream));
+    }
+    template<class T>
+    void upload(DeviceArray &array, const std::vector<T> &host, cudaStream_t stream) {
+        array.allocate(host.size() * sizeof(T));
+        if (!host.empty())
+            copy(array.ptr, host.data(), host.size() * sizeof(T), stream);
+    }
+};
+
 // core/optimizer.h:42-134
 struct HostOptimizer {
     gv_optimizer_t desc;

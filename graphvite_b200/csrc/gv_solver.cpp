@@ -275,6 +275,7 @@ struct Solver {
             cudaStreamDestroy(random_stream);
     }
 
+    StagedUploader uploader;  // pageable graph arrays -> device
     std::vector<void *> pinned_host;
     void unpin_host() {
         for (void *pointer : pinned_host)
@@ -575,15 +576,20 @@ struct Solver {
         }
         sampling_ready = false;
         PhaseTimer phase;  // GV_LOG=2
-        // edge_table.build(graph->edge_weights), core/solver.h:255-256
-        std::vector<float> edge_prob(m);
-        std::vector<uint64_t> edge_alias(m);
+        // edge_table.build(graph->edge_weights), core/solver.h:255-256.  When every edge weighs the same (any
+        // unweighted graph) AliasTable::build takes its trivial branch -- one probability, alias = identity -- and the
+        // table (12 bytes per directed edge) is written by the device instead of built on the host and uploaded.
+        float uniform_probability = 1;
+        const bool uniform = graph->uniform_edge_table(uniform_probability);
+        std::vector<float> edge_prob(uniform ? 0 : m);
+        std::vector<uint64_t> edge_alias(uniform ? 0 : m);
         // Vose over all directed edges is sequential (0.1 s for 1e7 edges): overlap it with the uploads
         // and with the per-vertex tables below
         std::exception_ptr edge_error;
         std::thread edge_builder([&]() {
             try {
-                build_alias<uint64_t>(graph->edge_w.data(), m, edge_prob.data(), edge_alias.data());
+                if (!uniform)
+                    build_alias<uint64_t>(graph->edge_w.data(), m, edge_prob.data(), edge_alias.data());
             } catch (...) {
                 edge_error = std::current_exception();
             }
@@ -595,9 +601,14 @@ struct Solver {
                     thread.join();
             }
         } joiner{edge_builder};
-        d_offsets.upload(graph->offsets, sample_stream);
-        d_edge_u.upload(graph->edge_u, sample_stream);
-        d_edge_v.upload(graph->edge_v, sample_stream);
+        // the CSR: offsets and targets travel (through page-locked staging), the source column is expanded from the
+        // offsets on the device
+        uploader.upload(d_offsets, graph->offsets, sample_stream);
+        uploader.upload(d_edge_v, graph->edge_v, sample_stream);
+        d_edge_u.allocate(m * sizeof(uint32_t));
+        GV_CHECK_ABI(gv_cuda_expand_sources(d_offsets.as<uint64_t>(), graph->num_vertex(), d_edge_u.as<uint32_t>(),
+                                            sample_stream));
+        stat_launches++;
         phase.mark("  CSR upload");
         device_graph.num_vertex = graph->num_vertex();
         device_graph.num_edge = m;
@@ -612,7 +623,12 @@ struct Solver {
             // build_vertex_edge, graph.cuh:645-653: one alias table per vertex over its out-edges, laid out at the
             // vertex's CSR range; built on the device (thread per vertex, the reference's pairing order)
             DeviceArray d_weights, d_little, d_large;
-            d_weights.upload(graph->edge_w, sample_stream);
+            if (uniform) {
+                d_weights.allocate(m * sizeof(float));
+                GV_CHECK_ABI(gv_cuda_fill_float(d_weights.as<float>(), m, graph->edge_w[0], sample_stream));
+                stat_launches++;
+            } else
+                uploader.upload(d_weights, graph->edge_w, sample_stream);
             d_vertex_tables.allocate(std::max<size_t>(m, 1) * sizeof(gv_alias_entry_t));
             d_little.allocate(std::max<size_t>(m, 1) * sizeof(uint32_t));
             d_large.allocate(std::max<size_t>(m, 1) * sizeof(uint32_t));
@@ -628,8 +644,16 @@ struct Solver {
         phase.mark("  edge alias table (rest)");
         if (edge_error)
             std::rethrow_exception(edge_error);
-        d_edge_prob.upload(edge_prob, sample_stream);
-        d_edge_alias.upload(edge_alias, sample_stream);
+        if (uniform) {
+            d_edge_prob.allocate(m * sizeof(float));
+            d_edge_alias.allocate(m * sizeof(uint64_t));
+            GV_CHECK_ABI(gv_cuda_fill_float(d_edge_prob.as<float>(), m, uniform_probability, sample_stream));
+            GV_CHECK_ABI(gv_cuda_fill_identity(d_edge_alias.as<uint64_t>(), m, sample_stream));
+            stat_launches += 2;
+        } else {
+            uploader.upload(d_edge_prob, edge_prob, sample_stream);
+            uploader.upload(d_edge_alias, edge_alias, sample_stream);
+        }
         device_graph.edge_prob = d_edge_prob.as<float>();
         device_graph.edge_alias = d_edge_alias.as<uint64_t>();
         if (sample_mode == 2)
@@ -1409,7 +1433,11 @@ struct Solver {
         GV_CHECK_CUDA(cudaSetDevice(device));
         while (step_in_episode != 0)  // never stop in the middle of an episode
             train_step();
+        PhaseTimer phase;  // GV_LOG=2
+        GV_CHECK_CUDA(cudaStreamSynchronize(work_stream));
+        phase.mark("last train launches drained");
         write_back();
+        phase.mark("write-back");
         training = false;
     }
 
@@ -1461,6 +1489,7 @@ struct Solver {
         negative_tables.clear();
         partition_ids.clear();
         close_peers();
+        uploader.release();
         pool_arena.release();
         for (int side = 0; side < 2; side++)
             pool_pointers[side].release();

@@ -325,6 +325,13 @@ int gv_cuda_kg_relation_apply(float *global, float *work, const float *delta, ui
  * dst[i] = src[ids[i]] when gather != 0, else dst[ids[i]] = src[i]. */
 int gv_cuda_move_rows(float *dst, const float *src, const uint32_t *ids, uint64_t num_row, int dim, int gather,
                       void *stream);
+/* Device-side construction of what the host would otherwise compute and upload for the samplers:
+ * dst[i] = value; dst[i] = i (the alias column of AliasTable::build for uniform weights, base/alias_table.cuh:84-128:
+ * every entry is a leftover that aliases to itself); edge_u[e] = v for offsets[v] <= e < offsets[v + 1] (the source
+ * column of GraphMixin::flatten's edge list, core/graph.h:87-101). */
+int gv_cuda_fill_float(float *dst, uint64_t n, float value, void *stream);
+int gv_cuda_fill_identity(uint64_t *dst, uint64_t n, void *stream);
+int gv_cuda_expand_sources(const uint64_t *offsets, uint32_t num_vertex, uint32_t *edge_u, void *stream);
 
 /* ---- host runtime: Graph (instance/graph.cuh:62-277, bind.h:109-187) ------------------- */
 
