@@ -358,7 +358,10 @@ def run_ours(args, cfg):
     e2e_steps = max(1, e2e_edges // (edges_per_step * world))
     matrix_bytes = graph.num_vertex * cfg["dim"] * 4
     directed = 2 * graph.num_edge
-    h2d = 2 * matrix_bytes + directed * (4 + 4 + 4 + 8 + 8) + graph.num_vertex * 24
+    # what train() copies to the device: the vertex matrix (the zero context matrix is cleared there), CSR offsets and
+    # targets, the negative table; an unweighted graph's source column, edge alias table and weights are built on the
+    # device (gv_solver.cpp::prepare_sampling)
+    h2d = matrix_bytes + directed * 4 + graph.num_vertex * (8 + 8)
     d2h = 2 * matrix_bytes
     e2e_stats = solver2.stats
     model_quality = None
