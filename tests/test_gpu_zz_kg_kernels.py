@@ -1,6 +1,6 @@
 """GPU parity of the knowledge-graph kernels (gv_cuda_kg_train_block / gv_cuda_kg_predict) against the
-knowledge-graph oracle.  NOT yet run on a GPU (written after the round's GPU budget was spent); the file
-sorts last so that it cannot mask the validated suites under `pytest -x`.
+knowledge-graph oracle (green on B200s: GPUTEST_r01 and `profiles/r02_kg_kernel_tests_after_diet.txt`); the file sorts
+behind the node-embedding suites under `pytest -x`.
 
 Tolerances: ids bit-exact; floats follow the same algorithm with a different summation order (slices of
 E contiguous floats per thread + butterfly / shared-memory sum instead of lane-strided + shfl_down) and
