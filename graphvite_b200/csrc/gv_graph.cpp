@@ -252,7 +252,9 @@ void Graph::load_file(const char *file_name, bool undirected, bool normalized, c
             log_w.reserve(directed);
         }
     }
-    const size_t kChunk = size_t(64) << 20;
+    // bytes read at a time (GV_LOAD_CHUNK: a small value makes every line straddle a chunk boundary -- tests)
+    const size_t kChunk = getenv("GV_LOAD_CHUNK") ? std::max<size_t>(16, strtoull(getenv("GV_LOAD_CHUNK"), nullptr, 10))
+                                                  : size_t(64) << 20;
     std::vector<char> buffer(kChunk + 1);
     size_t held = 0, line_no = 0;  // bytes of an incomplete line carried over from the previous chunk
     bool at_end = false;

@@ -8,10 +8,12 @@
 // (include/base/alias_table.cuh:148-152,175-183 over the all-ones table of
 // instance/knowledge_graph.cuh:316-319).
 //
-// STATUS: sm_100a, 224-234 registers for 8 floats per thread with Adam, no spills.  Parity: tests/test_gpu_zz_kg_*.py
-// and tests/test_gpu_zzzz_kg_full_size.py (green on a B200 in the round-1 driver run, GPUTEST_r01.json) against the
-// oracle and against golden vectors recorded from the reference's own kernels; the same files also run under the
-// CUDA emulation of tests/emu.
+// STATUS: sm_100a, 239 registers for 8 floats per thread with RotatE / Adam, no spills.  Parity: tests/test_gpu_zz_kg_*.py
+// and tests/test_gpu_zzzz_kg_full_size.py, green on B200s (GPUTEST_r01; profiles/r02_kg_kernel_tests_after_diet.txt for
+// the math of this revision) against the oracle and against golden vectors recorded from the reference's own kernels;
+// the same files also run under the CUDA emulation of tests/emu.  Measured (profiles/r02b_summary.md): RotatE d = 2048,
+// k = 64, Adam: 6.5e5 positives/s per B200 = 0.38 of the HBM roofline; bound by instruction issue at 8 warps per SM
+// (1 340 instructions per thread and target), not by memory (DRAM 23 % busy) -- see the math policy below.
 //
 // Design.  One positive sample = 1 + k targets that share the relation row and, each, either the
 // positive head or the positive tail.  The reference walks the targets with one warp and

@@ -354,3 +354,48 @@ int main() {
     assert float(worst) <= 1.6, worst
     assert float(far) < 1e-6, far
     assert nan_ok == "1"
+
+
+def test_graph_file_loader_chunk_boundaries_long_names_and_odd_lines(tmp_path):
+    """The file loader reads large chunks, carries incomplete lines over, hashes a batch of lines ahead of resolving it
+    and keeps the first 11 bytes of a name inline in its table: a file with names of 1 .. 300 bytes (shared prefixes
+    longer than 11 and than 255 bytes), blank and comment-only lines, CRLF, a weight column, no newline at the end --
+    loaded with chunk sizes that cut every line -- must equal the same edges loaded as a Python list."""
+    import subprocess
+    import sys
+    import graphvite_b200 as gv
+    rng = np.random.RandomState(11)
+    stem = "x" * 290
+    names = ["v%d" % i for i in range(40)] + ["abcdefghijk_%d" % i for i in range(20)] + \
+            ["abcdefghijkl" + "y" * int(n) for n in rng.randint(0, 40, 15)] + [stem + "%02d" % i for i in range(10)]
+    names = list(dict.fromkeys(names))
+    edges = [(names[a], names[b], round(float(w), 3)) for a, b, w in
+             zip(rng.randint(0, len(names), 600), rng.randint(0, len(names), 600), rng.rand(600) + 0.5)]
+    path = tmp_path / "odd.txt"
+    with open(path, "wb") as out:
+        out.write(b"# header comment\r\n\r\n   \n")
+        for i, (u, v, w) in enumerate(edges):
+            separator = b"\t" if i % 3 == 0 else b" "
+            ending = b"\r\n" if i % 5 == 0 else b"\n"
+            tail = b"  # trailing comment" if i % 7 == 0 else b""
+            if i == len(edges) - 1:
+                ending = b""  # no newline at the end of the file
+            out.write(u.encode() + separator + v.encode() + separator + (b"%.3f" % w) + tail + ending)
+            if i % 50 == 0:
+                out.write(b"#only a comment\n")
+    expected = gv.graph.Graph()
+    expected.load([(u, v, w) for u, v, w in edges])
+    reference = tmp_path / "expected.txt"
+    expected.save(str(reference))
+    script = ("import sys; import graphvite_b200 as gv; g = gv.graph.Graph(); g.load(sys.argv[1]); g.save(sys.argv[2]); "
+              "print(g.num_vertex, g.num_edge, g.name2id[%r], g.name2id[%r])" % (names[-1], names[3]))
+    for chunk in (None, 16, 37, 301, 4096):
+        env = dict(os.environ)
+        if chunk:
+            env["GV_LOAD_CHUNK"] = str(chunk)
+        saved = tmp_path / ("saved_%s.txt" % chunk)
+        done = subprocess.run([sys.executable, "-c", script, str(path), str(saved)], env=env, cwd=ROOT, check=True,
+                              stdout=subprocess.PIPE, text=True)
+        assert done.stdout.split() == [str(expected.num_vertex), str(expected.num_edge),
+                                       str(expected.name2id[names[-1]]), str(expected.name2id[names[3]])], chunk
+        assert saved.read_bytes() == reference.read_bytes(), chunk
