@@ -109,7 +109,9 @@ struct DeviceArray {
 // measured 1.4 GB/s on the B200 boxes (89 MB of CSR in 64 ms inside train()); here the bytes go through two page-locked
 // staging buffers -- the CPU copies chunk i + 1 while the DMA engine moves chunk i.
 struct StagedUploader {
-    static constexpr size_t kChunk = size_t(8) << 20;
+    // bytes per staging buffer (GV_UPLOAD_CHUNK: a few KB makes the toy graphs of the tests take the chunked path)
+    const size_t kChunk = getenv("GV_UPLOAD_CHUNK") ? std::max<size_t>(256, strtoull(getenv("GV_UPLOAD_CHUNK"), nullptr, 10))
+                                                    : size_t(8) << 20;
     void *staging[2] = {nullptr, nullptr};
     cudaEvent_t moved[2] = {nullptr, nullptr};
     StagedUploader() {}

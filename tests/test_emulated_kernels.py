@@ -39,7 +39,8 @@ GROUPS.append((["tests/test_gpu_zz_kg_kernels.py", "tests/test_gpu_y_fill.py"], 
                          ids=[g[0][0].split("test_gpu_")[1][:-3] + ("-reverse" if "reverse" in g[1] else "") for g in GROUPS])
 def test_gpu_suite_under_cuda_emulation(files, what):
     files = [f for f in files if os.path.exists(os.path.join(ROOT, f))]
-    env = dict(os.environ, GV_EMULATE="1", GV_EMU_BACKTRACE="1")
+    # GV_UPLOAD_CHUNK: the toy graphs' arrays go through the chunked, double-buffered staging path of the big ones
+    env = dict(os.environ, GV_EMULATE="1", GV_EMU_BACKTRACE="1", GV_UPLOAD_CHUNK="1024")
     if "reverse" in what:
         env["GV_EMU_WARP_ORDER"] = "reverse"
         env["GV_EMU_LANE_ORDER"] = "reverse"
