@@ -42,6 +42,11 @@ WORKLOADS = {
     "node2vec_youtube": dict(YOUTUBE, graph="youtube_capped", model="node2vec", p=0.25, q=0.25),
     # config/graph/line_friendster.yaml: d=96 in the yaml, BASELINE.json quotes d=128; augmentation 2, episode 2500
     "friendster_lite": dict(YOUTUBE, graph="friendster_lite", augmentation_step=2, episode_size=2500),
+    # the two configurations that need all 8 GPUs of a box (never run: the round had no 8-GPU lease long enough):
+    #   torchrun --nnodes=1 --nproc-per-node 8 ... bench.py --gpus 8 --workload friendster            (65.6 M / 1.8 G)
+    #   torchrun --nnodes=1 --nproc-per-node 8 ... bench.py --gpus 8 --workload node2vec_youtube_full (209 GB of tables)
+    "friendster": dict(YOUTUBE, graph="friendster", augmentation_step=2, episode_size=2500),
+    "node2vec_youtube_full": dict(YOUTUBE, graph="youtube", model="node2vec", p=0.25, q=0.25),
     # config/knowledge_graph/rotate_fb15k-237.yaml
     "rotate_fb15k237": dict(solver="kg", graph="fb15k-237", dim=2048, model="RotatE", lr=2e-6, weight_decay=0,
                             num_negative=64, batch_size=100000, episode_size=1, margin=9.0, adversarial_temperature=2.0,
