@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -13,6 +14,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gv_engine.h"
@@ -70,6 +72,66 @@ inline bool log_enabled() {
     return on;
 }
 
+// The [|V|][dim] host matrices behind the numpy views (and their moment copies): zero-filled float arrays like
+// std::vector<float>::assign(n, 0.f), but on 2-MB-aligned memory with MADV_HUGEPAGE and zeroed by a few threads --
+// first-touching 1.2 GB in 4-KB pages from one thread was the largest part of build() at Youtube size, and fewer,
+// larger pages also make cudaHostRegister cheaper.
+class HostMatrix {
+public:
+    HostMatrix() {}
+    HostMatrix(const HostMatrix &) = delete;
+    HostMatrix &operator=(const HostMatrix &) = delete;
+    ~HostMatrix() { free(base); }
+    float *data() { return base; }
+    const float *data() const { return base; }
+    size_t size() const { return count; }
+    bool empty() const { return count == 0; }
+    float *begin() { return base; }
+    float *end() { return base + count; }
+    void clear() {
+        free(base);
+        base = nullptr;
+        count = 0;
+    }
+    // n zeros (the previous contents are dropped)
+    void assign(size_t n, float value) {
+        if (value != 0.f)
+            throw std::logic_error("HostMatrix::assign: only zero fill");
+        if (n != count) {
+            clear();
+            if (n) {
+                const size_t huge = size_t(2) << 20, bytes = (n * sizeof(float) + huge - 1) / huge * huge;
+                void *memory = nullptr;
+                if (posix_memalign(&memory, n * sizeof(float) >= huge ? huge : 64, bytes) != 0)
+                    throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+                if (n * sizeof(float) >= huge)
+                    madvise(memory, bytes, MADV_HUGEPAGE);
+#endif
+                base = static_cast<float *>(memory);
+                count = n;
+            }
+        }
+        zero();
+    }
+    void zero() {
+        const size_t threads = count < (size_t(1) << 24) ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < threads; t++)
+            pool.emplace_back([this, t, threads]() {
+                memset(base + count * t / threads, 0, (count * (t + 1) / threads - count * t / threads) * sizeof(float));
+            });
+        if (count)
+            memset(base, 0, count / threads * sizeof(float));
+        for (auto &thread : pool)
+            thread.join();
+    }
+
+private:
+    float *base = nullptr;
+    size_t count = 0;
+};
+
 // RAII device allocation
 struct DeviceArray {
     void *ptr = nullptr;
@@ -100,6 +162,13 @@ struct DeviceArray {
         allocate(host.size() * sizeof(T));
         if (!host.empty()) {
             GV_CHECK_CUDA(cudaMemcpyAsync(ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+            GV_CHECK_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+    void upload(const HostMatrix &host, cudaStream_t stream = 0) {
+        allocate(host.size() * sizeof(float));
+        if (!host.empty()) {
+            GV_CHECK_CUDA(cudaMemcpyAsync(ptr, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
             GV_CHECK_CUDA(cudaStreamSynchronize(stream));
         }
     }

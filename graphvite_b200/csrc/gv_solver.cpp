@@ -118,8 +118,8 @@ struct Solver {
     std::vector<gv_location_t> locations;
     uint32_t partition_size = 0;
     bool built = false;
-    std::vector<float> vertex_host, context_host;                       // numpy views
-    std::vector<float> vertex_m1_host, context_m1_host, vertex_m2_host, context_m2_host;
+    HostMatrix vertex_host, context_host;                               // numpy views
+    HostMatrix vertex_m1_host, context_m1_host, vertex_m2_host, context_m2_host;
 
     // ---- train parameters (readonly attributes, bind.h:415-436) ----
     std::string model;
@@ -944,7 +944,7 @@ struct Solver {
 
     // ---- host <-> device block movement (replaces Memory::gather/scatter + to_device/to_host) ----
     struct HostState {
-        std::vector<float> *matrix[3];
+        HostMatrix *matrix[3];
     };
     HostState vertex_state() { return {{&vertex_host, &vertex_m1_host, &vertex_m2_host}}; }
     HostState context_state() { return {{&context_host, &context_m1_host, &context_m2_host}}; }
@@ -1092,20 +1092,7 @@ struct Solver {
         // x = init(seed) for every element, in row-major order -- drawn in bulk (gv_engine.h), same values
         std::uniform_real_distribution<float> init(-0.5 / dim, 0.5 / dim);
         g_engine.fill_uniform(vertex_host.data(), vertex_host.size(), init.a(), init.b());
-        zero_matrix(context_host);
-    }
-
-    // m = 0 on a few threads (583 MB per matrix at Youtube size: 60 ms on one core)
-    static void zero_matrix(std::vector<float> &m) {
-        const size_t threads = m.size() < (size_t(1) << 24) ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
-        std::vector<std::thread> pool;
-        for (size_t t = 1; t < threads; t++)
-            pool.emplace_back([&m, t, threads]() {
-                std::memset(m.data() + m.size() * t / threads, 0, (m.size() * (t + 1) / threads - m.size() * t / threads) * sizeof(float));
-            });
-        std::memset(m.data(), 0, m.size() / threads * sizeof(float));
-        for (auto &thread : pool)
-            thread.join();
+        context_host.zero();
     }
 
     // ---- GraphSolver::train prologue + SolverMixin::train up to the first pool fill ----
@@ -1159,7 +1146,7 @@ struct Solver {
             initializer = std::thread([this]() {
                 init_embeddings();
                 for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
-                    zero_matrix(*m);
+                    m->zero();
             });
             batch_id = 0;
         }
@@ -1500,7 +1487,7 @@ struct Solver {
                         &d_table_offsets})
             a->release();
         for (auto *m : {&vertex_m1_host, &context_m1_host, &vertex_m2_host, &context_m2_host})
-            std::vector<float>().swap(*m);
+            m->clear();
         partitions.clear();
         sampling_ready = false;
         built = false;
